@@ -1,0 +1,196 @@
+"""CPU ORACLE -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A plain-PyTorch (CPU, fp32 or fp64) restatement of the HComP-Net per-node prototype head and
+its fused losses, written against the reference's algorithm line by line.  Only `tests/`,
+`__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs may import
+it, and only as the checker / reported baseline.  The product (`pipnet_b200/`) never does:
+it fails loudly when its CUDA extension is missing.
+
+Pinning: the reference has NO tests or golden vectors for this path, so
+the oracle is pinned against the reference itself, imported unmodified in the build container
+(`oracle/ref_harness.py`): `tests/test_oracle_vs_reference.py` compares every output below with
+`PIPNet.forward` + `calculate_loss` + autograd on identical inputs, and
+`oracle/make_golden.py` freezes reference outputs into `tests/golden/*.npz` for the GPU box.
+
+Each function cites the reference lines it restates (paths relative to /root/reference).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- forward
+def head_forward(x, add_on_w: Dict[str, torch.Tensor], cls_w: Dict[str, torch.Tensor], root, *,
+                 softmax_tau=1.0, inference=False, cls_b: Optional[Dict[str, torch.Tensor]] = None):
+    """`PIPNet.forward` after the backbone (`pipnet/pipnet.py:124-170`), canonical recipe
+    (`--softmax "y|tau"`, plain Conv2d add-on without bias, NonNegLinear classifier).
+
+    x        [V, C, H, W]  backbone features
+    add_on_w name -> [P_n, C]   1x1 conv kernels (`pipnet/pipnet.py:125`, built `:1207-1208`)
+    cls_w    name -> [C_n, P_n] NonNegLinear weights (`pipnet/pipnet.py:1035-1036`)
+    returns proto_features (softmaxed maps), pooled, argmax (flat h*W+w, first max), out
+    """
+    V, C, H, W = x.shape
+    proto, pooled, argmax, out = {}, {}, {}, {}
+    for node in root.nodes_with_children():
+        w = add_on_w[node.name]
+        z = torch.einsum('vchw,pc->vphw', x, w)                    # 1x1 conv           pipnet.py:125
+        z = z / softmax_tau                                        #                    pipnet.py:146
+        s = torch.softmax(z, dim=1)                                # over the node's prototypes  :147
+        proto[node.name] = s
+        flat = s.flatten(2)                                        # [V, P_n, H*W]
+        pv, pi = flat.max(dim=2)                                   # AdaptiveMaxPool2d(1) + Flatten :159
+        # `Tensor.max(dim)` does not promise which index it returns on ties; the reference's
+        # index convention is F.max_pool2d(return_indices=True) (pipnet.py:24-25) == first in
+        # row-major order, which is what argmax documents.
+        pi = flat.argmax(dim=2)
+        if inference:
+            pv = torch.where(pv < 0.1, torch.zeros_like(pv), pv)  #                    pipnet.py:168-169
+        pooled[node.name] = pv
+        argmax[node.name] = pi
+        b = None if cls_b is None else cls_b.get(node.name)
+        out[node.name] = F.linear(pv, torch.relu(cls_w[node.name]), b)   # NonNegLinear  pipnet.py:1036
+    return proto, pooled, argmax, out
+
+
+# --------------------------------------------------------------------------- per-node masks
+def node_targets(root, ys, label2name):
+    """For every node: boolean mask of samples whose leaf lies below the node and, for those,
+    the label of the child on the path (`pipnet/train.py:934-937`)."""
+    names = [label2name[int(y)] for y in ys]
+    masks, targets = {}, {}
+    for node in root.nodes_with_children():
+        m = torch.tensor([n in node.leaf_descendents for n in names], dtype=torch.bool)
+        t = [node.children_to_labels[node.closest_descendent_for(n).name] for n in names if n in node.leaf_descendents]
+        masks[node.name] = m
+        targets[node.name] = torch.tensor(t, dtype=torch.long)
+    return masks, targets
+
+
+# --------------------------------------------------------------------------- loss terms
+def align_loss(inputs, targets, eps=1e-12):
+    """`pipnet/train.py:1399-1405`: -mean log(<x, y> + eps) over rows."""
+    return -torch.log((inputs * targets).sum(dim=1) + eps).mean()
+
+
+def align_pf_term(s_node, mask):
+    """`pipnet/train.py:1063-1069`: the masked batch is chunked into the two views, each
+    map flattened to [n*H*W, P_n]; symmetric loss with the other side detached."""
+    pf1, pf2 = s_node[mask].chunk(2)
+    e1 = pf1.flatten(2).permute(0, 2, 1).flatten(end_dim=1)
+    e2 = pf2.flatten(2).permute(0, 2, 1).flatten(end_dim=1)
+    return (align_loss(e1, e2.detach()) + align_loss(e2, e1.detach())) / 2.
+
+
+def tanh_term(pooled_node, mask, eps=1e-8):
+    """`pipnet/train.py:1080-1082` (EPS passed by train_pipnet is 1e-8, `pipnet/train.py:238`)."""
+    p1, p2 = pooled_node[mask].chunk(2)
+    return -(torch.log(torch.tanh(p1.sum(dim=0)) + eps).mean() + torch.log(torch.tanh(p2.sum(dim=0)) + eps).mean()) / 2.
+
+
+def orth_term(w_node, cls_w_node):
+    """`pipnet/train.py:1137-1142` + `orth_dist :1408-1412`: prototypes with any classifier
+    weight > 1e-3; Frobenius norm of (gram - I) on the smaller side."""
+    rel = w_node[(cls_w_node > 0.001).any(dim=0)]
+    mat = rel.reshape(rel.shape[0], -1)
+    if mat.shape[0] < mat.shape[1]:
+        mat = mat.permute(1, 0)
+    return torch.norm(mat.t() @ mat - torch.eye(mat.shape[1], dtype=mat.dtype))
+
+
+def class_term(out_node, mask, target, weights, multiplier=2.0):
+    """`pipnet/train.py:1158-1163` with `WeightedNLLLoss` (`util/custom_losses.py:22-34`):
+    x = log1p(out**m); per-sample NLL(log_softmax(x)) times the weight of the target class;
+    mean over the node's descendants in the batch."""
+    x = torch.log1p(out_node[mask] ** multiplier)
+    lp = F.log_softmax(x, dim=1)
+    nll = -lp.gather(1, target[:, None]).squeeze(1)
+    w = weights.to(lp.dtype)[target]
+    return (nll * w).mean()
+
+
+def head_losses(root, proto, pooled, out, ys, label2name, add_on_w, cls_w, *, pretrain, finetune,
+                epoch=1, nr_epochs=10, cl_weight=2.0, kernel_orth=True, tanh_during_second_phase=True,
+                multiplier=2.0):
+    """The head's share of `calculate_loss` (`pipnet/train.py:852-1341`) for the canonical recipe
+    (align_pf + tanh + kernel_orth + class loss), with `train_pipnet`'s weights
+    (`pipnet/train.py:148-177`) and the `/len(nodes)` normaliser.  Nodes with no descendant in
+    the batch are skipped (`:941-942`) but still counted in the normaliser."""
+    nodes = root.nodes_with_children()
+    n_nodes = len(nodes)
+    if pretrain:
+        align_pf_weight, t_weight, cw = (epoch / nr_epochs) * 1., 5., 0.
+    else:
+        align_pf_weight, t_weight, cw = 5., 2., cl_weight
+    orth_weight = 0.5
+    masks, targets = node_targets(root, ys, label2name)
+    res = dict(align={}, tanh={}, orth={}, cls={}, n_desc={}, acc={})
+    loss = 0.
+    for node in nodes:
+        m, t = masks[node.name], targets[node.name]
+        if t.numel() == 0:
+            continue
+        res['n_desc'][node.name] = int(t.numel())
+        if not finetune:
+            a = align_pf_term(proto[node.name], m)
+            res['align'][node.name] = a
+            loss = loss + align_pf_weight * a / n_nodes
+            if pretrain or tanh_during_second_phase:
+                th = tanh_term(pooled[node.name], m)
+                res['tanh'][node.name] = th
+                loss = loss + t_weight * th / n_nodes
+        if (not pretrain) and (not finetune) and kernel_orth:
+            o = orth_term(add_on_w[node.name], cls_w[node.name])
+            res['orth'][node.name] = o
+            loss = loss + orth_weight * o / n_nodes
+        if not pretrain:
+            c = class_term(out[node.name], m, t, node.weights, multiplier)
+            res['cls'][node.name] = c
+            loss = loss + cw * c / n_nodes
+        pred = out[node.name][m].argmax(dim=1)                     # pipnet/train.py:1189-1190
+        res['acc'][node.name] = (int(t.numel()), int((pred == t).sum()))
+    res['loss'] = loss
+    return res
+
+
+# --------------------------------------------------------------------------- joint leaf distribution
+def joint_distribution(root, out, softmax_tau=1.0):
+    """`PIPNet.get_joint_distribution` (`pipnet/pipnet.py:173-185`) -> `Node.distribution_over_furthest_descendents`
+    (`util/node.py:383-385`): product along each root->leaf path of
+    softmax(log1p(out[node]**2)/tau)[:, child]; columns re-ordered by sorted leaf name."""
+    V = out[root.name].shape[0]
+
+    def rec(node):
+        if node.is_leaf():
+            return torch.ones(V, 1, dtype=out[root.name].dtype), [node.name]
+        p = torch.softmax(torch.log1p(out[node.name] ** 2) / softmax_tau, dim=1)
+        cols, names = [], []
+        for i, c in enumerate(node.children):
+            sub, nm = rec(c)
+            cols.append(p[:, i:i + 1] * sub)
+            names += nm
+        return torch.cat(cols, 1), names
+
+    dist, names = rec(root)
+    order = sorted(range(len(names)), key=lambda i: names[i])
+    return dist[:, order]
+
+
+# --------------------------------------------------------------------------- convenience: one full step
+def full_step(x, add_on_w, cls_w, root, ys, label2name, *, pretrain, finetune, softmax_tau=1.0, **kw):
+    """Forward + losses + autograd backward; returns outputs and gradients w.r.t. x, add-on and
+    classifier weights (what `loss.backward()` at `pipnet/train.py:264` produces for the head)."""
+    x = x.detach().clone().requires_grad_(True)
+    aw = {k: v.detach().clone().requires_grad_(True) for k, v in add_on_w.items()}
+    cw = {k: v.detach().clone().requires_grad_(True) for k, v in cls_w.items()}
+    proto, pooled, argmax, out = head_forward(x, aw, cw, root, softmax_tau=softmax_tau)
+    res = head_losses(root, proto, pooled, out, ys, label2name, aw, cw, pretrain=pretrain, finetune=finetune, **kw)
+    loss = res['loss']
+    if torch.is_tensor(loss) and loss.requires_grad:
+        loss.backward()
+    res.update(proto=proto, pooled=pooled, argmax=argmax, out=out, grad_x=x.grad,
+               grad_w={k: v.grad for k, v in aw.items()}, grad_cls={k: v.grad for k, v in cw.items()})
+    return res
