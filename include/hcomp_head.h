@@ -1,0 +1,146 @@
+/* hcomp_head.h -- C ABI of the B200-native HComP-Net per-node prototype head.
+ *
+ * This is the drop-in boundary for ONE hot path of harishB97/PIPNet: everything between the
+ * backbone output and the loss scalar in `PIPNet.forward` (pipnet/pipnet.py:111-171) and the head's
+ * share of `calculate_loss` (pipnet/train.py:852-1341), forward and backward.  Plain pointers and
+ * sizes only, no torch types.  Every entry point
+ *   - takes DEVICE pointers (unless the name says host) and a CUDA stream (`cudaStream_t` as void*),
+ *   - never allocates device memory (workspaces are passed in), never synchronises the stream,
+ *   - returns 0 on success or a negative HCOMP_E_* code; `hcomp_last_error()` gives the text.
+ * There is no CPU fallback: on a machine without an sm_100 device the compute calls fail.
+ *
+ * Layout vocabulary (host code in pipnet_b200/layout.py builds the tables):
+ *   nodes      N internal tree nodes in `root.nodes_with_children()` order (util/node.py:174-185)
+ *   P          total prototypes = sum of P_n; flat prototype axis = nodes concatenated in that order
+ *   K          total child logits = sum of C_n; flat logit axis, same order
+ *   rows       one row per (view, location): M = V*HW rows of C channels, bf16, channels-last
+ *   tiles      the padded prototype axis: 128-column tiles of equal-length node segments
+ *              (int32 records of HCOMP_TILE_INTS words: {S, nseg, umma_n, 0, node[16], len[16], poff[16]})
+ *   P_pad      128 * number of tiles
+ */
+#ifndef HCOMP_HEAD_H
+#define HCOMP_HEAD_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HCOMP_ABI_VERSION 1
+#define HCOMP_TILE_INTS 52
+#define HCOMP_TILE_COLS 128
+#define HCOMP_MAX_SEGS 16
+
+#define HCOMP_E_ARG (-1)      /* invalid argument / unsupported shape */
+#define HCOMP_E_CUDA (-2)     /* CUDA runtime or driver error */
+#define HCOMP_E_DEVICE (-3)   /* not an sm_100 device */
+
+/* Static per-model tables (all DEVICE pointers, int32 unless noted). */
+typedef struct hcomp_tables {
+  int32_t n_nodes, n_protos, n_cols, n_leaves, n_welems, p_max;
+  const int32_t* proto_off;    /* [N+1] start of node n on the flat prototype axis            */
+  const int32_t* cls_off;      /* [N+1] start of node n on the flat child-logit axis          */
+  const int32_t* wc_off;       /* [N+1] start of node n's [C_n, P_n] classifier weights       */
+  const int32_t* proto_node;   /* [P]   node of flat prototype p                              */
+  const int32_t* col_node;     /* [K]   node of flat child column k                           */
+  const int32_t* welem_col;    /* [n_welems] flat child column of classifier weight element   */
+  const int32_t* welem_proto;  /* [n_welems] flat prototype of classifier weight element      */
+  const float* child_w;        /* [K]   class-loss weight min(d)/d_c (util/node.py:37-41)     */
+  const int32_t* path_off;     /* [L+1] root->leaf path of leaf l (leaves in sorted-name order)*/
+  const int32_t* path_col;     /* [..]  flat child column taken at each step of the path      */
+  const int8_t* anc;           /* [L,N] child label of leaf l at node n, -1 if not below n     */
+} hcomp_tables;
+
+int hcomp_abi_version(void);
+const char* hcomp_last_error(void);
+int hcomp_num_sms(void);
+
+/* ---- operand preparation -------------------------------------------------------------------- */
+/* fp32 add-on kernels (flat [P,C]; reference: nn.Conv2d weights built at pipnet/pipnet.py:1207) ->
+ * bf16 tile-padded [P_pad,C]; row_map[P_pad] gives the flat row of each padded row or -1. */
+int hcomp_pack_weights(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp_bf16, void* stream);
+/* channels-last fp32 features -> bf16 rows (ConvNeXt-26 output is NHWC in memory). n % 8 == 0. */
+int hcomp_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* NCHW-contiguous features (ResNet) -> bf16 rows [V*HW, C]. */
+int hcomp_nchw_to_rows_bf16(const void* src, int src_is_bf16, int V, int C, int HW, void* dst_bf16, void* stream);
+/* tgt[V,N], desc[V_first,N], n_desc[N] from labels (pipnet/train.py:934-937). ys is int64[V]. */
+int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc,
+                       int32_t* n_desc, void* stream);
+
+/* ---- K1: projection + softmax + max-pool (+ align loss) -------------------------------------- */
+/* Replaces conv1x1 -> /tau -> softmax(dim=1) -> AdaptiveMaxPool2d for every node
+ * (pipnet/pipnet.py:124-159) and the align_pf reduction (pipnet/train.py:1063-1069).
+ * x: bf16 [V*HW, C]; views [0,V_first) are paired with views [V_first, V) (train: V_first = V/2).
+ * pooled_packed[V,P] and align_sum[N] are cleared by the call.  desc/align_sum may be NULL. */
+int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
+                                const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
+                                int P_pad, int n_nodes, float tau, const uint8_t* desc,
+                                unsigned long long* pooled_packed, double* align_sum, void* stream);
+/* packed -> pooled fp32 [V,P] + argmax int32 [V,P] (flat h*W+w, first occurrence; pipnet/pipnet.py:24-25);
+ * thresh > 0 applies the inference rule pooled < thresh -> 0 (pipnet/pipnet.py:168-169). */
+int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
+                      void* stream);
+int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, int HW, float* loss, void* stream);
+
+/* ---- K5-K7: backward -------------------------------------------------------------------------- */
+/* dZ = S * (G - sum_p G*S) / tau with G = align gradient + g_pooled scattered at argmax; recomputes the
+ * logits tile (same GEMM as K1).  scat_ws: int2[V*P], coef_ws: float[V_first*N] workspaces.
+ * g_align (per node upstream gradient), desc may be NULL.  dz: bf16 [V*HW, P_pad], fully written. */
+int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host, const int32_t* tiles_dev,
+                      int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau,
+                      const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
+                      const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
+                      void* dz_bf16, void* stream);
+/* dX[rows,C] (bf16) = dZ[rows,P_pad] * Wp[P_pad,C]. */
+int hcomp_head_bwd_dx(const void* dz_bf16, const void* wp_bf16, long long rows, int P_pad, int C, void* dx_bf16,
+                      void* stream);
+/* dW[P,C] (fp32, ACCUMULATED into; clear it first) += dZ^T * X, padded rows dropped via row_map. */
+int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map, long long rows, int P_pad, int C,
+                      float* dw_flat, void* stream);
+
+/* ---- K2: per-node non-negative classifier (pipnet/pipnet.py:1035-1036) ------------------------- */
+int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias, const hcomp_tables* t, int V,
+                         float* out, void* stream);
+/* g_pooled (accumulate flag), g_wc[n_welems], g_bias[K] (may be NULL). */
+int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* wc, const hcomp_tables* t, int V,
+                         float* g_pooled, int accumulate, float* g_wc, float* g_bias, void* stream);
+
+/* ---- losses ------------------------------------------------------------------------------------ */
+/* class loss per node: NLL(log_softmax(log1p(out^2))) * w[target], mean over the node's samples
+ * (pipnet/train.py:1153-1163, util/custom_losses.py:22-34); n_correct[N] for the accuracy bookkeeping. */
+int hcomp_class_loss_fwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
+                         int sparsity, float* loss, int32_t* n_correct, void* stream);
+int hcomp_class_loss_bwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const float* g_loss,
+                         const hcomp_tables* t, int V, int sparsity, float* g_out, void* stream);
+/* tanh loss per node (pipnet/train.py:1076-1087); colsum: float[2*P] workspace kept for the backward. */
+int hcomp_tanh_loss_fwd(const float* pooled, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
+                        int V_first, float eps, float* loss, float* colsum, void* stream);
+int hcomp_tanh_loss_bwd(const float* colsum, const int8_t* tgt, const float* g_loss, const hcomp_tables* t, int V,
+                        int V_first, float eps, float* g_pooled, int accumulate, void* stream);
+/* kernel-orthogonality loss per node (pipnet/train.py:1136-1151, orth_dist :1408-1412); E: float[N*p_max*p_max],
+ * rel: uint8[P] workspaces kept for the backward; g_w[P,C] is accumulated into. */
+int hcomp_orth_loss_fwd(const float* w_flat, const float* wc, const int32_t* n_desc, const hcomp_tables* t, int C,
+                        float* loss, float* E, uint8_t* rel, void* stream);
+int hcomp_orth_loss_bwd(const float* w_flat, const float* loss, const float* E, const uint8_t* rel, const float* g_loss,
+                        const hcomp_tables* t, int C, float* g_w, void* stream);
+
+/* ---- predictions (util/node.py:300-385, pipnet/pipnet.py:173-185) ------------------------------ */
+/* probs_ws: float[V*K]; joint: float[V*L] (columns in sorted leaf-name order); pred: int64[V] argmax. */
+int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, float* probs_ws, float* joint,
+                     long long* pred, void* stream);
+
+/* ---- visualisation feed (util/vis_hpipnet.py:62-127) ------------------------------------------- */
+/* full softmax map of ONE node, fp32 [V, P_n, HW]; w_node: fp32 [P_n, C]. */
+int hcomp_materialize_map(const void* x_bf16, const float* w_node, int V, int HW, int C, int P_n, float tau, float* map,
+                          void* stream);
+
+/* ---- self-test hook: plain tcgen05 GEMM used by tests (D = A*B, bf16 in, fp32/bf16 out) --------- */
+/* a_mn/b_mn: operand stored with its M (resp. N) axis contiguous.  out_mode 0 bf16, 1 fp32, 2 fp32 red.add. */
+int hcomp_gemm_bf16(const void* a, const void* b, int M, int N, int K, int a_mn, int b_mn, int out_mode, int splits,
+                    void* out, long long ldo, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HCOMP_HEAD_H */

@@ -1,0 +1,89 @@
+"""Shared builders for the parity tests: one seeded problem instance expressed both ways --
+per-node dicts for the CPU oracle and flat tensors for the CUDA path."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from pipnet_b200.layout import build_layout
+from pipnet_b200.trees import get_tree, NAMED, build_tree
+
+
+def make_tree(tree, *, num_features=0, per_child=0, per_desc=0):
+    root = get_tree(tree) if isinstance(tree, str) else build_tree(tree)
+    for node in root.nodes_with_children():
+        node.set_num_protos(num_protos_per_descendant=per_desc, num_protos_per_child=per_child,
+                            min_protos=num_features, split_protos=True)
+        node.set_loss_weightage_using_descendants_count()
+    return root
+
+
+def bf16_round(t: torch.Tensor) -> torch.Tensor:
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class Problem:
+    """Seeded weights / features / labels.  Add-on kernels are xavier-uniform (util/func.py:8-10),
+    classifier weights N(1, 0.1) on each child's own prototype slice and -0.5 elsewhere
+    (pipnet/pipnet.py:1026, :1235-1248), features N(0,1) rounded to bf16 (the GEMM operand type)."""
+
+    def __init__(self, tree, C, H, B, *, seed=0, num_features=0, per_child=0, paired=True, V=None, feat_scale=1.0):
+        self.root = make_tree(tree, num_features=num_features, per_child=per_child)
+        self.layout = build_layout(self.root)
+        L = self.layout
+        g = torch.Generator().manual_seed(seed)
+        self.C, self.H, self.W = C, H, H
+        self.V = 2 * B if V is None else V
+        self.V_first = B if paired else (self.V + 1) // 2
+        self.w = {}
+        for name, pn in zip(L.node_names, L.P_n):
+            bound = float(np.sqrt(6.0 / (C + int(pn))))
+            self.w[name] = bf16_round((torch.rand(int(pn), C, generator=g, dtype=torch.float64) * 2 - 1) * bound)
+        self.wc = {}
+        for node in self.root.nodes_with_children():
+            pn, cn = node.num_protos, node.num_children()
+            w = 1.0 + 0.1 * torch.randn(cn, pn, generator=g, dtype=torch.float64)
+            if node.num_protos_per_child:
+                start = 0
+                for child in node.children:
+                    lab = node.children_to_labels[child.name]
+                    end = start + node.num_protos_per_child[child.name]
+                    w[lab, :start] = -0.5
+                    w[lab, end:] = -0.5
+                    start = end
+            self.wc[node.name] = w.float().double()
+        self.x = bf16_round(torch.randn(self.V, C, H, H, generator=g, dtype=torch.float64) * feat_scale)
+        ys = torch.randint(0, L.L, (self.V_first,), generator=g)
+        self.ys = torch.cat([ys, ys])[: self.V] if paired else torch.randint(0, L.L, (self.V,), generator=g)
+        self.label2name = {i: n for i, n in enumerate(L.leaf_names)}
+
+    # flat views for the CUDA path
+    def w_flat(self, device):
+        return torch.cat([self.w[n] for n in self.layout.node_names]).float().to(device)
+
+    def wc_flat(self, device):
+        return torch.cat([self.wc[n].reshape(-1) for n in self.layout.node_names]).float().to(device)
+
+    def features(self, device, dtype=torch.bfloat16, channels_last=True):
+        x = self.x.to(device=device, dtype=dtype)
+        return x.contiguous(memory_format=torch.channels_last) if channels_last else x.contiguous()
+
+    def cat_nodes(self, d, dim=1):
+        return torch.cat([d[n] for n in self.layout.node_names], dim=dim)
+
+
+def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.double().cpu(), b.double().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def argmax_report(arg_gpu, arg_ref, proto_ref_flat):
+    """Argmax must be bit-exact; when an entry differs report the gap between the reference's best and
+    the value at the location the GPU chose (a true tie up to accumulation order has gap ~1e-7)."""
+    arg_gpu, arg_ref = arg_gpu.cpu().long(), arg_ref.cpu().long()
+    bad = (arg_gpu != arg_ref).nonzero()
+    gaps = []
+    for v, p in bad.tolist():
+        row = proto_ref_flat[v, p]
+        gaps.append(float(row[arg_ref[v, p]] - row[arg_gpu[v, p]]) / max(float(row[arg_ref[v, p]]), 1e-30))
+    return bad.shape[0], gaps

@@ -1,0 +1,40 @@
+"""In-tree build of libhcomp_head.so (sm_100a only; nvcc cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, 'csrc', 'cabi.cu')
+OUT = os.path.join(HERE, 'libhcomp_head.so')
+DEPS = [os.path.join(HERE, 'csrc', f) for f in ('cabi.cu', 'ptx.cuh', 'head_pair.cuh', 'gemm_tc.cuh', 'small_kernels.cuh')]
+DEPS.append(os.path.join(os.path.dirname(HERE), 'include', 'hcomp_head.h'))
+
+NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
+              '-std=c++17']
+
+
+def up_to_date() -> bool:
+    if not os.path.isfile(OUT):
+        return False
+    t = os.path.getmtime(OUT)
+    return all(os.path.getmtime(d) <= t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and up_to_date():
+        return OUT
+    nvcc = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', OUT, SRC]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        sys.stderr.write(r.stdout + r.stderr)
+        raise RuntimeError('nvcc failed building libhcomp_head.so')
+    if verbose:
+        print(r.stderr)
+    return OUT
+
+
+if __name__ == '__main__':
+    print(build(force='--force' in sys.argv, verbose='-v' in sys.argv))

@@ -1,0 +1,453 @@
+// C-ABI entry points of libhcomp_head.so (declared in include/hcomp_head.h).
+// Host side only: argument checks, TMA tensor-map encoding, launch geometry.  No allocation,
+// no stream synchronisation, no CPU fallback.
+#include "../../include/hcomp_head.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "gemm_tc.cuh"
+#include "head_pair.cuh"
+#include "small_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define HC_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) return fail(HCOMP_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define HC_LAUNCH_CHECK(name)                                                                      \
+  do {                                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                           \
+    if (_e != cudaSuccess) return fail(HCOMP_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct DevInfo {
+  int ok = 0, sms = 0, cc_major = 0, cc_minor = 0;
+};
+int dev_info(DevInfo* out) {
+  int dev = 0;
+  HC_CUDA(cudaGetDevice(&dev));
+  static DevInfo cache[64];
+  if (dev < 64 && cache[dev].ok) { *out = cache[dev]; return 0; }
+  DevInfo d;
+  HC_CUDA(cudaDeviceGetAttribute(&d.sms, cudaDevAttrMultiProcessorCount, dev));
+  HC_CUDA(cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+  HC_CUDA(cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+  if (d.cc_major != 10) return fail(HCOMP_E_DEVICE, "device %d is sm_%d%d; this library is sm_100a only", dev, d.cc_major, d.cc_minor);
+  d.ok = 1;
+  if (dev < 64) cache[dev] = d;
+  *out = d;
+  return 0;
+}
+
+// 2D bf16 row-major tensor [outer, inner] (inner contiguous, pitch in elements), 128B-swizzled boxes.
+int make_tmap(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long outer,
+              unsigned long long pitch_elems, unsigned box_inner, unsigned box_outer) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(HCOMP_E_ARG, "operand base not 16-byte aligned");
+  if ((pitch_elems * 2) % 16 != 0) return fail(HCOMP_E_ARG, "row pitch %llu bytes is not a multiple of 16", pitch_elems * 2);
+  if (box_inner * 2 != 128 || box_outer > 256) return fail(HCOMP_E_ARG, "bad TMA box");
+  cuuint64_t gdim[2] = {inner, outer};
+  cuuint64_t gstr[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled failed with %d (inner %llu outer %llu pitch %llu)", int(r), inner, outer, pitch_elems);
+  return 0;
+}
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
+
+template <int SEG, bool BWD>
+int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms, cudaStream_t st) {
+  auto kern = hc::head_pair_kernel<SEG, BWD>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::PAIR_SMEM_BYTES));
+    attr_done = true;
+  }
+  const int items = p.num_m_tiles * p.num_tiles;
+  const int grid = items < sms ? items : sms;
+  kern<<<grid, hc::PAIR_THREADS, hc::PAIR_SMEM_BYTES, st>>>(tx, tw, p);
+  HC_LAUNCH_CHECK(BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>");
+  return 0;
+}
+
+template <bool BWD>
+int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms,
+                      cudaStream_t st) {
+  switch (seg) {
+    case 8: return launch_pair<8, BWD>(tx, tw, p, sms, st);
+    case 16: return launch_pair<16, BWD>(tx, tw, p, sms, st);
+    case 20: return launch_pair<20, BWD>(tx, tw, p, sms, st);
+    case 32: return launch_pair<32, BWD>(tx, tw, p, sms, st);
+    case 40: return launch_pair<40, BWD>(tx, tw, p, sms, st);
+    default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40)", seg);
+  }
+}
+
+// Shared driver of K1 / K5: one launch per segment class (tiles are sorted by class).
+template <bool BWD>
+int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int32_t* tiles_dev, int n_tiles, int V,
+             int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau, hc::HeadParams base, cudaStream_t st) {
+  DevInfo di;
+  if (int e = dev_info(&di)) return e;
+  if (V <= 0 || V_first <= 0 || V_first > V || V - V_first > V_first) return fail(HCOMP_E_ARG, "bad view split V=%d V_first=%d", V, V_first);
+  if (HW < 32) return fail(HCOMP_E_ARG, "HW=%d < 32 locations per image is not supported", HW);
+  if (C % 8 != 0 || C <= 0) return fail(HCOMP_E_ARG, "C=%d must be a positive multiple of 8", C);
+  if (P_pad != n_tiles * hc::TILE_N) return fail(HCOMP_E_ARG, "P_pad=%d != 128*n_tiles", P_pad);
+  if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
+  const long long M = (long long)V * HW;
+  if (M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
+  CUtensorMap tx, tw;
+  if (int e = make_tmap(&tx, x, C, M, C, hc::KBLK, hc::TILE_M)) return e;
+  if (int e = make_tmap(&tw, wp, C, P_pad, C, hc::KBLK, hc::TILE_N)) return e;
+  hc::HeadParams p = base;
+  p.M = int(M);
+  p.halfM = V_first * HW;
+  p.rowsB = int(M) - p.halfM;
+  p.HW = HW; p.C = C; p.P = P; p.P_pad = P_pad;
+  p.num_k_blocks = cdiv(C, hc::KBLK);
+  p.num_m_tiles = cdiv(p.halfM, hc::TILE_M);
+  p.n_nodes = n_nodes;
+  p.imgs_first = V_first;
+  p.scale_log2 = 1.4426950408889634f / tau;
+  p.inv_tau = 1.f / tau;
+  p.tiles = tiles_dev;
+  int t = 0;
+  while (t < n_tiles) {
+    const int seg = tiles_host[(size_t)t * hc::TILE_INTS];
+    int e = t;
+    while (e < n_tiles && tiles_host[(size_t)e * hc::TILE_INTS] == seg) {
+      const int32_t* rec = tiles_host + (size_t)e * hc::TILE_INTS;
+      if (rec[1] <= 0 || rec[1] * seg > hc::TILE_N || rec[2] % 16 != 0 || rec[2] < rec[1] * seg || rec[2] > hc::TILE_N)
+        return fail(HCOMP_E_ARG, "malformed tile record %d", e);
+      ++e;
+    }
+    p.tile_begin = t;
+    p.num_tiles = e - t;
+    if (int err = launch_pair_class<BWD>(seg, tx, tw, p, di.sms, st)) return err;
+    t = e;
+  }
+  return 0;
+}
+
+template <bool A_MN, bool B_MN, int OUT>
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const hc::GemmParams& p, int sms, cudaStream_t st) {
+  auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::G_SMEM_BYTES));
+    attr_done = true;
+  }
+  const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
+  const int grid = items < sms ? items : sms;
+  kern<<<grid, hc::G_THREADS, hc::G_SMEM_BYTES, st>>>(ta, tb, p);
+  HC_LAUNCH_CHECK("gemm_tc_kernel");
+  return 0;
+}
+
+// D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
+// else [N,K].  splits <= 0 picks a split-K factor that fills the GPU (only meaningful for OUT_RED_F32).
+int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool a_mn, bool b_mn, int out_mode, int splits,
+             void* out, long long ldo, const int32_t* row_map, cudaStream_t st) {
+  DevInfo di;
+  if (int e = dev_info(&di)) return e;
+  if (M <= 0 || N <= 0 || K <= 0) return fail(HCOMP_E_ARG, "empty GEMM");
+  if (M > 0x7fffffffLL || K > 0x7fffffffLL) return fail(HCOMP_E_ARG, "GEMM dimension overflow");
+  if ((out_mode == hc::OUT_BF16 && (N % 8 || ldo % 8)) || (out_mode != hc::OUT_BF16 && (N % 4 || ldo % 4)))
+    return fail(HCOMP_E_ARG, "N=%d / ldo=%lld alignment", N, ldo);
+  CUtensorMap ta, tb;
+  if (a_mn) { if (int e = make_tmap(&ta, a, M, K, M, 64, 64)) return e; }
+  else      { if (int e = make_tmap(&ta, a, K, M, K, hc::G_BK, hc::G_BM)) return e; }
+  if (b_mn) { if (int e = make_tmap(&tb, b, N, K, N, 64, 64)) return e; }
+  else      { if (int e = make_tmap(&tb, b, K, N, K, hc::G_BK, hc::G_BN)) return e; }
+  hc::GemmParams p{};
+  p.M = int(M); p.N = N; p.K = int(K);
+  p.num_m_tiles = cdiv(M, hc::G_BM);
+  p.num_n_tiles = cdiv(N, hc::G_BN);
+  p.num_k_blocks = cdiv(K, hc::G_BK);
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  if (out_mode != hc::OUT_RED_F32) splits = 1;
+  if (splits <= 0) splits = di.sms / tiles_mn;
+  if (splits < 1) splits = 1;
+  if (splits > p.num_k_blocks) splits = p.num_k_blocks;
+  p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
+  p.splits = cdiv(p.num_k_blocks, p.k_blocks_per_split);
+  p.out = out; p.ldo = ldo; p.row_map = row_map;
+#define HC_GEMM_CASE(AM, BM, OM) \
+  if (a_mn == AM && b_mn == BM && out_mode == OM) return launch_gemm<AM, BM, OM>(ta, tb, p, di.sms, st);
+  HC_GEMM_CASE(false, true, hc::OUT_BF16)      // dX
+  HC_GEMM_CASE(true, true, hc::OUT_RED_F32)    // dW
+  HC_GEMM_CASE(false, false, hc::OUT_F32)      // self-test: plain K-major GEMM
+  HC_GEMM_CASE(false, true, hc::OUT_F32)
+  HC_GEMM_CASE(true, true, hc::OUT_F32)
+  HC_GEMM_CASE(true, false, hc::OUT_F32)
+#undef HC_GEMM_CASE
+  return fail(HCOMP_E_ARG, "GEMM variant (a_mn=%d b_mn=%d out=%d) not instantiated", int(a_mn), int(b_mn), out_mode);
+}
+
+inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
+
+}  // namespace
+
+extern "C" {
+
+int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
+const char* hcomp_last_error(void) { return g_err; }
+int hcomp_num_sms(void) {
+  DevInfo di;
+  if (int e = dev_info(&di)) return e;
+  return di.sms;
+}
+
+int hcomp_pack_weights(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp_bf16, void* stream) {
+  if (C % 8) return fail(HCOMP_E_ARG, "C must be a multiple of 8");
+  const long long n = (long long)P_pad * (C / 8);
+  hc::pack_weights_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(w_flat, row_map, P_pad, C,
+                                                                  reinterpret_cast<__nv_bfloat16*>(wp_bf16));
+  HC_LAUNCH_CHECK("pack_weights");
+  return 0;
+}
+
+int hcomp_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream) {
+  if (n % 8) return fail(HCOMP_E_ARG, "n must be a multiple of 8");
+  const long long n8 = n / 8;
+  int grid = blocks(n8, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  hc::cast_f32_bf16_kernel<<<grid, 256, 0, S(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16), n8);
+  HC_LAUNCH_CHECK("cast_f32_bf16");
+  return 0;
+}
+
+int hcomp_nchw_to_rows_bf16(const void* src, int src_is_bf16, int V, int C, int HW, void* dst_bf16, void* stream) {
+  dim3 grid(cdiv(HW, 32), cdiv(C, 32), V), block(32, 8);
+  if (src_is_bf16)
+    hc::nchw_to_rows_bf16_kernel<__nv_bfloat16><<<grid, block, 0, S(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(src), reinterpret_cast<__nv_bfloat16*>(dst_bf16), C, HW);
+  else
+    hc::nchw_to_rows_bf16_kernel<float><<<grid, block, 0, S(stream)>>>(reinterpret_cast<const float*>(src),
+                                                                      reinterpret_cast<__nv_bfloat16*>(dst_bf16), C, HW);
+  HC_LAUNCH_CHECK("nchw_to_rows_bf16");
+  return 0;
+}
+
+int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc,
+                       int32_t* n_desc, void* stream) {
+  hc::label_tables_kernel<<<blocks(t->n_nodes, 128), 128, 0, S(stream)>>>(ys, t->anc, V, V_first, t->n_nodes, t->n_leaves,
+                                                                         tgt, desc, n_desc);
+  HC_LAUNCH_CHECK("label_tables");
+  return 0;
+}
+
+int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
+                                const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
+                                int P_pad, int n_nodes, float tau, const uint8_t* desc,
+                                unsigned long long* pooled_packed, double* align_sum, void* stream) {
+  hc::HeadParams p{};
+  p.pooled_packed = pooled_packed;
+  p.align_sum = align_sum;
+  p.desc = (align_sum != nullptr) ? desc : nullptr;
+  HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
+  if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
+  return run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau, p,
+                         S(stream));
+}
+
+int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
+                      void* stream) {
+  hc::unpack_pool_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(packed, n, thresh, pooled, argmax);
+  HC_LAUNCH_CHECK("unpack_pool");
+  return 0;
+}
+
+int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, int HW, float* loss, void* stream) {
+  hc::align_finalize_kernel<<<blocks(N, 128), 128, 0, S(stream)>>>(align_sum, n_desc, N, HW, loss);
+  HC_LAUNCH_CHECK("align_finalize");
+  return 0;
+}
+
+int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host, const int32_t* tiles_dev,
+                      int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau,
+                      const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
+                      const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
+                      void* dz_bf16, void* stream) {
+  const long long n = (long long)V * P;
+  hc::make_scat_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
+                                                               reinterpret_cast<int2*>(scat_ws));
+  HC_LAUNCH_CHECK("make_scat");
+  hc::HeadParams p{};
+  p.scat = reinterpret_cast<const int2*>(scat_ws);
+  p.dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
+  if (g_align != nullptr && desc != nullptr && n_desc != nullptr) {
+    hc::align_coef_kernel<<<blocks((long long)V_first * n_nodes, 256), 256, 0, S(stream)>>>(desc, n_desc, g_align, V_first,
+                                                                                           n_nodes, HW, coef_ws);
+    HC_LAUNCH_CHECK("align_coef");
+    p.coef_align = coef_ws;
+  }
+  return run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau, p,
+                        S(stream));
+}
+
+int hcomp_head_bwd_dx(const void* dz_bf16, const void* wp_bf16, long long rows, int P_pad, int C, void* dx_bf16,
+                      void* stream) {
+  return run_gemm(dz_bf16, wp_bf16, rows, C, P_pad, false, true, hc::OUT_BF16, 1, dx_bf16, C, nullptr, S(stream));
+}
+
+int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map, long long rows, int P_pad, int C,
+                      float* dw_flat, void* stream) {
+  return run_gemm(dz_bf16, x_bf16, P_pad, C, rows, true, true, hc::OUT_RED_F32, 0, dw_flat, C, row_map, S(stream));
+}
+
+int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias, const hcomp_tables* t, int V,
+                         float* out, void* stream) {
+  const long long n = (long long)V * t->n_cols;
+  hc::classifier_fwd_kernel<<<blocks(n, 128), 128, 0, S(stream)>>>(pooled, wc, bias, t->col_node, t->proto_off, t->cls_off,
+                                                                  t->wc_off, V, t->n_protos, t->n_cols, out);
+  HC_LAUNCH_CHECK("classifier_fwd");
+  return 0;
+}
+
+int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* wc, const hcomp_tables* t, int V,
+                         float* g_pooled, int accumulate, float* g_wc, float* g_bias, void* stream) {
+  if (g_pooled) {
+    const long long n = (long long)V * t->n_protos;
+    hc::classifier_bwd_pooled_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(g_out, wc, t->proto_node, t->proto_off,
+                                                                           t->cls_off, t->wc_off, V, t->n_protos,
+                                                                           t->n_cols, g_pooled, accumulate);
+    HC_LAUNCH_CHECK("classifier_bwd_pooled");
+  }
+  if (g_wc) {
+    const long long n = (long long)t->n_welems * 32;
+    hc::classifier_bwd_weight_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(g_out, pooled, wc, t->welem_col, t->welem_proto,
+                                                                           V, t->n_protos, t->n_cols, t->n_welems, g_wc,
+                                                                           nullptr);
+    HC_LAUNCH_CHECK("classifier_bwd_weight");
+  }
+  if (g_bias) {
+    hc::classifier_bwd_bias_kernel<<<blocks(t->n_cols, 128), 128, 0, S(stream)>>>(g_out, V, t->n_cols, g_bias);
+    HC_LAUNCH_CHECK("classifier_bwd_bias");
+  }
+  return 0;
+}
+
+int hcomp_class_loss_fwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
+                         int sparsity, float* loss, int32_t* n_correct, void* stream) {
+  hc::class_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(out, tgt, t->child_w, t->cls_off, n_desc, V, t->n_nodes,
+                                                              t->n_cols, sparsity, loss, n_correct);
+  HC_LAUNCH_CHECK("class_loss_fwd");
+  return 0;
+}
+
+int hcomp_class_loss_bwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const float* g_loss,
+                         const hcomp_tables* t, int V, int sparsity, float* g_out, void* stream) {
+  const long long n = (long long)V * t->n_cols;
+  hc::class_loss_bwd_kernel<<<blocks(n, 128), 128, 0, S(stream)>>>(out, tgt, t->child_w, t->col_node, t->cls_off, n_desc,
+                                                                  g_loss, V, t->n_nodes, t->n_cols, sparsity, g_out);
+  HC_LAUNCH_CHECK("class_loss_bwd");
+  return 0;
+}
+
+int hcomp_tanh_loss_fwd(const float* pooled, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
+                        int V_first, float eps, float* loss, float* colsum, void* stream) {
+  hc::tanh_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(pooled, tgt, t->proto_off, n_desc, V, V_first, t->n_nodes,
+                                                             t->n_protos, eps, loss, colsum);
+  HC_LAUNCH_CHECK("tanh_loss_fwd");
+  return 0;
+}
+
+int hcomp_tanh_loss_bwd(const float* colsum, const int8_t* tgt, const float* g_loss, const hcomp_tables* t, int V,
+                        int V_first, float eps, float* g_pooled, int accumulate, void* stream) {
+  const long long n = (long long)V * t->n_protos;
+  hc::tanh_loss_bwd_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(colsum, tgt, t->proto_node, t->proto_off, g_loss, V,
+                                                                 V_first, t->n_nodes, t->n_protos, eps, g_pooled,
+                                                                 accumulate);
+  HC_LAUNCH_CHECK("tanh_loss_bwd");
+  return 0;
+}
+
+int hcomp_orth_loss_fwd(const float* w_flat, const float* wc, const int32_t* n_desc, const hcomp_tables* t, int C,
+                        float* loss, float* E, uint8_t* rel, void* stream) {
+  if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
+  hc::orth_loss_fwd_kernel<<<t->n_nodes, 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off, n_desc, C,
+                                                             t->p_max, loss, E, rel);
+  HC_LAUNCH_CHECK("orth_loss_fwd");
+  return 0;
+}
+
+int hcomp_orth_loss_bwd(const float* w_flat, const float* loss, const float* E, const uint8_t* rel, const float* g_loss,
+                        const hcomp_tables* t, int C, float* g_w, void* stream) {
+  hc::orth_loss_bwd_kernel<<<t->n_protos, 128, 0, S(stream)>>>(w_flat, t->proto_off, C, t->p_max, loss, E, rel, g_loss,
+                                                              t->proto_node, g_w);
+  HC_LAUNCH_CHECK("orth_loss_bwd");
+  return 0;
+}
+
+int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, float* probs_ws, float* joint,
+                     long long* pred, void* stream) {
+  hc::node_probs_kernel<<<blocks((long long)V * t->n_nodes, 128), 128, 0, S(stream)>>>(out, t->cls_off, V, t->n_nodes,
+                                                                                      t->n_cols, 1.f / tau, probs_ws);
+  HC_LAUNCH_CHECK("node_probs");
+  hc::leaf_joint_kernel<<<blocks((long long)V * t->n_leaves, 128), 128, 0, S(stream)>>>(probs_ws, t->path_off, t->path_col,
+                                                                                       V, t->n_leaves, t->n_cols, joint);
+  HC_LAUNCH_CHECK("leaf_joint");
+  if (pred) {
+    hc::row_argmax_kernel<<<blocks(V, 128), 128, 0, S(stream)>>>(joint, V, t->n_leaves, pred);
+    HC_LAUNCH_CHECK("row_argmax");
+  }
+  return 0;
+}
+
+int hcomp_materialize_map(const void* x_bf16, const float* w_node, int V, int HW, int C, int P_n, float tau, float* map,
+                          void* stream) {
+  const int warps = 8;
+  const long long rows = (long long)V * HW;
+  hc::materialize_map_kernel<<<blocks(rows, warps), warps * 32, warps * P_n * sizeof(float), S(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x_bf16), w_node, V, HW, C, P_n, 1.f / tau, map);
+  HC_LAUNCH_CHECK("materialize_map");
+  return 0;
+}
+
+int hcomp_gemm_bf16(const void* a, const void* b, int M, int N, int K, int a_mn, int b_mn, int out_mode, int splits,
+                    void* out, long long ldo, void* stream) {
+  return run_gemm(a, b, M, N, K, a_mn != 0, b_mn != 0, out_mode, splits, out, ldo, nullptr, S(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,377 @@
+// Fused per-node prototype head: projection GEMM (tcgen05, TMA-fed, fp32 accumulators in TMEM)
+// whose epilogue does the per-location softmax over each node's prototypes and
+//   forward : global spatial max-pool with first-occurrence argmax + the CARL align loss
+//   backward: recomputes the softmax tile and emits dZ (bf16) for the dX / dW GEMMs
+// so the V x P x H x W activation map never touches HBM.
+//
+// Replaces, for all nodes at once, the reference's per-node loop
+//   conv1x1 (pipnet/pipnet.py:125) -> /tau (:146) -> softmax(dim=1) (:147) -> max-pool (:159)
+// and the align_pf term of calculate_loss (pipnet/train.py:1063-1069, align_loss :1399-1405).
+//
+// Work decomposition ("pair tile"): one CTA tile = 128 consecutive locations of view 1 AND the
+// same 128 locations of view 2 (rows + halfM) against one 128-column prototype tile.  Both
+// accumulators (2 x 128 TMEM columns) are live together because the align loss and its
+// gradient need S1 and S2 of the same (image, location); 2 accumulator stages => 512 columns.
+//
+// Warp roles (384 threads, 1 CTA/SM, persistent over items):
+//   warp 0   : TMA producer   (A1, A2, W tiles; 4-stage ring, 48 KB per stage)
+//   warp 1   : MMA issuer     (one thread; 2 x 4 tcgen05.mma per k-block)
+//   warp 2   : TMEM allocator
+//   warp 3   : idle
+//   warps 4-11: epilogue      (warp%4 selects the TMEM lane quadrant; the two warps of a
+//                              quadrant split the tile's node segments even/odd)
+#pragma once
+#include "ptx.cuh"
+
+namespace hc {
+
+constexpr int TILE_N = 128;          // prototype columns per tile (TMEM columns per accumulator)
+constexpr int TILE_M = 128;          // locations per tile
+constexpr int KBLK = 64;             // bf16 elements per k-block (one 128-byte swizzle row)
+constexpr int MAX_SEGS = 16;         // node segments per tile (S >= 8)
+constexpr int TILE_INTS = 4 + 3 * MAX_SEGS;   // {S, nseg, umma_n, 0, node[16], len[16], poff[16]}
+constexpr int PAIR_STAGES = 4;
+constexpr int PAIR_STAGE_BYTES = 3 * TILE_M * KBLK * 2;   // A1 + A2 + W = 48 KB
+constexpr int PAIR_THREADS = 384;
+constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+
+struct HeadParams {
+  int M, halfM, rowsB;      // rows total; rows of the first half (= second half's row offset); valid rows in 2nd half
+  int HW, C, P, P_pad;
+  int num_k_blocks;
+  int tile_begin, num_tiles, num_m_tiles;
+  int n_nodes, imgs_first;  // images in the first half (= B for paired training batches)
+  float scale_log2, inv_tau;
+  const int32_t* tiles;
+  // forward
+  unsigned long long* pooled_packed;   // [V,P]  (float bits << 32) | (0xFFFFFFFF - flat location)
+  double* align_sum;                   // [n_nodes] sum over masked rows of -log(ip + 1e-12); may be null
+  const uint8_t* desc;                 // [imgs_first, n_nodes] 1 if image's leaf is below node; null -> no align
+  // backward
+  const int2* scat;                    // [V,P] {argmax location, g_pooled bits}
+  const float* coef_align;             // [imgs_first, n_nodes] upstream * 0.5 / (n_desc * HW) (0 if masked); may be null
+  __nv_bfloat16* dz;                   // [M, P_pad]
+};
+
+struct PairSmem {
+  uint64_t full[PAIR_STAGES];
+  uint64_t empty[PAIR_STAGES];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int S>
+__device__ __forceinline__ void softmax_row(uint32_t* raw, int len, float scale_log2, float* s) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    float x = (i < len) ? __uint_as_float(raw[i]) : -INFINITY;
+    s[i] = x;
+    m = fmaxf(m, x);
+  }
+  const float mk = m * scale_log2;
+  float l = 0.f;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    s[i] = ex2(fmaf(s[i], scale_log2, -mk));
+    l += s[i];
+  }
+  const float inv = __frcp_rn(l);
+#pragma unroll
+  for (int i = 0; i < S; ++i) s[i] *= inv;
+}
+
+// Max over the warp's rows (per column) with first-row tie break, merged into the packed
+// [V,P] table with one 64-bit atomicMax per (row group, column).
+template <int S>
+__device__ __forceinline__ void pool_segment(const float* s, bool valid, int v_row, int v_first, bool has_boundary,
+                                             int loc_first, int lane_b, int len, int lane,
+                                             unsigned long long* packed_v0 /* &packed[(view img 0 of warp)*P + poff] */,
+                                             int P) {
+#pragma unroll 1
+  for (int g = 0; g < 2; ++g) {
+    if (g == 1 && !has_boundary) break;
+    const bool in_g = valid && ((g == 0) ? (v_row == v_first) : (v_row != v_first));
+    if (__ballot_sync(0xffffffffu, in_g) == 0u) continue;
+    uint32_t m0 = 0, b0 = 0, m1 = 0, b1 = 0;
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      const uint32_t bits = in_g ? __float_as_uint(s[i]) : 0u;   // softmax >= 0: uint order == float order
+      const uint32_t m = redux_max_u32(bits);
+      const uint32_t bal = __ballot_sync(0xffffffffu, in_g && bits == m);
+      if ((i & 31) == lane) {
+        if (i < 32) { m0 = m; b0 = bal; } else { m1 = m; b1 = bal; }
+      }
+    }
+    unsigned long long* dst = packed_v0 + (size_t)g * P;
+    if (lane < len) {
+      const int fl = __ffs(b0) - 1;
+      const uint32_t loc = (g == 0) ? (loc_first + fl) : (fl - lane_b);
+      atomicMax(dst + lane, ((unsigned long long)m0 << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
+    }
+    if (S > 32 && lane + 32 < len) {
+      const int fl = __ffs(b1) - 1;
+      const uint32_t loc = (g == 0) ? (loc_first + fl) : (fl - lane_b);
+      atomicMax(dst + 32 + lane, ((unsigned long long)m1 << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
+    }
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void store_dz(__nv_bfloat16* dst, const float* d) {
+  // dst is 8-byte aligned: row pitch P_pad*2 (multiple of 256) + column offset j*S*2 with S % 4 == 0
+  uint2* p = reinterpret_cast<uint2*>(dst);
+#pragma unroll
+  for (int i = 0; i < S / 4; ++i) {
+    uint2 v;
+    v.x = pack_bf16x2(d[4 * i + 0], d[4 * i + 1]);
+    v.y = pack_bf16x2(d[4 * i + 2], d[4 * i + 3]);
+    p[i] = v;
+  }
+}
+
+template <int S, bool BWD>
+__global__ void __launch_bounds__(PAIR_THREADS, 1)
+head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const HeadParams p) {
+  static_assert(S % 4 == 0 && S >= 8 && S <= 40, "segment class");
+  constexpr int NSEG_MAX = TILE_N / S;
+  constexpr int SLOTS = (NSEG_MAX + 1) / 2;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  PairSmem* sb = reinterpret_cast<PairSmem*>(smem + PAIR_STAGES * PAIR_STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_items = p.num_m_tiles * p.num_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_x);
+    prefetch_tmap(&tmap_w);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < PAIR_STAGES; ++i) {
+      mbar_init(&sb->full[i], 1);
+      mbar_init(&sb->empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sb->tmem_full[i], 1);
+      mbar_init(&sb->tmem_empty[i], 8);   // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&sb->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sb->tmem_base;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int mt = item / p.num_tiles;
+        const int nt = item - mt * p.num_tiles;
+        const int row_a = mt * TILE_M;
+        const int row_b = p.halfM + row_a;
+        const int row_w = (p.tile_begin + nt) * TILE_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&sb->empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * PAIR_STAGE_BYTES;
+          mbar_arrive_expect_tx(&sb->full[stage], PAIR_STAGE_BYTES);
+          tma_load_2d(st, &tmap_x, &sb->full[stage], kb * KBLK, row_a);
+          tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kb * KBLK, row_b);
+          tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kb * KBLK, row_w);
+          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+        const int mt = item / p.num_tiles;
+        const int nt = item - mt * p.num_tiles;
+        const int umma_n = __ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2);
+        const uint32_t idesc = make_idesc(TILE_M, umma_n, false, false);
+        mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d0 = tmem_base + acc * (2 * TILE_N);
+        const uint32_t d1 = d0 + TILE_N;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&sb->full[stage], phase);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + stage * PAIR_STAGE_BYTES);
+          const uint32_t a1 = a0 + TILE_M * KBLK * 2;
+          const uint32_t b = a1 + TILE_M * KBLK * 2;
+#pragma unroll
+          for (int k = 0; k < KBLK / 16; ++k) {
+            const uint64_t bd = smem_desc(b + k * 32, DESC_KMAJOR);
+            const uint32_t accum = (kb | k) ? 1u : 0u;
+            umma_bf16(d0, smem_desc(a0 + k * 32, DESC_KMAJOR), bd, idesc, accum);
+            umma_bf16(d1, smem_desc(a1 + k * 32, DESC_KMAJOR), bd, idesc, accum);
+          }
+          umma_commit(&sb->empty[stage]);
+          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&sb->tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int imgs_first = p.imgs_first;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
+      const int mt = item / p.num_tiles;
+      const int nt = item - mt * p.num_tiles;
+      const int32_t* tile = p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS;
+      const int nseg = __ldg(tile + 1);
+
+      const int row_a = mt * TILE_M + quad * 32 + lane;
+      const bool valid_a = row_a < p.halfM;
+      const bool valid_b = row_a < p.rowsB;
+      const int v_a = row_a / p.HW;
+      const int loc = row_a - v_a * p.HW;
+      const int v_first = __shfl_sync(0xffffffffu, v_a, 0);
+      const int loc_first = __shfl_sync(0xffffffffu, loc, 0);
+      const bool has_boundary = __ballot_sync(0xffffffffu, v_a != v_first) != 0u;
+      const int lane_b = p.HW - loc_first;    // first lane of the next image (if has_boundary)
+
+      float align_acc[SLOTS];
+#pragma unroll
+      for (int i = 0; i < SLOTS; ++i) align_acc[i] = 0.f;
+
+      mbar_wait(&sb->tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * (2 * TILE_N);
+
+#pragma unroll
+      for (int js = 0; js < SLOTS; ++js) {
+        const int j = 2 * js + half;
+        if (j < NSEG_MAX && j < nseg) {     // warp-uniform
+          const int node = __ldg(tile + 4 + j);
+          const int len = __ldg(tile + 4 + MAX_SEGS + j);
+          const int poff = __ldg(tile + 4 + 2 * MAX_SEGS + j);
+          uint32_t ra[S], rb[S];
+          tmem_ld_cols<S>(t0 + j * S, ra);
+          tmem_ld_cols<S>(t0 + TILE_N + j * S, rb);
+          tmem_ld_wait();
+          float s1[S], s2[S];
+          softmax_row<S>(ra, len, p.scale_log2, s1);
+          softmax_row<S>(rb, len, p.scale_log2, s2);
+          float ip = 0.f;
+#pragma unroll
+          for (int i = 0; i < S; ++i) ip = fmaf(s1[i], s2[i], ip);
+
+          if constexpr (!BWD) {
+            if (p.desc != nullptr) {
+              const bool on = valid_a && valid_b && (v_a < imgs_first) && p.desc[(size_t)v_a * p.n_nodes + node];
+              if (on) align_acc[js] = -logf(ip + 1e-12f);
+            }
+            if (__ballot_sync(0xffffffffu, valid_a) != 0u)
+              pool_segment<S>(s1, valid_a, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
+                              p.pooled_packed + (size_t)v_first * p.P + poff, p.P);
+            if (__ballot_sync(0xffffffffu, valid_b) != 0u)
+              pool_segment<S>(s2, valid_b, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
+                              p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff, p.P);
+          } else {
+            float ca = 0.f;
+            if (p.coef_align != nullptr && valid_a && valid_b && v_a < imgs_first)
+              ca = p.coef_align[(size_t)v_a * p.n_nodes + node] * __frcp_rn(ip + 1e-12f);
+            const int col0 = (p.tile_begin + nt) * TILE_N + j * S;
+            if (valid_a) {
+              const int2* sc = p.scat + (size_t)v_a * p.P + poff;
+              float g[S];
+              float dot = 0.f;
+#pragma unroll
+              for (int i = 0; i < S; ++i) {
+                float gi = -ca * s2[i];
+                if (i < len) {
+                  const int2 e = __ldg(sc + i);
+                  if (e.x == loc) gi += __int_as_float(e.y);
+                }
+                g[i] = gi;
+                dot = fmaf(gi, s1[i], dot);
+              }
+#pragma unroll
+              for (int i = 0; i < S; ++i) g[i] = s1[i] * (g[i] - dot) * p.inv_tau;
+              store_dz<S>(p.dz + (size_t)row_a * p.P_pad + col0, g);
+            }
+            if (valid_b) {
+              const int2* sc = p.scat + (size_t)(v_a + imgs_first) * p.P + poff;
+              float g[S];
+              float dot = 0.f;
+#pragma unroll
+              for (int i = 0; i < S; ++i) {
+                float gi = -ca * s1[i];
+                if (i < len) {
+                  const int2 e = __ldg(sc + i);
+                  if (e.x == loc) gi += __int_as_float(e.y);
+                }
+                g[i] = gi;
+                dot = fmaf(gi, s2[i], dot);
+              }
+#pragma unroll
+              for (int i = 0; i < S; ++i) g[i] = s2[i] * (g[i] - dot) * p.inv_tau;
+              store_dz<S>(p.dz + (size_t)(p.halfM + row_a) * p.P_pad + col0, g);
+            }
+          }
+        }
+      }
+      // accumulators fully read -> hand the TMEM stage back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
+
+      if constexpr (!BWD) {
+        if (p.desc != nullptr) {
+#pragma unroll
+          for (int js = 0; js < SLOTS; ++js) {
+            const int j = 2 * js + half;
+            if (j < NSEG_MAX && j < nseg) {
+              float v = align_acc[js];
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+              if (lane == 0 && v != 0.f) atomicAdd(p.align_sum + __ldg(tile + 4 + j), (double)v);
+            }
+          }
+        }
+      } else {
+        // zero the padding columns [nseg*S, 128) of this tile's dZ rows (the dX GEMM reads them)
+        if (half == 0) {
+          const int c_begin = nseg * S;
+          const int col0 = (p.tile_begin + nt) * TILE_N;
+          for (int c = c_begin; c < TILE_N; c += 4) {
+            if (valid_a) *reinterpret_cast<uint2*>(p.dz + (size_t)row_a * p.P_pad + col0 + c) = make_uint2(0u, 0u);
+            if (valid_b)
+              *reinterpret_cast<uint2*>(p.dz + (size_t)(p.halfM + row_a) * p.P_pad + col0 + c) = make_uint2(0u, 0u);
+          }
+        }
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace hc

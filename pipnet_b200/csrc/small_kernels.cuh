@@ -1,0 +1,428 @@
+// Small SIMT kernels around the fused projection: weight packing, pool unpacking, the per-node
+// non-negative classifier, class / tanh / orthogonality losses (forward + backward) and the joint
+// leaf distribution.  All operate on FLAT tensors ([V,P] prototypes, [V,K] child logits with
+// K = sum of children over nodes) driven by small int32 node tables, replacing the reference's
+// per-node Python loops (pipnet/pipnet.py:124-170, pipnet/train.py:933-1194).
+#pragma once
+#include "ptx.cuh"
+
+namespace hc {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float block_sum(float v, float* sh /* >= 32 floats */) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float r = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.f;
+  if (w == 0) r = warp_sum(r);
+  if (threadIdx.x == 0) sh[0] = r;
+  __syncthreads();
+  r = sh[0];
+  return r;
+}
+
+// ---------------------------------------------------------------- packing / casting
+// Wp[r, :] = bf16(W[row_map[r], :]) or 0 for padding rows.  8 channels per thread.
+__global__ void pack_weights_kernel(const float* __restrict__ w, const int32_t* __restrict__ row_map, int P_pad, int C,
+                                    __nv_bfloat16* __restrict__ wp) {
+  const int c8 = C >> 3;
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P_pad * c8) return;
+  const int r = int(idx / c8), c = int(idx - (long long)r * c8) * 8;
+  const int src = row_map[r];
+  uint4 o = make_uint4(0, 0, 0, 0);
+  if (src >= 0) {
+    const float4 a = *reinterpret_cast<const float4*>(w + (size_t)src * C + c);
+    const float4 b = *reinterpret_cast<const float4*>(w + (size_t)src * C + c + 4);
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+  }
+  *reinterpret_cast<uint4*>(wp + (size_t)r * C + c) = o;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n8) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    uint4 o;
+    o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+    o.z = pack_bf16x2(b.x, b.y); o.w = pack_bf16x2(b.z, b.w);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+}
+
+// NCHW fp32/bf16 -> NHWC bf16 rows (ResNet features are NCHW-contiguous).  32x32 smem transpose.
+template <typename T>
+__global__ void nchw_to_rows_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int v = blockIdx.z;
+  const int c0 = blockIdx.y * 32, l0 = blockIdx.x * 32;
+  const T* s = src + (size_t)v * C * HW;
+  __nv_bfloat16* d = dst + (size_t)v * HW * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, l = l0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && l < HW) ? float(s[(size_t)c * HW + l]) : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int l = l0 + i, c = c0 + threadIdx.x;
+    if (c < C && l < HW) d[(size_t)l * C + c] = __float2bfloat16(tile[threadIdx.x][i]);
+  }
+}
+
+// ---------------------------------------------------------------- pool unpack
+// packed = (float bits << 32) | (0xFFFFFFFF - location)  ->  pooled, argmax (+ inference threshold,
+// pipnet/pipnet.py:168-169: pooled < 0.1 -> 0).
+__global__ void unpack_pool_kernel(const unsigned long long* __restrict__ packed, long long n, float thresh,
+                                   float* __restrict__ pooled, int32_t* __restrict__ argmax) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned long long k = packed[i];
+  float v = __uint_as_float((uint32_t)(k >> 32));
+  if (v < thresh) v = 0.f;
+  pooled[i] = v;
+  argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+}
+
+// ---------------------------------------------------------------- label tables
+// tgt[v,n] = child label of sample v at node n, or -1 (pipnet/train.py:934-937) from the static
+// leaf->node table anc[L,N]; n_desc[n] = number of samples below node n; desc = tgt >= 0 for the
+// first-half images.
+__global__ void label_tables_kernel(const long long* __restrict__ ys, const int8_t* __restrict__ anc, int V, int V_first,
+                                    int N, int L, int8_t* __restrict__ tgt, uint8_t* __restrict__ desc,
+                                    int32_t* __restrict__ n_desc) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  int cnt = 0;
+  for (int v = 0; v < V; ++v) {
+    const long long y = ys[v];
+    const int8_t t = (y >= 0 && y < L) ? anc[(size_t)y * N + n] : int8_t(-1);
+    tgt[(size_t)v * N + n] = t;
+    if (v < V_first) desc[(size_t)v * N + n] = (t >= 0);
+    cnt += (t >= 0);
+  }
+  n_desc[n] = cnt;
+}
+
+// ---------------------------------------------------------------- classifier (NonNegLinear, pipnet/pipnet.py:1035-1036)
+// out[v, k] = sum_p relu(Wc[k-th row]) * pooled[v, proto_off[node]+p] (+ bias[k]); one thread per (v, k).
+// col_node[k] = node of flat child column k; Wc rows are stored row-major per node at wc_off[node].
+__global__ void classifier_fwd_kernel(const float* __restrict__ pooled, const float* __restrict__ wc,
+                                      const float* __restrict__ bias, const int32_t* __restrict__ col_node,
+                                      const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
+                                      const int32_t* __restrict__ wc_off, int V, int P, int K, float* __restrict__ out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * K) return;
+  const int v = idx / K, k = idx - v * K;
+  const int n = col_node[k];
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const float* w = wc + wc_off[n] + (size_t)(k - cls_off[n]) * pn;
+  const float* x = pooled + (size_t)v * P + p0;
+  float acc = 0.f;
+  for (int p = 0; p < pn; ++p) acc = fmaf(fmaxf(w[p], 0.f), x[p], acc);
+  out[idx] = acc + (bias ? bias[k] : 0.f);
+}
+
+// g_pooled[v, p] += sum_c g_out[v, c] * relu(Wc[c, p]); one thread per (v, p).
+__global__ void classifier_bwd_pooled_kernel(const float* __restrict__ g_out, const float* __restrict__ wc,
+                                             const int32_t* __restrict__ proto_node, const int32_t* __restrict__ proto_off,
+                                             const int32_t* __restrict__ cls_off, const int32_t* __restrict__ wc_off, int V,
+                                             int P, int K, float* __restrict__ g_pooled, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)V * P) return;
+  const int v = int(idx / P), p = int(idx - (long long)v * P);
+  const int n = proto_node[p];
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const int k0 = cls_off[n], kn = cls_off[n + 1] - k0;
+  float acc = 0.f;
+  for (int c = 0; c < kn; ++c) acc = fmaf(g_out[(size_t)v * K + k0 + c], fmaxf(wc[wc_off[n] + (size_t)c * pn + (p - p0)], 0.f), acc);
+  g_pooled[idx] = accumulate ? g_pooled[idx] + acc : acc;
+}
+
+// g_Wc[c, p] = [Wc > 0] * sum_v g_out[v, c] * pooled[v, p]; one warp per weight element.
+__global__ void classifier_bwd_weight_kernel(const float* __restrict__ g_out, const float* __restrict__ pooled,
+                                             const float* __restrict__ wc, const int32_t* __restrict__ welem_col,
+                                             const int32_t* __restrict__ welem_proto, int V, int P, int K, int n_w,
+                                             float* __restrict__ g_wc, float* __restrict__ g_bias) {
+  const int wid = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (wid >= n_w) return;
+  const int k = welem_col[wid], p = welem_proto[wid];
+  float acc = 0.f;
+  if (wc[wid] > 0.f)
+    for (int v = lane; v < V; v += 32) acc = fmaf(g_out[(size_t)v * K + k], pooled[(size_t)v * P + p], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) g_wc[wid] = acc;
+  (void)g_bias;
+}
+__global__ void classifier_bwd_bias_kernel(const float* __restrict__ g_out, int V, int K, float* __restrict__ g_bias) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  float acc = 0.f;
+  for (int v = 0; v < V; ++v) acc += g_out[(size_t)v * K + k];
+  g_bias[k] = acc;
+}
+
+// ---------------------------------------------------------------- class loss (pipnet/train.py:1153-1163, util/custom_losses.py:22-34)
+// One block per node.  x = log1p(out^2) (multiplier 2, main_dist.py:426) or out (pipnet_sparsity n);
+// loss[n] = mean over descendants of w[t] * (logsumexp(x) - x[t]); also per-node accuracy counts.
+__global__ void class_loss_fwd_kernel(const float* __restrict__ out, const int8_t* __restrict__ tgt,
+                                      const float* __restrict__ child_w, const int32_t* __restrict__ cls_off,
+                                      const int32_t* __restrict__ n_desc, int V, int N, int K, int sparsity,
+                                      float* __restrict__ loss, int32_t* __restrict__ n_correct) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x;
+  const int k0 = cls_off[n], kn = cls_off[n + 1] - k0;
+  float acc = 0.f, corr = 0.f;
+  for (int v = threadIdx.x; v < V; v += blockDim.x) {
+    const int t = tgt[(size_t)v * N + n];
+    if (t < 0) continue;
+    const float* o = out + (size_t)v * K + k0;
+    float mx = -INFINITY, best = -INFINITY;
+    int arg = 0;
+    for (int c = 0; c < kn; ++c) {
+      const float x = sparsity ? log1pf(o[c] * o[c]) : o[c];
+      mx = fmaxf(mx, x);
+      if (o[c] > best) { best = o[c]; arg = c; }     // torch.max(node_logits, 1): first max (pipnet/train.py:1189)
+    }
+    float se = 0.f, xt = 0.f;
+    for (int c = 0; c < kn; ++c) {
+      const float x = sparsity ? log1pf(o[c] * o[c]) : o[c];
+      se += expf(x - mx);
+      if (c == t) xt = x;
+    }
+    acc += child_w[k0 + t] * (logf(se) + mx - xt);
+    corr += (arg == t) ? 1.f : 0.f;
+  }
+  acc = block_sum(acc, sh);
+  corr = block_sum(corr, sh);
+  if (threadIdx.x == 0) {
+    const int nd = n_desc[n];
+    loss[n] = nd > 0 ? acc / float(nd) : 0.f;
+    n_correct[n] = int(corr + 0.5f);
+  }
+}
+// g_out[v, k] = g_loss[n] / n_desc * w[t] * (softmax(x)[c] - [c == t]) * dx/dout; one thread per (v, k).
+__global__ void class_loss_bwd_kernel(const float* __restrict__ out, const int8_t* __restrict__ tgt,
+                                      const float* __restrict__ child_w, const int32_t* __restrict__ col_node,
+                                      const int32_t* __restrict__ cls_off, const int32_t* __restrict__ n_desc,
+                                      const float* __restrict__ g_loss, int V, int N, int K, int sparsity,
+                                      float* __restrict__ g_out) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * K) return;
+  const int v = idx / K, k = idx - v * K;
+  const int n = col_node[k];
+  const int t = tgt[(size_t)v * N + n];
+  float g = 0.f;
+  if (t >= 0) {
+    const int k0 = cls_off[n], kn = cls_off[n + 1] - k0;
+    const float* o = out + (size_t)v * K + k0;
+    float mx = -INFINITY;
+    for (int c = 0; c < kn; ++c) mx = fmaxf(mx, sparsity ? log1pf(o[c] * o[c]) : o[c]);
+    float se = 0.f;
+    for (int c = 0; c < kn; ++c) se += expf((sparsity ? log1pf(o[c] * o[c]) : o[c]) - mx);
+    const float ok = o[k - k0];
+    const float xk = sparsity ? log1pf(ok * ok) : ok;
+    const float sm = expf(xk - mx) / se;
+    const float dx = sparsity ? (2.f * ok / (1.f + ok * ok)) : 1.f;
+    g = g_loss[n] / float(n_desc[n]) * child_w[k0 + t] * (sm - ((k - k0) == t ? 1.f : 0.f)) * dx;
+  }
+  g_out[idx] = g;
+}
+
+// ---------------------------------------------------------------- tanh loss (pipnet/train.py:1076-1087)
+// Per node: -1/2 * sum_{view half h} mean_p log(tanh(sum_{desc b in h} pooled[b,p]) + eps).  One block per node.
+// colsum[h*P + p] keeps the masked column sums for the backward.
+__global__ void tanh_loss_fwd_kernel(const float* __restrict__ pooled, const int8_t* __restrict__ tgt,
+                                     const int32_t* __restrict__ proto_off, const int32_t* __restrict__ n_desc, int V,
+                                     int V_first, int N, int P, float eps, float* __restrict__ loss,
+                                     float* __restrict__ colsum) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x;
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < 2 * pn; i += blockDim.x) {
+    const int h = i / pn, p = i - h * pn;
+    const int vb = h ? V_first : 0, ve = h ? V : V_first;
+    float t = 0.f;
+    for (int v = vb; v < ve; ++v)
+      if (tgt[(size_t)v * N + n] >= 0) t += pooled[(size_t)v * P + p0 + p];
+    colsum[(size_t)h * P + p0 + p] = t;
+    acc += logf(tanhf(t) + eps);
+  }
+  acc = block_sum(acc, sh);
+  // nodes without a descendant in the batch are skipped by the reference (pipnet/train.py:941-942)
+  if (threadIdx.x == 0) loss[n] = n_desc[n] > 0 ? -0.5f * acc / float(pn) : 0.f;
+}
+// g_pooled[v,p] (+)= g_loss[n] * (-1/(2 P_n)) * (1 - th^2) / (th + eps) for descendant rows; thread per (v,p).
+__global__ void tanh_loss_bwd_kernel(const float* __restrict__ colsum, const int8_t* __restrict__ tgt,
+                                     const int32_t* __restrict__ proto_node, const int32_t* __restrict__ proto_off,
+                                     const float* __restrict__ g_loss, int V, int V_first, int N, int P, float eps,
+                                     float* __restrict__ g_pooled, int accumulate) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)V * P) return;
+  const int v = int(idx / P), p = int(idx - (long long)v * P);
+  const int n = proto_node[p];
+  float g = 0.f;
+  if (tgt[(size_t)v * N + n] >= 0) {
+    const int pn = proto_off[n + 1] - proto_off[n];
+    const float th = tanhf(colsum[(size_t)(v >= V_first) * P + p]);
+    g = g_loss[n] * (-0.5f / float(pn)) * (1.f - th * th) / (th + eps);
+  }
+  g_pooled[idx] = accumulate ? g_pooled[idx] + g : g;
+}
+
+// ---------------------------------------------------------------- kernel-orthogonality loss (pipnet/train.py:1136-1151, orth_dist :1408-1412)
+// Per node: rows of W whose classifier column has any weight > 1e-3; E = W_rel W_rel^T - I (P_rel < C);
+// loss = ||E||_F.  One block per node; E kept in a [P_max x P_max] workspace slab for the backward.
+__global__ void orth_loss_fwd_kernel(const float* __restrict__ w, const float* __restrict__ wc,
+                                     const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
+                                     const int32_t* __restrict__ wc_off, const int32_t* __restrict__ n_desc, int C,
+                                     int P_max, float* __restrict__ loss, float* __restrict__ E,
+                                     uint8_t* __restrict__ rel) {
+  __shared__ float sh[32];
+  const int n = blockIdx.x;
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const int kn = cls_off[n + 1] - cls_off[n];
+  for (int p = threadIdx.x; p < pn; p += blockDim.x) {
+    bool r = false;
+    for (int c = 0; c < kn; ++c) r |= wc[wc_off[n] + (size_t)c * pn + p] > 0.001f;
+    rel[p0 + p] = r;
+  }
+  __syncthreads();
+  float* En = E + (size_t)n * P_max * P_max;
+  float acc = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int ij = warp; ij < pn * pn; ij += nw) {           // one warp per Gram entry
+    const int i = ij / pn, j = ij - i * pn;
+    float e = 0.f;
+    if (rel[p0 + i] && rel[p0 + j]) {
+      const float* a = w + (size_t)(p0 + i) * C;
+      const float* b = w + (size_t)(p0 + j) * C;
+      float d = 0.f;
+      for (int c = lane; c < C; c += 32) d = fmaf(a[c], b[c], d);
+      d = warp_sum(d);
+      e = d - (i == j ? 1.f : 0.f);
+    }
+    if (lane == 0) { En[i * P_max + j] = e; acc += e * e; }
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) loss[n] = n_desc[n] > 0 ? sqrtf(acc) : 0.f;   // skipped nodes contribute nothing
+}
+// dW[i,:] += g[n] * (2/L) * sum_j E[i,j] W[j,:]   (E symmetric); one block per (node, row i).
+__global__ void orth_loss_bwd_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off, int C, int P_max,
+                                     const float* __restrict__ loss, const float* __restrict__ E,
+                                     const uint8_t* __restrict__ rel, const float* __restrict__ g_loss,
+                                     const int32_t* __restrict__ row_node, float* __restrict__ g_w) {
+  const int row = blockIdx.x;
+  const int n = row_node[row];
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const int i = row - p0;
+  const float L = loss[n];
+  if (!rel[row] || L <= 0.f || g_loss[n] == 0.f) return;
+  const float s = g_loss[n] * 2.f / L;
+  const float* En = E + (size_t)n * P_max * P_max + (size_t)i * P_max;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < pn; ++j)
+      if (rel[p0 + j]) acc = fmaf(En[j], w[(size_t)(p0 + j) * C + c], acc);
+    g_w[(size_t)row * C + c] += s * acc;
+  }
+}
+
+// ---------------------------------------------------------------- align loss finalize / backward prep
+// loss[n] = align_sum[n] / ((n_desc/2) * HW)   (mean over rows of the masked view-1 images, pipnet/train.py:1403)
+__global__ void align_finalize_kernel(const double* __restrict__ align_sum, const int32_t* __restrict__ n_desc, int N, int HW,
+                                      float* __restrict__ loss) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int nd = n_desc[n] / 2;
+  loss[n] = nd > 0 ? float(align_sum[n] / (double(nd) * double(HW))) : 0.f;
+}
+// coef[b,n] = desc[b,n] * g_align[n] * 0.5 / ((n_desc/2) * HW): each side of the symmetric loss gets half
+// (the other side is detached, pipnet/train.py:1068-1069).
+__global__ void align_coef_kernel(const uint8_t* __restrict__ desc, const int32_t* __restrict__ n_desc,
+                                  const float* __restrict__ g_align, int B, int N, int HW, float* __restrict__ coef) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * N) return;
+  const int n = idx % N;
+  const int nd = n_desc[n] / 2;
+  coef[idx] = (desc[idx] && nd > 0) ? g_align[n] * 0.5f / (float(nd) * float(HW)) : 0.f;
+}
+__global__ void make_scat_kernel(const int32_t* __restrict__ argmax, const float* __restrict__ g_pooled,
+                                 const float* __restrict__ pooled, float thresh, long long n, int2* __restrict__ scat) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float g = g_pooled[i];
+  if (pooled != nullptr && pooled[i] < thresh) g = 0.f;   // inference threshold kills the gradient too
+  scat[i] = make_int2(argmax[i], __float_as_int(g));
+}
+
+// ---------------------------------------------------------------- joint leaf distribution (util/node.py:383-385, pipnet/pipnet.py:173-185)
+// probs[v,k] = softmax_c(log1p(out^2)/tau) within each node; leaf[v,l] = product of probs along the path.
+__global__ void node_probs_kernel(const float* __restrict__ out, const int32_t* __restrict__ cls_off, int V, int N, int K,
+                                  float inv_tau, float* __restrict__ probs) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * N) return;
+  const int v = idx / N, n = idx - v * N;
+  const int k0 = cls_off[n], kn = cls_off[n + 1] - k0;
+  const float* o = out + (size_t)v * K + k0;
+  float mx = -INFINITY;
+  for (int c = 0; c < kn; ++c) mx = fmaxf(mx, log1pf(o[c] * o[c]) * inv_tau);
+  float se = 0.f;
+  for (int c = 0; c < kn; ++c) se += expf(log1pf(o[c] * o[c]) * inv_tau - mx);
+  for (int c = 0; c < kn; ++c) probs[(size_t)v * K + k0 + c] = expf(log1pf(o[c] * o[c]) * inv_tau - mx) / se;
+}
+__global__ void leaf_joint_kernel(const float* __restrict__ probs, const int32_t* __restrict__ path_off,
+                                  const int32_t* __restrict__ path_col, int V, int L, int K, float* __restrict__ joint) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * L) return;
+  const int v = idx / L, l = idx - v * L;
+  float pr = 1.f;
+  for (int i = path_off[l]; i < path_off[l + 1]; ++i) pr *= probs[(size_t)v * K + path_col[i]];
+  joint[idx] = pr;
+}
+__global__ void row_argmax_kernel(const float* __restrict__ x, int V, int L, long long* __restrict__ pred) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= V) return;
+  float best = -INFINITY;
+  int arg = 0;
+  for (int l = 0; l < L; ++l) {
+    const float t = x[(size_t)v * L + l];
+    if (t > best) { best = t; arg = l; }
+  }
+  pred[v] = arg;
+}
+
+// ---------------------------------------------------------------- full softmax map of ONE node (visualisation path)
+// Rebuilds S_n[v, p, hw] for a single node in fp32 from bf16 features (util/vis_hpipnet.py:62-127 reads it
+// at batch size 1); one warp per (v, hw).
+__global__ void materialize_map_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w, int V, int HW,
+                                       int C, int pn, float inv_tau, float* __restrict__ map /* [V, pn, HW] */) {
+  extern __shared__ float zbuf[];   // [warps][pn]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const long long r = (long long)blockIdx.x * nw + warp;
+  if (r >= (long long)V * HW) return;
+  const int v = int(r / HW), hw = int(r - (long long)v * HW);
+  float* z = zbuf + warp * pn;
+  const __nv_bfloat16* xr = x + (size_t)r * C;
+  for (int p = 0; p < pn; ++p) {
+    float d = 0.f;
+    for (int c = lane; c < C; c += 32) d = fmaf(__bfloat162float(xr[c]), w[(size_t)p * C + c], d);
+    d = warp_sum(d);
+    if (lane == 0) z[p] = d * inv_tau;
+  }
+  __syncwarp();
+  float mx = -INFINITY;
+  for (int p = 0; p < pn; ++p) mx = fmaxf(mx, z[p]);
+  float se = 0.f;
+  for (int p = 0; p < pn; ++p) se += expf(z[p] - mx);
+  for (int p = lane; p < pn; p += 32) map[((size_t)v * pn + p) * HW + hw] = expf(z[p] - mx) / se;
+}
+
+}  // namespace hc

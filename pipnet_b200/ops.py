@@ -1,0 +1,347 @@
+"""Host-side operators of the prototype head: thin wrappers that hand torch device memory and the
+current CUDA stream to the C ABI (include/hcomp_head.h), plus the `torch.autograd.Function`s that
+splice the kernels into autograd.  PyTorch is plumbing here (memory, streams, autograd graph); all
+arithmetic of the path runs in libhcomp_head.so.  There is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import Tables, call, ptr
+from .layout import HeadLayout
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _cabi.HcompError(f'{what} must live on a CUDA device: the prototype head has no CPU path')
+
+
+class DeviceLayout:
+    """`HeadLayout` tables resident on one GPU + the ctypes view the C ABI takes."""
+
+    def __init__(self, layout: HeadLayout, device):
+        self.layout = layout
+        self.device = torch.device(device)
+        d = self.device
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(device=d, dtype=dt)
+
+        L = layout
+        self.proto_off, self.cls_off, self.wc_off = up(L.proto_off, torch.int32), up(L.cls_off, torch.int32), up(L.wc_off, torch.int32)
+        self.proto_node, self.col_node = up(L.proto_node, torch.int32), up(L.col_node, torch.int32)
+        self.welem_col, self.welem_proto = up(L.welem_col, torch.int32), up(L.welem_proto, torch.int32)
+        self.child_w = up(L.child_w, torch.float32)
+        self.path_off, self.path_col = up(L.path_off, torch.int32), up(L.path_col, torch.int32)
+        self.anc = up(L.anc, torch.int8)
+        self.tiles_host = torch.from_numpy(np.ascontiguousarray(L.tiles)).to(torch.int32)
+        self.tiles_dev = self.tiles_host.to(d)
+        self.row_map = up(L.row_map, torch.int32)
+        self.tables = Tables(L.N, L.P, L.K, L.L, L.n_welems, L.p_max,
+                             self.proto_off.data_ptr(), self.cls_off.data_ptr(), self.wc_off.data_ptr(),
+                             self.proto_node.data_ptr(), self.col_node.data_ptr(), self.welem_col.data_ptr(),
+                             self.welem_proto.data_ptr(), self.child_w.data_ptr(), self.path_off.data_ptr(),
+                             self.path_col.data_ptr(), self.anc.data_ptr())
+        self.tref = C.byref(self.tables)
+        self.n_tiles = int(L.tiles.shape[0])
+
+    # convenient aliases
+    @property
+    def N(self): return self.layout.N
+    @property
+    def P(self): return self.layout.P
+    @property
+    def K(self): return self.layout.K
+    @property
+    def L(self): return self.layout.L
+    @property
+    def P_pad(self): return self.layout.P_pad
+
+
+# --------------------------------------------------------------------------- operand preparation
+def feature_rows(features: torch.Tensor):
+    """features [V,C,H,W] (any memory format, fp32 or bf16) -> bf16 rows [V*H*W, C] for the GEMM.
+    Channels-last bf16 input (the layout ConvNeXt-26 produces) is a zero-copy view."""
+    _require_cuda(features, 'features')
+    V, Cc, H, W = features.shape
+    HW = H * W
+    if features.is_contiguous(memory_format=torch.channels_last) or Cc == 1 or HW == 1:
+        nhwc = features.permute(0, 2, 3, 1)
+        if features.dtype == torch.bfloat16:
+            return nhwc.reshape(V * HW, Cc)
+        if features.dtype == torch.float32:
+            src = nhwc.reshape(V * HW, Cc)
+            out = torch.empty(V * HW, Cc, device=features.device, dtype=torch.bfloat16)
+            call('hcomp_cast_f32_to_bf16', ptr(src), ptr(out), C.c_longlong(src.numel()), _stream())
+            return out
+    if features.dtype not in (torch.float32, torch.bfloat16):
+        raise _cabi.HcompError(f'unsupported feature dtype {features.dtype}')
+    src = features.contiguous()
+    out = torch.empty(V * HW, Cc, device=features.device, dtype=torch.bfloat16)
+    call('hcomp_nchw_to_rows_bf16', ptr(src), int(src.dtype == torch.bfloat16), V, Cc, HW, ptr(out), _stream())
+    return out
+
+
+def pack_weights(w_flat: torch.Tensor, dl: DeviceLayout) -> torch.Tensor:
+    _require_cuda(w_flat, 'prototype kernels')
+    assert w_flat.dtype == torch.float32 and w_flat.is_contiguous() and w_flat.shape[0] == dl.P
+    Cc = w_flat.shape[1]
+    wp = torch.empty(dl.P_pad, Cc, device=w_flat.device, dtype=torch.bfloat16)
+    call('hcomp_pack_weights', ptr(w_flat), ptr(dl.row_map), dl.P_pad, Cc, ptr(wp), _stream())
+    return wp
+
+
+class LabelTables:
+    """Per-batch tables derived from the labels (pipnet/train.py:934-937): tgt[V,N] child label or -1,
+    desc[V_first,N], n_desc[N]."""
+
+    def __init__(self, ys: torch.Tensor, dl: DeviceLayout, V_first: int):
+        _require_cuda(ys, 'labels')
+        ys = ys.to(torch.int64).contiguous()
+        V = ys.numel()
+        self.V, self.V_first = V, V_first
+        self.tgt = torch.empty(V, dl.N, device=ys.device, dtype=torch.int8)
+        self.desc = torch.empty(V_first, dl.N, device=ys.device, dtype=torch.uint8)
+        self.n_desc = torch.empty(dl.N, device=ys.device, dtype=torch.int32)
+        call('hcomp_label_tables', ptr(ys), dl.tref, V, V_first, ptr(self.tgt), ptr(self.desc), ptr(self.n_desc), _stream())
+
+
+# --------------------------------------------------------------------------- raw kernels (no autograd)
+def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, labels: Optional[LabelTables], thresh=0.0):
+    Cc = x_rows.shape[1]
+    dev = x_rows.device
+    packed = torch.empty(V * dl.P, device=dev, dtype=torch.int64)
+    align_sum = torch.empty(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
+    call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
+         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), ptr(labels.desc) if labels is not None else None, ptr(packed),
+         ptr(align_sum), _stream())
+    pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)
+    argmax = torch.empty(V, dl.P, device=dev, dtype=torch.int32)
+    call('hcomp_unpack_pool', ptr(packed), C.c_longlong(V * dl.P), float(thresh), ptr(pooled), ptr(argmax), _stream())
+    align = None
+    if labels is not None:
+        align = torch.empty(dl.N, device=dev, dtype=torch.float32)
+        call('hcomp_align_finalize', ptr(align_sum), ptr(labels.n_desc), dl.N, HW, ptr(align), _stream())
+    return pooled, argmax, align
+
+
+def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
+                      pooled=None, thresh=0.0, need_dx=True, need_dw=True):
+    Cc = x_rows.shape[1]
+    dev = x_rows.device
+    M = V * HW
+    dz = torch.empty(M, dl.P_pad, device=dev, dtype=torch.bfloat16)
+    scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
+    coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
+    use_align = labels is not None and g_align is not None
+    call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
+         dl.P, dl.P_pad, dl.N, float(tau), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
+         ptr(labels.desc) if use_align else None, ptr(labels.n_desc) if use_align else None,
+         ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), _stream())
+    dx = dw = None
+    if need_dx:
+        dx = torch.empty(M, Cc, device=dev, dtype=torch.bfloat16)
+        call('hcomp_head_bwd_dx', ptr(dz), ptr(wp), C.c_longlong(M), dl.P_pad, Cc, ptr(dx), _stream())
+    if need_dw:
+        dw = torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32)
+        call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map), C.c_longlong(M), dl.P_pad, Cc, ptr(dw), _stream())
+    return dx, dw, dz
+
+
+def gemm_bf16(a, b, M, N, K, a_mn, b_mn, out_mode=1, splits=1):
+    """self-test hook for the tcgen05 GEMM mainloop"""
+    dev = a.device
+    if out_mode == 0:
+        out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    elif out_mode == 1:
+        out = torch.empty(M, N, device=dev, dtype=torch.float32)
+    else:
+        out = torch.zeros(M, N, device=dev, dtype=torch.float32)
+    call('hcomp_gemm_bf16', ptr(a), ptr(b), M, N, K, int(a_mn), int(b_mn), out_mode, splits, ptr(out), C.c_longlong(N), _stream())
+    return out
+
+
+# --------------------------------------------------------------------------- autograd
+class HeadProjPool(torch.autograd.Function):
+    """features, flat prototype kernels -> pooled [V,P], per-node align loss [N] (zeros without labels).
+    Saves only the bf16 operands + argmax: the V x P x H x W map is recomputed tile by tile in backward."""
+
+    @staticmethod
+    def forward(ctx, features, w_flat, dl: DeviceLayout, V_first, tau, labels, thresh):
+        V, Cc, H, W = features.shape
+        HW = H * W
+        x_rows = feature_rows(features.detach())
+        wp = pack_weights(w_flat.detach().contiguous(), dl)
+        pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh)
+        ctx.dl, ctx.geom, ctx.labels, ctx.thresh = dl, (V, V_first, H, W, Cc, tau), labels, thresh
+        ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
+        ctx.save_for_backward(x_rows, wp, argmax, pooled)
+        ctx.mark_non_differentiable(argmax)
+        if align is None:
+            align = torch.zeros(dl.N, device=features.device, dtype=torch.float32)
+        return pooled, align, argmax
+
+    @staticmethod
+    def backward(ctx, g_pooled, g_align, _g_argmax):
+        x_rows, wp, argmax, pooled = ctx.saved_tensors
+        V, V_first, H, W, Cc, tau = ctx.geom
+        dl = ctx.dl
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if g_pooled is None:
+            g_pooled = torch.zeros(V, dl.P, device=x_rows.device, dtype=torch.float32)
+        g_pooled = g_pooled.contiguous().float()
+        if g_align is not None:
+            g_align = g_align.contiguous().float()
+        dx, dw, _ = head_backward_raw(x_rows, wp, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
+                                      pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw)
+        d_feat = None
+        if need_dx:
+            dtype, _cl = ctx.feat_meta
+            d_feat = dx.view(V, H, W, Cc).permute(0, 3, 1, 2)     # channels-last view of the row buffer
+            if dtype != torch.bfloat16:
+                d_feat = d_feat.to(dtype)
+        return d_feat, dw, None, None, None, None, None
+
+
+class NonNegClassifier(torch.autograd.Function):
+    """out[V,K] = pooled . relu(Wc)^T per node (pipnet/pipnet.py:1035-1036) on the flat axes."""
+
+    @staticmethod
+    def forward(ctx, pooled, wc_flat, bias, dl: DeviceLayout):
+        V = pooled.shape[0]
+        pooled = pooled.contiguous()
+        wc_flat = wc_flat.contiguous()
+        out = torch.empty(V, dl.K, device=pooled.device, dtype=torch.float32)
+        call('hcomp_classifier_fwd', ptr(pooled), ptr(wc_flat), ptr(bias), dl.tref, V, ptr(out), _stream())
+        ctx.dl = dl
+        ctx.save_for_backward(pooled, wc_flat)
+        ctx.has_bias = bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pooled, wc_flat = ctx.saved_tensors
+        dl = ctx.dl
+        V = pooled.shape[0]
+        g_out = g_out.contiguous()
+        g_pooled = torch.empty_like(pooled) if ctx.needs_input_grad[0] else None
+        g_wc = torch.empty_like(wc_flat) if ctx.needs_input_grad[1] else None
+        g_bias = torch.empty(dl.K, device=pooled.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        call('hcomp_classifier_bwd', ptr(g_out), ptr(pooled), ptr(wc_flat), dl.tref, V, ptr(g_pooled), 0, ptr(g_wc),
+             ptr(g_bias), _stream())
+        return g_pooled, g_wc, g_bias, None
+
+
+class ClassLoss(torch.autograd.Function):
+    """per-node weighted NLL on log1p(out^2) (pipnet/train.py:1153-1163) -> loss [N]"""
+
+    @staticmethod
+    def forward(ctx, out, labels: LabelTables, dl: DeviceLayout, sparsity):
+        out = out.contiguous()
+        V = out.shape[0]
+        loss = torch.empty(dl.N, device=out.device, dtype=torch.float32)
+        n_correct = torch.empty(dl.N, device=out.device, dtype=torch.int32)
+        call('hcomp_class_loss_fwd', ptr(out), ptr(labels.tgt), ptr(labels.n_desc), dl.tref, V, int(sparsity), ptr(loss),
+             ptr(n_correct), _stream())
+        ctx.dl, ctx.labels, ctx.sparsity = dl, labels, int(sparsity)
+        ctx.save_for_backward(out)
+        ctx.mark_non_differentiable(n_correct)
+        return loss, n_correct
+
+    @staticmethod
+    def backward(ctx, g_loss, _g):
+        (out,) = ctx.saved_tensors
+        dl, labels = ctx.dl, ctx.labels
+        g_out = torch.empty_like(out)
+        g_loss = g_loss.contiguous().float()
+        call('hcomp_class_loss_bwd', ptr(out), ptr(labels.tgt), ptr(labels.n_desc), ptr(g_loss), dl.tref, out.shape[0],
+             ctx.sparsity, ptr(g_out), _stream())
+        return g_out, None, None, None
+
+
+class TanhLoss(torch.autograd.Function):
+    """per-node tanh uniformity loss (pipnet/train.py:1076-1087) -> loss [N]"""
+
+    @staticmethod
+    def forward(ctx, pooled, labels: LabelTables, dl: DeviceLayout, eps):
+        pooled = pooled.contiguous()
+        V = pooled.shape[0]
+        loss = torch.empty(dl.N, device=pooled.device, dtype=torch.float32)
+        colsum = torch.empty(2 * dl.P, device=pooled.device, dtype=torch.float32)
+        call('hcomp_tanh_loss_fwd', ptr(pooled), ptr(labels.tgt), ptr(labels.n_desc), dl.tref, V, labels.V_first, float(eps),
+             ptr(loss), ptr(colsum), _stream())
+        ctx.dl, ctx.labels, ctx.eps, ctx.V = dl, labels, float(eps), V
+        ctx.save_for_backward(colsum)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (colsum,) = ctx.saved_tensors
+        dl, labels = ctx.dl, ctx.labels
+        g_pooled = torch.empty(ctx.V, dl.P, device=colsum.device, dtype=torch.float32)
+        g_loss = g_loss.contiguous().float()
+        call('hcomp_tanh_loss_bwd', ptr(colsum), ptr(labels.tgt), ptr(g_loss), dl.tref, ctx.V, labels.V_first, ctx.eps,
+             ptr(g_pooled), 0, _stream())
+        return g_pooled, None, None, None
+
+
+class OrthLoss(torch.autograd.Function):
+    """per-node kernel-orthogonality loss (pipnet/train.py:1136-1151) -> loss [N]; the relevance mask comes
+    from the classifier weights, which get no gradient from this term (boolean indexing in the reference)."""
+
+    @staticmethod
+    def forward(ctx, w_flat, wc_flat, labels: LabelTables, dl: DeviceLayout):
+        w_flat = w_flat.contiguous()
+        wc_flat = wc_flat.detach().contiguous()
+        Cc = w_flat.shape[1]
+        dev = w_flat.device
+        loss = torch.empty(dl.N, device=dev, dtype=torch.float32)
+        E = torch.empty(dl.N * dl.layout.p_max * dl.layout.p_max, device=dev, dtype=torch.float32)
+        rel = torch.empty(dl.P, device=dev, dtype=torch.uint8)
+        call('hcomp_orth_loss_fwd', ptr(w_flat), ptr(wc_flat), ptr(labels.n_desc), dl.tref, Cc, ptr(loss), ptr(E), ptr(rel),
+             _stream())
+        ctx.dl = dl
+        ctx.save_for_backward(w_flat, loss, E, rel)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        w_flat, loss, E, rel = ctx.saved_tensors
+        dl = ctx.dl
+        g_w = torch.zeros_like(w_flat)
+        g_loss = g_loss.contiguous().float()
+        call('hcomp_orth_loss_bwd', ptr(w_flat), ptr(loss), ptr(E), ptr(rel), ptr(g_loss), dl.tref, w_flat.shape[1], ptr(g_w),
+             _stream())
+        return g_w, None, None, None
+
+
+def joint_leaf_distribution(out_flat: torch.Tensor, dl: DeviceLayout, tau=1.0):
+    """[V,K] child logits -> ([V,L] joint leaf probabilities in sorted-leaf order, [V] argmax)
+    (util/node.py:300-385 + pipnet/pipnet.py:173-185 as one pass over a flattened path table)."""
+    out_flat = out_flat.detach().contiguous()
+    V = out_flat.shape[0]
+    dev = out_flat.device
+    probs = torch.empty(V, dl.K, device=dev, dtype=torch.float32)
+    joint = torch.empty(V, dl.L, device=dev, dtype=torch.float32)
+    pred = torch.empty(V, device=dev, dtype=torch.int64)
+    call('hcomp_joint_leaf', ptr(out_flat), dl.tref, V, float(tau), ptr(probs), ptr(joint), ptr(pred), _stream())
+    return joint, pred
+
+
+def materialize_map(features: torch.Tensor, w_node: torch.Tensor, tau=1.0) -> torch.Tensor:
+    """Full softmax map [V,P_n,H,W] of ONE node (visualisation path only, util/vis_hpipnet.py:62-127)."""
+    V, Cc, H, W = features.shape
+    x_rows = feature_rows(features.detach())
+    w = w_node.detach().reshape(w_node.shape[0], -1).contiguous().float()
+    out = torch.empty(V, w.shape[0], H * W, device=features.device, dtype=torch.float32)
+    call('hcomp_materialize_map', ptr(x_rows), ptr(w), V, H * W, Cc, w.shape[0], float(tau), ptr(out), _stream())
+    return out.view(V, w.shape[0], H, W)

@@ -1,0 +1,387 @@
+"""`PIPNet` / `get_network` with the reference's public surface (`pipnet/pipnet.py:54-185`, `:1134-1258`)
+over the fused sm_100a head.
+
+What stays identical for callers (`main_dist.py`, `pipnet/train.py`, `util/args.py`, visualisers):
+  * constructor signature, `forward(xs, inference=False, apply_overspecificity_mask=False)` returning
+    `(features, proto_features, pooled, out)` keyed by node name, `get_joint_distribution`;
+  * attributes `_net`, `_pool`, `_softmax`, `_multiplier`, `root`, `_num_classes` and per node
+    `_<node>_add_on` (a real `nn.Conv2d`, so `util/func.py:8-10` xavier init and the optimizer's
+    `dir(net.module)` scan `util/args.py:528-556` keep working), `_<node>_num_protos`,
+    `_<node>_classification` (`NonNegLinear`), `_<node>_proto_presence`;
+  * state-dict keys and shapes.
+
+What changes underneath: the per-node Python loop is gone.  All add-on kernels alias one flat
+[P, C] buffer, all classifier weights one flat vector; `forward` makes three kernel calls for the whole
+tree (projection+softmax+pool, classifier, optional threshold) and never materialises the
+[V, P_n, H, W] maps -- `proto_features[node]` is produced on demand for the visualisation tools.
+Unsupported research variants raise `Exception` like the reference does for invalid flag combinations
+(`pipnet/pipnet.py:104-105,135`); nothing silently falls back to PyTorch.
+"""
+from __future__ import annotations
+
+import argparse
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from . import ops
+from .layout import build_layout
+from .node import Node
+
+
+# --------------------------------------------------------------------------- small modules kept for API parity
+class NonNegLinear(nn.Module):
+    """Parameter holder with the reference layout (`pipnet/pipnet.py:1016-1036`): weight [out, in] ~ N(1, 0.1),
+    `normalization_multiplier`, optional zero bias.  `PIPNet.forward` does NOT call this module -- all nodes go
+    through one classifier kernel on the flat axes; `forward` here only serves tools that call a single node's
+    layer directly (`util/vis_hpipnet.py:62-127`, batch size 1)."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None) -> None:
+        kw = {'device': device, 'dtype': dtype}
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = nn.Parameter(torch.empty((out_features, in_features), **kw))
+        nn.init.normal_(self.weight, mean=1.0, std=0.1)
+        self.normalization_multiplier = nn.Parameter(torch.ones((1,), requires_grad=True))
+        if bias:
+            self.bias = nn.Parameter(torch.zeros(out_features, **kw))
+        else:
+            self.register_parameter('bias', None)
+
+    def forward(self, input: Tensor) -> Tensor:
+        return F.linear(input, torch.relu(self.weight), self.bias)
+
+
+class _GatherParams(torch.autograd.Function):
+    """Autograd bridge from the per-node `nn.Parameter`s (which alias a flat buffer) to that flat buffer:
+    forward is zero-copy, backward hands each parameter its slice of the flat gradient."""
+
+    @staticmethod
+    def forward(ctx, holder, *params):
+        ctx.meta = holder.meta
+        return holder.flat.detach()
+
+    @staticmethod
+    def backward(ctx, g):
+        g = g.contiguous()
+        flat = g.view(-1)
+        grads = []
+        for i, (off, numel, shape) in enumerate(ctx.meta):
+            grads.append(flat[off:off + numel].view(shape) if ctx.needs_input_grad[i + 1] else None)
+        return (None, *grads)
+
+
+class _FlatGroup:
+    """A set of parameters re-homed into one contiguous buffer (`param.data` becomes a view).  The
+    `Parameter` objects are never replaced, so optimizers built before or after keep working."""
+
+    def __init__(self, params: List[nn.Parameter]):
+        self.params = params
+        self.flat: Optional[Tensor] = None
+        self.meta = []
+
+    def ensure(self):
+        p0 = self.params[0]
+        ok = self.flat is not None and self.flat.device == p0.device
+        if ok:
+            base, es = self.flat.data_ptr(), self.flat.element_size()
+            for p, (off, numel, _) in zip(self.params, self.meta):
+                if p.data_ptr() != base + off * es:
+                    ok = False
+                    break
+        if ok:
+            return self.flat
+        # (re)build: happens once after construction and again after `.to(device)` / load_state_dict(assign=True)
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1).float() for p in self.params])
+            meta, off = [], 0
+            for p in self.params:
+                n = p.numel()
+                meta.append((off, n, tuple(p.shape)))
+                p.data = flat[off:off + n].view(p.shape)
+                off += n
+        self.flat, self.meta = flat, meta
+        return flat
+
+    def gather(self) -> Tensor:
+        self.ensure()
+        return _GatherParams.apply(self, *self.params)
+
+
+class NodeDict:
+    """Read-only mapping node name -> column slice of a flat [V, total] tensor, shaped like the dicts the
+    reference returns (`pipnet/pipnet.py:115-116`).  `.flat` is what the fused losses consume."""
+
+    def __init__(self, flat: Tensor, names: List[str], offsets: np.ndarray):
+        self.flat, self._names, self._off = flat, names, offsets
+        self._idx = {n: i for i, n in enumerate(names)}
+        self._cache: Dict[str, Tensor] = {}
+
+    def __getitem__(self, name):
+        t = self._cache.get(name)
+        if t is None:
+            i = self._idx[name]
+            t = self.flat[:, int(self._off[i]):int(self._off[i + 1])]
+            self._cache[name] = t
+        return t
+
+    def __contains__(self, name): return name in self._idx
+    def __iter__(self): return iter(self._names)
+    def __len__(self): return len(self._names)
+    def keys(self): return list(self._names)
+    def values(self): return [self[n] for n in self._names]
+    def items(self): return [(n, self[n]) for n in self._names]
+
+
+class LazyProtoFeatures:
+    """`proto_features[node]` = softmaxed map [V, P_n, H, W].  The fused head never writes these maps;
+    one is rebuilt on access for the callers that really want it (`main_dist.py:444` reads a shape,
+    the visualisers read batch-1 maps).  Not differentiable by design."""
+
+    def __init__(self, net: "PIPNet", features: Tensor, tau: float, argmax: NodeDict):
+        self._net, self._features, self._tau = net, features, tau
+        self.argmax = argmax                      # node -> [V, P_n] flat h*W+w location of the max
+        self._names = list(argmax.keys())
+        self._cache: Dict[str, Tensor] = {}
+
+    def __getitem__(self, name):
+        t = self._cache.get(name)
+        if t is None:
+            conv = getattr(self._net, '_' + name + '_add_on')
+            t = ops.materialize_map(self._features, conv.weight, self._tau)
+            self._cache[name] = t
+        return t
+
+    def shape_of(self, name):
+        V, _, H, W = self._features.shape
+        return (V, getattr(self._net, '_' + name + '_num_protos'), H, W)
+
+    def __contains__(self, name): return name in self._names
+    def __iter__(self): return iter(self._names)
+    def __len__(self): return len(self._names)
+    def keys(self): return list(self._names)
+    def items(self): return [(n, self[n]) for n in self._names]
+
+
+# --------------------------------------------------------------------------- the model
+_UNSUPPORTED = (('gumbel_softmax', 'y'), ('multiply_cs_softmax', 'y'), ('focal', 'y'), ('softmax_over_channel', 'y'))
+
+
+class PIPNet(nn.Module):
+    def __init__(self,
+                 num_classes: int,
+                 num_prototypes: int,
+                 feature_net: nn.Module,
+                 args: argparse.Namespace,
+                 add_on_layers: dict,
+                 pool_layer: nn.Module,
+                 classification_layers: dict,
+                 num_parent_nodes: int,
+                 root: Node):
+        super().__init__()
+        assert num_classes > 0
+        self._num_classes = num_classes
+        self._net = feature_net
+        for node_name, layer in add_on_layers.items():
+            if type(layer) is not nn.Conv2d or layer.kernel_size != (1, 1):
+                raise Exception('the B200 head supports plain 1x1 nn.Conv2d prototype layers only '
+                                '(UnitConv2D / L2Conv2D / ProjectConv2D are out of scope, SURVEY.md section 2.1)')
+            if layer.bias is not None:
+                raise Exception('--add_on_bias is not supported by the fused head')
+            setattr(self, '_' + node_name + '_add_on', layer)
+            setattr(self, '_' + node_name + '_num_protos', layer.weight.shape[0])
+        self._pool = pool_layer
+        self._avg_pool = nn.Sequential(nn.AdaptiveAvgPool2d(output_size=(1, 1)), nn.Flatten())
+        for node_name, layer in classification_layers.items():
+            setattr(self, '_' + node_name + '_classification', layer)
+        self._multiplier = nn.Parameter(torch.ones((1,), requires_grad=True))
+        if args.softmax.split('|')[0] == 'y':
+            self._softmax = nn.Softmax(dim=1)
+        else:
+            raise Exception('the B200 head implements the --softmax "y|tau" recipe only')
+        for flag, bad in _UNSUPPORTED:
+            if getattr(args, flag, 'n') == bad:
+                raise Exception(f'--{flag} {bad} is not supported by the B200 head')
+        self._num_parent_nodes = num_parent_nodes
+        self.root = root
+        for node_name in add_on_layers:
+            pp = nn.Parameter(torch.zeros(getattr(self, '_' + node_name + '_num_protos'), 2), requires_grad=True)
+            nn.init.xavier_normal_(pp, gain=1.0)
+            setattr(self, '_' + node_name + '_proto_presence', pp)
+        self.args = args
+        self.conc_log_ip = ('y' in getattr(args, 'conc_log_ip', 'n'))
+
+        parts = args.softmax.split('|')
+        self.softmax_tau = float(int(parts[1])) if len(parts) > 1 else 0.2        # pipnet/pipnet.py:131-136
+        # ---- flat layout (host tables) + parameter groups
+        self.layout = build_layout(root)
+        names = self.layout.node_names
+        if list(add_on_layers.keys()) != names or list(classification_layers.keys()) != names:
+            raise Exception('add_on_layers / classification_layers must follow root.nodes_with_children() order')
+        self._has_cls_bias = any(getattr(self, '_' + n + '_classification').bias is not None for n in names)
+        self._w_group = _FlatGroup([getattr(self, '_' + n + '_add_on').weight for n in names])
+        self._wc_group = _FlatGroup([getattr(self, '_' + n + '_classification').weight for n in names])
+        self._bias_group = (_FlatGroup([getattr(self, '_' + n + '_classification').bias for n in names])
+                            if self._has_cls_bias else None)
+        self._dl: Optional[ops.DeviceLayout] = None
+
+    # ------------------------------------------------------------------ plumbing
+    def device_layout(self, device) -> ops.DeviceLayout:
+        if self._dl is None or self._dl.device != torch.device(device):
+            self._dl = ops.DeviceLayout(self.layout, device)
+        return self._dl
+
+    def flat_prototype_kernels(self) -> Tensor:
+        """[P, C] view of all add-on kernels with autograd edges to the per-node parameters."""
+        C = self._w_group.params[0].shape[1]
+        return self._w_group.gather().view(self.layout.P, C)
+
+    def flat_classifier_weights(self) -> Tensor:
+        return self._wc_group.gather()
+
+    # ------------------------------------------------------------------ forward
+    def head(self, features: Tensor, *, inference=False, labels: Optional[ops.LabelTables] = None,
+             V_first: Optional[int] = None):
+        """The fused head on backbone features.  Returns flat tensors:
+        pooled [V,P], out [V,K], align [N] (zeros unless `labels` given), argmax [V,P] int32."""
+        V = features.shape[0]
+        dl = self.device_layout(features.device)
+        if V_first is None:
+            V_first = labels.V_first if labels is not None else (V + 1) // 2
+        x = features.detach() if getattr(self.args, 'sg_before_protos', 'n') == 'y' else features
+        w_flat = self.flat_prototype_kernels()
+        pooled, align, argmax = ops.HeadProjPool.apply(x, w_flat, dl, V_first, self.softmax_tau, labels,
+                                                       0.1 if inference else 0.0)
+        return pooled, align, argmax, dl
+
+    def classify(self, pooled_flat: Tensor, dl: ops.DeviceLayout) -> Tensor:
+        bias = self._bias_group.gather() if self._bias_group is not None else None
+        return ops.NonNegClassifier.apply(pooled_flat, self.flat_classifier_weights(), bias, dl)
+
+    def forward(self, xs, inference=False, apply_overspecificity_mask=False, labels: Optional[ops.LabelTables] = None):
+        features = self._net(xs)
+        pooled_flat, align, argmax, dl = self.head(features, inference=inference, labels=labels)
+        if apply_overspecificity_mask:
+            # Gumbel hard sample on proto_presence (pipnet/pipnet.py:164-166), one draw for the whole flat axis
+            pres = torch.cat([getattr(self, '_' + n + '_proto_presence') for n in self.layout.node_names])
+            mask = F.gumbel_softmax(pres, tau=0.5, hard=True, dim=-1)[:, 1].unsqueeze(0)
+            pooled_flat = mask * pooled_flat
+        out_flat = self.classify(pooled_flat, dl)
+        L = self.layout
+        pooled = NodeDict(pooled_flat, L.node_names, L.proto_off)
+        out = NodeDict(out_flat, L.node_names, L.cls_off)
+        pooled.align = align                                    # per-node align_pf loss (zeros without labels)
+        proto_features = LazyProtoFeatures(self, features, self.softmax_tau, NodeDict(argmax, L.node_names, L.proto_off))
+        return features, proto_features, pooled, out
+
+    def get_joint_distribution(self, out, leave_out_classes=None, apply_overspecificity_mask=False, device='cuda',
+                               softmax_tau=1):
+        """(`pipnet/pipnet.py:173-185`) -> (out['root'], [V, L] joint leaf probabilities, sorted-leaf columns)."""
+        if leave_out_classes or apply_overspecificity_mask:
+            raise Exception('leave_out_classes / overspecificity mask are outside the fused joint-distribution path')
+        flat = out.flat if isinstance(out, NodeDict) else torch.cat([out[n] for n in self.layout.node_names], dim=1)
+        joint, _ = ops.joint_leaf_distribution(flat, self.device_layout(flat.device), float(softmax_tau))
+        return out['root'], joint
+
+    def get_classification_layers(self):
+        return [getattr(self, attr) for attr in dir(self) if attr.endswith('_classification')]
+
+
+# --------------------------------------------------------------------------- backbones (hand-off only)
+def _relax_strides(model: nn.Module, threshold: int) -> nn.Module:
+    """Halve the stride of every stride-2 conv with more than `threshold` input channels: ConvNeXt-tiny then
+    ends at 26x26 (threshold 100) or 13x13 (300) for 224px input (`features/convnext_features.py:7-16`)."""
+    for m in model.modules():
+        if isinstance(m, nn.Conv2d) and m.stride[0] == 2 and m.in_channels > threshold:
+            m.stride = tuple(s // 2 for s in m.stride)
+    return model
+
+
+def _convnext_tiny(threshold, pretrained=False):
+    from torchvision import models
+    weights = models.ConvNeXt_Tiny_Weights.DEFAULT if pretrained else None
+    model = models.convnext_tiny(weights=weights)
+    model.avgpool = nn.Identity()
+    model.classifier = nn.Identity()
+    if threshold is not None:
+        _relax_strides(model, threshold)
+    return model
+
+
+def convnext_tiny_26_features(pretrained=False, **kw): return _convnext_tiny(100, pretrained)
+def convnext_tiny_13_features(pretrained=False, **kw): return _convnext_tiny(300, pretrained)
+def convnext_tiny_7_features(pretrained=False, **kw): return _convnext_tiny(None, pretrained)
+
+
+class _ResNetFeatures(nn.Module):
+    def __init__(self, name, pretrained):
+        super().__init__()
+        from torchvision import models
+        m = getattr(models, name)(weights='DEFAULT' if pretrained else None)
+        self.stem = nn.Sequential(m.conv1, m.bn1, m.relu, m.maxpool)
+        self.layers = nn.Sequential(m.layer1, m.layer2, m.layer3, m.layer4)
+        # the reference's ResNet feature nets end at 28x28 for 224px input: undo the last two strides
+        for blk in (m.layer3[0], m.layer4[0]):
+            for mod in blk.modules():
+                if isinstance(mod, nn.Conv2d) and mod.stride == (2, 2):
+                    mod.stride = (1, 1)
+
+    def forward(self, x):
+        return self.layers(self.stem(x))
+
+
+base_architecture_to_features = {
+    'convnext_tiny_26': convnext_tiny_26_features,
+    'convnext_tiny_13': convnext_tiny_13_features,
+    'convnext_tiny_7': convnext_tiny_7_features,
+    'resnet18': lambda pretrained=False: _ResNetFeatures('resnet18', pretrained),
+    'resnet34': lambda pretrained=False: _ResNetFeatures('resnet34', pretrained),
+    'resnet50': lambda pretrained=False: _ResNetFeatures('resnet50', pretrained),
+    'resnet101': lambda pretrained=False: _ResNetFeatures('resnet101', pretrained),
+}
+
+
+def get_network(num_classes: int, args: argparse.Namespace, root=None):
+    """Same contract as `pipnet/pipnet.py:1134-1258`: returns
+    (feature_net, add_on_layers, pool_layer, classification_layers, num_prototypes) with one bias-free 1x1
+    `nn.Conv2d` and one `NonNegLinear` per internal node; with `--protopool n` each child's classifier row
+    keeps N(1, 0.1) on its own prototype slice and -0.5 elsewhere (`:1235-1248`)."""
+    for flag in ('unitconv2d', 'projectconv2d', 'l2conv2d'):
+        if getattr(args, flag, 'n') == 'y':
+            raise Exception(f'--{flag} y is not supported by the B200 head (plain 1x1 conv prototypes only)')
+    if getattr(args, 'basic_cnext_gaussian_multiplier', '') != '' or getattr(args, 'stage4_reducer_net', '') != '':
+        raise Exception('gaussian-multiplier / stage4 reducer backbones are outside the B200 head scope')
+    if getattr(args, 'classifier', 'NonNegative') == 'Linear':
+        raise Exception('--classifier Linear is not supported (NonNegative only)')
+    if getattr(args, 'add_on_bias', False):
+        raise Exception('--add_on_bias is not supported by the fused head')
+    if args.net not in base_architecture_to_features:
+        raise Exception('other base architecture NOT implemented')
+    features = base_architecture_to_features[args.net](pretrained=not args.disable_pretrained)
+    in_channels = [m for m in features.modules() if isinstance(m, nn.Conv2d)][-1].out_channels
+    num_prototypes = in_channels if args.num_features == 0 else args.num_features
+
+    parent_nodes = root.nodes_with_children()
+    add_on_layers = OrderedDict()
+    for node in parent_nodes:
+        add_on_layers[node.name] = nn.Conv2d(in_channels, node.num_protos, kernel_size=1, stride=1, padding=0, bias=False)
+    pool_layer = nn.Sequential(nn.AdaptiveMaxPool2d(output_size=(1, 1)), nn.Flatten())
+    classification_layers = OrderedDict()
+    for node in parent_nodes:
+        layer = NonNegLinear(node.num_protos, node.num_children(), bias=bool(args.bias))
+        if args.protopool == 'n':
+            with torch.no_grad():
+                start = 0
+                for child in node.children:
+                    lab = node.children_to_labels[child.name]
+                    end = start + node.num_protos_per_child[child.name]
+                    layer.weight[lab, :start] = -0.5
+                    layer.weight[lab, end:] = -0.5
+                    start = end
+        classification_layers[node.name] = layer
+    return features, add_on_layers, pool_layer, classification_layers, num_prototypes

@@ -1,0 +1,112 @@
+"""Parity of the CUDA prototype head (through the C ABI) against the CPU oracle on identical,
+bf16-representable inputs.  Tolerances: argmax bit-exact; pooled / losses <= 1e-5 relative (the GEMM
+products are exact in fp32, only the accumulation order differs from the oracle's fp64); gradients are
+carried through a bf16 dZ, so they get the bf16 tolerance 2e-2 of BASELINE.json."""
+import pytest
+import torch
+
+from oracle import head_oracle as ho
+from oracle.problems import Problem, rel_err, argmax_report
+
+pytestmark = pytest.mark.gpu
+
+FWD_CASES = [
+    # tree, C, H, B, kwargs
+    ("cub08", 64, 6, 4, dict(num_features=20)),
+    ("cub08", 128, 7, 3, dict(per_child=20)),           # P_n = 20 / 40 (single-child root)
+    ("cub27", 96, 6, 5, dict(num_features=20)),
+    ("cub18", 64, 8, 4, dict(num_features=12)),          # masked tail inside the S=16 class
+    ("synth12:3", 72, 6, 6, dict(per_child=16)),         # S=32 class, C not a multiple of 64
+    ("cub27", 768, 26, 2, dict(num_features=20)),        # real ConvNeXt-26 geometry, image straddles tiles
+]
+
+
+def _oracle_forward(pb, tau=1.0):
+    return ho.head_forward(pb.x, pb.w, pb.wc, pb.root, softmax_tau=tau)
+
+
+@pytest.mark.parametrize("case", FWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}" for c in FWD_CASES])
+def test_forward_pool_argmax_align(case):
+    from pipnet_b200 import ops
+    tree, C, H, B, kw = case
+    pb = Problem(tree, C, H, B, seed=7, **kw)
+    dl = ops.DeviceLayout(pb.layout, 'cuda')
+    feats = pb.features('cuda')
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    x_rows = ops.feature_rows(feats)
+    wp = ops.pack_weights(pb.w_flat('cuda'), dl)
+    pooled, argmax, align = ops.proj_softmax_pool_raw(x_rows, wp, dl, pb.V, pb.V_first, H * H, 1.0, labels)
+    torch.cuda.synchronize()
+
+    proto, pooled_ref, argmax_ref, _ = _oracle_forward(pb)
+    pr = pb.cat_nodes(pooled_ref)
+    ar = pb.cat_nodes(argmax_ref)
+    assert rel_err(pooled, pr) <= 1e-5, f'pooled rel err {rel_err(pooled, pr)}'
+    proto_flat = torch.cat([proto[n].flatten(2) for n in pb.layout.node_names], dim=1)
+    nbad, gaps = argmax_report(argmax, ar, proto_flat)
+    assert nbad == 0, f'{nbad} argmax mismatches, relative gaps {gaps[:8]}'
+
+    masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
+    for i, name in enumerate(pb.layout.node_names):
+        if masks[name].any():
+            ref = ho.align_pf_term(proto[name], masks[name])
+            assert abs(float(align[i]) - float(ref)) <= 1e-5 * max(1.0, abs(float(ref))), (name, float(align[i]), float(ref))
+        else:
+            assert float(align[i]) == 0.0
+
+
+@pytest.mark.parametrize("V", [1, 3, 8])
+def test_forward_unpaired_inference(V):
+    """test_pipnet / visualisation call the head without view pairing and with any batch size."""
+    from pipnet_b200 import ops
+    pb = Problem("cub08", 64, 6, 0, seed=3, num_features=20, paired=False, V=V)
+    dl = ops.DeviceLayout(pb.layout, 'cuda')
+    x_rows = ops.feature_rows(pb.features('cuda'))
+    wp = ops.pack_weights(pb.w_flat('cuda'), dl)
+    pooled, argmax, _ = ops.proj_softmax_pool_raw(x_rows, wp, dl, pb.V, pb.V_first, 36, 1.0, None, thresh=0.1)
+    torch.cuda.synchronize()
+    _, pooled_ref, argmax_ref, _ = ho.head_forward(pb.x, pb.w, pb.wc, pb.root, inference=True)
+    assert rel_err(pooled, pb.cat_nodes(pooled_ref)) <= 1e-5
+    assert torch.equal(argmax.cpu().long(), pb.cat_nodes(argmax_ref))
+
+
+BWD_CASES = [
+    ("cub08", 64, 6, 4, dict(num_features=20)),
+    ("cub08", 128, 7, 3, dict(per_child=20)),
+    ("cub18", 64, 8, 4, dict(num_features=12)),
+    ("cub27", 768, 26, 1, dict(num_features=20)),
+]
+
+
+@pytest.mark.parametrize("case", BWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}" for c in BWD_CASES])
+def test_backward_dx_dw(case):
+    """d(sum pooled*G + sum_n a_n * align_n) w.r.t. features and prototype kernels vs oracle autograd."""
+    from pipnet_b200 import ops
+    tree, C, H, B, kw = case
+    pb = Problem(tree, C, H, B, seed=11, **kw)
+    L = pb.layout
+    dl = ops.DeviceLayout(L, 'cuda')
+    g = torch.Generator().manual_seed(5)
+    G = torch.randn(pb.V, L.P, generator=g, dtype=torch.float64)
+    a = torch.rand(L.N, generator=g, dtype=torch.float64) + 0.5
+
+    feats = pb.features('cuda').requires_grad_(True)
+    w_flat = pb.w_flat('cuda').requires_grad_(True)
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    pooled, align, _ = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0)
+    loss = (pooled.double() * G.cuda()).sum() + (align.double() * a.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+
+    x = pb.x.clone().requires_grad_(True)
+    w = {k: v.clone().requires_grad_(True) for k, v in pb.w.items()}
+    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root)
+    masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
+    ref = (pb.cat_nodes(pooled_ref) * G).sum()
+    for i, name in enumerate(L.node_names):
+        if masks[name].any():
+            ref = ref + a[i] * ho.align_pf_term(proto[name], masks[name])
+    ref.backward()
+    gw_ref = torch.cat([w[n].grad for n in L.node_names])
+    assert rel_err(feats.grad, x.grad) <= 2e-2, f'dX rel err {rel_err(feats.grad, x.grad)}'
+    assert rel_err(w_flat.grad, gw_ref) <= 2e-2, f'dW rel err {rel_err(w_flat.grad, gw_ref)}'
