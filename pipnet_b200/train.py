@@ -1,0 +1,402 @@
+"""`train_pipnet` / `test_pipnet` / `calculate_loss` with the reference's signatures
+(`pipnet/train.py:73-77`, `:525-530`, `:852-855`) on top of the fused head.
+
+Differences that matter for speed, not for results:
+  * the per-node Python loop of `calculate_loss` (`pipnet/train.py:933-1194`: host-built masks, H2D per node,
+    `.item()` per node per loss, `.cpu()` per child) is replaced by a handful of kernel calls on flat
+    [V,P] / [V,K] tensors driven by label tables built on the device (`ops.LabelTables`);
+  * nothing synchronises with the host inside a step: per-node loss values are handed back as lazy
+    dictionaries that copy one [N] vector on first access, epoch statistics are accumulated on the device;
+  * the per-step `barrier` + broadcast of every parameter (`pipnet/train.py:54-65`) is dropped: its rank-0
+    mutation tests `name.endswith('_classification')` on *parameter* names and never fires.
+
+Loss terms implemented as kernels: align_pf, tanh, kernel_orth, class (the shipped recipe).  Terms marked
+"next" in SURVEY 8f (tanh_desc, minimize_contrasting_set, mask-prune, OOD, BYOL, align/uni) raise.
+"""
+from __future__ import annotations
+
+import os
+from collections import defaultdict
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import ops
+from .pipnet import NodeDict, PIPNet
+
+OOD_LABEL = -1
+
+
+# --------------------------------------------------------------------------- lazy per-node values
+class _Scalar:
+    __slots__ = ('v',)
+
+    def __init__(self, v): self.v = float(v)
+    def item(self): return self.v
+    def __float__(self): return self.v
+    def __repr__(self): return f'{self.v:.6f}'
+
+
+class LazyNodeLosses:
+    """dict-like {node name: value} over a device vector [N]; only nodes with descendants in the batch are
+    present (the reference `continue`s over the others, `pipnet/train.py:941-942`).  One D2H copy on first use."""
+
+    def __init__(self, values: Optional[torch.Tensor], n_desc: torch.Tensor, names):
+        self._values, self._n_desc, self._names, self._d = values, n_desc, names, None
+
+    def _mat(self):
+        if self._d is None:
+            if self._values is None:
+                self._d = {}
+            else:
+                both = torch.stack([self._values.detach().float(), self._n_desc.float()]).cpu().numpy()
+                self._d = {n: _Scalar(both[0, i]) for i, n in enumerate(self._names) if both[1, i] > 0}
+        return self._d
+
+    def items(self): return self._mat().items()
+    def keys(self): return self._mat().keys()
+    def values(self): return self._mat().values()
+    def __getitem__(self, k): return self._mat()[k]
+    def __contains__(self, k): return k in self._mat()
+    def __len__(self): return len(self._mat())
+    def __iter__(self): return iter(self._mat())
+
+    def mean_tensor(self):
+        """mean over present nodes as a device scalar (what `np.mean([... .item() ...])` computes)"""
+        if self._values is None:
+            return None
+        act = (self._n_desc > 0).float()
+        return (self._values.detach() * act).sum() / act.sum().clamp_min(1.0)
+
+
+def _unwrap(net):
+    return net.module if hasattr(net, 'module') else net
+
+
+def _reject(flag_name, on):
+    if on:
+        raise Exception(f'{flag_name} is not part of the fused B200 head path yet (SURVEY.md section 8f); '
+                        f'run it on the reference or disable it')
+
+
+def make_labels(net, ys: torch.Tensor, V_first: Optional[int] = None) -> ops.LabelTables:
+    m = _unwrap(net)
+    V = ys.numel()
+    return ops.LabelTables(ys, m.device_layout(ys.device), V // 2 if V_first is None else V_first)
+
+
+# --------------------------------------------------------------------------- the loss
+def calculate_loss(epoch, net, additional_network_outputs, features, proto_features, pooled, out, ys, align_weight,
+                   align_pf_weight, t_weight, mm_weight, unif_weight, cl_weight, OOD_loss_weight, orth_weight,
+                   cluster_desc_weight, sep_desc_weight, subspace_sep_weight, byol_weight, net_normalization_multiplier,
+                   pretrain, finetune, criterion, train_iter, print=True, EPS=1e-10, root=None, label2name=None,
+                   node_accuracy=None, OOD_loss_required=False, kernel_orth=False, tanh_desc=False, align=True, uni=True,
+                   align_pf=False, tanh=False, minmaximize=False, cluster_desc=False, sep_desc=False, subspace_sep=False,
+                   byol=False, train=True, args=None, device=None, labels: Optional[ops.LabelTables] = None):
+    """Same positional contract and 21-tuple as `pipnet/train.py:852-1341`.  `pooled` / `out` are the
+    `NodeDict`s returned by `PIPNet.forward`; `labels` are the device label tables of this batch (built here
+    from `ys` when not given).  `criterion` is accepted for signature parity: the class term is always the
+    weighted NLL of `util/custom_losses.py:17-34`."""
+    m: PIPNet = _unwrap(net)
+    _reject('align/uni', (not finetune) and (align or uni))
+    _reject('byol', (not finetune) and byol)
+    _reject('tanh_desc', (not finetune) and (not pretrain) and tanh_desc)
+    _reject('minmaximize / cluster_desc / sep_desc / subspace_sep', minmaximize or cluster_desc or sep_desc or subspace_sep)
+    _reject('OOD loss', OOD_loss_required)
+    if args is not None:
+        _reject('--mask_prune_overspecific', (not pretrain) and 'y' in getattr(args, 'mask_prune_overspecific', 'n'))
+        _reject('--minimize_contrasting_set', (not pretrain) and (not finetune) and 'y' in getattr(args, 'minimize_contrasting_set', 'n'))
+        _reject('--OOD_ent', 'y' in getattr(args, 'OOD_ent', 'n'))
+    if not isinstance(pooled, NodeDict) or not isinstance(out, NodeDict):
+        raise Exception('calculate_loss expects the outputs of pipnet_b200.PIPNet.forward')
+    dl = m.device_layout(pooled.flat.device)
+    if labels is None:
+        labels = make_labels(net, ys)
+    N = dl.N
+    names = m.layout.node_names
+    zero = torch.zeros((), device=pooled.flat.device)
+    loss = zero
+    losses_used = []
+
+    a_vec = t_vec = o_vec = c_vec = n_correct = None
+    if (not finetune) and align_pf:
+        a_vec = getattr(pooled, 'align', None)
+        if a_vec is None or not getattr(a_vec, 'requires_grad', False) and torch.is_grad_enabled() and train:
+            if a_vec is None:
+                raise Exception('align_pf needs the per-node align loss of the fused forward: call net(xs, labels=...)')
+        loss = loss + (align_pf_weight / N) * a_vec.sum()
+        losses_used.append('AL_PF')
+    if (not finetune) and tanh:
+        if not (getattr(args, 'tanh_during_second_phase', 'y') == 'n' and not pretrain):
+            t_vec = ops.TanhLoss.apply(pooled.flat, labels, dl, EPS)
+            loss = loss + (t_weight / N) * t_vec.sum()
+            losses_used.append('TANH')
+    if (not pretrain) and (not finetune) and kernel_orth:
+        o_vec = ops.OrthLoss.apply(m.flat_prototype_kernels(), m.flat_classifier_weights(), labels, dl)
+        loss = loss + (orth_weight / N) * o_vec.sum()
+        losses_used.append('KO')
+    sparsity = not (args is not None and getattr(args, 'pipnet_sparsity', 'y') == 'n')
+    if not pretrain:
+        c_vec, n_correct = ops.ClassLoss.apply(out.flat, labels, dl, sparsity)
+        loss = loss + (cl_weight / N) * c_vec.sum()
+        losses_used.append('CL')
+    else:
+        with torch.no_grad():
+            _, n_correct = ops.ClassLoss.apply(out.flat.detach(), labels, dl, sparsity)
+
+    if node_accuracy is not None:
+        acc = node_accuracy.setdefault('__device__', {'n_examples': torch.zeros(N, device=zero.device, dtype=torch.int64),
+                                                      'n_correct': torch.zeros(N, device=zero.device, dtype=torch.int64)})
+        acc['n_examples'] += labels.n_desc
+        acc['n_correct'] += n_correct
+
+    class_loss = LazyNodeLosses(c_vec, labels.n_desc, names)
+    tanh_loss = LazyNodeLosses(t_vec, labels.n_desc, names)
+    orth_loss = LazyNodeLosses(o_vec, labels.n_desc, names)
+    a_loss_pf = LazyNodeLosses(a_vec, labels.n_desc, names)
+    placeholder = -5
+    avg = lambda d: (d.mean_tensor() if d.mean_tensor() is not None else placeholder)
+    avg_class_loss = avg(class_loss) if not pretrain else None
+    avg_a_loss_pf, avg_tanh_loss, avg_orth = avg(a_loss_pf), avg(tanh_loss), avg(orth_loss)
+    if print and train_iter is not None and hasattr(train_iter, 'set_postfix_str'):
+        train_iter.lazy_postfix = (loss.detach(), avg_class_loss, avg_a_loss_pf, avg_tanh_loss, avg_orth, '+'.join(losses_used))
+    a_loss = torch.tensor(-5)
+    uni_loss = torch.tensor(-5)
+    return (loss, class_loss, a_loss, tanh_loss, {}, {}, orth_loss, uni_loss, avg_class_loss, avg_a_loss_pf, avg_tanh_loss,
+            placeholder, (placeholder if pretrain else -5), avg_orth, -5, -5, -5, -5, -5, -5, 0.)
+
+
+# --------------------------------------------------------------------------- epoch drivers
+def _class_to_idx(loader):
+    ds = loader.dataset
+    while not hasattr(ds, 'class_to_idx'):
+        if not hasattr(ds, 'dataset'):
+            raise Exception('the dataset chain must end in an object with class_to_idx (ImageFolder-like)')
+        ds = ds.dataset
+    return ds.class_to_idx
+
+
+def _phase_weights(pretrain, epoch, nr_epochs, args):
+    """`pipnet/train.py:148-177`"""
+    if pretrain:
+        return dict(align_pf_weight=(epoch / nr_epochs) * 1., byol_weight=0.5, align_weight=0.5, unif_weight=3., t_weight=5.,
+                    mm_weight=0., cl_weight=0., OOD_loss_weight=0., orth_weight=0.5, cluster_desc_weight=0.8,
+                    sep_desc_weight=0.08, subspace_sep_weight=1e-2)
+    return dict(align_pf_weight=5., byol_weight=2, align_weight=0.5, unif_weight=3., t_weight=2., mm_weight=2.,
+                cl_weight=args.cl_weight, OOD_loss_weight=0.2, orth_weight=0.5, cluster_desc_weight=0.8,
+                sep_desc_weight=0.08, subspace_sep_weight=1e-2)
+
+
+def _to_float(x):
+    if x is None:
+        return -5.0
+    if torch.is_tensor(x):
+        return float(x)
+    return float(x)
+
+
+class _Acc:
+    """device-side running sums; one host copy at the end of the epoch"""
+
+    def __init__(self, device):
+        self.d: Dict[str, torch.Tensor] = {}
+        self.device = device
+
+    def add(self, k, v):
+        if v is None:
+            v = -5.0
+        v = v.detach().float() if torch.is_tensor(v) else torch.tensor(float(v), device=self.device)
+        self.d[k] = self.d.get(k, torch.zeros((), device=self.device)) + v.to(self.device)
+
+    def result(self, steps):
+        if not self.d:
+            return {}
+        keys = list(self.d)
+        vals = (torch.stack([self.d[k] for k in keys]) / float(steps)).cpu().tolist()
+        return dict(zip(keys, vals))
+
+
+def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, scheduler_classifier, criterion, epoch,
+               nr_epochs, device, pretrain, finetune, progress_prefix, kw, train: bool):
+    from tqdm import tqdm
+    m: PIPNet = _unwrap(net)
+    args = kw.get('args')
+    _reject('OOD loader', kw.get('train_loader_OOD') is not None or kw.get('test_loader_OOD') is not None)
+    name2label = _class_to_idx(loader)
+    names = m.layout.node_names
+    if sorted(name2label, key=name2label.get) != m.layout.leaf_names:
+        raise Exception('dataset classes must be the tree leaves in sorted order (label i <-> i-th sorted leaf name)')
+    node_accuracy = {}
+    w = _phase_weights(pretrain, epoch, nr_epochs, args)
+    iters = len(loader)
+    it = tqdm(enumerate(loader), total=iters, desc=progress_prefix + '%s' % epoch, mininterval=2., ncols=0)
+    acc = _Acc(device)
+    n_fine_correct = torch.zeros((), device=device, dtype=torch.int64)
+    n_samples = 0
+    lrs_net, lrs_class = [], []
+    node_sums = {k: torch.zeros(len(names), device=device) for k in ('class_loss', 'tanh_loss', 'kernel_orth_loss')}
+    node_cnt = torch.zeros(len(names), device=device)
+    steps = 0
+    ctx = torch.enable_grad() if train else torch.no_grad()
+    with ctx:
+        for i, batch in it:
+            if train:
+                xs1, xs2, ys = batch
+                xs1, xs2, ys = xs1.to(device, non_blocking=True), xs2.to(device, non_blocking=True), ys.to(device, non_blocking=True)
+                xs, ys = torch.cat([xs1, xs2]), torch.cat([ys, ys])                     # pipnet/train.py:213-214
+                optimizer_classifier.zero_grad(set_to_none=True)
+                optimizer_net.zero_grad(set_to_none=True)
+            else:
+                xs, ys = batch
+                xs, ys = xs.to(device, non_blocking=True), ys.to(device, non_blocking=True)
+                xs, ys = torch.cat([xs, xs]), torch.cat([ys, ys])                       # pipnet/train.py:652-653
+            labels = make_labels(net, ys)
+            if train:
+                features, proto_features, pooled, out = net(xs, labels=labels)
+            else:
+                features, proto_features, pooled, out = net(xs, apply_overspecificity_mask=kw.get('apply_overspecificity_mask', False),
+                                                            labels=labels)
+            res = calculate_loss(epoch, net, {}, features, proto_features, pooled, out, ys,
+                                 net_normalization_multiplier=m._multiplier, pretrain=pretrain, finetune=finetune,
+                                 criterion=criterion, train_iter=it, print=True, EPS=1e-8, root=m.root, label2name=None,
+                                 node_accuracy=node_accuracy, OOD_loss_required=False, kernel_orth=kw.get('kernel_orth', False),
+                                 tanh_desc=kw.get('tanh_desc', False), align=kw.get('align', True), uni=kw.get('uni', True),
+                                 align_pf=kw.get('align_pf', False), tanh=kw.get('tanh', False),
+                                 minmaximize=kw.get('minmaximize', False), cluster_desc=kw.get('cluster_desc', False),
+                                 sep_desc=kw.get('sep_desc', False), subspace_sep=kw.get('subspace_sep', False),
+                                 byol=kw.get('byol', False), train=train, args=args, device=device, labels=labels, **w)
+            loss, class_d, _, tanh_d, _, _, orth_d = res[:7]
+            if train:
+                loss.backward()
+                if not pretrain:
+                    optimizer_classifier.step()
+                    scheduler_classifier.step(epoch - 1 + (i / iters))
+                    lrs_class.append(scheduler_classifier.get_last_lr()[0])
+                if not finetune:
+                    optimizer_net.step()
+                    scheduler_net.step()
+                    lrs_net.append(scheduler_net.get_last_lr()[0])
+                else:
+                    lrs_net.append(0.)
+            with torch.no_grad():
+                acc.add('loss', loss)
+                acc.add('class_loss', res[8]); acc.add('tanh_loss', res[10]); acc.add('kernel_orth_loss', res[13])
+                acc.add('a_loss_pf', res[9])
+                act = (labels.n_desc > 0).float()
+                node_cnt += act
+                for key, d in (('class_loss', class_d), ('tanh_loss', tanh_d), ('kernel_orth_loss', orth_d)):
+                    if d._values is not None:
+                        node_sums[key] += d._values.detach() * act
+                _, pred = ops.joint_leaf_distribution(out.flat, m.device_layout(out.flat.device), kw.get('path_prob_softmax_tau', 1))
+                n_fine_correct += (pred == ys).sum()                                     # pipnet/train.py:363-369
+                n_samples += ys.numel()
+            steps += 1
+            if hasattr(it, 'lazy_postfix') and (i % 50 == 0):
+                lz = it.lazy_postfix
+                it.set_postfix_str(f'L:{float(lz[0]):.3f}, losses_used:{lz[5]}', refresh=False)
+
+    steps = max(steps, 1)
+    means = acc.result(steps)
+    info = dict()
+    info['fine_accuracy'] = float(n_fine_correct) / max(n_samples, 1)
+    info['train_accuracy' if train else 'test_accuracy'] = 0.
+    info['loss'] = means.get('loss', 0.)
+    info['class_loss (mean over epoch nodes)'] = means.get('class_loss', -5.)
+    info['kernel_orth_loss (mean over epoch nodes)'] = means.get('kernel_orth_loss', -5.)
+    info['tanh_loss (mean over epoch nodes)'] = means.get('tanh_loss', -5.)
+    info['minmaximize_loss (mean over epoch nodes)'] = -5
+    info['OOD_loss (mean over epoch nodes)'] = -5
+    info['a_loss (mean over epoch)'] = -5
+    info['a_loss_pf (mean over epoch nodes)'] = means.get('a_loss_pf', -5.)
+    info['uni_loss (mean over epoch)'] = -5
+    info['true_uni_loss (without averaging)'] = -5
+    info['lrs_net'], info['lrs_class'] = lrs_net, lrs_class
+
+    # node-level accuracy (pipnet/train.py:1187-1194, :484-489) from the device counters
+    dev_acc = node_accuracy.pop('__device__', None)
+    node_stats = {}
+    if dev_acc is not None:
+        ne, nc = dev_acc['n_examples'].cpu().tolist(), dev_acc['n_correct'].cpu().tolist()
+        for n, e, c in zip(names, ne, nc):
+            node_stats[n] = {'n_examples': e, 'n_correct': c, 'accuracy': round(100.0 * c / e, 2) if e else None, 'f1': None}
+    info['node_accuracy'] = node_stats
+
+    sub = ('pretrain' if pretrain else 'train') if train else 'test'
+    log_dict = {}
+    if kw.get('wandb_logging', True):
+        log_dict[sub + '/epoch loss'] = info['loss']
+        log_dict[sub + '/fine_accuracy'] = info['fine_accuracy']
+        log_dict[sub + '/class_loss'] = info['class_loss (mean over epoch nodes)']
+        log_dict[sub + '/tanh_loss'] = info['tanh_loss (mean over epoch nodes)']
+        log_dict[sub + '/kernel_orth_loss'] = info['kernel_orth_loss (mean over epoch nodes)']
+        log_dict[sub + '/a_loss_pf'] = info['a_loss_pf (mean over epoch nodes)']
+        for n, st in node_stats.items():
+            if st['accuracy'] is not None:
+                log_dict[sub + f'/node_wise/acc:{n}'] = st['accuracy']
+        cnt = node_cnt.clamp_min(1.0)
+        per_node = {k: (v / cnt).cpu().tolist() for k, v in node_sums.items()}
+        for k, vals in per_node.items():
+            for n, v in zip(names, vals):
+                log_dict[sub + f'/node_wise_{k}/{n}'] = v
+        run = kw.get('wandb_run')
+        if run is not None:
+            run.log(log_dict, step=epoch if pretrain else (epoch + kw.get('pretrain_epochs', 0)))
+    log = kw.get('log')
+    if log is not None:
+        table = f'epoch_wise_metrics_{"train" if train else "test"}'
+        cols = ['fine_accuracy', 'loss', 'class_loss (mean over epoch nodes)', 'kernel_orth_loss (mean over epoch nodes)',
+                'tanh_loss (mean over epoch nodes)', 'minmaximize_loss (mean over epoch nodes)',
+                'OOD_loss (mean over epoch nodes)', 'a_loss (mean over epoch)', 'uni_loss (mean over epoch)',
+                'true_uni_loss (without averaging)']
+        try:
+            log.create_log(table, 'epoch', *cols)
+        except Exception:
+            pass
+        log.log_values(table, epoch if pretrain else (epoch + kw.get('pretrain_epochs', 0)), *[info[c] for c in cols])
+    print_fn = __builtins__['print'] if isinstance(__builtins__, dict) else getattr(__builtins__, 'print')
+    print_fn('\tFine accuracy:', round(info['fine_accuracy'], 2))
+    return info, log_dict
+
+
+def train_pipnet(net, train_loader, optimizer_net, optimizer_classifier, scheduler_net, scheduler_classifier, criterion,
+                 epoch, nr_epochs, device, pretrain=False, finetune=False, progress_prefix: str = 'Train Epoch',
+                 wandb_logging=True, train_loader_OOD=None, kernel_orth=False, tanh_desc=False, align=True, uni=True,
+                 align_pf=False, tanh=False, minmaximize=False, cluster_desc=False, sep_desc=False, subspace_sep=False,
+                 byol=False, byol_tau_base=0.9995, byol_tau_max=1., step_info=None, wandb_run=None, pretrain_epochs=0,
+                 log=None, args=None, dist_training=False):
+    """One training epoch (`pipnet/train.py:73-522`).  Returns (train_info, log_dict)."""
+    net.train()
+    m = _unwrap(net)
+    # `pipnet/train.py:101-110` sets `.requires_grad` on the classification *modules* (a no-op attribute);
+    # the real freezing is done by the driver on the parameters (`main_dist.py:472-485`), which we respect.
+    if pretrain:
+        progress_prefix = 'Pretrain Epoch'
+    kw = dict(wandb_logging=wandb_logging, train_loader_OOD=train_loader_OOD, kernel_orth=kernel_orth, tanh_desc=tanh_desc,
+              align=align, uni=uni, align_pf=align_pf, tanh=tanh, minmaximize=minmaximize, cluster_desc=cluster_desc,
+              sep_desc=sep_desc, subspace_sep=subspace_sep, byol=byol, wandb_run=wandb_run, pretrain_epochs=pretrain_epochs,
+              log=log, args=args)
+    return _run_epoch(net, train_loader, optimizer_net, optimizer_classifier, scheduler_net, scheduler_classifier, criterion,
+                      epoch, nr_epochs, device, pretrain, finetune, progress_prefix, kw, train=True)
+
+
+def test_pipnet(net, test_loader, optimizer_net, optimizer_classifier, scheduler_net, scheduler_classifier, criterion,
+                epoch, nr_epochs, device, pretrain=False, finetune=False, progress_prefix: str = 'Test Epoch',
+                wandb_logging=True, test_loader_OOD=None, kernel_orth=False, tanh_desc=False, align=True, uni=True,
+                align_pf=False, tanh=False, minmaximize=False, cluster_desc=False, sep_desc=False, subspace_sep=False,
+                byol=False, byol_tau_base=0.9995, step_info=None, wandb_run=None, pretrain_epochs=0, log=None, args=None,
+                apply_overspecificity_mask=False, leave_out_classes=None, path_prob_softmax_tau=1):
+    """One evaluation epoch (`pipnet/train.py:525-849`): the test batch is duplicated like the reference does
+    (`:652-653`) so the same paired kernels and losses apply.  Returns (test_info, log_dict)."""
+    net.eval()
+    _reject('leave_out_classes', bool(leave_out_classes))
+    kw = dict(wandb_logging=wandb_logging, test_loader_OOD=test_loader_OOD, kernel_orth=kernel_orth, tanh_desc=tanh_desc,
+              align=align, uni=uni, align_pf=align_pf, tanh=tanh, minmaximize=minmaximize, cluster_desc=cluster_desc,
+              sep_desc=sep_desc, subspace_sep=subspace_sep, byol=byol, wandb_run=wandb_run, pretrain_epochs=pretrain_epochs,
+              log=log, args=args, apply_overspecificity_mask=apply_overspecificity_mask,
+              path_prob_softmax_tau=path_prob_softmax_tau)
+    return _run_epoch(net, test_loader, optimizer_net, optimizer_classifier, scheduler_net, scheduler_classifier, criterion,
+                      epoch, nr_epochs, device, pretrain, finetune, progress_prefix, kw, train=False)
+
+
+test_pipnet.__test__ = False   # not a pytest test
