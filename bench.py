@@ -1,0 +1,315 @@
+#!/usr/bin/env python
+"""Benchmark of the HComP-Net prototype head (forward + fused losses + backward) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores (oracle port)
+
+One "step" = one pass of the hot path over one synthetic batch: `PIPNet.forward` on backbone features
+(projection + softmax + max-pool + classifier) + `calculate_loss` (align_pf, tanh, kernel_orth, class) +
+backward (dZ recompute, dX, dW, classifier / loss gradients) [+ NCCL mean all-reduce of the head gradients
+when N > 1].  The backbone is outside the path (identity here); the workload is BASELINE.json configs[1]:
+cub27 tree, 20 prototypes per node (P = 500), batch 64 (=> 128 views of 26x26x768 bf16 features) per GPU.
+
+Prints ONE JSON line (rank 0).  `value` = images/s with the batch resident in HBM; `e2e` = the same step
+driven from pinned HOST buffers (H2D of the feature batch + labels and D2H of the loss inside the timed
+region); `roofline` = the fused projection+softmax+pool kernel against the measured bf16 tensor peak;
+`cpu_baseline` = the oracle port of the reference algorithm on this box's host cores (bounded sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch
+
+WORKLOADS = {
+    # name: tree, protos/node, per-GPU batch, C, H
+    'cub27': dict(tree='cub27', num_features=20, batch=64, C=768, H=26),
+    'cub08': dict(tree='cub08', num_features=20, batch=8, C=768, H=26),
+    'cub190': dict(tree='synth190', num_features=20, batch=32, C=768, H=26),
+}
+METRIC = 'train images/sec (prototype head fwd+bwd)'
+UNIT = 'images/s'
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(bf16_burst=d['bf16_tflops'], bf16_sustained=d.get('bf16_tflops_sustained', d['bf16_tflops']),
+                    hbm=d['hbm_gbs'], source='measured (MEASURED_PEAKS.json)')
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+                                          '-i', str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(',')]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[3:7]):
+                if v.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# --------------------------------------------------------------------------- reference arm / cpu baseline
+def oracle_cpu_throughput(wl, batch, steps, warmup, budget_s=25.0):
+    """The reference algorithm (oracle port, fp32, all host threads) on a bounded sample of the workload:
+    same tree / prototypes / feature geometry, `batch` images per step.  Returns images/s and details."""
+    from oracle import head_oracle as ho
+    from oracle.problems import Problem
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pb = Problem(wl['tree'], wl['C'], wl['H'], batch, seed=1234, num_features=wl['num_features'])
+    x = pb.x.float()
+    aw = {k: v.float() for k, v in pb.w.items()}
+    cw = {k: v.float() for k, v in pb.wc.items()}
+    times = []
+    t_begin = time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        ho.full_step(x, aw, cw, pb.root, pb.ys, pb.label2name, pretrain=False, finetune=False)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+        if time.perf_counter() - t_begin > budget_s and len(times) >= 1:
+            break
+    mean = sum(times) / len(times)
+    return batch / mean, dict(cores=cores, steps=len(times), s_per_step=mean,
+                              sample=f'{wl["tree"]} tree, P={pb.layout.P}, batch {batch} ({2 * batch} views of '
+                                     f'{wl["H"]}x{wl["H"]}x{wl["C"]}), fp32 oracle port, fwd+losses+bwd')
+
+
+def run_reference(a):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    wl = WORKLOADS[a.workload]
+    batch = min(8, wl['batch'])
+    val, det = oracle_cpu_throughput(wl, batch, a.steps, a.warmup, budget_s=150.0)
+    line = {'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': a.gpus, 'steps': det['steps'],
+            'warmup': a.warmup, 'ms_per_step': det['s_per_step'] * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': f'{a.workload}: {det["sample"]}'},
+            'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': det['cores'], 'kind': 'port', 'sample': det['sample']},
+            'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- our arm
+def run_ours(a):
+    import torch.distributed as dist
+    from pipnet_b200 import _cabi, ops
+    from pipnet_b200 import train as tr
+    from oracle.problems import build_net, make_args      # builders only (identity backbone, seeded weights)
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the prototype head has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+        ops.GRAD_ALLREDUCE_GROUP = dist.group.WORLD
+    wl = WORKLOADS[a.workload]
+    B, C, H = wl['batch'], wl['C'], wl['H']
+    V, HW = 2 * B, H * H
+    args = make_args(num_features=wl['num_features'])
+    net, root = build_net(wl['tree'], C, args, seed=1)
+    net = net.to(dev)
+    net.train()
+    L = net.layout
+    names = L.node_names
+    cls_params = [getattr(net, '_' + n + '_classification').weight for n in names]
+
+    # two alternating feature batches (each 133 MB for cub27 > L2 126 MB), channels-last bf16 like ConvNeXt-26 emits
+    g = torch.Generator().manual_seed(1234 + rank)
+    feats, labels_h = [], []
+    for i in range(2):
+        x = torch.randn(V, H, H, C, generator=g, dtype=torch.float32).to(torch.bfloat16)
+        feats.append(x.to(dev).permute(0, 3, 1, 2))           # [V,C,H,W] view with NHWC strides
+        y = torch.randint(0, L.L, (B,), generator=torch.Generator().manual_seed(7 + i + 100 * rank))
+        labels_h.append(torch.cat([y, y]))
+    labels_d = [y.to(dev) for y in labels_h]
+    w = tr._phase_weights(False, 1, 10, args)
+
+    def step(x, ys):
+        x = x.detach().requires_grad_(True)
+        for p in net.parameters():
+            p.grad = None
+        labels = tr.make_labels(net, ys)
+        features, pf, pooled, out = net(x, labels=labels)
+        res = tr.calculate_loss(1, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                                device=dev, labels=labels, **w)
+        loss = res[0]
+        loss.backward()
+        if world > 1:      # tiny classifier gradients: one flat all-reduce (prototype kernels overlap inside backward)
+            flat = torch.cat([p.grad.reshape(-1) for p in cls_params])
+            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        return loss, x.grad
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(a.warmup, 3)):
+        step(feats[i % 2], labels_d[i % 2])
+    barrier()
+
+    # ---------------- device-resident timing
+    ops.PROFILE.reset()
+    ops.PROFILE.enabled = True
+    launches0 = _cabi.lib().hcomp_launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(a.steps):
+        step(feats[i % 2], labels_d[i % 2])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = _cabi.lib().hcomp_launch_count() - launches0
+    ops.PROFILE.enabled = False
+    prof = ops.PROFILE.totals_ms()
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t)
+    ms_per_step = ms / a.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    # ---------------- end-to-end from pinned host buffers
+    host_x = [f.permute(0, 2, 3, 1).contiguous().cpu().pin_memory() for f in feats]
+    host_y = [y.pin_memory() for y in labels_h]
+    dev_x = torch.empty(V, H, H, C, device=dev, dtype=torch.bfloat16)
+    dev_y = torch.empty(V, device=dev, dtype=torch.int64)
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+    e2e_steps = max(3, min(a.steps, 20))
+
+    def e2e_step(i):
+        dev_x.copy_(host_x[i % 2], non_blocking=True)
+        dev_y.copy_(host_y[i % 2], non_blocking=True)
+        loss, _ = step(dev_x.permute(0, 3, 1, 2), dev_y)
+        host_loss.copy_(loss.detach(), non_blocking=True)
+
+    for i in range(2):
+        e2e_step(i)
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / e2e_steps
+    e2e = {'value': world * B / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_x[0].numel() * 2 + V * 8),
+           'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms}
+
+    if rank == 0:
+        peaks = load_peaks()
+        # roofline of the dominant fused kernel (K1): algorithmic flops = 2 * M * C * P per launch
+        M = V * HW
+        k1_ms, k1_n = prof.get('k1_proj_softmax_pool_fwd', (0.0, 0))
+        k1_avg = k1_ms / max(k1_n, 1)
+        flops = 2.0 * M * C * L.P
+        achieved = flops / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
+        long_region = ms > 1000.0
+        peak = peaks['bf16_sustained'] if long_region else peaks['bf16_burst']
+        kernels = {k: {'ms_per_step': v[0] / a.steps, 'calls': v[1]} for k, v in prof.items()}
+        step_flops = 4.0 * flops          # fwd + recompute + dX + dW ; algorithmic = 3 GEMMs
+        roofline = {'bound': 'tensor', 'kernel': 'head_pair_kernel<20,fwd> (projection+softmax+maxpool+align)',
+                    'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
+                    'peak_kind': ('sustained' if long_region else 'burst') + ', ' + peaks['source'],
+                    'avg_launch_ms': k1_avg, 'algorithmic_flops_per_launch': flops, 'traffic': None,
+                    'step_algorithmic_tflops': 3.0 * flops / (ms_per_step * 1e-3) / 1e12,
+                    'step_executed_tflops': step_flops / (ms_per_step * 1e-3) / 1e12, 'kernels': kernels}
+        cpu = None
+        if world == 1 and not a.no_cpu_baseline:
+            v, det = oracle_cpu_throughput(wl, min(8, B), steps=3, warmup=1, budget_s=25.0)
+            cpu = {'value': v, 'unit': UNIT, 'cores': det['cores'], 'kind': 'port', 'sample': det['sample']}
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
+                'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+                'data': 'synthetic',
+                'config': {'workload': f'{a.workload}: tree {wl["tree"]} ({L.N} nodes), {wl["num_features"]} protos/node '
+                                       f'(P={L.P}), batch {B}/GPU = {V} views of {H}x{H}x{C} bf16 features, full-training '
+                                       f'phase losses (align_pf+tanh+kernel_orth+class), fwd+bwd',
+                           'global_batch': world * B, 'parallelism': f'dp{world}',
+                           'l2_policy': f'two alternating input batches of {feats[0].numel() * 2 / 1e6:.0f} MB each (> 126 MB L2)'},
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cub27', choices=sorted(WORKLOADS))
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == '__main__':
+    main()

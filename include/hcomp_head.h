@@ -55,6 +55,8 @@ typedef struct hcomp_tables {
 int hcomp_abi_version(void);
 const char* hcomp_last_error(void);
 int hcomp_num_sms(void);
+/* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
+long long hcomp_launch_count(void);
 
 /* ---- operand preparation -------------------------------------------------------------------- */
 /* fp32 add-on kernels (flat [P,C]; reference: nn.Conv2d weights built at pipnet/pipnet.py:1207) ->

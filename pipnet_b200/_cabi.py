@@ -56,7 +56,7 @@ SIGNATURES = {
     'hcomp_materialize_map': [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }
-EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms'] + list(SIGNATURES)
+EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count'] + list(SIGNATURES)
 
 _lib = None
 
@@ -73,6 +73,7 @@ def lib():
     L.hcomp_abi_version.restype = C.c_int
     L.hcomp_last_error.restype = C.c_char_p
     L.hcomp_num_sms.restype = C.c_int
+    L.hcomp_launch_count.restype = C.c_longlong
     for name, args in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = args

@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 
 #include "gemm_tc.cuh"
@@ -15,6 +16,7 @@
 namespace {
 
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -34,6 +36,7 @@ int fail(int code, const char* fmt, ...) {
   do {                                                                                             \
     cudaError_t _e = cudaGetLastError();                                                           \
     if (_e != cudaSuccess) return fail(HCOMP_E_CUDA, "launch %s: %s", name, cudaGetErrorString(_e)); \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                            \
   } while (0)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -231,6 +234,7 @@ extern "C" {
 
 int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
 const char* hcomp_last_error(void) { return g_err; }
+long long hcomp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int hcomp_num_sms(void) {
   DevInfo di;
   if (int e = dev_info(&di)) return e;

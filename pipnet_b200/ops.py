@@ -20,6 +20,50 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Profile:
+    """Optional CUDA-event brackets around named C-ABI calls on the launching stream (bench.py uses this to
+    time the fused kernels inside the step; off by default, zero cost)."""
+
+    def __init__(self):
+        self.enabled = False
+        self.events = {}
+
+    def start(self, name):
+        if not self.enabled:
+            return None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        self.events.setdefault(name, []).append((a, b))
+        return b
+
+    @staticmethod
+    def stop(tok):
+        if tok is not None:
+            tok.record()
+
+    def totals_ms(self):
+        return {k: (sum(a.elapsed_time(b) for a, b in v), len(v)) for k, v in self.events.items()}
+
+    def reset(self):
+        self.events = {}
+
+
+PROFILE = _Profile()
+
+# Data-parallel training: when set (a torch.distributed process group), the flat prototype-kernel gradient
+# is all-reduced (mean) on a side stream right after the dW GEMM so it overlaps the dX GEMM and whatever
+# backbone backward follows (SURVEY.md section 8e).
+GRAD_ALLREDUCE_GROUP = None
+_side_stream = None
+
+
+def _side():
+    global _side_stream
+    if _side_stream is None:
+        _side_stream = torch.cuda.Stream()
+    return _side_stream
+
+
 def _require_cuda(t: torch.Tensor, what: str):
     if not t.is_cuda:
         raise _cabi.HcompError(f'{what} must live on a CUDA device: the prototype head has no CPU path')
@@ -121,9 +165,11 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
     dev = x_rows.device
     packed = torch.empty(V * dl.P, device=dev, dtype=torch.int64)
     align_sum = torch.empty(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
+    tok = PROFILE.start('k1_proj_softmax_pool_fwd')
     call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
          HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), ptr(labels.desc) if labels is not None else None, ptr(packed),
          ptr(align_sum), _stream())
+    PROFILE.stop(tok)
     pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)
     argmax = torch.empty(V, dl.P, device=dev, dtype=torch.int32)
     call('hcomp_unpack_pool', ptr(packed), C.c_longlong(V * dl.P), float(thresh), ptr(pooled), ptr(argmax), _stream())
@@ -143,17 +189,34 @@ def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax,
     scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
     coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
     use_align = labels is not None and g_align is not None
+    tok = PROFILE.start('k5_bwd_dz')
     call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
          dl.P, dl.P_pad, dl.N, float(tau), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
          ptr(labels.desc) if use_align else None, ptr(labels.n_desc) if use_align else None,
          ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), _stream())
+    PROFILE.stop(tok)
     dx = dw = None
-    if need_dx:
-        dx = torch.empty(M, Cc, device=dev, dtype=torch.bfloat16)
-        call('hcomp_head_bwd_dx', ptr(dz), ptr(wp), C.c_longlong(M), dl.P_pad, Cc, ptr(dx), _stream())
+    pending = None
     if need_dw:
         dw = torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32)
+        tok = PROFILE.start('k7_bwd_dw')
         call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map), C.c_longlong(M), dl.P_pad, Cc, ptr(dw), _stream())
+        PROFILE.stop(tok)
+        if GRAD_ALLREDUCE_GROUP is not None:
+            import torch.distributed as dist
+            side = _side()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                dist.all_reduce(dw, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
+            dw.record_stream(side)
+            pending = side
+    if need_dx:
+        dx = torch.empty(M, Cc, device=dev, dtype=torch.bfloat16)
+        tok = PROFILE.start('k6_bwd_dx')
+        call('hcomp_head_bwd_dx', ptr(dz), ptr(wp), C.c_longlong(M), dl.P_pad, Cc, ptr(dx), _stream())
+        PROFILE.stop(tok)
+    if pending is not None:
+        torch.cuda.current_stream().wait_stream(pending)      # dW is consumed by autograd on this stream
     return dx, dw, dz
 
 
