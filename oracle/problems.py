@@ -73,7 +73,7 @@ class Problem:
 
 
 def rel_err(a: torch.Tensor, b: torch.Tensor) -> float:
-    a, b = a.double().cpu(), b.double().cpu()
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
 
 
