@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HCOMP_ABI_VERSION 1
+#define HCOMP_ABI_VERSION 2
 #define HCOMP_TILE_INTS 52
 #define HCOMP_TILE_COLS 128
 #define HCOMP_MAX_SEGS 16
@@ -108,24 +108,31 @@ int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias
 int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* wc, const hcomp_tables* t, int V,
                          float* g_pooled, int accumulate, float* g_wc, float* g_bias, void* stream);
 
-/* ---- losses ------------------------------------------------------------------------------------ */
-/* class loss per node: NLL(log_softmax(log1p(out^2))) * w[target], mean over the node's samples
- * (pipnet/train.py:1153-1163, util/custom_losses.py:22-34); n_correct[N] for the accuracy bookkeeping. */
-int hcomp_class_loss_fwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
-                         int sparsity, float* loss, int32_t* n_correct, void* stream);
-int hcomp_class_loss_bwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const float* g_loss,
-                         const hcomp_tables* t, int V, int sparsity, float* g_out, void* stream);
-/* tanh loss per node (pipnet/train.py:1076-1087); colsum: float[2*P] workspace kept for the backward. */
-int hcomp_tanh_loss_fwd(const float* pooled, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
-                        int V_first, float eps, float* loss, float* colsum, void* stream);
-int hcomp_tanh_loss_bwd(const float* colsum, const int8_t* tgt, const float* g_loss, const hcomp_tables* t, int V,
-                        int V_first, float eps, float* g_pooled, int accumulate, void* stream);
-/* kernel-orthogonality loss per node (pipnet/train.py:1136-1151, orth_dist :1408-1412); E: float[N*p_max*p_max],
- * rel: uint8[P] workspaces kept for the backward; g_w[P,C] is accumulated into. */
-int hcomp_orth_loss_fwd(const float* w_flat, const float* wc, const int32_t* n_desc, const hcomp_tables* t, int C,
-                        float* loss, float* E, uint8_t* rel, void* stream);
-int hcomp_orth_loss_bwd(const float* w_flat, const float* loss, const float* E, const uint8_t* rel, const float* g_loss,
-                        const hcomp_tables* t, int C, float* g_w, void* stream);
+/* ---- losses (one call forward, one backward) -------------------------------------------------- */
+/* Per-node loss terms of calculate_loss for the shipped recipe, on the flat axes:
+ *   align  [N] as produced by hcomp_align_finalize (NULL = term off)              pipnet/train.py:1063-1074
+ *   tanh   -1/2 sum_views mean_p log(tanh(sum_desc pooled)+eps)                   pipnet/train.py:1076-1087
+ *   orth   ||W_rel W_rel^T - I||_F over prototypes with a classifier weight > 1e-3 pipnet/train.py:1136-1151, :1408-1412
+ *   class  weighted NLL(log_softmax(log1p(out^2)))                                pipnet/train.py:1153-1163, util/custom_losses.py:22-34
+ * Nodes without a descendant in the batch contribute nothing (pipnet/train.py:941-942).
+ * stats[4*N] = per-node {align, tanh, orth, class}; total = sum_k weights[k] * sum_n stats[k][n]
+ * (weights_host: 4 floats on the HOST, already divided by N); n_correct[N] = argmax accuracy counters.
+ * ws: hcomp_head_losses_ws_floats(t) floats, rel: uint8[P]; both are kept for the backward. */
+#define HCOMP_LOSS_TANH 1
+#define HCOMP_LOSS_ORTH 2
+#define HCOMP_LOSS_CLASS 4
+#define HCOMP_LOSS_SPARSITY 8   /* class term on log1p(out^2) (default recipe) instead of out */
+long long hcomp_head_losses_ws_floats(const hcomp_tables* t);
+int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* align, const float* w_flat, const float* wc,
+                          const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V, int V_first, int C,
+                          int flags, const float* weights_host, float eps, float* total, float* stats,
+                          int32_t* n_correct, float* ws, uint8_t* rel, void* stream);
+/* g_total: device scalar.  gvec: float[4*N] workspace; on return gvec[0..N) is the gradient w.r.t. align.
+ * g_pooled [V,P], g_out [V,K], g_w [P,C] are fully written (zero where a term is off); any may be NULL. */
+int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w_flat, const int8_t* tgt,
+                          const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V, int V_first, int C,
+                          int flags, const float* weights_host, float eps, const float* ws, const uint8_t* rel,
+                          float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream);
 
 /* ---- predictions (util/node.py:300-385, pipnet/pipnet.py:173-185) ------------------------------ */
 /* probs_ws: float[V*K]; joint: float[V*L] (columns in sorted leaf-name order); pred: int64[V] argmax. */

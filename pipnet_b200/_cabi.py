@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhcomp_head.so')
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class HcompError(RuntimeError):
@@ -46,17 +46,13 @@ SIGNATURES = {
     'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p],
     'hcomp_classifier_fwd': [_p, _p, _p, _T, _i, _p, _p],
     'hcomp_classifier_bwd': [_p, _p, _p, _T, _i, _p, _i, _p, _p, _p],
-    'hcomp_class_loss_fwd': [_p, _p, _p, _T, _i, _i, _p, _p, _p],
-    'hcomp_class_loss_bwd': [_p, _p, _p, _p, _T, _i, _i, _p, _p],
-    'hcomp_tanh_loss_fwd': [_p, _p, _p, _T, _i, _i, _f, _p, _p, _p],
-    'hcomp_tanh_loss_bwd': [_p, _p, _p, _T, _i, _i, _f, _p, _i, _p],
-    'hcomp_orth_loss_fwd': [_p, _p, _p, _T, _i, _p, _p, _p, _p],
-    'hcomp_orth_loss_bwd': [_p, _p, _p, _p, _p, _T, _i, _p, _p],
+    'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p],
     'hcomp_materialize_map': [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }
-EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count'] + list(SIGNATURES)
+EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats'] + list(SIGNATURES)
 
 _lib = None
 
@@ -74,6 +70,8 @@ def lib():
     L.hcomp_last_error.restype = C.c_char_p
     L.hcomp_num_sms.restype = C.c_int
     L.hcomp_launch_count.restype = C.c_longlong
+    L.hcomp_head_losses_ws_floats.restype = C.c_longlong
+    L.hcomp_head_losses_ws_floats.argtypes = [_T]
     for name, args in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = args

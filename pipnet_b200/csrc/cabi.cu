@@ -5,6 +5,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <mutex>
@@ -17,6 +18,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+bool g_no_multicast = false;          // HCOMP_NO_MULTICAST=1: single-CTA variants only (A/B measurements)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -97,30 +99,53 @@ int make_tmap(CUtensorMap* m, const void* base, unsigned long long inner, unsign
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 
-template <int SEG, bool BWD>
+// Plain or 2-CTA-cluster launch of a persistent kernel; `workers` = CTAs (or clusters) that loop over the items.
+template <typename Kern, typename... Args>
+int launch_persistent(Kern kern, const char* name, int cluster, int workers, int threads, int smem, cudaStream_t st,
+                      Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(unsigned(workers * cluster));
+  cfg.blockDim = dim3(unsigned(threads));
+  cfg.dynamicSmemBytes = size_t(smem);
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = unsigned(cluster);
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, args...);
+  if (e != cudaSuccess) return fail(HCOMP_E_CUDA, "launch %s: %s", name, cudaGetErrorString(e));
+  HC_LAUNCH_CHECK(name);
+  return 0;
+}
+
+template <int SEG, bool BWD, bool MC>
 int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms, cudaStream_t st) {
-  auto kern = hc::head_pair_kernel<SEG, BWD>;
+  auto kern = hc::head_pair_kernel<SEG, BWD, MC>;
   static bool attr_done = false;
   if (!attr_done) {
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::PAIR_SMEM_BYTES));
     attr_done = true;
   }
-  const int items = p.num_m_tiles * p.num_tiles;
-  const int grid = items < sms ? items : sms;
-  kern<<<grid, hc::PAIR_THREADS, hc::PAIR_SMEM_BYTES, st>>>(tx, tw, p);
-  HC_LAUNCH_CHECK(BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>");
-  return 0;
+  constexpr int CL = MC ? 2 : 1;
+  const int items = p.num_m_tiles * ((p.num_tiles + CL - 1) / CL);
+  const int slots = sms / CL;
+  const int workers = items < slots ? items : slots;
+  return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", CL, workers,
+                           hc::PairCfg<SEG>::THREADS, hc::PAIR_SMEM_BYTES, st, tx, tw, p);
 }
 
-template <bool BWD>
+template <bool BWD, bool MC>
 int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms,
                       cudaStream_t st) {
   switch (seg) {
-    case 8: return launch_pair<8, BWD>(tx, tw, p, sms, st);
-    case 16: return launch_pair<16, BWD>(tx, tw, p, sms, st);
-    case 20: return launch_pair<20, BWD>(tx, tw, p, sms, st);
-    case 32: return launch_pair<32, BWD>(tx, tw, p, sms, st);
-    case 40: return launch_pair<40, BWD>(tx, tw, p, sms, st);
+    case 8: return launch_pair<8, BWD, MC>(tx, tw, p, sms, st);
+    case 16: return launch_pair<16, BWD, MC>(tx, tw, p, sms, st);
+    case 20: return launch_pair<20, BWD, MC>(tx, tw, p, sms, st);
+    case 32: return launch_pair<32, BWD, MC>(tx, tw, p, sms, st);
+    case 40: return launch_pair<40, BWD, MC>(tx, tw, p, sms, st);
     default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40)", seg);
   }
 }
@@ -138,8 +163,9 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
   const long long M = (long long)V * HW;
   if (M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
-  CUtensorMap tx, tw;
+  CUtensorMap tx, tx_half, tw;                      // tx_half: 64-row boxes for the multicast (cluster) variant
   if (int e = make_tmap(&tx, x, C, M, C, hc::KBLK, hc::TILE_M)) return e;
+  if (int e = make_tmap(&tx_half, x, C, M, C, hc::KBLK, hc::TILE_M / 2)) return e;
   if (int e = make_tmap(&tw, wp, C, P_pad, C, hc::KBLK, hc::TILE_N)) return e;
   hc::HeadParams p = base;
   p.M = int(M);
@@ -165,25 +191,29 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
     }
     p.tile_begin = t;
     p.num_tiles = e - t;
-    if (int err = launch_pair_class<BWD>(seg, tx, tw, p, di.sms, st)) return err;
+    // >= 2 tiles of this class: CTA pairs share the feature tiles by TMA multicast
+    const bool mc = p.num_tiles >= 2 && !g_no_multicast;
+    if (int err = mc ? launch_pair_class<BWD, true>(seg, tx_half, tw, p, di.sms, st)
+                     : launch_pair_class<BWD, false>(seg, tx, tw, p, di.sms, st))
+      return err;
     t = e;
   }
   return 0;
 }
 
-template <bool A_MN, bool B_MN, int OUT>
+template <bool A_MN, bool B_MN, int OUT, bool MC>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const hc::GemmParams& p, int sms, cudaStream_t st) {
-  auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT>;
+  auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT, MC>;
   static bool attr_done = false;
   if (!attr_done) {
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::G_SMEM_BYTES));
     attr_done = true;
   }
-  const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
-  const int grid = items < sms ? items : sms;
-  kern<<<grid, hc::G_THREADS, hc::G_SMEM_BYTES, st>>>(ta, tb, p);
-  HC_LAUNCH_CHECK("gemm_tc_kernel");
-  return 0;
+  constexpr int CL = MC ? 2 : 1;
+  const int items = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * p.splits;
+  const int slots = sms / CL;
+  const int workers = items < slots ? items : slots;
+  return launch_persistent(kern, "gemm_tc_kernel", CL, workers, hc::G_THREADS, hc::G_SMEM_BYTES, st, ta, tb, p);
 }
 
 // D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
@@ -206,16 +236,21 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   p.num_m_tiles = cdiv(M, hc::G_BM);
   p.num_n_tiles = cdiv(N, hc::G_BN);
   p.num_k_blocks = cdiv(K, hc::G_BK);
-  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const bool mc_possible = b_mn && p.num_m_tiles >= 2;
+  const int tiles_mn = (mc_possible ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
   if (out_mode != hc::OUT_RED_F32) splits = 1;
-  if (splits <= 0) splits = di.sms / tiles_mn;
+  if (splits <= 0) splits = (mc_possible ? di.sms / 2 : di.sms) / tiles_mn;
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
   p.splits = cdiv(p.num_k_blocks, p.k_blocks_per_split);
   p.out = out; p.ldo = ldo; p.row_map = row_map;
-#define HC_GEMM_CASE(AM, BM, OM) \
-  if (a_mn == AM && b_mn == BM && out_mode == OM) return launch_gemm<AM, BM, OM>(ta, tb, p, di.sms, st);
+  const bool mc = b_mn && p.num_m_tiles >= 2 && !g_no_multicast;   // CTA pairs share the B tile by TMA multicast
+#define HC_GEMM_CASE(AM, BM, OM)                                                              \
+  if (a_mn == AM && b_mn == BM && out_mode == OM) {                                           \
+    if constexpr (BM) { if (mc) return launch_gemm<AM, BM, OM, true>(ta, tb, p, di.sms, st); } \
+    return launch_gemm<AM, BM, OM, false>(ta, tb, p, di.sms, st);                             \
+  }
   HC_GEMM_CASE(false, true, hc::OUT_BF16)      // dX
   HC_GEMM_CASE(true, true, hc::OUT_RED_F32)    // dW
   HC_GEMM_CASE(false, false, hc::OUT_F32)      // self-test: plain K-major GEMM
@@ -232,7 +267,11 @@ inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
 
 extern "C" {
 
-int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
+int hcomp_abi_version(void) {
+  const char* e = getenv("HCOMP_NO_MULTICAST");
+  g_no_multicast = e != nullptr && e[0] == '1';
+  return HCOMP_ABI_VERSION;
+}
 const char* hcomp_last_error(void) { return g_err; }
 long long hcomp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int hcomp_num_sms(void) {
@@ -275,8 +314,9 @@ int hcomp_nchw_to_rows_bf16(const void* src, int src_is_bf16, int V, int C, int 
 
 int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc,
                        int32_t* n_desc, void* stream) {
-  hc::label_tables_kernel<<<blocks(t->n_nodes, 128), 128, 0, S(stream)>>>(ys, t->anc, V, V_first, t->n_nodes, t->n_leaves,
-                                                                         tgt, desc, n_desc);
+  HC_CUDA(cudaMemsetAsync(n_desc, 0, sizeof(int32_t) * t->n_nodes, S(stream)));
+  hc::label_tables_kernel<<<blocks((long long)V * t->n_nodes, 256), 256, 0, S(stream)>>>(ys, t->anc, V, V_first, t->n_nodes,
+                                                                                        t->n_leaves, tgt, desc, n_desc);
   HC_LAUNCH_CHECK("label_tables");
   return 0;
 }
@@ -372,55 +412,96 @@ int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* w
   return 0;
 }
 
-int hcomp_class_loss_fwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
-                         int sparsity, float* loss, int32_t* n_correct, void* stream) {
+namespace {
+struct LossWs {            // carve-up of the float workspace shared by hcomp_head_losses_fwd / _bwd
+  float *colsum, *tanh_part, *orth_sq, *cls, *E;
+};
+LossWs loss_ws(float* ws, const hcomp_tables* t) {
+  LossWs w;
+  w.colsum = ws;
+  w.tanh_part = w.colsum + 2 * (size_t)t->n_protos;
+  w.orth_sq = w.tanh_part + 2 * (size_t)t->n_nodes;
+  w.cls = w.orth_sq + t->n_nodes;
+  w.E = w.cls + t->n_nodes;
+  return w;
+}
+}  // namespace
+
+long long hcomp_head_losses_ws_floats(const hcomp_tables* t) {
+  return 2LL * t->n_protos + 4LL * t->n_nodes + (long long)t->n_nodes * t->p_max * t->p_max;
+}
+
+int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* align, const float* w_flat, const float* wc,
+                          const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V, int V_first, int C,
+                          int flags, const float* weights_host, float eps, float* total, float* stats,
+                          int32_t* n_correct, float* ws, uint8_t* rel, void* stream) {
+  const LossWs w = loss_ws(ws, t);
+  const bool do_tanh = flags & HCOMP_LOSS_TANH, do_orth = flags & HCOMP_LOSS_ORTH, do_cls = flags & HCOMP_LOSS_CLASS;
+  const int sparsity = (flags & HCOMP_LOSS_SPARSITY) ? 1 : 0;
+  if (do_tanh) {
+    if (t->p_max > 64 * 1024) return fail(HCOMP_E_ARG, "P_max too large");
+    hc::tanh_loss_fwd_kernel<<<dim3(t->n_nodes, 2), 256, 0, S(stream)>>>(pooled, tgt, t->proto_off, n_desc, V, V_first,
+                                                                        t->n_nodes, t->n_protos, eps, w.tanh_part, w.colsum);
+    HC_LAUNCH_CHECK("tanh_loss_fwd");
+  }
+  if (do_orth) {
+    if (t->p_max >= C || t->p_max > 128) return fail(HCOMP_E_ARG, "orth loss needs P_n < C and P_n <= 128 (P_max=%d, C=%d)", t->p_max, C);
+    HC_CUDA(cudaMemsetAsync(w.orth_sq, 0, sizeof(float) * t->n_nodes, S(stream)));
+    hc::orth_loss_fwd_kernel<<<t->n_protos, 128, 0, S(stream)>>>(w_flat, wc, t->proto_node, t->proto_off, t->cls_off, t->wc_off,
+                                                                C, t->p_max, w.orth_sq, w.E, rel);
+    HC_LAUNCH_CHECK("orth_loss_fwd");
+  }
+  // class kernel also produces the per-node accuracy counters, so it always runs
   hc::class_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(out, tgt, t->child_w, t->cls_off, n_desc, V, t->n_nodes,
-                                                              t->n_cols, sparsity, loss, n_correct);
+                                                              t->n_cols, sparsity, w.cls, n_correct);
   HC_LAUNCH_CHECK("class_loss_fwd");
+  hc::LossWeights lw;
+  for (int i = 0; i < 4; ++i) lw.w[i] = weights_host[i];
+  hc::loss_combine_kernel<<<1, 256, 0, S(stream)>>>(align, do_tanh ? w.tanh_part : nullptr, do_orth ? w.orth_sq : nullptr,
+                                                   do_cls ? w.cls : nullptr, n_desc, t->n_nodes, lw, stats, total);
+  HC_LAUNCH_CHECK("loss_combine");
   return 0;
 }
 
-int hcomp_class_loss_bwd(const float* out, const int8_t* tgt, const int32_t* n_desc, const float* g_loss,
-                         const hcomp_tables* t, int V, int sparsity, float* g_out, void* stream) {
-  const long long n = (long long)V * t->n_cols;
-  hc::class_loss_bwd_kernel<<<blocks(n, 128), 128, 0, S(stream)>>>(out, tgt, t->child_w, t->col_node, t->cls_off, n_desc,
-                                                                  g_loss, V, t->n_nodes, t->n_cols, sparsity, g_out);
-  HC_LAUNCH_CHECK("class_loss_bwd");
-  return 0;
-}
-
-int hcomp_tanh_loss_fwd(const float* pooled, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
-                        int V_first, float eps, float* loss, float* colsum, void* stream) {
-  hc::tanh_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(pooled, tgt, t->proto_off, n_desc, V, V_first, t->n_nodes,
-                                                             t->n_protos, eps, loss, colsum);
-  HC_LAUNCH_CHECK("tanh_loss_fwd");
-  return 0;
-}
-
-int hcomp_tanh_loss_bwd(const float* colsum, const int8_t* tgt, const float* g_loss, const hcomp_tables* t, int V,
-                        int V_first, float eps, float* g_pooled, int accumulate, void* stream) {
-  const long long n = (long long)V * t->n_protos;
-  hc::tanh_loss_bwd_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(colsum, tgt, t->proto_node, t->proto_off, g_loss, V,
-                                                                 V_first, t->n_nodes, t->n_protos, eps, g_pooled,
-                                                                 accumulate);
-  HC_LAUNCH_CHECK("tanh_loss_bwd");
-  return 0;
-}
-
-int hcomp_orth_loss_fwd(const float* w_flat, const float* wc, const int32_t* n_desc, const hcomp_tables* t, int C,
-                        float* loss, float* E, uint8_t* rel, void* stream) {
-  if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
-  hc::orth_loss_fwd_kernel<<<t->n_nodes, 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off, n_desc, C,
-                                                             t->p_max, loss, E, rel);
-  HC_LAUNCH_CHECK("orth_loss_fwd");
-  return 0;
-}
-
-int hcomp_orth_loss_bwd(const float* w_flat, const float* loss, const float* E, const uint8_t* rel, const float* g_loss,
-                        const hcomp_tables* t, int C, float* g_w, void* stream) {
-  hc::orth_loss_bwd_kernel<<<t->n_protos, 128, 0, S(stream)>>>(w_flat, t->proto_off, C, t->p_max, loss, E, rel, g_loss,
-                                                              t->proto_node, g_w);
-  HC_LAUNCH_CHECK("orth_loss_bwd");
+int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w_flat, const int8_t* tgt,
+                          const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V, int V_first, int C,
+                          int flags, const float* weights_host, float eps, const float* ws, const uint8_t* rel,
+                          float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream) {
+  const LossWs w = loss_ws(const_cast<float*>(ws), t);
+  const int N = t->n_nodes;
+  const int sparsity = (flags & HCOMP_LOSS_SPARSITY) ? 1 : 0;
+  hc::LossWeights lw;
+  for (int i = 0; i < 4; ++i) lw.w[i] = weights_host[i];
+  hc::loss_grads_kernel<<<blocks(4 * N, 128), 128, 0, S(stream)>>>(g_total, N, lw, gvec);   // gvec[0..N) is g_align
+  HC_LAUNCH_CHECK("loss_grads");
+  if (g_pooled) {
+    if (flags & HCOMP_LOSS_TANH) {
+      const long long n = (long long)V * t->n_protos;
+      hc::tanh_loss_bwd_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(w.colsum, tgt, t->proto_node, t->proto_off, gvec + N, V,
+                                                                     V_first, N, t->n_protos, eps, g_pooled, 0);
+      HC_LAUNCH_CHECK("tanh_loss_bwd");
+    } else {
+      HC_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * (size_t)V * t->n_protos, S(stream)));
+    }
+  }
+  if (g_out) {
+    if (flags & HCOMP_LOSS_CLASS) {
+      const long long n = (long long)V * t->n_cols;
+      hc::class_loss_bwd_kernel<<<blocks(n, 128), 128, 0, S(stream)>>>(out, tgt, t->child_w, t->col_node, t->cls_off, n_desc,
+                                                                      gvec + 3 * N, V, N, t->n_cols, sparsity, g_out);
+      HC_LAUNCH_CHECK("class_loss_bwd");
+    } else {
+      HC_CUDA(cudaMemsetAsync(g_out, 0, sizeof(float) * (size_t)V * t->n_cols, S(stream)));
+    }
+  }
+  if (g_w) {
+    HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
+    if (flags & HCOMP_LOSS_ORTH) {
+      hc::orth_loss_bwd_kernel<<<t->n_protos, 256, 0, S(stream)>>>(w_flat, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel,
+                                                                  gvec + 2 * N, t->proto_node, g_w);
+      HC_LAUNCH_CHECK("orth_loss_bwd");
+    }
+  }
   return 0;
 }
 

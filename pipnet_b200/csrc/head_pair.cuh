@@ -13,13 +13,15 @@
 // accumulators (2 x 128 TMEM columns) are live together because the align loss and its
 // gradient need S1 and S2 of the same (image, location); 2 accumulator stages => 512 columns.
 //
-// Warp roles (384 threads, 1 CTA/SM, persistent over items):
+// Warp roles (1 CTA/SM, persistent over items):
 //   warp 0   : TMA producer   (A1, A2, W tiles; 4-stage ring, 48 KB per stage)
 //   warp 1   : MMA issuer     (one thread; 2 x 4 tcgen05.mma per k-block)
 //   warp 2   : TMEM allocator
 //   warp 3   : idle
-//   warps 4-11: epilogue      (warp%4 selects the TMEM lane quadrant; the two warps of a
-//                              quadrant split the tile's node segments even/odd)
+//   warps 4..: epilogue       (warp%4 selects the TMEM lane quadrant; the EW/4 warps of a quadrant
+//                              split the tile's node segments round-robin).  EW = 12 for segment
+//                              classes <= 20 columns (register budget 128/thread), 8 otherwise (168):
+//                              the epilogue is latency-bound, more warps per scheduler hide it.
 #pragma once
 #include "ptx.cuh"
 
@@ -32,7 +34,13 @@ constexpr int MAX_SEGS = 16;         // node segments per tile (S >= 8)
 constexpr int TILE_INTS = 4 + 3 * MAX_SEGS;   // {S, nseg, umma_n, 0, node[16], len[16], poff[16]}
 constexpr int PAIR_STAGES = 4;
 constexpr int PAIR_STAGE_BYTES = 3 * TILE_M * KBLK * 2;   // A1 + A2 + W = 48 KB
-constexpr int PAIR_THREADS = 384;
+template <int S> struct PairCfg {
+  static constexpr int EPI_WARPS = (S <= 20) ? 12 : 8;
+  static constexpr int PARTS = EPI_WARPS / 4;               // epilogue warps per TMEM lane quadrant
+  static constexpr int THREADS = 128 + 32 * EPI_WARPS;
+  static constexpr int NSEG_MAX = 128 / S;
+  static constexpr int SLOTS = (NSEG_MAX + PARTS - 1) / PARTS;
+};
 constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct HeadParams {
@@ -63,21 +71,23 @@ struct PairSmem {
 
 template <int S>
 __device__ __forceinline__ void softmax_row(uint32_t* raw, int len, float scale_log2, float* s) {
-  float m = -INFINITY;
+  // four interleaved partial maxima / sums keep the dependency chains short (the epilogue is latency-bound)
+  float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int i = 0; i < S; ++i) {
-    float x = (i < len) ? __uint_as_float(raw[i]) : -INFINITY;
+    const float x = (i < len) ? __uint_as_float(raw[i]) : -INFINITY;
     s[i] = x;
-    m = fmaxf(m, x);
+    m4[i & 3] = fmaxf(m4[i & 3], x);
   }
+  const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
   const float mk = m * scale_log2;
-  float l = 0.f;
+  float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
   for (int i = 0; i < S; ++i) {
     s[i] = ex2(fmaf(s[i], scale_log2, -mk));
-    l += s[i];
+    l4[i & 3] += s[i];
   }
-  const float inv = __frcp_rn(l);
+  const float inv = __frcp_rn((l4[0] + l4[1]) + (l4[2] + l4[3]));
 #pragma unroll
   for (int i = 0; i < S; ++i) s[i] *= inv;
 }
@@ -95,13 +105,15 @@ __device__ __forceinline__ void pool_segment(const float* s, bool valid, int v_r
     const bool in_g = valid && ((g == 0) ? (v_row == v_first) : (v_row != v_first));
     if (__ballot_sync(0xffffffffu, in_g) == 0u) continue;
     uint32_t m0 = 0, b0 = 0, m1 = 0, b1 = 0;
+    uint32_t mx[S];
+#pragma unroll
+    for (int i = 0; i < S; ++i)     // S independent REDUX back to back (softmax >= 0: uint order == float order)
+      mx[i] = redux_max_u32(in_g ? __float_as_uint(s[i]) : 0u);
 #pragma unroll
     for (int i = 0; i < S; ++i) {
-      const uint32_t bits = in_g ? __float_as_uint(s[i]) : 0u;   // softmax >= 0: uint order == float order
-      const uint32_t m = redux_max_u32(bits);
-      const uint32_t bal = __ballot_sync(0xffffffffu, in_g && bits == m);
+      const uint32_t bal = __ballot_sync(0xffffffffu, in_g && __float_as_uint(s[i]) == mx[i]);
       if ((i & 31) == lane) {
-        if (i < 32) { m0 = m; b0 = bal; } else { m1 = m; b1 = bal; }
+        if (i < 32) { m0 = mx[i]; b0 = bal; } else { m1 = mx[i]; b1 = bal; }
       }
     }
     unsigned long long* dst = packed_v0 + (size_t)g * P;
@@ -131,13 +143,54 @@ __device__ __forceinline__ void store_dz(__nv_bfloat16* dst, const float* d) {
   }
 }
 
-template <int S, bool BWD>
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
+// Scatter term of the pooled gradient for one (view, segment): lane c holds column c's {argmax location,
+// g_pooled} for the (at most two) images this warp's rows belong to; each hit (the one row of an image whose
+// location is the argmax) is broadcast and added to that row's G[c].  Expected hits per warp and segment ~ 1.
+template <int S>
+__device__ __forceinline__ void add_scatter(float* g, const int2* __restrict__ scat_v0, int P, int len, int lane,
+                                            int loc_first, int lane_b, bool has_boundary, int n_valid) {
+  int2 e0 = make_int2(-1, 0), e1 = make_int2(-1, 0);
+#pragma unroll
+  for (int h = 0; h < (S + 31) / 32; ++h) {
+    const int c = h * 32 + lane;
+    if (c < len) {
+      e0 = __ldg(scat_v0 + c);
+      if (has_boundary) e1 = __ldg(scat_v0 + P + c);
+    }
+    const int lim0 = min(min(32, lane_b), n_valid);
+    const int t0 = e0.x - loc_first;
+    const int t1 = e1.x + lane_b;
+    const bool v0 = (c < len) && t0 >= 0 && t0 < lim0;
+    const bool v1 = (c < len) && has_boundary && e1.x >= 0 && t1 < min(32, n_valid);
+#pragma unroll 1
+    for (int grp = 0; grp < 2; ++grp) {
+      uint32_t hits = __ballot_sync(0xffffffffu, grp == 0 ? v0 : v1);
+      while (hits) {
+        const int src = __ffs(hits) - 1;
+        hits &= hits - 1;
+        const int t = __shfl_sync(0xffffffffu, grp == 0 ? t0 : t1, src);
+        const float gv = __int_as_float(__shfl_sync(0xffffffffu, grp == 0 ? e0.y : e1.y, src));
+        const int col = h * 32 + src;
+#pragma unroll
+        for (int i = 0; i < S; ++i)
+          if (i == col && lane == t) g[i] += gv;
+      }
+    }
+  }
+}
+
+// MC: clusters of 2 CTAs take two neighbouring prototype tiles of the same pair tile and share the feature
+// tiles A1/A2: each CTA fetches 64 of the 128 rows and TMA-multicasts them to both, so a CTA pulls
+// 32 KB instead of 48 KB per k-block out of L2 (the kernel is operand-delivery-bound otherwise).
+// tmap_x has a 64-row box when MC (128 rows otherwise).
+template <int S, bool BWD, bool MC>
+__global__ void __launch_bounds__(PairCfg<S>::THREADS, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const HeadParams p) {
   static_assert(S % 4 == 0 && S >= 8 && S <= 40, "segment class");
-  constexpr int NSEG_MAX = TILE_N / S;
-  constexpr int SLOTS = (NSEG_MAX + 1) / 2;
+  constexpr int NSEG_MAX = PairCfg<S>::NSEG_MAX;
+  constexpr int SLOTS = PairCfg<S>::SLOTS;
+  constexpr int PARTS = PairCfg<S>::PARTS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -145,7 +198,11 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_items = p.num_m_tiles * p.num_tiles;
+  constexpr int CL = MC ? 2 : 1;
+  const int crank = MC ? int(cluster_ctarank()) : 0;
+  const int n_groups = (p.num_tiles + CL - 1) / CL;
+  const int total_items = p.num_m_tiles * n_groups;
+  const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
@@ -154,17 +211,18 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < PAIR_STAGES; ++i) {
       mbar_init(&sb->full[i], 1);
-      mbar_init(&sb->empty[i], 1);
+      mbar_init(&sb->empty[i], CL);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->tmem_full[i], 1);
-      mbar_init(&sb->tmem_empty[i], 8);   // one arrive per epilogue warp
+      mbar_init(&sb->tmem_empty[i], PairCfg<S>::EPI_WARPS);   // one arrive per epilogue warp
     }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc<512>(&sb->tmem_base);
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
 
@@ -173,9 +231,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int mt = item / p.num_tiles;
-        const int nt = item - mt * p.num_tiles;
+      for (int item = worker; item < total_items; item += num_workers) {
+        const int mt = item / n_groups;
+        const int nt = (item - mt * n_groups) * CL + crank;     // may be one past the last tile (dummy, zero-filled)
         const int row_a = mt * TILE_M;
         const int row_b = p.halfM + row_a;
         const int row_w = (p.tile_begin + nt) * TILE_N;
@@ -183,8 +241,14 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           mbar_wait(&sb->empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * PAIR_STAGE_BYTES;
           mbar_arrive_expect_tx(&sb->full[stage], PAIR_STAGE_BYTES);
-          tma_load_2d(st, &tmap_x, &sb->full[stage], kb * KBLK, row_a);
-          tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kb * KBLK, row_b);
+          if constexpr (!MC) {
+            tma_load_2d(st, &tmap_x, &sb->full[stage], kb * KBLK, row_a);
+            tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kb * KBLK, row_b);
+          } else {                                    // my 64 rows of each feature tile, delivered to both CTAs
+            const int ro = crank * 64;
+            tma_load_2d_mc(st + ro * 128, &tmap_x, &sb->full[stage], kb * KBLK, row_a + ro, uint16_t(3));
+            tma_load_2d_mc(st + TILE_M * KBLK * 2 + ro * 128, &tmap_x, &sb->full[stage], kb * KBLK, row_b + ro, uint16_t(3));
+          }
           tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kb * KBLK, row_w);
           if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -197,10 +261,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-        const int mt = item / p.num_tiles;
-        const int nt = item - mt * p.num_tiles;
-        const int umma_n = __ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2);
+      for (int item = worker; item < total_items; item += num_workers) {
+        const int nt = (item % n_groups) * CL + crank;
+        const int umma_n = (nt < p.num_tiles) ? __ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2) : 16;
         const uint32_t idesc = make_idesc(TILE_M, umma_n, false, false);
         mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -219,7 +282,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             umma_bf16(d0, smem_desc(a0 + k * 32, DESC_KMAJOR), bd, idesc, accum);
             umma_bf16(d1, smem_desc(a1 + k * 32, DESC_KMAJOR), bd, idesc, accum);
           }
-          umma_commit(&sb->empty[stage]);
+          if constexpr (MC) umma_commit_mc(&sb->empty[stage], uint16_t(3));
+          else umma_commit(&sb->empty[stage]);
           if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
         }
         umma_commit(&sb->tmem_full[acc]);
@@ -230,15 +294,16 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
     const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int part = (warp - 4) >> 2;
     const int imgs_first = p.imgs_first;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < total_items; item += gridDim.x) {
-      const int mt = item / p.num_tiles;
-      const int nt = item - mt * p.num_tiles;
-      const int32_t* tile = p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS;
-      const int nseg = __ldg(tile + 1);
+    for (int item = worker; item < total_items; item += num_workers) {
+      const int mt = item / n_groups;
+      const int nt = (item - mt * n_groups) * CL + crank;
+      const bool real_tile = nt < p.num_tiles;
+      const int32_t* tile = p.tiles + (size_t)(p.tile_begin + (real_tile ? nt : 0)) * TILE_INTS;
+      const int nseg = real_tile ? __ldg(tile + 1) : 0;
 
       const int row_a = mt * TILE_M + quad * 32 + lane;
       const bool valid_a = row_a < p.halfM;
@@ -249,6 +314,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int loc_first = __shfl_sync(0xffffffffu, loc, 0);
       const bool has_boundary = __ballot_sync(0xffffffffu, v_a != v_first) != 0u;
       const int lane_b = p.HW - loc_first;    // first lane of the next image (if has_boundary)
+      const int nv_a = __popc(__ballot_sync(0xffffffffu, valid_a));   // valid rows are a prefix of the warp
+      const int nv_b = __popc(__ballot_sync(0xffffffffu, valid_b));
 
       float align_acc[SLOTS];
 #pragma unroll
@@ -260,7 +327,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
 #pragma unroll
       for (int js = 0; js < SLOTS; ++js) {
-        const int j = 2 * js + half;
+        const int j = PARTS * js + part;
         if (j < NSEG_MAX && j < nseg) {     // warp-uniform
           const int node = __ldg(tile + 4 + j);
           const int len = __ldg(tile + 4 + MAX_SEGS + j);
@@ -272,14 +339,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           float s1[S], s2[S];
           softmax_row<S>(ra, len, p.scale_log2, s1);
           softmax_row<S>(rb, len, p.scale_log2, s2);
-          float ip = 0.f;
+          float ip4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < S; ++i) ip = fmaf(s1[i], s2[i], ip);
+          for (int i = 0; i < S; ++i) ip4[i & 3] = fmaf(s1[i], s2[i], ip4[i & 3]);
+          const float ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
 
           if constexpr (!BWD) {
             if (p.desc != nullptr) {
               const bool on = valid_a && valid_b && (v_a < imgs_first) && p.desc[(size_t)v_a * p.n_nodes + node];
-              if (on) align_acc[js] = -logf(ip + 1e-12f);
+              if (on) align_acc[js] = -__logf(ip + 1e-12f);
             }
             if (__ballot_sync(0xffffffffu, valid_a) != 0u)
               pool_segment<S>(s1, valid_a, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
@@ -292,41 +360,34 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (p.coef_align != nullptr && valid_a && valid_b && v_a < imgs_first)
               ca = p.coef_align[(size_t)v_a * p.n_nodes + node] * __frcp_rn(ip + 1e-12f);
             const int col0 = (p.tile_begin + nt) * TILE_N + j * S;
-            if (valid_a) {
-              const int2* sc = p.scat + (size_t)v_a * p.P + poff;
+            {
               float g[S];
-              float dot = 0.f;
 #pragma unroll
-              for (int i = 0; i < S; ++i) {
-                float gi = -ca * s2[i];
-                if (i < len) {
-                  const int2 e = __ldg(sc + i);
-                  if (e.x == loc) gi += __int_as_float(e.y);
-                }
-                g[i] = gi;
-                dot = fmaf(gi, s1[i], dot);
-              }
+              for (int i = 0; i < S; ++i) g[i] = -ca * s2[i];
+              if (nv_a > 0)
+                add_scatter<S>(g, p.scat + (size_t)v_first * p.P + poff, p.P, len, lane, loc_first, lane_b, has_boundary, nv_a);
+              float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int i = 0; i < S; ++i) d4[i & 3] = fmaf(g[i], s1[i], d4[i & 3]);
+              const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = s1[i] * (g[i] - dot) * p.inv_tau;
-              store_dz<S>(p.dz + (size_t)row_a * p.P_pad + col0, g);
+              if (valid_a) store_dz<S>(p.dz + (size_t)row_a * p.P_pad + col0, g);
             }
-            if (valid_b) {
-              const int2* sc = p.scat + (size_t)(v_a + imgs_first) * p.P + poff;
+            {
               float g[S];
-              float dot = 0.f;
 #pragma unroll
-              for (int i = 0; i < S; ++i) {
-                float gi = -ca * s1[i];
-                if (i < len) {
-                  const int2 e = __ldg(sc + i);
-                  if (e.x == loc) gi += __int_as_float(e.y);
-                }
-                g[i] = gi;
-                dot = fmaf(gi, s2[i], dot);
-              }
+              for (int i = 0; i < S; ++i) g[i] = -ca * s1[i];
+              if (nv_b > 0)
+                add_scatter<S>(g, p.scat + (size_t)(v_first + imgs_first) * p.P + poff, p.P, len, lane, loc_first, lane_b,
+                               has_boundary, nv_b);
+              float d4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int i = 0; i < S; ++i) d4[i & 3] = fmaf(g[i], s2[i], d4[i & 3]);
+              const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = s2[i] * (g[i] - dot) * p.inv_tau;
-              store_dz<S>(p.dz + (size_t)(p.halfM + row_a) * p.P_pad + col0, g);
+              if (valid_b) store_dz<S>(p.dz + (size_t)(p.halfM + row_a) * p.P_pad + col0, g);
             }
           }
         }
@@ -340,7 +401,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         if (p.desc != nullptr) {
 #pragma unroll
           for (int js = 0; js < SLOTS; ++js) {
-            const int j = 2 * js + half;
+            const int j = PARTS * js + part;
             if (j < NSEG_MAX && j < nseg) {
               float v = align_acc[js];
 #pragma unroll
@@ -351,7 +412,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       } else {
         // zero the padding columns [nseg*S, 128) of this tile's dZ rows (the dX GEMM reads them)
-        if (half == 0) {
+        if (part == 0 && real_tile) {
           const int c_begin = nseg * S;
           const int col0 = (p.tile_begin + nt) * TILE_N;
           for (int c = c_begin; c < TILE_N; c += 4) {
@@ -368,6 +429,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (MC) cluster_sync();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

@@ -96,18 +96,15 @@ __global__ void unpack_pool_kernel(const unsigned long long* __restrict__ packed
 // first-half images.
 __global__ void label_tables_kernel(const long long* __restrict__ ys, const int8_t* __restrict__ anc, int V, int V_first,
                                     int N, int L, int8_t* __restrict__ tgt, uint8_t* __restrict__ desc,
-                                    int32_t* __restrict__ n_desc) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  int cnt = 0;
-  for (int v = 0; v < V; ++v) {
-    const long long y = ys[v];
-    const int8_t t = (y >= 0 && y < L) ? anc[(size_t)y * N + n] : int8_t(-1);
-    tgt[(size_t)v * N + n] = t;
-    if (v < V_first) desc[(size_t)v * N + n] = (t >= 0);
-    cnt += (t >= 0);
-  }
-  n_desc[n] = cnt;
+                                    int32_t* __restrict__ n_desc /* zeroed by the caller */) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * N) return;
+  const int v = idx / N, n = idx - v * N;
+  const long long y = ys[v];
+  const int8_t t = (y >= 0 && y < L) ? anc[(size_t)y * N + n] : int8_t(-1);
+  tgt[idx] = t;
+  if (v < V_first) desc[idx] = (t >= 0);
+  if (t >= 0) atomicAdd(n_desc + n, 1);
 }
 
 // ---------------------------------------------------------------- classifier (NonNegLinear, pipnet/pipnet.py:1035-1036)
@@ -238,26 +235,43 @@ __global__ void class_loss_bwd_kernel(const float* __restrict__ out, const int8_
 // ---------------------------------------------------------------- tanh loss (pipnet/train.py:1076-1087)
 // Per node: -1/2 * sum_{view half h} mean_p log(tanh(sum_{desc b in h} pooled[b,p]) + eps).  One block per node.
 // colsum[h*P + p] keeps the masked column sums for the backward.
+// grid (N, 2 view halves), 256 threads: warps stride over the half's rows, lanes over the node's prototypes.
+// part[h*N + n] = -1/2 * mean_p log(tanh(colsum)+eps)  (0 for nodes without descendants, pipnet/train.py:941-942)
 __global__ void tanh_loss_fwd_kernel(const float* __restrict__ pooled, const int8_t* __restrict__ tgt,
                                      const int32_t* __restrict__ proto_off, const int32_t* __restrict__ n_desc, int V,
-                                     int V_first, int N, int P, float eps, float* __restrict__ loss,
+                                     int V_first, int N, int P, float eps, float* __restrict__ part,
                                      float* __restrict__ colsum) {
-  __shared__ float sh[32];
-  const int n = blockIdx.x;
+  __shared__ float sh[8][64];
+  __shared__ float red[32];
+  const int n = blockIdx.x, h = blockIdx.y;
   const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int vb = h ? V_first : 0, ve = h ? V : V_first;
   float acc = 0.f;
-  for (int i = threadIdx.x; i < 2 * pn; i += blockDim.x) {
-    const int h = i / pn, p = i - h * pn;
-    const int vb = h ? V_first : 0, ve = h ? V : V_first;
-    float t = 0.f;
-    for (int v = vb; v < ve; ++v)
-      if (tgt[(size_t)v * N + n] >= 0) t += pooled[(size_t)v * P + p0 + p];
-    colsum[(size_t)h * P + p0 + p] = t;
-    acc += logf(tanhf(t) + eps);
+  for (int pc = 0; pc < pn; pc += 64) {          // 64 prototypes per pass (two per lane)
+    float t0 = 0.f, t1 = 0.f;
+    const int pa = pc + lane, pb = pc + 32 + lane;
+    for (int v = vb + warp; v < ve; v += 8) {
+      if (tgt[(size_t)v * N + n] >= 0) {
+        const float* row = pooled + (size_t)v * P + p0;
+        if (pa < pn) t0 += row[pa];
+        if (pb < pn) t1 += row[pb];
+      }
+    }
+    sh[warp][lane] = t0;
+    sh[warp][32 + lane] = t1;
+    __syncthreads();
+    if (threadIdx.x < 64 && pc + threadIdx.x < pn) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+      colsum[(size_t)h * P + p0 + pc + threadIdx.x] = t;
+      acc += logf(tanhf(t) + eps);
+    }
+    __syncthreads();
   }
-  acc = block_sum(acc, sh);
-  // nodes without a descendant in the batch are skipped by the reference (pipnet/train.py:941-942)
-  if (threadIdx.x == 0) loss[n] = n_desc[n] > 0 ? -0.5f * acc / float(pn) : 0.f;
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[h * N + n] = n_desc[n] > 0 ? -0.5f * acc / float(pn) : 0.f;
 }
 // g_pooled[v,p] (+)= g_loss[n] * (-1/(2 P_n)) * (1 - th^2) / (th + eps) for descendant rows; thread per (v,p).
 __global__ void tanh_loss_bwd_kernel(const float* __restrict__ colsum, const int8_t* __restrict__ tgt,
@@ -279,46 +293,53 @@ __global__ void tanh_loss_bwd_kernel(const float* __restrict__ colsum, const int
 
 // ---------------------------------------------------------------- kernel-orthogonality loss (pipnet/train.py:1136-1151, orth_dist :1408-1412)
 // Per node: rows of W whose classifier column has any weight > 1e-3; E = W_rel W_rel^T - I (P_rel < C);
-// loss = ||E||_F.  One block per node; E kept in a [P_max x P_max] workspace slab for the backward.
+// loss = ||E||_F.  One block per prototype ROW (row i of its node's Gram matrix): warps stride over the columns
+// j, lanes over channels.  E is kept in a [N, P_max, P_max] slab for the backward; sumsq[n] (zeroed by the caller)
+// collects the squared norm.
 __global__ void orth_loss_fwd_kernel(const float* __restrict__ w, const float* __restrict__ wc,
-                                     const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
-                                     const int32_t* __restrict__ wc_off, const int32_t* __restrict__ n_desc, int C,
-                                     int P_max, float* __restrict__ loss, float* __restrict__ E,
+                                     const int32_t* __restrict__ proto_node, const int32_t* __restrict__ proto_off,
+                                     const int32_t* __restrict__ cls_off, const int32_t* __restrict__ wc_off, int C,
+                                     int P_max, float* __restrict__ sumsq, float* __restrict__ E,
                                      uint8_t* __restrict__ rel) {
   __shared__ float sh[32];
-  const int n = blockIdx.x;
+  __shared__ uint8_t srel[128];
+  const int row = blockIdx.x;
+  const int n = proto_node[row];
   const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
   const int kn = cls_off[n + 1] - cls_off[n];
+  const int i = row - p0;
   for (int p = threadIdx.x; p < pn; p += blockDim.x) {
     bool r = false;
     for (int c = 0; c < kn; ++c) r |= wc[wc_off[n] + (size_t)c * pn + p] > 0.001f;
-    rel[p0 + p] = r;
+    srel[p] = r;
+    if (p == i) rel[row] = r;
   }
   __syncthreads();
-  float* En = E + (size_t)n * P_max * P_max;
-  float acc = 0.f;
+  float* Er = E + ((size_t)n * P_max + i) * P_max;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int ij = warp; ij < pn * pn; ij += nw) {           // one warp per Gram entry
-    const int i = ij / pn, j = ij - i * pn;
+  float acc = 0.f;
+  const float* a = w + (size_t)row * C;
+  for (int j = warp; j < pn; j += nw) {
     float e = 0.f;
-    if (rel[p0 + i] && rel[p0 + j]) {
-      const float* a = w + (size_t)(p0 + i) * C;
+    if (srel[i] && srel[j]) {
       const float* b = w + (size_t)(p0 + j) * C;
-      float d = 0.f;
-      for (int c = lane; c < C; c += 32) d = fmaf(a[c], b[c], d);
-      d = warp_sum(d);
-      e = d - (i == j ? 1.f : 0.f);
+      float d0 = 0.f, d1 = 0.f;
+      int c = lane;
+      for (; c + 32 < C; c += 64) { d0 = fmaf(a[c], b[c], d0); d1 = fmaf(a[c + 32], b[c + 32], d1); }
+      if (c < C) d0 = fmaf(a[c], b[c], d0);
+      e = warp_sum(d0 + d1) - (i == j ? 1.f : 0.f);
     }
-    if (lane == 0) { En[i * P_max + j] = e; acc += e * e; }
+    if (lane == 0) { Er[j] = e; acc += e * e; }
   }
   acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) loss[n] = n_desc[n] > 0 ? sqrtf(acc) : 0.f;   // skipped nodes contribute nothing
+  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(sumsq + n, acc);
 }
-// dW[i,:] += g[n] * (2/L) * sum_j E[i,j] W[j,:]   (E symmetric); one block per (node, row i).
+// dW[i,:] += g[n] * (2/L) * sum_j E[i,j] W[j,:]   (E symmetric, zero outside the relevant rows); one block per row.
 __global__ void orth_loss_bwd_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off, int C, int P_max,
                                      const float* __restrict__ loss, const float* __restrict__ E,
                                      const uint8_t* __restrict__ rel, const float* __restrict__ g_loss,
                                      const int32_t* __restrict__ row_node, float* __restrict__ g_w) {
+  __shared__ float coef[128];
   const int row = blockIdx.x;
   const int n = row_node[row];
   const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
@@ -326,13 +347,44 @@ __global__ void orth_loss_bwd_kernel(const float* __restrict__ w, const int32_t*
   const float L = loss[n];
   if (!rel[row] || L <= 0.f || g_loss[n] == 0.f) return;
   const float s = g_loss[n] * 2.f / L;
-  const float* En = E + (size_t)n * P_max * P_max + (size_t)i * P_max;
+  const float* En = E + ((size_t)n * P_max + i) * P_max;
+  for (int j = threadIdx.x; j < pn; j += blockDim.x) coef[j] = s * En[j];
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     float acc = 0.f;
-    for (int j = 0; j < pn; ++j)
-      if (rel[p0 + j]) acc = fmaf(En[j], w[(size_t)(p0 + j) * C + c], acc);
-    g_w[(size_t)row * C + c] += s * acc;
+#pragma unroll 4
+    for (int j = 0; j < pn; ++j) acc = fmaf(coef[j], w[(size_t)(p0 + j) * C + c], acc);
+    g_w[(size_t)row * C + c] += acc;
   }
+}
+
+// ---------------------------------------------------------------- loss combination (one block)
+// stats[0..3][n] = per-node align / tanh / orth / class loss (0 for nodes without descendants or disabled terms);
+// total = sum_n sum_k weight[k] * stats[k][n]  (weights already contain the 1/N of pipnet/train.py:1071 etc.)
+struct LossWeights { float w[4]; };
+__global__ void loss_combine_kernel(const float* __restrict__ align, const float* __restrict__ tanh_part,
+                                    const float* __restrict__ orth_sq, const float* __restrict__ cls,
+                                    const int32_t* __restrict__ n_desc, int N, LossWeights lw, float* __restrict__ stats,
+                                    float* __restrict__ total) {
+  __shared__ float sh[32];
+  float acc = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const bool on = n_desc[n] > 0;
+    const float a = (align && on) ? align[n] : 0.f;
+    const float t = (tanh_part && on) ? tanh_part[n] + tanh_part[N + n] : 0.f;
+    const float o = (orth_sq && on) ? sqrtf(orth_sq[n]) : 0.f;
+    const float c = (cls && on) ? cls[n] : 0.f;
+    stats[n] = a; stats[N + n] = t; stats[2 * N + n] = o; stats[3 * N + n] = c;
+    acc += lw.w[0] * a + lw.w[1] * t + lw.w[2] * o + lw.w[3] * c;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) *total = acc;
+}
+// gvec[k][n] = g_total * weight[k] (upstream gradient of every per-node term)
+__global__ void loss_grads_kernel(const float* __restrict__ g_total, int N, LossWeights lw, float* __restrict__ gvec) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * N) return;
+  gvec[idx] = g_total[0] * lw.w[idx / N];
 }
 
 // ---------------------------------------------------------------- align loss finalize / backward prep

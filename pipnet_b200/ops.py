@@ -304,87 +304,60 @@ class NonNegClassifier(torch.autograd.Function):
         return g_pooled, g_wc, g_bias, None
 
 
-class ClassLoss(torch.autograd.Function):
-    """per-node weighted NLL on log1p(out^2) (pipnet/train.py:1153-1163) -> loss [N]"""
+LOSS_TANH, LOSS_ORTH, LOSS_CLASS, LOSS_SPARSITY = 1, 2, 4, 8
+
+
+class HeadLosses(torch.autograd.Function):
+    """All per-node loss terms of the shipped recipe in one forward / one backward call:
+    total = sum_n (w_align*align[n] + w_tanh*tanh[n] + w_orth*orth[n] + w_class*class[n]) (weights include the 1/N
+    of `pipnet/train.py:1071,1084,1149,1165`).  Returns (total, stats[4,N], n_correct[N]); only `total` is
+    differentiable.  The relevance mask of the orth term comes from the classifier weights, which get no
+    gradient from it (boolean indexing in the reference, `pipnet/train.py:1140`)."""
 
     @staticmethod
-    def forward(ctx, out, labels: LabelTables, dl: DeviceLayout, sparsity):
-        out = out.contiguous()
-        V = out.shape[0]
-        loss = torch.empty(dl.N, device=out.device, dtype=torch.float32)
-        n_correct = torch.empty(dl.N, device=out.device, dtype=torch.int32)
-        call('hcomp_class_loss_fwd', ptr(out), ptr(labels.tgt), ptr(labels.n_desc), dl.tref, V, int(sparsity), ptr(loss),
-             ptr(n_correct), _stream())
-        ctx.dl, ctx.labels, ctx.sparsity = dl, labels, int(sparsity)
-        ctx.save_for_backward(out)
-        ctx.mark_non_differentiable(n_correct)
-        return loss, n_correct
-
-    @staticmethod
-    def backward(ctx, g_loss, _g):
-        (out,) = ctx.saved_tensors
-        dl, labels = ctx.dl, ctx.labels
-        g_out = torch.empty_like(out)
-        g_loss = g_loss.contiguous().float()
-        call('hcomp_class_loss_bwd', ptr(out), ptr(labels.tgt), ptr(labels.n_desc), ptr(g_loss), dl.tref, out.shape[0],
-             ctx.sparsity, ptr(g_out), _stream())
-        return g_out, None, None, None
-
-
-class TanhLoss(torch.autograd.Function):
-    """per-node tanh uniformity loss (pipnet/train.py:1076-1087) -> loss [N]"""
-
-    @staticmethod
-    def forward(ctx, pooled, labels: LabelTables, dl: DeviceLayout, eps):
-        pooled = pooled.contiguous()
+    def forward(ctx, pooled, out, align, w_flat, wc_flat, labels: LabelTables, dl: DeviceLayout, flags, weights, eps):
+        pooled, out = pooled.contiguous(), out.contiguous()
         V = pooled.shape[0]
-        loss = torch.empty(dl.N, device=pooled.device, dtype=torch.float32)
-        colsum = torch.empty(2 * dl.P, device=pooled.device, dtype=torch.float32)
-        call('hcomp_tanh_loss_fwd', ptr(pooled), ptr(labels.tgt), ptr(labels.n_desc), dl.tref, V, labels.V_first, float(eps),
-             ptr(loss), ptr(colsum), _stream())
-        ctx.dl, ctx.labels, ctx.eps, ctx.V = dl, labels, float(eps), V
-        ctx.save_for_backward(colsum)
-        return loss
-
-    @staticmethod
-    def backward(ctx, g_loss):
-        (colsum,) = ctx.saved_tensors
-        dl, labels = ctx.dl, ctx.labels
-        g_pooled = torch.empty(ctx.V, dl.P, device=colsum.device, dtype=torch.float32)
-        g_loss = g_loss.contiguous().float()
-        call('hcomp_tanh_loss_bwd', ptr(colsum), ptr(labels.tgt), ptr(g_loss), dl.tref, ctx.V, labels.V_first, ctx.eps,
-             ptr(g_pooled), 0, _stream())
-        return g_pooled, None, None, None
-
-
-class OrthLoss(torch.autograd.Function):
-    """per-node kernel-orthogonality loss (pipnet/train.py:1136-1151) -> loss [N]; the relevance mask comes
-    from the classifier weights, which get no gradient from this term (boolean indexing in the reference)."""
-
-    @staticmethod
-    def forward(ctx, w_flat, wc_flat, labels: LabelTables, dl: DeviceLayout):
-        w_flat = w_flat.contiguous()
-        wc_flat = wc_flat.detach().contiguous()
-        Cc = w_flat.shape[1]
-        dev = w_flat.device
-        loss = torch.empty(dl.N, device=dev, dtype=torch.float32)
-        E = torch.empty(dl.N * dl.layout.p_max * dl.layout.p_max, device=dev, dtype=torch.float32)
+        dev = pooled.device
+        use_orth = bool(flags & LOSS_ORTH)
+        Cc = w_flat.shape[1] if w_flat is not None else 0
+        wts = (C.c_float * 4)(*[float(x) for x in weights])
+        total = torch.empty((), device=dev, dtype=torch.float32)
+        stats = torch.empty(4, dl.N, device=dev, dtype=torch.float32)
+        n_correct = torch.empty(dl.N, device=dev, dtype=torch.int32)
+        ws = torch.empty(int(_cabi.lib().hcomp_head_losses_ws_floats(dl.tref)), device=dev, dtype=torch.float32)
         rel = torch.empty(dl.P, device=dev, dtype=torch.uint8)
-        call('hcomp_orth_loss_fwd', ptr(w_flat), ptr(wc_flat), ptr(labels.n_desc), dl.tref, Cc, ptr(loss), ptr(E), ptr(rel),
-             _stream())
-        ctx.dl = dl
-        ctx.save_for_backward(w_flat, loss, E, rel)
-        return loss
+        wf = w_flat.detach().contiguous() if use_orth else None
+        wc = wc_flat.detach().contiguous() if wc_flat is not None else None
+        al = align.detach().contiguous() if align is not None else None
+        call('hcomp_head_losses_fwd', ptr(pooled), ptr(out), ptr(al), ptr(wf), ptr(wc), ptr(labels.tgt), ptr(labels.n_desc),
+             dl.tref, V, labels.V_first, Cc, int(flags), wts, float(eps), ptr(total), ptr(stats), ptr(n_correct), ptr(ws),
+             ptr(rel), _stream())
+        ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc)
+        ctx.has = (align is not None, w_flat is not None and use_orth)
+        ctx.save_for_backward(out, wf if use_orth else None, stats, ws, rel)
+        ctx.mark_non_differentiable(stats, n_correct)
+        return total, stats, n_correct
 
     @staticmethod
-    def backward(ctx, g_loss):
-        w_flat, loss, E, rel = ctx.saved_tensors
-        dl = ctx.dl
-        g_w = torch.zeros_like(w_flat)
-        g_loss = g_loss.contiguous().float()
-        call('hcomp_orth_loss_bwd', ptr(w_flat), ptr(loss), ptr(E), ptr(rel), ptr(g_loss), dl.tref, w_flat.shape[1], ptr(g_w),
+    def backward(ctx, g_total, _gs, _gc):
+        out, wf, stats, ws, rel = ctx.saved_tensors
+        dl, labels = ctx.dl, ctx.labels
+        flags, weights, eps, V, Cc = ctx.cfg
+        dev = out.device
+        wts = (C.c_float * 4)(*weights)
+        g_total = g_total.contiguous().float()
+        gvec = torch.empty(4, dl.N, device=dev, dtype=torch.float32)
+        need_pooled, need_out, need_align, need_w = (ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                                     ctx.needs_input_grad[2] and ctx.has[0],
+                                                     ctx.needs_input_grad[3] and ctx.has[1])
+        g_pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32) if need_pooled else None
+        g_out = torch.empty(V, dl.K, device=dev, dtype=torch.float32) if need_out else None
+        g_w = torch.empty(dl.P, Cc, device=dev, dtype=torch.float32) if need_w else None
+        call('hcomp_head_losses_bwd', ptr(g_total), ptr(out), ptr(wf), ptr(labels.tgt), ptr(labels.n_desc), ptr(stats), dl.tref,
+             V, labels.V_first, Cc, flags, wts, eps, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out), ptr(g_w),
              _stream())
-        return g_w, None, None, None
+        return g_pooled, g_out, (gvec[0] if need_align else None), g_w, None, None, None, None, None, None
 
 
 def joint_leaf_distribution(out_flat: torch.Tensor, dl: DeviceLayout, tau=1.0):

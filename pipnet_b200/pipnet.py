@@ -84,6 +84,8 @@ class _FlatGroup:
         self.params = params
         self.flat: Optional[Tensor] = None
         self.meta = []
+        self._gathered: Optional[Tensor] = None
+        self._gathered_grad = None
 
     def ensure(self):
         p0 = self.params[0]
@@ -109,8 +111,17 @@ class _FlatGroup:
         return flat
 
     def gather(self) -> Tensor:
+        """Flat view with autograd edges to the parameters.  Cached until `invalidate()` (called at the start of
+        every forward) so that several consumers in one step (head GEMM, orth loss) share ONE autograd node and
+        their gradients are summed once on the flat buffer instead of once per node."""
         self.ensure()
-        return _GatherParams.apply(self, *self.params)
+        if self._gathered is None or not torch.is_grad_enabled() or self._gathered_grad != torch.is_grad_enabled():
+            self._gathered = _GatherParams.apply(self, *self.params)
+            self._gathered_grad = torch.is_grad_enabled()
+        return self._gathered
+
+    def invalidate(self):
+        self._gathered = None
 
 
 class NodeDict:
@@ -264,6 +275,9 @@ class PIPNet(nn.Module):
         return ops.NonNegClassifier.apply(pooled_flat, self.flat_classifier_weights(), bias, dl)
 
     def forward(self, xs, inference=False, apply_overspecificity_mask=False, labels: Optional[ops.LabelTables] = None):
+        for grp in (self._w_group, self._wc_group, self._bias_group):
+            if grp is not None:
+                grp.invalidate()
         features = self._net(xs)
         pooled_flat, align, argmax, dl = self.head(features, inference=inference, labels=labels)
         if apply_overspecificity_mask:
@@ -276,6 +290,7 @@ class PIPNet(nn.Module):
         pooled = NodeDict(pooled_flat, L.node_names, L.proto_off)
         out = NodeDict(out_flat, L.node_names, L.cls_off)
         pooled.align = align                                    # per-node align_pf loss (zeros without labels)
+        pooled.align_valid = labels is not None
         proto_features = LazyProtoFeatures(self, features, self.softmax_tau, NodeDict(argmax, L.node_names, L.proto_off))
         return features, proto_features, pooled, out
 

@@ -70,6 +70,29 @@ class LazyNodeLosses:
         return (self._values.detach() * act).sum() / act.sum().clamp_min(1.0)
 
 
+class LazyMean:
+    """mean over the nodes present in the batch (what the reference computes with `np.mean([v.item() ...])`),
+    evaluated only when somebody asks for it"""
+
+    def __init__(self, d: LazyNodeLosses): self._d = d
+    def tensor(self): return self._d.mean_tensor()
+    def item(self):
+        t = self._d.mean_tensor()
+        return -5.0 if t is None else float(t)
+    def __float__(self): return self.item()
+    def __bool__(self): return True
+    def __repr__(self): return f'{self.item():.6f}'
+
+
+class _LossResult(tuple):
+    """the reference's 21-tuple, plus the raw device statistics for sync-free epoch accounting"""
+
+    def __new__(cls, items, stats, n_desc):
+        self = super().__new__(cls, items)
+        self.stats, self.n_desc = stats, n_desc
+        return self
+
+
 def _unwrap(net):
     return net.module if hasattr(net, 'module') else net
 
@@ -119,31 +142,35 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
     loss = zero
     losses_used = []
 
-    a_vec = t_vec = o_vec = c_vec = n_correct = None
-    if (not finetune) and align_pf:
-        a_vec = getattr(pooled, 'align', None)
-        if a_vec is None or not getattr(a_vec, 'requires_grad', False) and torch.is_grad_enabled() and train:
-            if a_vec is None:
-                raise Exception('align_pf needs the per-node align loss of the fused forward: call net(xs, labels=...)')
-        loss = loss + (align_pf_weight / N) * a_vec.sum()
+    flags = 0
+    wts = [0.0, 0.0, 0.0, 0.0]
+    align_vec = None
+    use_align = (not finetune) and align_pf
+    if use_align:
+        align_vec = getattr(pooled, 'align', None)
+        if align_vec is None or not getattr(pooled, 'align_valid', False):
+            raise Exception('align_pf needs the per-node align loss of the fused forward: call net(xs, labels=...)')
+        wts[0] = align_pf_weight / N
         losses_used.append('AL_PF')
-    if (not finetune) and tanh:
-        if not (getattr(args, 'tanh_during_second_phase', 'y') == 'n' and not pretrain):
-            t_vec = ops.TanhLoss.apply(pooled.flat, labels, dl, EPS)
-            loss = loss + (t_weight / N) * t_vec.sum()
-            losses_used.append('TANH')
-    if (not pretrain) and (not finetune) and kernel_orth:
-        o_vec = ops.OrthLoss.apply(m.flat_prototype_kernels(), m.flat_classifier_weights(), labels, dl)
-        loss = loss + (orth_weight / N) * o_vec.sum()
+    use_tanh = (not finetune) and tanh and not (getattr(args, 'tanh_during_second_phase', 'y') == 'n' and not pretrain)
+    if use_tanh:
+        flags |= ops.LOSS_TANH
+        wts[1] = t_weight / N
+        losses_used.append('TANH')
+    use_orth = (not pretrain) and (not finetune) and kernel_orth
+    if use_orth:
+        flags |= ops.LOSS_ORTH
+        wts[2] = orth_weight / N
         losses_used.append('KO')
-    sparsity = not (args is not None and getattr(args, 'pipnet_sparsity', 'y') == 'n')
-    if not pretrain:
-        c_vec, n_correct = ops.ClassLoss.apply(out.flat, labels, dl, sparsity)
-        loss = loss + (cl_weight / N) * c_vec.sum()
+    use_cls = not pretrain
+    if use_cls:
+        flags |= ops.LOSS_CLASS
+        wts[3] = cl_weight / N
         losses_used.append('CL')
-    else:
-        with torch.no_grad():
-            _, n_correct = ops.ClassLoss.apply(out.flat.detach(), labels, dl, sparsity)
+    if not (args is not None and getattr(args, 'pipnet_sparsity', 'y') == 'n'):
+        flags |= ops.LOSS_SPARSITY
+    loss, stats, n_correct = ops.HeadLosses.apply(pooled.flat, out.flat, align_vec, m.flat_prototype_kernels() if use_orth else None,
+                                                  m.flat_classifier_weights(), labels, dl, flags, wts, EPS)
 
     if node_accuracy is not None:
         acc = node_accuracy.setdefault('__device__', {'n_examples': torch.zeros(N, device=zero.device, dtype=torch.int64),
@@ -151,20 +178,20 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         acc['n_examples'] += labels.n_desc
         acc['n_correct'] += n_correct
 
-    class_loss = LazyNodeLosses(c_vec, labels.n_desc, names)
-    tanh_loss = LazyNodeLosses(t_vec, labels.n_desc, names)
-    orth_loss = LazyNodeLosses(o_vec, labels.n_desc, names)
-    a_loss_pf = LazyNodeLosses(a_vec, labels.n_desc, names)
+    a_loss_pf = LazyNodeLosses(stats[0] if use_align else None, labels.n_desc, names)
+    tanh_loss = LazyNodeLosses(stats[1] if use_tanh else None, labels.n_desc, names)
+    orth_loss = LazyNodeLosses(stats[2] if use_orth else None, labels.n_desc, names)
+    class_loss = LazyNodeLosses(stats[3] if use_cls else None, labels.n_desc, names)
     placeholder = -5
-    avg = lambda d: (d.mean_tensor() if d.mean_tensor() is not None else placeholder)
-    avg_class_loss = avg(class_loss) if not pretrain else None
-    avg_a_loss_pf, avg_tanh_loss, avg_orth = avg(a_loss_pf), avg(tanh_loss), avg(orth_loss)
+    avg_class_loss = LazyMean(class_loss) if use_cls else None
+    avg_a_loss_pf, avg_tanh_loss, avg_orth = LazyMean(a_loss_pf), LazyMean(tanh_loss), LazyMean(orth_loss)
     if print and train_iter is not None and hasattr(train_iter, 'set_postfix_str'):
         train_iter.lazy_postfix = (loss.detach(), avg_class_loss, avg_a_loss_pf, avg_tanh_loss, avg_orth, '+'.join(losses_used))
     a_loss = torch.tensor(-5)
     uni_loss = torch.tensor(-5)
-    return (loss, class_loss, a_loss, tanh_loss, {}, {}, orth_loss, uni_loss, avg_class_loss, avg_a_loss_pf, avg_tanh_loss,
-            placeholder, (placeholder if pretrain else -5), avg_orth, -5, -5, -5, -5, -5, -5, 0.)
+    res = (loss, class_loss, a_loss, tanh_loss, {}, {}, orth_loss, uni_loss, avg_class_loss, avg_a_loss_pf, avg_tanh_loss,
+           placeholder, (placeholder if pretrain else -5), avg_orth, -5, -5, -5, -5, -5, -5, 0.)
+    return _LossResult(res, stats, labels.n_desc)
 
 
 # --------------------------------------------------------------------------- epoch drivers
@@ -235,7 +262,8 @@ def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, 
     n_fine_correct = torch.zeros((), device=device, dtype=torch.int64)
     n_samples = 0
     lrs_net, lrs_class = [], []
-    node_sums = {k: torch.zeros(len(names), device=device) for k in ('class_loss', 'tanh_loss', 'kernel_orth_loss')}
+    stat_sums = torch.zeros(4, len(names), device=device)
+    step_means = torch.zeros(4, device=device)
     node_cnt = torch.zeros(len(names), device=device)
     steps = 0
     ctx = torch.enable_grad() if train else torch.no_grad()
@@ -281,13 +309,10 @@ def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, 
                     lrs_net.append(0.)
             with torch.no_grad():
                 acc.add('loss', loss)
-                acc.add('class_loss', res[8]); acc.add('tanh_loss', res[10]); acc.add('kernel_orth_loss', res[13])
-                acc.add('a_loss_pf', res[9])
                 act = (labels.n_desc > 0).float()
                 node_cnt += act
-                for key, d in (('class_loss', class_d), ('tanh_loss', tanh_d), ('kernel_orth_loss', orth_d)):
-                    if d._values is not None:
-                        node_sums[key] += d._values.detach() * act
+                stat_sums += res.stats                       # [4,N]: align, tanh, orth, class (0 where absent)
+                step_means += res.stats.sum(dim=1) / act.sum().clamp_min(1.0)
                 _, pred = ops.joint_leaf_distribution(out.flat, m.device_layout(out.flat.device), kw.get('path_prob_softmax_tau', 1))
                 n_fine_correct += (pred == ys).sum()                                     # pipnet/train.py:363-369
                 n_samples += ys.numel()
@@ -298,6 +323,9 @@ def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, 
 
     steps = max(steps, 1)
     means = acc.result(steps)
+    sm = (step_means / steps).cpu().tolist()
+    means.update({'a_loss_pf': sm[0], 'tanh_loss': sm[1], 'kernel_orth_loss': sm[2], 'class_loss': sm[3]})
+    node_sums = {'a_loss_pf': stat_sums[0], 'tanh_loss': stat_sums[1], 'kernel_orth_loss': stat_sums[2], 'class_loss': stat_sums[3]}
     info = dict()
     info['fine_accuracy'] = float(n_fine_correct) / max(n_samples, 1)
     info['train_accuracy' if train else 'test_accuracy'] = 0.
