@@ -174,7 +174,12 @@ def joint_distribution(root, out, softmax_tau=1.0):
             names += nm
         return torch.cat(cols, 1), names
 
-    dist, names = rec(root)
+    dist, _ = rec(root)
+    # The reference orders (and SELECTS) columns with np.argsort over names_of_joint_distribution()
+    # (pipnet/pipnet.py:179-181).  That name list stops at single-child nodes (util/node.py:397-403), so on a tree
+    # with a single-child node (e.g. the CUB-08 root) it is shorter than the leaf list and the result keeps only
+    # the first len(names) depth-first columns.  Restated as is.
+    names = root.unwrap_names_of_joint(root.names_of_joint_distribution())
     order = sorted(range(len(names)), key=lambda i: names[i])
     return dist[:, order]
 

@@ -18,7 +18,8 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-bool g_no_multicast = false;          // HCOMP_NO_MULTICAST=1: single-CTA variants only (A/B measurements)
+bool g_no_multicast = true;           // cluster/TMA-multicast variants are opt-in (hcomp_set_multicast): measured
+                                      // equal or slower than unicast on B200 for 2-CTA clusters (L2 dedups anyway)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -267,10 +268,11 @@ inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
 
 extern "C" {
 
-int hcomp_abi_version(void) {
-  const char* e = getenv("HCOMP_NO_MULTICAST");
-  g_no_multicast = e != nullptr && e[0] == '1';
-  return HCOMP_ABI_VERSION;
+int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
+int hcomp_set_multicast(int on) {
+  const int prev = g_no_multicast ? 0 : 1;
+  g_no_multicast = (on == 0);
+  return prev;
 }
 const char* hcomp_last_error(void) { return g_err; }
 long long hcomp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

@@ -69,13 +69,13 @@ struct PairSmem {
   uint32_t tmem_base;
 };
 
-template <int S>
+template <int S, bool MASK>
 __device__ __forceinline__ void softmax_row(uint32_t* raw, int len, float scale_log2, float* s) {
   // four interleaved partial maxima / sums keep the dependency chains short (the epilogue is latency-bound)
   float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
   for (int i = 0; i < S; ++i) {
-    const float x = (i < len) ? __uint_as_float(raw[i]) : -INFINITY;
+    const float x = (!MASK || i < len) ? __uint_as_float(raw[i]) : -INFINITY;
     s[i] = x;
     m4[i & 3] = fmaxf(m4[i & 3], x);
   }
@@ -318,37 +318,78 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int nv_b = __popc(__ballot_sync(0xffffffffu, valid_b));
 
       float align_acc[SLOTS];
+      int seg_node[SLOTS], seg_len[SLOTS], seg_poff[SLOTS];
+      float seg_aux[SLOTS];      // fwd: align mask (1/0) of this row for the segment's node; bwd: align gradient coefficient
+      int my_cnt = 0;
+      // tile metadata and per-(image,node) scalars are fetched BEFORE waiting for the accumulators
 #pragma unroll
-      for (int i = 0; i < SLOTS; ++i) align_acc[i] = 0.f;
+      for (int js = 0; js < SLOTS; ++js) {
+        align_acc[js] = 0.f;
+        seg_node[js] = seg_len[js] = seg_poff[js] = 0;
+        seg_aux[js] = 0.f;
+        const int j = PARTS * js + part;
+        if (j < NSEG_MAX && j < nseg) {
+          my_cnt = js + 1;
+          seg_node[js] = __ldg(tile + 4 + j);
+          seg_len[js] = __ldg(tile + 4 + MAX_SEGS + j);
+          seg_poff[js] = __ldg(tile + 4 + 2 * MAX_SEGS + j);
+        }
+      }
+      if (valid_a && valid_b && v_a < imgs_first) {
+#pragma unroll
+        for (int js = 0; js < SLOTS; ++js) {
+          if (js < my_cnt) {
+            if constexpr (!BWD) {
+              if (p.desc != nullptr) seg_aux[js] = p.desc[(size_t)v_a * p.n_nodes + seg_node[js]] ? 1.f : 0.f;
+            } else {
+              if (p.coef_align != nullptr) seg_aux[js] = p.coef_align[(size_t)v_a * p.n_nodes + seg_node[js]];
+            }
+          }
+        }
+      }
 
       mbar_wait(&sb->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * (2 * TILE_N);
+      if (my_cnt == 0) {          // nothing to read from this stage: release it at once
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
+      }
 
 #pragma unroll
       for (int js = 0; js < SLOTS; ++js) {
         const int j = PARTS * js + part;
-        if (j < NSEG_MAX && j < nseg) {     // warp-uniform
-          const int node = __ldg(tile + 4 + j);
-          const int len = __ldg(tile + 4 + MAX_SEGS + j);
-          const int poff = __ldg(tile + 4 + 2 * MAX_SEGS + j);
+        if (js < my_cnt) {     // warp-uniform
+          const int node = seg_node[js];
+          const int len = seg_len[js];
+          const int poff = seg_poff[js];
           uint32_t ra[S], rb[S];
           tmem_ld_cols<S>(t0 + j * S, ra);
           tmem_ld_cols<S>(t0 + TILE_N + j * S, rb);
           tmem_ld_wait();
+          if (js == my_cnt - 1) {
+            // last segment of this warp is in registers: hand the TMEM stage back to the MMA warp now, the
+            // arithmetic below overlaps the next item's MMAs
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
+          }
           float s1[S], s2[S];
-          softmax_row<S>(ra, len, p.scale_log2, s1);
-          softmax_row<S>(rb, len, p.scale_log2, s2);
+          if (len == S) {
+            softmax_row<S, false>(ra, len, p.scale_log2, s1);
+            softmax_row<S, false>(rb, len, p.scale_log2, s2);
+          } else {
+            softmax_row<S, true>(ra, len, p.scale_log2, s1);
+            softmax_row<S, true>(rb, len, p.scale_log2, s2);
+          }
           float ip4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
           for (int i = 0; i < S; ++i) ip4[i & 3] = fmaf(s1[i], s2[i], ip4[i & 3]);
           const float ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
 
           if constexpr (!BWD) {
-            if (p.desc != nullptr) {
-              const bool on = valid_a && valid_b && (v_a < imgs_first) && p.desc[(size_t)v_a * p.n_nodes + node];
-              if (on) align_acc[js] = -__logf(ip + 1e-12f);
-            }
+            if (seg_aux[js] != 0.f) align_acc[js] = -__logf(ip + 1e-12f);
             if (__ballot_sync(0xffffffffu, valid_a) != 0u)
               pool_segment<S>(s1, valid_a, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
                               p.pooled_packed + (size_t)v_first * p.P + poff, p.P);
@@ -356,9 +397,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               pool_segment<S>(s2, valid_b, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
                               p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff, p.P);
           } else {
-            float ca = 0.f;
-            if (p.coef_align != nullptr && valid_a && valid_b && v_a < imgs_first)
-              ca = p.coef_align[(size_t)v_a * p.n_nodes + node] * __frcp_rn(ip + 1e-12f);
+            const float ca = seg_aux[js] * __frcp_rn(ip + 1e-12f);
             const int col0 = (p.tile_begin + nt) * TILE_N + j * S;
             {
               float g[S];
@@ -392,21 +431,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
         }
       }
-      // accumulators fully read -> hand the TMEM stage back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
-
       if constexpr (!BWD) {
         if (p.desc != nullptr) {
 #pragma unroll
           for (int js = 0; js < SLOTS; ++js) {
-            const int j = PARTS * js + part;
-            if (j < NSEG_MAX && j < nseg) {
+            if (js < my_cnt) {
               float v = align_acc[js];
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              if (lane == 0 && v != 0.f) atomicAdd(p.align_sum + __ldg(tile + 4 + j), (double)v);
+              if (lane == 0 && v != 0.f) atomicAdd(p.align_sum + seg_node[js], (double)v);
             }
           }
         }

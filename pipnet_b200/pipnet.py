@@ -240,6 +240,27 @@ class PIPNet(nn.Module):
         self._bias_group = (_FlatGroup([getattr(self, '_' + n + '_classification').bias for n in names])
                             if self._has_cls_bias else None)
         self._dl: Optional[ops.DeviceLayout] = None
+        # Column selection of get_joint_distribution, replicating the reference exactly: np.argsort over
+        # names_of_joint_distribution() (pipnet/pipnet.py:179-181).  For trees without single-child nodes this is
+        # the sorted-leaf order the kernel already produces (None = identity); with a single-child node the
+        # reference's name list is truncated (util/node.py:397-403) and so is its result.
+        dfs = [n.name for n in self._dfs_leaves(root)]
+        ref_names = root.unwrap_names_of_joint(root.names_of_joint_distribution())
+        order = sorted(range(len(ref_names)), key=lambda i: ref_names[i])
+        sorted_pos = {nm: i for i, nm in enumerate(self.layout.leaf_names)}
+        cols = [sorted_pos[dfs[i]] for i in order]
+        self._joint_cols = None if cols == list(range(self.layout.L)) else cols
+
+    @staticmethod
+    def _dfs_leaves(root):
+        out, stack = [], [root]
+        while stack:
+            n = stack.pop()
+            if n.is_leaf():
+                out.append(n)
+            else:
+                stack.extend(reversed(n.children))
+        return out
 
     # ------------------------------------------------------------------ plumbing
     def device_layout(self, device) -> ops.DeviceLayout:
@@ -301,6 +322,8 @@ class PIPNet(nn.Module):
             raise Exception('leave_out_classes / overspecificity mask are outside the fused joint-distribution path')
         flat = out.flat if isinstance(out, NodeDict) else torch.cat([out[n] for n in self.layout.node_names], dim=1)
         joint, _ = ops.joint_leaf_distribution(flat, self.device_layout(flat.device), float(softmax_tau))
+        if self._joint_cols is not None:
+            joint = joint[:, torch.as_tensor(self._joint_cols, device=joint.device)]
         return out['root'], joint
 
     def get_classification_layers(self):

@@ -313,8 +313,8 @@ def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, 
                 node_cnt += act
                 stat_sums += res.stats                       # [4,N]: align, tanh, orth, class (0 where absent)
                 step_means += res.stats.sum(dim=1) / act.sum().clamp_min(1.0)
-                _, pred = ops.joint_leaf_distribution(out.flat, m.device_layout(out.flat.device), kw.get('path_prob_softmax_tau', 1))
-                n_fine_correct += (pred == ys).sum()                                     # pipnet/train.py:363-369
+                _, joint = m.get_joint_distribution(out, softmax_tau=kw.get('path_prob_softmax_tau', 1))
+                n_fine_correct += (joint.argmax(dim=1) == ys).sum()                      # pipnet/train.py:363-369
                 n_samples += ys.numel()
             steps += 1
             if hasattr(it, 'lazy_postfix') and (i % 50 == 0):

@@ -1,0 +1,113 @@
+"""CPU tests of the host side: tree class vs the reference's, flat layout tables, tile packing, the
+data-parallel helpers on a world_size-2 gloo group."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_harness as rh
+from oracle.problems import make_tree
+from pipnet_b200 import layout as lay
+from pipnet_b200.node import Node
+from pipnet_b200.trees import CUB08, CUB18, CUB27, build_tree, get_tree, synthetic_edges
+
+
+@pytest.mark.skipif(not rh.available(), reason="reference checkout not present")
+@pytest.mark.parametrize("edges", [CUB08, CUB18, CUB27, synthetic_edges(40, 2)], ids=["cub08", "cub18", "cub27", "synth40"])
+def test_node_matches_reference_node(edges):
+    _, _, ref_node, _ = rh.load()
+    a, b = build_tree(edges, Node), build_tree(edges, ref_node.Node)
+    na, nb = a.nodes_with_children(), b.nodes_with_children()
+    assert [n.name for n in na] == [n.name for n in nb]
+    for x, y in zip(na, nb):
+        assert x.children_to_labels == y.children_to_labels
+        assert x.leaf_descendents == y.leaf_descendents and x.descendents == y.descendents
+        assert {k: set(v) for k, v in x.leaf_descendents_of_child.items()} == {k: set(v) for k, v in y.leaf_descendents_of_child.items()}
+        for leaf in x.leaf_descendents:
+            assert x.closest_descendent_for(leaf).name == y.closest_descendent_for(leaf).name
+        for kw in (dict(num_protos_per_descendant=0, num_protos_per_child=0, min_protos=20, split_protos=True),
+                   dict(num_protos_per_descendant=0, num_protos_per_child=7, min_protos=0, split_protos=True),
+                   dict(num_protos_per_descendant=2, num_protos_per_child=0, min_protos=3, split_protos=True)):
+            x.set_num_protos(**kw); y.set_num_protos(**kw)
+            assert x.num_protos == y.num_protos and x.num_protos_per_child == y.num_protos_per_child
+        x.set_loss_weightage_using_descendants_count(); y.set_loss_weightage_using_descendants_count()
+        assert torch.equal(x.weights, y.weights)
+    assert a.unwrap_names_of_joint(a.names_of_joint_distribution()) == b.unwrap_names_of_joint(b.names_of_joint_distribution())
+
+
+def test_tree_fixture_shapes():
+    for name, nodes, leaves in (("cub08", 8, 8), ("cub18", 17, 18), ("cub27", 25, 27), ("synth190", 189, 190)):
+        r = get_tree(name)
+        assert len(r.nodes_with_children()) == nodes and len(r.leaf_descendents) == leaves
+    assert get_tree("cub08").num_children() == 1              # single-child root
+    assert max(n.num_children() for n in get_tree("cub27").nodes_with_children()) == 3
+
+
+@pytest.mark.parametrize("tree,kw", [("cub27", dict(num_features=20)), ("cub08", dict(per_child=20)),
+                                     ("cub18", dict(num_features=12)), ("synth190", dict(num_features=20))])
+def test_layout_tables(tree, kw):
+    root = make_tree(tree, **kw)
+    L = lay.build_layout(root)
+    nodes = root.nodes_with_children()
+    assert L.P == sum(n.num_protos for n in nodes) and L.K == sum(n.num_children() for n in nodes)
+    assert L.P_pad == 128 * L.tiles.shape[0]
+    # every flat prototype appears exactly once on the padded axis, at segment j*S + i of its tile
+    used = L.row_map[L.row_map >= 0]
+    assert sorted(used.tolist()) == list(range(L.P))
+    for t, rec in enumerate(L.tiles):
+        S, nseg, umma_n = int(rec[0]), int(rec[1]), int(rec[2])
+        assert S in lay.SEG_CLASSES and 0 < nseg <= 128 // S and umma_n % 16 == 0 and nseg * S <= umma_n <= 128
+        for j in range(nseg):
+            ni, ln, po = int(rec[4 + j]), int(rec[4 + 16 + j]), int(rec[4 + 32 + j])
+            assert ln == nodes[ni].num_protos <= S and po == L.proto_off[ni]
+            assert L.row_map[t * 128 + j * S: t * 128 + j * S + ln].tolist() == list(range(po, po + ln))
+    assert (np.diff(L.tiles[:, 0]) >= 0).all()                # tiles sorted by class: one launch per class
+    # anc / path tables agree with the tree
+    for li, leaf in enumerate(L.leaf_names):
+        for ni, n in enumerate(nodes):
+            want = n.children_to_labels[n.closest_descendent_for(leaf).name] if leaf in n.leaf_descendents else -1
+            assert int(L.anc[li, ni]) == want
+        cols = L.path_col[L.path_off[li]:L.path_off[li + 1]].tolist()
+        assert len(cols) == int((L.anc[li] >= 0).sum())
+
+
+def test_layout_rejects_wide_nodes():
+    root = make_tree("cub27", per_child=20)                     # 3-child node -> 60 prototypes
+    with pytest.raises(Exception):
+        lay.build_layout(root)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from pipnet_b200 import dist as hd
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)
+    a, b = torch.randn(7, 5, generator=g), torch.randn(3, generator=g)
+    a0, b0 = a.clone(), b.clone()
+    hd.flat_allreduce_mean_([a, None, b])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (a0, b0))
+    want_a = sum(t[0] for t in gathered) / world
+    want_b = sum(t[1] for t in gathered) / world
+    ok = torch.allclose(a, want_a, atol=1e-6) and torch.allclose(b, want_b, atol=1e-6)
+    lo, hi = hd.shard_range(11, rank, world)
+    q.put((rank, bool(ok), lo, hi))
+    dist.destroy_process_group()
+
+
+def test_flat_allreduce_mean_world2_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+    assert all(r[1] for r in res)
+    assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 6, 6, 11)     # shards cover the batch exactly once
