@@ -57,9 +57,6 @@ const char* hcomp_last_error(void);
 int hcomp_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 long long hcomp_launch_count(void);
-/* opt into the 2-CTA-cluster variants that share operand tiles by TMA multicast (default off); returns the
- * previous setting.  Results are identical either way. */
-int hcomp_set_multicast(int on);
 
 /* ---- operand preparation -------------------------------------------------------------------- */
 /* fp32 add-on kernels (flat [P,C]; reference: nn.Conv2d weights built at pipnet/pipnet.py:1207) ->

@@ -18,8 +18,6 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
-bool g_no_multicast = true;           // cluster/TMA-multicast variants are opt-in (hcomp_set_multicast): measured
-                                      // equal or slower than unicast on B200 for 2-CTA clusters (L2 dedups anyway)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -122,31 +120,29 @@ int launch_persistent(Kern kern, const char* name, int cluster, int workers, int
   return 0;
 }
 
-template <int SEG, bool BWD, bool MC>
+template <int SEG, bool BWD>
 int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms, cudaStream_t st) {
-  auto kern = hc::head_pair_kernel<SEG, BWD, MC>;
+  auto kern = hc::head_pair_kernel<SEG, BWD>;
   static bool attr_done = false;
   if (!attr_done) {
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::PAIR_SMEM_BYTES));
     attr_done = true;
   }
-  constexpr int CL = MC ? 2 : 1;
-  const int items = p.num_m_tiles * ((p.num_tiles + CL - 1) / CL);
-  const int slots = sms / CL;
-  const int workers = items < slots ? items : slots;
-  return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", CL, workers,
+  const int items = p.num_m_tiles * p.num_tiles;
+  const int workers = items < sms ? items : sms;
+  return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", 1, workers,
                            hc::PairCfg<SEG>::THREADS, hc::PAIR_SMEM_BYTES, st, tx, tw, p);
 }
 
-template <bool BWD, bool MC>
+template <bool BWD>
 int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms,
                       cudaStream_t st) {
   switch (seg) {
-    case 8: return launch_pair<8, BWD, MC>(tx, tw, p, sms, st);
-    case 16: return launch_pair<16, BWD, MC>(tx, tw, p, sms, st);
-    case 20: return launch_pair<20, BWD, MC>(tx, tw, p, sms, st);
-    case 32: return launch_pair<32, BWD, MC>(tx, tw, p, sms, st);
-    case 40: return launch_pair<40, BWD, MC>(tx, tw, p, sms, st);
+    case 8: return launch_pair<8, BWD>(tx, tw, p, sms, st);
+    case 16: return launch_pair<16, BWD>(tx, tw, p, sms, st);
+    case 20: return launch_pair<20, BWD>(tx, tw, p, sms, st);
+    case 32: return launch_pair<32, BWD>(tx, tw, p, sms, st);
+    case 40: return launch_pair<40, BWD>(tx, tw, p, sms, st);
     default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40)", seg);
   }
 }
@@ -164,9 +160,8 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
   const long long M = (long long)V * HW;
   if (M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
-  CUtensorMap tx, tx_half, tw;                      // tx_half: 64-row boxes for the multicast (cluster) variant
+  CUtensorMap tx, tw;
   if (int e = make_tmap(&tx, x, C, M, C, hc::KBLK, hc::TILE_M)) return e;
-  if (int e = make_tmap(&tx_half, x, C, M, C, hc::KBLK, hc::TILE_M / 2)) return e;
   if (int e = make_tmap(&tw, wp, C, P_pad, C, hc::KBLK, hc::TILE_N)) return e;
   hc::HeadParams p = base;
   p.M = int(M);
@@ -192,29 +187,23 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
     }
     p.tile_begin = t;
     p.num_tiles = e - t;
-    // >= 2 tiles of this class: CTA pairs share the feature tiles by TMA multicast
-    const bool mc = p.num_tiles >= 2 && !g_no_multicast;
-    if (int err = mc ? launch_pair_class<BWD, true>(seg, tx_half, tw, p, di.sms, st)
-                     : launch_pair_class<BWD, false>(seg, tx, tw, p, di.sms, st))
-      return err;
+    if (int err = launch_pair_class<BWD>(seg, tx, tw, p, di.sms, st)) return err;
     t = e;
   }
   return 0;
 }
 
-template <bool A_MN, bool B_MN, int OUT, bool MC>
+template <bool A_MN, bool B_MN, int OUT>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const hc::GemmParams& p, int sms, cudaStream_t st) {
-  auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT, MC>;
+  auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT>;
   static bool attr_done = false;
   if (!attr_done) {
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::G_SMEM_BYTES));
     attr_done = true;
   }
-  constexpr int CL = MC ? 2 : 1;
-  const int items = ((p.num_m_tiles + CL - 1) / CL) * p.num_n_tiles * p.splits;
-  const int slots = sms / CL;
-  const int workers = items < slots ? items : slots;
-  return launch_persistent(kern, "gemm_tc_kernel", CL, workers, hc::G_THREADS, hc::G_SMEM_BYTES, st, ta, tb, p);
+  const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
+  const int workers = items < sms ? items : sms;
+  return launch_persistent(kern, "gemm_tc_kernel", 1, workers, hc::G_THREADS, hc::G_SMEM_BYTES, st, ta, tb, p);
 }
 
 // D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
@@ -237,21 +226,16 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   p.num_m_tiles = cdiv(M, hc::G_BM);
   p.num_n_tiles = cdiv(N, hc::G_BN);
   p.num_k_blocks = cdiv(K, hc::G_BK);
-  const bool mc_possible = b_mn && p.num_m_tiles >= 2;
-  const int tiles_mn = (mc_possible ? (p.num_m_tiles + 1) / 2 : p.num_m_tiles) * p.num_n_tiles;
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
   if (out_mode != hc::OUT_RED_F32) splits = 1;
-  if (splits <= 0) splits = (mc_possible ? di.sms / 2 : di.sms) / tiles_mn;
+  if (splits <= 0) splits = di.sms / tiles_mn;
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
   p.splits = cdiv(p.num_k_blocks, p.k_blocks_per_split);
   p.out = out; p.ldo = ldo; p.row_map = row_map;
-  const bool mc = b_mn && p.num_m_tiles >= 2 && !g_no_multicast;   // CTA pairs share the B tile by TMA multicast
-#define HC_GEMM_CASE(AM, BM, OM)                                                              \
-  if (a_mn == AM && b_mn == BM && out_mode == OM) {                                           \
-    if constexpr (BM) { if (mc) return launch_gemm<AM, BM, OM, true>(ta, tb, p, di.sms, st); } \
-    return launch_gemm<AM, BM, OM, false>(ta, tb, p, di.sms, st);                             \
-  }
+#define HC_GEMM_CASE(AM, BM, OM) \
+  if (a_mn == AM && b_mn == BM && out_mode == OM) return launch_gemm<AM, BM, OM>(ta, tb, p, di.sms, st);
   HC_GEMM_CASE(false, true, hc::OUT_BF16)      // dX
   HC_GEMM_CASE(true, true, hc::OUT_RED_F32)    // dW
   HC_GEMM_CASE(false, false, hc::OUT_F32)      // self-test: plain K-major GEMM
@@ -269,11 +253,7 @@ inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
 extern "C" {
 
 int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
-int hcomp_set_multicast(int on) {
-  const int prev = g_no_multicast ? 0 : 1;
-  g_no_multicast = (on == 0);
-  return prev;
-}
+
 const char* hcomp_last_error(void) { return g_err; }
 long long hcomp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 int hcomp_num_sms(void) {

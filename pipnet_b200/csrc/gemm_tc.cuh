@@ -41,10 +41,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// MC: launched as clusters of 2 CTAs that work on two neighbouring M tiles of the same (N tile, k range) and
-// share the B tile: each CTA fetches half of it and TMA-multicasts it to both (32 KB instead of 48 KB per CTA and
-// k-block from L2 -- all GEMM-class kernels of this head sit at the L2->SM ceiling otherwise).
-template <bool A_MN, bool B_MN, int OUT, bool MC>
+template <bool A_MN, bool B_MN, int OUT>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -54,13 +51,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  static_assert(!MC || B_MN, "B multicast is implemented for MN-major B");
-  constexpr int CL = MC ? 2 : 1;
-  const int crank = MC ? int(cluster_ctarank()) : 0;
-  const int m_groups = (p.num_m_tiles + CL - 1) / CL;
-  const int tiles_mn = m_groups * p.num_n_tiles;
+  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
   const int total_items = tiles_mn * p.splits;
-  const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;
+  const int worker = blockIdx.x, num_workers = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_a);
@@ -69,7 +62,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < G_STAGES; ++i) {
       mbar_init(&sb->full[i], 1);
-      mbar_init(&sb->empty[i], CL);
+      mbar_init(&sb->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->tmem_full[i], 1);
@@ -80,7 +73,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   if (warp == 2) tmem_alloc<512>(&sb->tmem_base);
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync();      // peer barriers are initialised before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
 
@@ -88,9 +80,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   auto decode = [&](int item, int& mt, int& nt, int& kb0, int& kb1) {
     const int sp = item / tiles_mn;
     const int r = item - sp * tiles_mn;
-    const int mg = r / p.num_n_tiles;
-    nt = r - mg * p.num_n_tiles;
-    mt = mg * CL + crank;                // may be one past the last M tile: loads are zero-filled, rows masked
+    mt = r / p.num_n_tiles;
+    nt = r - mt * p.num_n_tiles;
     kb0 = sp * p.k_blocks_per_split;
     kb1 = min(p.num_k_blocks, kb0 + p.k_blocks_per_split);
   };
@@ -116,55 +107,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           }
           if constexpr (!B_MN) {
             tma_load_2d(sbm, &tmap_b, &sb->full[stage], kb * G_BK, nt * G_BN);           // box [64 k, 256 n]
-          } else if constexpr (!MC) {
+          } else {
 #pragma unroll
             for (int c = 0; c < G_BN / 64; ++c)                                            // box [64 n, 64 k]
               tma_load_2d(sbm + c * 8192, &tmap_b, &sb->full[stage], nt * G_BN + c * 64, kb * G_BK);
-          } else {
-#pragma unroll
-            for (int c2 = 0; c2 < G_BN / 128; ++c2) {                                      // my half, to both CTAs
-              const int c = crank * (G_BN / 128) + c2;
-              tma_load_2d_mc(sbm + c * 8192, &tmap_b, &sb->full[stage], nt * G_BN + c * 64, kb * G_BK, uint16_t(3));
-            }
           }
           if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(G_BM, G_BN, A_MN, B_MN);
-      constexpr uint64_t a_hi = A_MN ? DESC_MNMAJOR : DESC_KMAJOR;
-      constexpr uint64_t b_hi = B_MN ? DESC_MNMAJOR : DESC_KMAJOR;
-      constexpr uint32_t a_step = A_MN ? 2048 : 32;
-      constexpr uint32_t b_step = B_MN ? 2048 : 32;
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int item = worker; item < total_items; item += num_workers) {
-        int mt, nt, kb0, kb1;
-        decode(item, mt, nt, kb0, kb1);
-        mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
+    // MMA issuer: warp-uniform loop, single elected lane issues (see head_pair.cuh)
+    constexpr uint32_t idesc = make_idesc(G_BM, G_BN, A_MN, B_MN);
+    constexpr uint32_t HI = desc_hi32(1024);
+    constexpr uint32_t A_LOF = desc_lo_flags(A_MN ? 8192 : 16);
+    constexpr uint32_t B_LOF = desc_lo_flags(B_MN ? 8192 : 16);
+    constexpr uint32_t a_step = (A_MN ? 2048 : 32) >> 4;
+    constexpr uint32_t b_step = (B_MN ? 2048 : 32) >> 4;
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = worker; item < total_items; item += num_workers) {
+      int mt, nt, kb0, kb1;
+      decode(item, mt, nt, kb0, kb1);
+      mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d = tmem_base + acc * G_BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&sb->full[stage], phase);
         tc_fence_after();
-        const uint32_t d = tmem_base + acc * G_BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
-          mbar_wait(&sb->full[stage], phase);
-          tc_fence_after();
-          const uint32_t a = smem_u32(smem + stage * G_STAGE_BYTES);
-          const uint32_t b = a + G_A_BYTES;
+        if (elect_one()) {
+          const uint32_t a = ((smem_base + stage * G_STAGE_BYTES) >> 4);
+          const uint32_t b = a + (G_A_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < G_BK / 16; ++k)
-            umma_bf16(d, smem_desc(a + k * a_step, a_hi), smem_desc(b + k * b_step, b_hi), idesc,
+            umma_bf16(d, desc64((a + k * a_step) | A_LOF, HI), desc64((b + k * b_step) | B_LOF, HI), idesc,
                       (kb > kb0 || k > 0) ? 1u : 0u);
-          if constexpr (MC) umma_commit_mc(&sb->empty[stage], uint16_t(3));
-          else umma_commit(&sb->empty[stage]);
-          if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&sb->empty[stage]);
+          if (kb == kb1 - 1) umma_commit(&sb->tmem_full[acc]);
         }
-        umma_commit(&sb->tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == G_STAGES) { stage = 0; phase ^= 1; }
       }
+      if (kb1 <= kb0) {                      // empty split: nothing was issued, still hand the stage to the epilogue
+        if (elect_one()) umma_commit(&sb->tmem_full[acc]);
+        __syncwarp();
+      }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     const int quad = warp & 3;
@@ -234,7 +226,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync();      // nobody exits while the peer may still multicast into / arrive on this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

@@ -144,24 +144,41 @@ __device__ __forceinline__ void store_dz(__nv_bfloat16* dst, const float* d) {
 }
 
 // Scatter term of the pooled gradient for one (view, segment): lane c holds column c's {argmax location,
-// g_pooled} for the (at most two) images this warp's rows belong to; each hit (the one row of an image whose
-// location is the argmax) is broadcast and added to that row's G[c].  Expected hits per warp and segment ~ 1.
+// g_pooled} for the (at most two) images this warp's rows belong to (e0: image of lane 0, e1: the next image);
+// each hit (the one row of an image whose location is the argmax) is broadcast and added to that row's G[c].
+// Expected hits per warp and segment ~ 1.  The entries are fetched by `load_scatter` BEFORE the accumulator wait.
 template <int S>
-__device__ __forceinline__ void add_scatter(float* g, const int2* __restrict__ scat_v0, int P, int len, int lane,
-                                            int loc_first, int lane_b, bool has_boundary, int n_valid) {
-  int2 e0 = make_int2(-1, 0), e1 = make_int2(-1, 0);
+struct ScatEntries {
+  static constexpr int H = (S + 31) / 32;
+  int2 e0[H], e1[H];
+};
+
+template <int S>
+__device__ __forceinline__ void load_scatter(ScatEntries<S>& se, const int2* __restrict__ scat_v0, int P, int len, int lane,
+                                             bool first_img, bool second_img) {
 #pragma unroll
-  for (int h = 0; h < (S + 31) / 32; ++h) {
+  for (int h = 0; h < ScatEntries<S>::H; ++h) {
     const int c = h * 32 + lane;
+    se.e0[h] = make_int2(-1, 0);
+    se.e1[h] = make_int2(-1, 0);
     if (c < len) {
-      e0 = __ldg(scat_v0 + c);
-      if (has_boundary) e1 = __ldg(scat_v0 + P + c);
+      if (first_img) se.e0[h] = __ldg(scat_v0 + c);
+      if (second_img) se.e1[h] = __ldg(scat_v0 + P + c);
     }
+  }
+}
+
+template <int S>
+__device__ __forceinline__ void add_scatter(float* g, const ScatEntries<S>& se, int lane, int loc_first, int lane_b,
+                                            int n_valid) {
+#pragma unroll
+  for (int h = 0; h < ScatEntries<S>::H; ++h) {
+    const int2 e0 = se.e0[h], e1 = se.e1[h];
     const int lim0 = min(min(32, lane_b), n_valid);
     const int t0 = e0.x - loc_first;
     const int t1 = e1.x + lane_b;
-    const bool v0 = (c < len) && t0 >= 0 && t0 < lim0;
-    const bool v1 = (c < len) && has_boundary && e1.x >= 0 && t1 < min(32, n_valid);
+    const bool v0 = e0.x >= 0 && t0 >= 0 && t0 < lim0;
+    const bool v1 = e1.x >= 0 && t1 < min(32, n_valid);
 #pragma unroll 1
     for (int grp = 0; grp < 2; ++grp) {
       uint32_t hits = __ballot_sync(0xffffffffu, grp == 0 ? v0 : v1);
@@ -179,11 +196,7 @@ __device__ __forceinline__ void add_scatter(float* g, const int2* __restrict__ s
   }
 }
 
-// MC: clusters of 2 CTAs take two neighbouring prototype tiles of the same pair tile and share the feature
-// tiles A1/A2: each CTA fetches 64 of the 128 rows and TMA-multicasts them to both, so a CTA pulls
-// 32 KB instead of 48 KB per k-block out of L2 (the kernel is operand-delivery-bound otherwise).
-// tmap_x has a 64-row box when MC (128 rows otherwise).
-template <int S, bool BWD, bool MC>
+template <int S, bool BWD>
 __global__ void __launch_bounds__(PairCfg<S>::THREADS, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const HeadParams p) {
@@ -198,11 +211,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr int CL = MC ? 2 : 1;
-  const int crank = MC ? int(cluster_ctarank()) : 0;
-  const int n_groups = (p.num_tiles + CL - 1) / CL;
+  const int n_groups = p.num_tiles;
   const int total_items = p.num_m_tiles * n_groups;
-  const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;
+  const int worker = blockIdx.x, num_workers = gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
@@ -211,7 +222,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < PAIR_STAGES; ++i) {
       mbar_init(&sb->full[i], 1);
-      mbar_init(&sb->empty[i], CL);
+      mbar_init(&sb->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->tmem_full[i], 1);
@@ -222,7 +233,6 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (warp == 2) tmem_alloc<512>(&sb->tmem_base);
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
 
@@ -233,7 +243,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       uint32_t phase = 0;
       for (int item = worker; item < total_items; item += num_workers) {
         const int mt = item / n_groups;
-        const int nt = (item - mt * n_groups) * CL + crank;     // may be one past the last tile (dummy, zero-filled)
+        const int nt = item - mt * n_groups;
         const int row_a = mt * TILE_M;
         const int row_b = p.halfM + row_a;
         const int row_w = (p.tile_begin + nt) * TILE_N;
@@ -241,14 +251,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           mbar_wait(&sb->empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * PAIR_STAGE_BYTES;
           mbar_arrive_expect_tx(&sb->full[stage], PAIR_STAGE_BYTES);
-          if constexpr (!MC) {
-            tma_load_2d(st, &tmap_x, &sb->full[stage], kb * KBLK, row_a);
-            tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kb * KBLK, row_b);
-          } else {                                    // my 64 rows of each feature tile, delivered to both CTAs
-            const int ro = crank * 64;
-            tma_load_2d_mc(st + ro * 128, &tmap_x, &sb->full[stage], kb * KBLK, row_a + ro, uint16_t(3));
-            tma_load_2d_mc(st + TILE_M * KBLK * 2 + ro * 128, &tmap_x, &sb->full[stage], kb * KBLK, row_b + ro, uint16_t(3));
-          }
+          tma_load_2d(st, &tmap_x, &sb->full[stage], kb * KBLK, row_a);
+          tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kb * KBLK, row_b);
           tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kb * KBLK, row_w);
           if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
         }
@@ -256,40 +260,46 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int item = worker; item < total_items; item += num_workers) {
-        const int nt = (item % n_groups) * CL + crank;
-        const int umma_n = (nt < p.num_tiles) ? __ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2) : 16;
-        const uint32_t idesc = make_idesc(TILE_M, umma_n, false, false);
-        mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
+    // The whole warp walks the (warp-uniform) loop so that addresses and descriptors stay in uniform registers;
+    // only the issue block is single-lane (elect.sync elects the same lane every time, which matters because
+    // tcgen05.commit tracks the MMAs of the executing thread).
+    constexpr uint32_t HI = desc_hi32(1024);
+    constexpr uint32_t LOF = desc_lo_flags(16);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = worker; item < total_items; item += num_workers) {
+      const int nt = item % n_groups;
+      const int umma_n = __ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2);
+      const uint32_t idesc = make_idesc(TILE_M, umma_n, false, false);
+      mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d0 = tmem_base + acc * (2 * TILE_N);
+      const uint32_t d1 = d0 + TILE_N;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&sb->full[stage], phase);
         tc_fence_after();
-        const uint32_t d0 = tmem_base + acc * (2 * TILE_N);
-        const uint32_t d1 = d0 + TILE_N;
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          mbar_wait(&sb->full[stage], phase);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + stage * PAIR_STAGE_BYTES);
-          const uint32_t a1 = a0 + TILE_M * KBLK * 2;
-          const uint32_t b = a1 + TILE_M * KBLK * 2;
+        if (elect_one()) {
+          const uint32_t a0 = ((smem_base + stage * PAIR_STAGE_BYTES) >> 4) | LOF;   // 16-byte units
+          const uint32_t a1 = a0 + (TILE_M * KBLK * 2 >> 4);
+          const uint32_t b = a1 + (TILE_M * KBLK * 2 >> 4);
 #pragma unroll
           for (int k = 0; k < KBLK / 16; ++k) {
-            const uint64_t bd = smem_desc(b + k * 32, DESC_KMAJOR);
+            const uint64_t bd = desc64(b + 2 * k, HI);
             const uint32_t accum = (kb | k) ? 1u : 0u;
-            umma_bf16(d0, smem_desc(a0 + k * 32, DESC_KMAJOR), bd, idesc, accum);
-            umma_bf16(d1, smem_desc(a1 + k * 32, DESC_KMAJOR), bd, idesc, accum);
+            umma_bf16(d0, desc64(a0 + 2 * k, HI), bd, idesc, accum);
+            umma_bf16(d1, desc64(a1 + 2 * k, HI), bd, idesc, accum);
           }
-          if constexpr (MC) umma_commit_mc(&sb->empty[stage], uint16_t(3));
-          else umma_commit(&sb->empty[stage]);
-          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&sb->empty[stage]);
+          if (kb == p.num_k_blocks - 1) umma_commit(&sb->tmem_full[acc]);
         }
-        umma_commit(&sb->tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
       }
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue
@@ -300,10 +310,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     uint32_t acc_phase = 0;
     for (int item = worker; item < total_items; item += num_workers) {
       const int mt = item / n_groups;
-      const int nt = (item - mt * n_groups) * CL + crank;
-      const bool real_tile = nt < p.num_tiles;
-      const int32_t* tile = p.tiles + (size_t)(p.tile_begin + (real_tile ? nt : 0)) * TILE_INTS;
-      const int nseg = real_tile ? __ldg(tile + 1) : 0;
+      const int nt = item - mt * n_groups;
+      const int32_t* tile = p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS;
+      const int nseg = __ldg(tile + 1);
 
       const int row_a = mt * TILE_M + quad * 32 + lane;
       const bool valid_a = row_a < p.halfM;
@@ -344,6 +353,20 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             } else {
               if (p.coef_align != nullptr) seg_aux[js] = p.coef_align[(size_t)v_a * p.n_nodes + seg_node[js]];
             }
+          }
+        }
+      }
+
+      [[maybe_unused]] ScatEntries<S> scat_e[BWD ? SLOTS : 1][2];
+      if constexpr (BWD) {
+        // a second image exists in this warp's rows only if some VALID row lies past the boundary
+#pragma unroll
+        for (int js = 0; js < SLOTS; ++js) {
+          if (js < my_cnt) {
+            load_scatter<S>(scat_e[js][0], p.scat + (size_t)v_first * p.P + seg_poff[js], p.P, seg_len[js], lane, nv_a > 0,
+                            has_boundary && nv_a > lane_b);
+            load_scatter<S>(scat_e[js][1], p.scat + (size_t)(v_first + imgs_first) * p.P + seg_poff[js], p.P, seg_len[js],
+                            lane, nv_b > 0, has_boundary && nv_b > lane_b);
           }
         }
       }
@@ -403,8 +426,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               float g[S];
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = -ca * s2[i];
-              if (nv_a > 0)
-                add_scatter<S>(g, p.scat + (size_t)v_first * p.P + poff, p.P, len, lane, loc_first, lane_b, has_boundary, nv_a);
+              if (nv_a > 0) add_scatter<S>(g, scat_e[js][0], lane, loc_first, lane_b, nv_a);
               float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int i = 0; i < S; ++i) d4[i & 3] = fmaf(g[i], s1[i], d4[i & 3]);
@@ -417,9 +439,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               float g[S];
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = -ca * s1[i];
-              if (nv_b > 0)
-                add_scatter<S>(g, p.scat + (size_t)(v_first + imgs_first) * p.P + poff, p.P, len, lane, loc_first, lane_b,
-                               has_boundary, nv_b);
+              if (nv_b > 0) add_scatter<S>(g, scat_e[js][1], lane, loc_first, lane_b, nv_b);
               float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
               for (int i = 0; i < S; ++i) d4[i & 3] = fmaf(g[i], s2[i], d4[i & 3]);
@@ -445,7 +465,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         }
       } else {
         // zero the padding columns [nseg*S, 128) of this tile's dZ rows (the dX GEMM reads them)
-        if (part == 0 && real_tile) {
+        if (part == 0) {
           const int c_begin = nseg * S;
           const int col0 = (p.tile_begin + nt) * TILE_N;
           for (int c = c_begin; c < TILE_N; c += 4) {
@@ -462,7 +482,6 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if constexpr (MC) cluster_sync();
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);

@@ -195,6 +195,13 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
 //   SBO = 1024 (8 rows), LBO unused; advance K by 16 elements = +32 bytes on the start address.
 // MN-major tile (64-element MN chunks; inside a chunk 64 K-rows of 128 bytes):
 //   SBO = 1024 (8 K-rows), LBO = 8192 (next 64-element MN chunk); advance K by 16 = +2048 bytes.
+// split form used by the MMA issue loops: the high word is a compile-time constant, the low word is
+// (start >> 4) | (LBO >> 4) << 16 and advancing K is a plain 32-bit add on it.
+__host__ __device__ constexpr uint32_t desc_hi32(uint32_t sbo_bytes) {
+  return ((sbo_bytes >> 4) & 0x3FFF) | (1u << 14) | (2u << 29);
+}
+__host__ __device__ constexpr uint32_t desc_lo_flags(uint32_t lbo_bytes) { return ((lbo_bytes >> 4) & 0x3FFF) << 16; }
+__device__ __forceinline__ uint64_t desc64(uint32_t lo, uint32_t hi) { return (uint64_t(hi) << 32) | uint64_t(lo); }
 __host__ __device__ constexpr uint64_t make_smem_desc_hi(uint32_t lbo_bytes, uint32_t sbo_bytes) {
   return (uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16) | (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32) | (uint64_t(1) << 46) |
          (uint64_t(2) << 61);

@@ -111,28 +111,3 @@ def test_backward_dx_dw(case):
     assert rel_err(feats.grad, x.grad) <= 2e-2, f'dX rel err {rel_err(feats.grad, x.grad)}'
     assert rel_err(w_flat.grad, gw_ref) <= 2e-2, f'dW rel err {rel_err(w_flat.grad, gw_ref)}'
 
-
-def test_multicast_cluster_variants_match():
-    """The opt-in 2-CTA-cluster kernels (TMA multicast of the shared operand tile) give the same results."""
-    from pipnet_b200 import ops, _cabi
-    pb = Problem("cub27", 96, 6, 5, seed=21, num_features=20)
-    dl = ops.DeviceLayout(pb.layout, 'cuda')
-    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
-    g = torch.Generator().manual_seed(2)
-    G = torch.randn(pb.V, pb.layout.P, generator=g).cuda()
-    res = []
-    for on in (0, 1):
-        prev = _cabi.lib().hcomp_set_multicast(on)
-        try:
-            feats = pb.features('cuda').requires_grad_(True)
-            w_flat = pb.w_flat('cuda').requires_grad_(True)
-            pooled, align, argmax = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0)
-            ((pooled * G).sum() + align.sum()).backward()
-            torch.cuda.synchronize()
-            res.append((pooled.detach().clone(), argmax.clone(), align.detach().clone(), feats.grad.clone(), w_flat.grad.clone()))
-        finally:
-            _cabi.lib().hcomp_set_multicast(prev)
-    assert torch.equal(res[0][0], res[1][0]) and torch.equal(res[0][1], res[1][1])
-    torch.testing.assert_close(res[0][2], res[1][2], rtol=1e-6, atol=1e-7)
-    torch.testing.assert_close(res[0][3].float(), res[1][3].float(), rtol=1e-2, atol=1e-5)
-    torch.testing.assert_close(res[0][4], res[1][4], rtol=1e-4, atol=1e-6)
