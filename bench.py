@@ -154,6 +154,8 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
+            os.environ.pop('NCCL_DEBUG')                 # NCCL prints its version banner on stdout: keep it to the JSON line
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         dist.init_process_group('nccl', device_id=dev)
         ops.GRAD_ALLREDUCE_GROUP = dist.group.WORLD
@@ -190,10 +192,7 @@ def run_ours(a):
                                 root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
                                 device=dev, labels=labels, **w)
         loss = res[0]
-        loss.backward()
-        if world > 1:      # tiny classifier gradients: one flat all-reduce (prototype kernels overlap inside backward)
-            flat = torch.cat([p.grad.reshape(-1) for p in cls_params])
-            dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+        loss.backward()        # N > 1: both flat gradient buffers are mean all-reduced inside backward (ops.GRAD_ALLREDUCE_GROUP)
         return loss, x.grad
 
     def barrier():
@@ -238,13 +237,6 @@ def run_ours(a):
                                         tanh=True, args=args, device=dev, labels=labels, **w)
                 return res[0]
 
-            if world > 1:
-                # classifier gradients ride on a backward hook so that the all-reduce is inside the captured step
-                def _hook(grad):
-                    dist.all_reduce(grad, op=dist.ReduceOp.AVG)
-                    return grad
-                for p in cls_params:
-                    p.register_hook(_hook)
             graphs = [GraphedHeadStep(loss_fn, list(net.parameters()), feats[i], labels_d[i]) for i in range(2)]
         except Exception as ex:                        # capture is an optimisation of the launch path, not of the math
             if a.graph == 'on':
@@ -350,8 +342,13 @@ def run_ours(a):
                            'l2_policy': f'two alternating input batches of {feats[0].numel() * 2 / 1e6:.0f} MB each (> 126 MB L2)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
         print(json.dumps(line), flush=True)
+    sys.stdout.flush()
     if world > 1:
-        dist.destroy_process_group()
+        # graph-captured NCCL work makes process-group teardown unreliable: synchronise, then leave without it
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 def main():

@@ -301,6 +301,11 @@ class NonNegClassifier(torch.autograd.Function):
         g_bias = torch.empty(dl.K, device=pooled.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         call('hcomp_classifier_bwd', ptr(g_out), ptr(pooled), ptr(wc_flat), dl.tref, V, ptr(g_pooled), 0, ptr(g_wc),
              ptr(g_bias), _stream())
+        if GRAD_ALLREDUCE_GROUP is not None:        # data-parallel: ONE flat mean all-reduce for all nodes' classifiers
+            import torch.distributed as dist
+            for g in (g_wc, g_bias):
+                if g is not None:
+                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
         return g_pooled, g_wc, g_bias, None
 
 
