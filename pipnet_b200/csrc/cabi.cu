@@ -121,28 +121,30 @@ int launch_persistent(Kern kern, const char* name, int cluster, int workers, int
 }
 
 template <int SEG, bool BWD>
-int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms, cudaStream_t st) {
+int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& td1, const CUtensorMap& td2,
+                const hc::HeadParams& p, int sms, cudaStream_t st) {
   auto kern = hc::head_pair_kernel<SEG, BWD>;
+  constexpr int SMEM = hc::PairMem<BWD>::SMEM_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
-    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::PAIR_SMEM_BYTES));
+    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
   const int items = p.num_m_tiles * p.num_tiles;
   const int workers = items < sms ? items : sms;
   return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", 1, workers,
-                           hc::PairCfg<SEG>::THREADS, hc::PAIR_SMEM_BYTES, st, tx, tw, p);
+                           hc::PairCfg<SEG>::THREADS, SMEM, st, tx, tw, td1, td2, p);
 }
 
 template <bool BWD>
-int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const hc::HeadParams& p, int sms,
-                      cudaStream_t st) {
+int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& td1,
+                      const CUtensorMap& td2, const hc::HeadParams& p, int sms, cudaStream_t st) {
   switch (seg) {
-    case 8: return launch_pair<8, BWD>(tx, tw, p, sms, st);
-    case 16: return launch_pair<16, BWD>(tx, tw, p, sms, st);
-    case 20: return launch_pair<20, BWD>(tx, tw, p, sms, st);
-    case 32: return launch_pair<32, BWD>(tx, tw, p, sms, st);
-    case 40: return launch_pair<40, BWD>(tx, tw, p, sms, st);
+    case 8: return launch_pair<8, BWD>(tx, tw, td1, td2, p, sms, st);
+    case 16: return launch_pair<16, BWD>(tx, tw, td1, td2, p, sms, st);
+    case 20: return launch_pair<20, BWD>(tx, tw, td1, td2, p, sms, st);
+    case 32: return launch_pair<32, BWD>(tx, tw, td1, td2, p, sms, st);
+    case 40: return launch_pair<40, BWD>(tx, tw, td1, td2, p, sms, st);
     default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40)", seg);
   }
 }
@@ -167,6 +169,17 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   p.M = int(M);
   p.halfM = V_first * HW;
   p.rowsB = int(M) - p.halfM;
+  CUtensorMap td1, td2;                 // backward: dZ leaves through TMA stores, one map per view half (row clipping)
+  memset(&td1, 0, sizeof(td1));
+  memset(&td2, 0, sizeof(td2));
+  if (BWD) {
+    if (int e = make_tmap(&td1, p.dz, P_pad, p.halfM, P_pad, 64, hc::TILE_M)) return e;
+    if (p.rowsB > 0) {
+      if (int e = make_tmap(&td2, p.dz + (size_t)p.halfM * P_pad, P_pad, p.rowsB, P_pad, 64, hc::TILE_M)) return e;
+    } else {
+      td2 = td1;                        // no second half: every store of it would be fully clipped; keep a valid map
+    }
+  }
   p.HW = HW; p.C = C; p.P = P; p.P_pad = P_pad;
   p.num_k_blocks = cdiv(C, hc::KBLK);
   p.num_m_tiles = cdiv(p.halfM, hc::TILE_M);
@@ -187,23 +200,25 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
     }
     p.tile_begin = t;
     p.num_tiles = e - t;
-    if (int err = launch_pair_class<BWD>(seg, tx, tw, p, di.sms, st)) return err;
+    if (int err = launch_pair_class<BWD>(seg, tx, tw, td1, td2, p, di.sms, st)) return err;
     t = e;
   }
   return 0;
 }
 
 template <bool A_MN, bool B_MN, int OUT>
-int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const hc::GemmParams& p, int sms, cudaStream_t st) {
+int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const hc::GemmParams& p, int sms,
+                cudaStream_t st) {
   auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT>;
+  constexpr int SMEM = hc::GemmCfg<OUT>::SMEM_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
-    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, hc::G_SMEM_BYTES));
+    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
   const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int workers = items < sms ? items : sms;
-  return launch_persistent(kern, "gemm_tc_kernel", 1, workers, hc::G_THREADS, hc::G_SMEM_BYTES, st, ta, tb, p);
+  return launch_persistent(kern, "gemm_tc_kernel", 1, workers, hc::G_THREADS, SMEM, st, ta, tb, to, p);
 }
 
 // D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
@@ -216,7 +231,12 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   if (M > 0x7fffffffLL || K > 0x7fffffffLL) return fail(HCOMP_E_ARG, "GEMM dimension overflow");
   if ((out_mode == hc::OUT_BF16 && (N % 8 || ldo % 8)) || (out_mode != hc::OUT_BF16 && (N % 4 || ldo % 4)))
     return fail(HCOMP_E_ARG, "N=%d / ldo=%lld alignment", N, ldo);
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, to;
+  if (out_mode == hc::OUT_BF16) {          // bf16 output leaves through TMA stores of [128 rows x 64 cols] boxes
+    if (int e = make_tmap(&to, out, N, M, ldo, 64, hc::G_BM)) return e;
+  } else {
+    memset(&to, 0, sizeof(to));
+  }
   if (a_mn) { if (int e = make_tmap(&ta, a, M, K, M, 64, 64)) return e; }
   else      { if (int e = make_tmap(&ta, a, K, M, K, hc::G_BK, hc::G_BM)) return e; }
   if (b_mn) { if (int e = make_tmap(&tb, b, N, K, N, 64, 64)) return e; }
@@ -235,7 +255,7 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   p.splits = cdiv(p.num_k_blocks, p.k_blocks_per_split);
   p.out = out; p.ldo = ldo; p.row_map = row_map;
 #define HC_GEMM_CASE(AM, BM, OM) \
-  if (a_mn == AM && b_mn == BM && out_mode == OM) return launch_gemm<AM, BM, OM>(ta, tb, p, di.sms, st);
+  if (a_mn == AM && b_mn == BM && out_mode == OM) return launch_gemm<AM, BM, OM>(ta, tb, to, p, di.sms, st);
   HC_GEMM_CASE(false, true, hc::OUT_BF16)      // dX
   HC_GEMM_CASE(true, true, hc::OUT_RED_F32)    // dW
   HC_GEMM_CASE(false, false, hc::OUT_F32)      // self-test: plain K-major GEMM

@@ -12,12 +12,17 @@
 namespace hc {
 
 constexpr int G_BM = 128, G_BN = 256, G_BK = 64;
-constexpr int G_STAGES = 4;
 constexpr int G_A_BYTES = G_BM * G_BK * 2;   // 16 KB
 constexpr int G_B_BYTES = G_BN * G_BK * 2;   // 32 KB
 constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
 constexpr int G_THREADS = 384;
-constexpr int G_SMEM_BYTES = G_STAGES * G_STAGE_BYTES + 1024 + 256;
+constexpr int G_OUT_STAGE_BYTES = G_BM * G_BN * 2;       // bf16 output tile staged for TMA stores (64 KB)
+// bf16 output: 3 operand stages + the 64 KB store staging; otherwise 4 operand stages
+template <int OUT> struct GemmCfg {
+  static constexpr int STAGES = (OUT == 0) ? 3 : 4;
+  static constexpr int SMEM_BYTES = STAGES * G_STAGE_BYTES + (OUT == 0 ? G_OUT_STAGE_BYTES : 0) + 1024 + 256;
+};
+constexpr int G_MAX_STAGES = 4;
 
 enum GemmOut : int { OUT_BF16 = 0, OUT_F32 = 1, OUT_RED_F32 = 2 };
 
@@ -30,8 +35,8 @@ struct GemmParams {
 };
 
 struct GemmSmem {
-  uint64_t full[G_STAGES];
-  uint64_t empty[G_STAGES];
+  uint64_t full[G_MAX_STAGES];
+  uint64_t empty[G_MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -44,10 +49,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 template <bool A_MN, bool B_MN, int OUT>
 __global__ void __launch_bounds__(G_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_o, const GemmParams p) {
+  constexpr int G_STAGES = GemmCfg<OUT>::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  GemmSmem* sb = reinterpret_cast<GemmSmem*>(smem + G_STAGES * G_STAGE_BYTES);
+  uint8_t* ostage = smem + G_STAGES * G_STAGE_BYTES;        // OUT_BF16 only: 4 boxes [128 rows x 64 cols], 128B-swizzled
+  GemmSmem* sb = reinterpret_cast<GemmSmem*>(ostage + (OUT == OUT_BF16 ? G_OUT_STAGE_BYTES : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -178,6 +185,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_after();
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * G_BN + half * 128;
       const bool empty_k = kb1 <= kb0;   // split with no k-blocks: accumulator is stale, contributes nothing
+      if constexpr (OUT == OUT_BF16) {
+        // registers -> 128B-swizzled smem boxes -> TMA bulk store (full 128-byte lines; a direct store from the
+        // TMEM register layout writes 16 bytes per lane to 32 different rows and is LSU-bound)
+        if (warp == 4 && lane == 0) tma_store_wait_read();          // previous tile has left the staging buffer
+        named_bar_sync(1, 256);
+        const int r = quad * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < 128; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t0 + c, v);
+          tmem_ld_wait();
+          const int col = half * 128 + c;                   // first of 32 columns
+          uint8_t* box = ostage + (col >> 6) * (G_BM * 128);
+          const int ch0 = (col & 63) >> 3;                  // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            uint4 o;
+            o.x = pack_bf16x2(__uint_as_float(v[8 * i + 0]), __uint_as_float(v[8 * i + 1]));
+            o.y = pack_bf16x2(__uint_as_float(v[8 * i + 2]), __uint_as_float(v[8 * i + 3]));
+            o.z = pack_bf16x2(__uint_as_float(v[8 * i + 4]), __uint_as_float(v[8 * i + 5]));
+            o.w = pack_bf16x2(__uint_as_float(v[8 * i + 6]), __uint_as_float(v[8 * i + 7]));
+            *reinterpret_cast<uint4*>(box + swz128(r, ch0 + i)) = o;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);   // accumulator drained: MMA may reuse the stage
+        fence_proxy_async();
+        named_bar_sync(1, 256);
+        if (warp == 4 && lane == 0 && !empty_k) {
+#pragma unroll
+          for (int b = 0; b < G_BN / 64; ++b)
+            if (nt * G_BN + b * 64 < p.N) tma_store_2d(&tmap_o, ostage + b * (G_BM * 128), nt * G_BN + b * 64, mt * G_BM);
+          tma_store_commit();
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < 128; c += 32) {
         uint32_t r[32];
@@ -185,20 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         tmem_ld_wait();
         const int n0 = nt * G_BN + half * 128 + c;
         if (row_ok && !empty_k) {
-          if constexpr (OUT == OUT_BF16) {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.ldo + n0;
-#pragma unroll
-            for (int i = 0; i < 32; i += 8) {
-              if (n0 + i < p.N) {
-                uint4 v;
-                v.x = pack_bf16x2(__uint_as_float(r[i + 0]), __uint_as_float(r[i + 1]));
-                v.y = pack_bf16x2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
-                v.z = pack_bf16x2(__uint_as_float(r[i + 4]), __uint_as_float(r[i + 5]));
-                v.w = pack_bf16x2(__uint_as_float(r[i + 6]), __uint_as_float(r[i + 7]));
-                *reinterpret_cast<uint4*>(o + i) = v;
-              }
-            }
-          } else if constexpr (OUT == OUT_F32) {
+          if constexpr (OUT == OUT_F32) {
             float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n0;
 #pragma unroll
             for (int i = 0; i < 32; i += 4) {
@@ -219,8 +249,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
+      }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (OUT == OUT_BF16) {
+      if (warp == 4 && lane == 0) tma_store_wait_all();     // global writes complete before the kernel ends
     }
   }
 

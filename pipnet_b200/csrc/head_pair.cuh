@@ -32,8 +32,14 @@ constexpr int TILE_M = 128;          // locations per tile
 constexpr int KBLK = 64;             // bf16 elements per k-block (one 128-byte swizzle row)
 constexpr int MAX_SEGS = 16;         // node segments per tile (S >= 8)
 constexpr int TILE_INTS = 4 + 3 * MAX_SEGS;   // {S, nseg, umma_n, 0, node[16], len[16], poff[16]}
-constexpr int PAIR_STAGES = 4;
 constexpr int PAIR_STAGE_BYTES = 3 * TILE_M * KBLK * 2;   // A1 + A2 + W = 48 KB
+constexpr int PAIR_MAX_STAGES = 4;
+constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both views' bf16 dZ tiles staged for TMA stores (64 KB)
+// forward: 4 operand stages; backward: 3 operand stages + the dZ store staging
+template <bool BWD> struct PairMem {
+  static constexpr int STAGES = BWD ? 3 : 4;
+  static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256;
+};
 template <int S> struct PairCfg {
   static constexpr int EPI_WARPS = (S <= 20) ? 12 : 8;
   static constexpr int PARTS = EPI_WARPS / 4;               // epilogue warps per TMEM lane quadrant
@@ -41,7 +47,6 @@ template <int S> struct PairCfg {
   static constexpr int NSEG_MAX = 128 / S;
   static constexpr int SLOTS = (NSEG_MAX + PARTS - 1) / PARTS;
 };
-constexpr int PAIR_SMEM_BYTES = PAIR_STAGES * PAIR_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 
 struct HeadParams {
   int M, halfM, rowsB;      // rows total; rows of the first half (= second half's row offset); valid rows in 2nd half
@@ -62,8 +67,8 @@ struct HeadParams {
 };
 
 struct PairSmem {
-  uint64_t full[PAIR_STAGES];
-  uint64_t empty[PAIR_STAGES];
+  uint64_t full[PAIR_MAX_STAGES];
+  uint64_t empty[PAIR_MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
@@ -130,16 +135,17 @@ __device__ __forceinline__ void pool_segment(const float* s, bool valid, int v_r
   }
 }
 
+// dZ values of one (row, segment) -> the row's slot in the 128B-swizzled staging boxes of its view
+// (two [128 rows x 64 cols] boxes per view); col_byte = byte offset of the segment inside the 256-byte tile row.
 template <int S>
-__device__ __forceinline__ void store_dz(__nv_bfloat16* dst, const float* d) {
-  // dst is 8-byte aligned: row pitch P_pad*2 (multiple of 256) + column offset j*S*2 with S % 4 == 0
-  uint2* p = reinterpret_cast<uint2*>(dst);
+__device__ __forceinline__ void stage_dz(uint8_t* view_stage, int row, int col_byte, const float* d) {
 #pragma unroll
   for (int i = 0; i < S / 4; ++i) {
+    const int byte = col_byte + 8 * i;
     uint2 v;
     v.x = pack_bf16x2(d[4 * i + 0], d[4 * i + 1]);
     v.y = pack_bf16x2(d[4 * i + 2], d[4 * i + 3]);
-    p[i] = v;
+    *reinterpret_cast<uint2*>(view_stage + (byte >> 7) * (TILE_M * 128) + swz128(row, (byte & 127) >> 4) + (byte & 15)) = v;
   }
 }
 
@@ -199,7 +205,9 @@ __device__ __forceinline__ void add_scatter(float* g, const ScatEntries<S>& se, 
 template <int S, bool BWD>
 __global__ void __launch_bounds__(PairCfg<S>::THREADS, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                 const __grid_constant__ CUtensorMap tmap_dz1, const __grid_constant__ CUtensorMap tmap_dz2,
                  const HeadParams p) {
+  constexpr int PAIR_STAGES = PairMem<BWD>::STAGES;
   static_assert(S % 4 == 0 && S >= 8 && S <= 40, "segment class");
   constexpr int NSEG_MAX = PairCfg<S>::NSEG_MAX;
   constexpr int SLOTS = PairCfg<S>::SLOTS;
@@ -207,7 +215,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  PairSmem* sb = reinterpret_cast<PairSmem*>(smem + PAIR_STAGES * PAIR_STAGE_BYTES);
+  uint8_t* dzstage = smem + PAIR_STAGES * PAIR_STAGE_BYTES;     // backward only: view 1 boxes, then view 2 boxes
+  PairSmem* sb = reinterpret_cast<PairSmem*>(dzstage + (BWD ? PAIR_DZ_STAGE_BYTES : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -374,6 +383,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_wait(&sb->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * (2 * TILE_N);
+      if constexpr (BWD) {
+        if (warp == 4 && lane == 0) tma_store_wait_read();       // previous item's dZ has left the staging buffer
+        named_bar_sync(1, 32 * PairCfg<S>::EPI_WARPS);
+      }
       if (my_cnt == 0) {          // nothing to read from this stage: release it at once
         tc_fence_before();
         __syncwarp();
@@ -421,7 +434,6 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
                               p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff, p.P);
           } else {
             const float ca = seg_aux[js] * __frcp_rn(ip + 1e-12f);
-            const int col0 = (p.tile_begin + nt) * TILE_N + j * S;
             {
               float g[S];
 #pragma unroll
@@ -433,7 +445,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = s1[i] * (g[i] - dot) * p.inv_tau;
-              if (valid_a) store_dz<S>(p.dz + (size_t)row_a * p.P_pad + col0, g);
+              stage_dz<S>(dzstage, quad * 32 + lane, 2 * j * S, g);
             }
             {
               float g[S];
@@ -446,7 +458,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = s2[i] * (g[i] - dot) * p.inv_tau;
-              if (valid_b) store_dz<S>(p.dz + (size_t)(p.halfM + row_a) * p.P_pad + col0, g);
+              stage_dz<S>(dzstage + PAIR_DZ_STAGE_BYTES / 2, quad * 32 + lane, 2 * j * S, g);
             }
           }
         }
@@ -464,19 +476,36 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
         }
       } else {
-        // zero the padding columns [nseg*S, 128) of this tile's dZ rows (the dX GEMM reads them)
+        // zero the padding columns [nseg*S, 128) of the staged rows (the dX GEMM reads all P_pad columns), then
+        // one elected thread writes both views' tiles with TMA bulk stores: full 128-byte lines, rows clipped at
+        // the end of each view half by the two tensor maps
         if (part == 0) {
-          const int c_begin = nseg * S;
-          const int col0 = (p.tile_begin + nt) * TILE_N;
-          for (int c = c_begin; c < TILE_N; c += 4) {
-            if (valid_a) *reinterpret_cast<uint2*>(p.dz + (size_t)row_a * p.P_pad + col0 + c) = make_uint2(0u, 0u);
-            if (valid_b)
-              *reinterpret_cast<uint2*>(p.dz + (size_t)(p.halfM + row_a) * p.P_pad + col0 + c) = make_uint2(0u, 0u);
+          const int r = quad * 32 + lane;
+          for (int byte = 2 * nseg * S; byte < 2 * TILE_N; byte += 8) {
+            const uint32_t off = (byte >> 7) * (TILE_M * 128) + swz128(r, (byte & 127) >> 4) + (byte & 15);
+            *reinterpret_cast<uint2*>(dzstage + off) = make_uint2(0u, 0u);
+            *reinterpret_cast<uint2*>(dzstage + PAIR_DZ_STAGE_BYTES / 2 + off) = make_uint2(0u, 0u);
           }
+        }
+        fence_proxy_async();
+        named_bar_sync(1, 32 * PairCfg<S>::EPI_WARPS);
+        if (warp == 4 && lane == 0) {
+          const int col0 = (p.tile_begin + nt) * TILE_N;
+          const int row0 = mt * TILE_M;
+#pragma unroll
+          for (int b = 0; b < 2; ++b) {
+            tma_store_2d(&tmap_dz1, dzstage + b * (TILE_M * 128), col0 + 64 * b, row0);
+            if (p.rowsB > 0)
+              tma_store_2d(&tmap_dz2, dzstage + PAIR_DZ_STAGE_BYTES / 2 + b * (TILE_M * 128), col0 + 64 * b, row0);
+          }
+          tma_store_commit();
         }
       }
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    if constexpr (BWD) {
+      if (warp == 4 && lane == 0) tma_store_wait_all();
     }
   }
 

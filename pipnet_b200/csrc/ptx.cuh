@@ -87,6 +87,20 @@ __device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map
       : "memory");
 }
 
+// 2D tiled store, shared -> global (bulk async group).  The smem tile must be in the box layout of the tensor map
+// (128B-swizzled rows here); out-of-bounds parts of the box are clipped by the hardware.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all committed bulk stores of this thread have finished READING shared memory (the staging buffer is reusable)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// byte offset of 16-byte chunk `chunk` of row `row` inside a 128B-swizzled [rows x 128 B] box
+__device__ __forceinline__ uint32_t swz128(int row, int chunk) { return uint32_t(row) * 128u + (uint32_t(chunk ^ (row & 7)) << 4); }
+
 // ---------------------------------------------------------------- clusters
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
