@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HCOMP_ABI_VERSION 2
+#define HCOMP_ABI_VERSION 3
 #define HCOMP_TILE_INTS 52
 #define HCOMP_TILE_COLS 128
 #define HCOMP_MAX_SEGS 16
@@ -58,12 +58,25 @@ int hcomp_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 long long hcomp_launch_count(void);
 
+/* Operand precision of the projection GEMM (K1 / K5):
+ *   HCOMP_PREC_BF16   bf16 operands, fp32 accumulate (<= 2e-2 relative on pooled scores / losses for fp32 inputs)
+ *   HCOMP_PREC_FP32X3 fp32-accurate: every fp32 operand is split into three bf16 terms (hi+mid+lo = 24 bits) and the six
+ *                     leading cross products are accumulated in fp32 by the same tcgen05 kernel (<= 1e-5 relative, 6x the
+ *                     MMA work).  x / wp then point at 3 stacked planes: x[3*M, C] (hcomp_split3_f32) and
+ *                     wp[3*P_pad, C] (hcomp_pack_weights_split3); plane 0 alone is the plain bf16 operand. */
+#define HCOMP_PREC_BF16 0
+#define HCOMP_PREC_FP32X3 1
+
 /* ---- operand preparation -------------------------------------------------------------------- */
 /* fp32 add-on kernels (flat [P,C]; reference: nn.Conv2d weights built at pipnet/pipnet.py:1207) ->
  * bf16 tile-padded [P_pad,C]; row_map[P_pad] gives the flat row of each padded row or -1. */
 int hcomp_pack_weights(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp_bf16, void* stream);
 /* channels-last fp32 features -> bf16 rows (ConvNeXt-26 output is NHWC in memory). n % 8 == 0. */
 int hcomp_cast_f32_to_bf16(const float* src, void* dst_bf16, long long n, void* stream);
+/* fp32 rows -> 3 stacked bf16 planes dst[3][n] (hi, mid, lo) for HCOMP_PREC_FP32X3. */
+int hcomp_split3_f32(const float* src, void* dst_bf16_3planes, long long n, void* stream);
+/* fp32 add-on kernels -> 3 stacked tile-padded bf16 planes wp3[3][P_pad, C] for HCOMP_PREC_FP32X3. */
+int hcomp_pack_weights_split3(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp3_bf16, void* stream);
 /* NCHW-contiguous features (ResNet) -> bf16 rows [V*HW, C]. */
 int hcomp_nchw_to_rows_bf16(const void* src, int src_is_bf16, int V, int C, int HW, void* dst_bf16, void* stream);
 /* tgt[V,N], desc[V_first,N], n_desc[N] from labels (pipnet/train.py:934-937). ys is int64[V]. */
@@ -77,7 +90,7 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
  * pooled_packed[V,P] and align_sum[N] are cleared by the call.  desc/align_sum may be NULL. */
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
-                                int P_pad, int n_nodes, float tau, const uint8_t* desc,
+                                int P_pad, int n_nodes, float tau, int precision, const uint8_t* desc,
                                 unsigned long long* pooled_packed, double* align_sum, void* stream);
 /* packed -> pooled fp32 [V,P] + argmax int32 [V,P] (flat h*W+w, first occurrence; pipnet/pipnet.py:24-25);
  * thresh > 0 applies the inference rule pooled < thresh -> 0 (pipnet/pipnet.py:168-169). */
@@ -91,7 +104,7 @@ int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, 
  * g_align (per node upstream gradient), desc may be NULL.  dz: bf16 [V*HW, P_pad], fully written. */
 int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host, const int32_t* tiles_dev,
                       int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau,
-                      const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
+                      int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
                       void* dz_bf16, void* stream);
 /* dX[rows,C] (bf16) = dZ[rows,P_pad] * Wp[P_pad,C]. */

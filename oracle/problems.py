@@ -27,7 +27,8 @@ class Problem:
     classifier weights N(1, 0.1) on each child's own prototype slice and -0.5 elsewhere
     (pipnet/pipnet.py:1026, :1235-1248), features N(0,1) rounded to bf16 (the GEMM operand type)."""
 
-    def __init__(self, tree, C, H, B, *, seed=0, num_features=0, per_child=0, paired=True, V=None, feat_scale=1.0):
+    def __init__(self, tree, C, H, B, *, seed=0, num_features=0, per_child=0, paired=True, V=None, feat_scale=1.0,
+                 round_bf16=True):
         self.root = make_tree(tree, num_features=num_features, per_child=per_child)
         self.layout = build_layout(self.root)
         L = self.layout
@@ -38,7 +39,8 @@ class Problem:
         self.w = {}
         for name, pn in zip(L.node_names, L.P_n):
             bound = float(np.sqrt(6.0 / (C + int(pn))))
-            self.w[name] = bf16_round((torch.rand(int(pn), C, generator=g, dtype=torch.float64) * 2 - 1) * bound)
+            w = ((torch.rand(int(pn), C, generator=g, dtype=torch.float64) * 2 - 1) * bound)
+            self.w[name] = bf16_round(w) if round_bf16 else w.float().double()
         self.wc = {}
         for node in self.root.nodes_with_children():
             pn, cn = node.num_protos, node.num_children()
@@ -52,7 +54,8 @@ class Problem:
                     w[lab, end:] = -0.5
                     start = end
             self.wc[node.name] = w.float().double()
-        self.x = bf16_round(torch.randn(self.V, C, H, H, generator=g, dtype=torch.float64) * feat_scale)
+        x = torch.randn(self.V, C, H, H, generator=g, dtype=torch.float64) * feat_scale
+        self.x = bf16_round(x) if round_bf16 else x.float().double()
         ys = torch.randint(0, L.L, (self.V_first,), generator=g)
         self.ys = torch.cat([ys, ys])[: self.V] if paired else torch.randint(0, L.L, (self.V,), generator=g)
         self.label2name = {i: n for i, n in enumerate(L.leaf_names)}

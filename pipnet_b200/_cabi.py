@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhcomp_head.so')
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class HcompError(RuntimeError):
@@ -38,10 +38,12 @@ SIGNATURES = {
     'hcomp_cast_f32_to_bf16': [_p, _p, _ll, _p],
     'hcomp_nchw_to_rows_bf16': [_p, _i, _i, _i, _i, _p, _p],
     'hcomp_label_tables': [_p, _T, _i, _i, _p, _p, _p, _p],
-    'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p],
+    'hcomp_split3_f32': [_p, _p, _ll, _p],
+    'hcomp_pack_weights_split3': [_p, _p, _i, _i, _p, _p],
+    'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p],
     'hcomp_unpack_pool': [_p, _ll, _f, _p, _p, _p],
     'hcomp_align_finalize': [_p, _p, _i, _i, _p, _p],
-    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_head_bwd_dx': [_p, _p, _ll, _i, _i, _p, _p],
     'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p],
     'hcomp_classifier_fwd': [_p, _p, _p, _T, _i, _p, _p],

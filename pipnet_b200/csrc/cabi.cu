@@ -152,7 +152,10 @@ int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, con
 // Shared driver of K1 / K5: one launch per segment class (tiles are sorted by class).
 template <bool BWD>
 int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int32_t* tiles_dev, int n_tiles, int V,
-             int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau, hc::HeadParams base, cudaStream_t st) {
+             int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau, int precision, hc::HeadParams base,
+             cudaStream_t st) {
+  if (precision != HCOMP_PREC_BF16 && precision != HCOMP_PREC_FP32X3) return fail(HCOMP_E_ARG, "unknown precision %d", precision);
+  const int split = (precision == HCOMP_PREC_FP32X3) ? 6 : 1;   // x / wp hold 3 stacked bf16 split planes
   DevInfo di;
   if (int e = dev_info(&di)) return e;
   if (V <= 0 || V_first <= 0 || V_first > V || V - V_first > V_first) return fail(HCOMP_E_ARG, "bad view split V=%d V_first=%d", V, V_first);
@@ -162,9 +165,11 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
   const long long M = (long long)V * HW;
   if (M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
+  const int planes = split > 1 ? 3 : 1;
+  if (planes * M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
   CUtensorMap tx, tw;
-  if (int e = make_tmap(&tx, x, C, M, C, hc::KBLK, hc::TILE_M)) return e;
-  if (int e = make_tmap(&tw, wp, C, P_pad, C, hc::KBLK, hc::TILE_N)) return e;
+  if (int e = make_tmap(&tx, x, C, planes * M, C, hc::KBLK, hc::TILE_M)) return e;
+  if (int e = make_tmap(&tw, wp, C, (unsigned long long)planes * P_pad, C, hc::KBLK, hc::TILE_N)) return e;
   hc::HeadParams p = base;
   p.M = int(M);
   p.halfM = V_first * HW;
@@ -181,7 +186,8 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
     }
   }
   p.HW = HW; p.C = C; p.P = P; p.P_pad = P_pad;
-  p.num_k_blocks = cdiv(C, hc::KBLK);
+  p.split_terms = split;
+  p.num_k_blocks = cdiv(C, hc::KBLK) * split;
   p.num_m_tiles = cdiv(p.halfM, hc::TILE_M);
   p.n_nodes = n_nodes;
   p.imgs_first = V_first;
@@ -273,6 +279,21 @@ inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
 extern "C" {
 
 int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
+int hcomp_split3_f32(const float* src, void* dst_bf16_3planes, long long n, void* stream) {
+  int grid = blocks(n, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  hc::split3_f32_kernel<<<grid, 256, 0, S(stream)>>>(src, reinterpret_cast<__nv_bfloat16*>(dst_bf16_3planes), n);
+  HC_LAUNCH_CHECK("split3_f32");
+  return 0;
+}
+int hcomp_pack_weights_split3(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp3_bf16, void* stream) {
+  const long long n = (long long)P_pad * C;
+  hc::pack_weights_split3_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(w_flat, row_map, P_pad, C,
+                                                                       reinterpret_cast<__nv_bfloat16*>(wp3_bf16));
+  HC_LAUNCH_CHECK("pack_weights_split3");
+  return 0;
+}
 
 const char* hcomp_last_error(void) { return g_err; }
 long long hcomp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
@@ -325,7 +346,7 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
 
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
-                                int P_pad, int n_nodes, float tau, const uint8_t* desc,
+                                int P_pad, int n_nodes, float tau, int precision, const uint8_t* desc,
                                 unsigned long long* pooled_packed, double* align_sum, void* stream) {
   hc::HeadParams p{};
   p.pooled_packed = pooled_packed;
@@ -333,8 +354,8 @@ int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const i
   p.desc = (align_sum != nullptr) ? desc : nullptr;
   HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
   if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
-  return run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau, p,
-                         S(stream));
+  return run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
+                         precision, p, S(stream));
 }
 
 int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
@@ -352,7 +373,7 @@ int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, 
 
 int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host, const int32_t* tiles_dev,
                       int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau,
-                      const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
+                      int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
                       void* dz_bf16, void* stream) {
   const long long n = (long long)V * P;
@@ -368,8 +389,8 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
     HC_LAUNCH_CHECK("align_coef");
     p.coef_align = coef_ws;
   }
-  return run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau, p,
-                        S(stream));
+  return run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
+                        precision, p, S(stream));
 }
 
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wp_bf16, long long rows, int P_pad, int C, void* dx_bf16,

@@ -54,6 +54,9 @@ struct HeadParams {
   int num_k_blocks;
   int tile_begin, num_tiles, num_m_tiles;
   int n_nodes, imgs_first;  // images in the first half (= B for paired training batches)
+  // fp32-accurate mode: operands are 3-way bf16 splits stacked along rows (X: [3*M, C], Wp: [3*P_pad, C]);
+  // the k loop runs over `split_terms` (1 or 6) cross products lo*hi, hi*lo, mid*mid, mid*hi, hi*mid, hi*hi
+  int split_terms;
   float scale_log2, inv_tau;
   const int32_t* tiles;
   // forward
@@ -256,13 +259,23 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int row_a = mt * TILE_M;
         const int row_b = p.halfM + row_a;
         const int row_w = (p.tile_begin + nt) * TILE_N;
+        const int kb_per_term = p.num_k_blocks / p.split_terms;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&sb->empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * PAIR_STAGE_BYTES;
           mbar_arrive_expect_tx(&sb->full[stage], PAIR_STAGE_BYTES);
-          tma_load_2d(st, &tmap_x, &sb->full[stage], kb * KBLK, row_a);
-          tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kb * KBLK, row_b);
-          tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kb * KBLK, row_w);
+          int kc = kb, xo = 0, wo = 0;
+          if (p.split_terms > 1) {            // term -> (feature split, prototype split): packed 2-bit pairs
+            const int term = kb / kb_per_term;
+            kc = kb - term * kb_per_term;
+            // smallest terms first: the tensor core's fp32 accumulation truncates, so only the last (hi*hi) pass
+            // should run at full accumulator magnitude
+            xo = ((0x001102 >> (4 * term)) & 3) * p.M;          // lo, hi, mid, mid, hi, hi
+            wo = ((0x010120 >> (4 * term)) & 3) * p.P_pad;      // hi, lo, mid, hi, mid, hi
+          }
+          tma_load_2d(st, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_a);
+          tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_b);
+          tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kc * KBLK, wo + row_w);
           if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
         }
       }

@@ -57,6 +57,34 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ src, __nv_bfloat1
   }
 }
 
+// fp32 -> three bf16 terms hi + mid + lo (24 significant bits), written as stacked planes dst[t*n + i].
+// Used by the fp32-accurate projection: X*W ~ sum of six bf16 cross products accumulated in fp32.
+__device__ __forceinline__ void split3(float x, __nv_bfloat16& a, __nv_bfloat16& b, __nv_bfloat16& c) {
+  a = __float2bfloat16_rn(x);
+  const float r1 = x - __bfloat162float(a);
+  b = __float2bfloat16_rn(r1);
+  c = __float2bfloat16_rn(r1 - __bfloat162float(b));
+}
+__global__ void split3_f32_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    __nv_bfloat16 a, b, c;
+    split3(src[i], a, b, c);
+    dst[i] = a; dst[n + i] = b; dst[2 * n + i] = c;
+  }
+}
+// same for the prototype kernels, combined with the tile padding: Wp3[t*P_pad + r, :] = term t of W[row_map[r], :]
+__global__ void pack_weights_split3_kernel(const float* __restrict__ w, const int32_t* __restrict__ row_map, int P_pad,
+                                           int C, __nv_bfloat16* __restrict__ wp3) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)P_pad * C) return;
+  const int r = int(idx / C), c = int(idx - (long long)r * C);
+  const int src = row_map[r];
+  __nv_bfloat16 a = __float2bfloat16(0.f), b = a, d = a;
+  if (src >= 0) split3(w[(size_t)src * C + c], a, b, d);
+  const size_t plane = (size_t)P_pad * C;
+  wp3[idx] = a; wp3[plane + idx] = b; wp3[2 * plane + idx] = d;
+}
+
 // NCHW fp32/bf16 -> NHWC bf16 rows (ResNet features are NCHW-contiguous).  32x32 smem transpose.
 template <typename T>
 __global__ void nchw_to_rows_bf16_kernel(const T* __restrict__ src, __nv_bfloat16* __restrict__ dst, int C, int HW) {

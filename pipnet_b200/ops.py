@@ -135,13 +135,31 @@ def feature_rows(features: torch.Tensor):
     return out
 
 
-def pack_weights(w_flat: torch.Tensor, dl: DeviceLayout) -> torch.Tensor:
+PREC_BF16, PREC_FP32X3 = 0, 1
+
+
+def pack_weights(w_flat: torch.Tensor, dl: DeviceLayout, precision=PREC_BF16) -> torch.Tensor:
+    """fp32 flat kernels [P,C] -> tile-padded bf16 [P_pad,C] (or 3 stacked split planes in fp32-accurate mode)"""
     _require_cuda(w_flat, 'prototype kernels')
     assert w_flat.dtype == torch.float32 and w_flat.is_contiguous() and w_flat.shape[0] == dl.P
     Cc = w_flat.shape[1]
+    if precision == PREC_FP32X3:
+        wp = torch.empty(3 * dl.P_pad, Cc, device=w_flat.device, dtype=torch.bfloat16)
+        call('hcomp_pack_weights_split3', ptr(w_flat), ptr(dl.row_map), dl.P_pad, Cc, ptr(wp), _stream())
+        return wp
     wp = torch.empty(dl.P_pad, Cc, device=w_flat.device, dtype=torch.bfloat16)
     call('hcomp_pack_weights', ptr(w_flat), ptr(dl.row_map), dl.P_pad, Cc, ptr(wp), _stream())
     return wp
+
+
+def feature_rows_split3(features: torch.Tensor) -> torch.Tensor:
+    """fp32 features [V,C,H,W] -> 3 stacked bf16 planes [3*V*H*W, C] (hi, mid, lo) for the fp32-accurate projection"""
+    _require_cuda(features, 'features')
+    V, Cc, H, W = features.shape
+    src = features.float().permute(0, 2, 3, 1).contiguous().view(V * H * W, Cc)
+    out = torch.empty(3 * V * H * W, Cc, device=features.device, dtype=torch.bfloat16)
+    call('hcomp_split3_f32', ptr(src), ptr(out), C.c_longlong(src.numel()), _stream())
+    return out
 
 
 class LabelTables:
@@ -160,15 +178,16 @@ class LabelTables:
 
 
 # --------------------------------------------------------------------------- raw kernels (no autograd)
-def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, labels: Optional[LabelTables], thresh=0.0):
+def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, labels: Optional[LabelTables], thresh=0.0,
+                          precision=PREC_BF16):
     Cc = x_rows.shape[1]
     dev = x_rows.device
     packed = torch.empty(V * dl.P, device=dev, dtype=torch.int64)
     align_sum = torch.empty(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
     tok = PROFILE.start('k1_proj_softmax_pool_fwd')
     call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
-         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), ptr(labels.desc) if labels is not None else None, ptr(packed),
-         ptr(align_sum), _stream())
+         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), ptr(labels.desc) if labels is not None else None,
+         ptr(packed), ptr(align_sum), _stream())
     PROFILE.stop(tok)
     pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)
     argmax = torch.empty(V, dl.P, device=dev, dtype=torch.int32)
@@ -181,7 +200,7 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
 
 
 def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
-                      pooled=None, thresh=0.0, need_dx=True, need_dw=True):
+                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16):
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
@@ -191,7 +210,7 @@ def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax,
     use_align = labels is not None and g_align is not None
     tok = PROFILE.start('k5_bwd_dz')
     call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
-         dl.P, dl.P_pad, dl.N, float(tau), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
+         dl.P, dl.P_pad, dl.N, float(tau), int(precision), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
          ptr(labels.desc) if use_align else None, ptr(labels.n_desc) if use_align else None,
          ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), _stream())
     PROFILE.stop(tok)
@@ -239,13 +258,16 @@ class HeadProjPool(torch.autograd.Function):
     Saves only the bf16 operands + argmax: the V x P x H x W map is recomputed tile by tile in backward."""
 
     @staticmethod
-    def forward(ctx, features, w_flat, dl: DeviceLayout, V_first, tau, labels, thresh):
+    def forward(ctx, features, w_flat, dl: DeviceLayout, V_first, tau, labels, thresh, precision=PREC_BF16):
         V, Cc, H, W = features.shape
         HW = H * W
-        x_rows = feature_rows(features.detach())
-        wp = pack_weights(w_flat.detach().contiguous(), dl)
-        pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh)
-        ctx.dl, ctx.geom, ctx.labels, ctx.thresh = dl, (V, V_first, H, W, Cc, tau), labels, thresh
+        if precision == PREC_FP32X3:
+            x_rows = feature_rows_split3(features.detach())
+        else:
+            x_rows = feature_rows(features.detach())
+        wp = pack_weights(w_flat.detach().contiguous(), dl, precision)
+        pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision)
+        ctx.dl, ctx.geom, ctx.labels, ctx.thresh, ctx.precision = dl, (V, V_first, H, W, Cc, tau), labels, thresh, precision
         ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
         ctx.save_for_backward(x_rows, wp, argmax, pooled)
         ctx.mark_non_differentiable(argmax)
@@ -265,14 +287,15 @@ class HeadProjPool(torch.autograd.Function):
         if g_align is not None:
             g_align = g_align.contiguous().float()
         dx, dw, _ = head_backward_raw(x_rows, wp, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
-                                      pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw)
+                                      pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw,
+                                      precision=ctx.precision)
         d_feat = None
         if need_dx:
             dtype, _cl = ctx.feat_meta
             d_feat = dx.view(V, H, W, Cc).permute(0, 3, 1, 2)     # channels-last view of the row buffer
             if dtype != torch.bfloat16:
                 d_feat = d_feat.to(dtype)
-        return d_feat, dw, None, None, None, None, None
+        return d_feat, dw, None, None, None, None, None, None
 
 
 class NonNegClassifier(torch.autograd.Function):

@@ -240,6 +240,9 @@ class PIPNet(nn.Module):
         self._bias_group = (_FlatGroup([getattr(self, '_' + n + '_classification').bias for n in names])
                             if self._has_cls_bias else None)
         self._dl: Optional[ops.DeviceLayout] = None
+        # 'bf16': bf16 GEMM operands (default, the benchmarked path); 'fp32': fp32-accurate projection (3-way bf16 split
+        # operands, six cross terms through the same tcgen05 kernel) for the <= 1e-5 contract on fp32 inputs
+        self.head_precision = getattr(args, 'head_precision', 'bf16')
         # Column selection of get_joint_distribution, replicating the reference exactly: np.argsort over
         # names_of_joint_distribution() (pipnet/pipnet.py:179-181).  For trees without single-child nodes this is
         # the sorted-leaf order the kernel already produces (None = identity); with a single-child node the
@@ -287,8 +290,9 @@ class PIPNet(nn.Module):
             V_first = labels.V_first if labels is not None else (V + 1) // 2
         x = features.detach() if getattr(self.args, 'sg_before_protos', 'n') == 'y' else features
         w_flat = self.flat_prototype_kernels()
+        prec = ops.PREC_FP32X3 if self.head_precision == 'fp32' else ops.PREC_BF16
         pooled, align, argmax = ops.HeadProjPool.apply(x, w_flat, dl, V_first, self.softmax_tau, labels,
-                                                       0.1 if inference else 0.0)
+                                                       0.1 if inference else 0.0, prec)
         return pooled, align, argmax, dl
 
     def classify(self, pooled_flat: Tensor, dl: ops.DeviceLayout) -> Tensor:

@@ -111,3 +111,64 @@ def test_backward_dx_dw(case):
     assert rel_err(feats.grad, x.grad) <= 2e-2, f'dX rel err {rel_err(feats.grad, x.grad)}'
     assert rel_err(w_flat.grad, gw_ref) <= 2e-2, f'dW rel err {rel_err(w_flat.grad, gw_ref)}'
 
+
+
+@pytest.mark.parametrize("case", [("cub08", 64, 6, 4, dict(num_features=20)), ("cub27", 768, 26, 1, dict(num_features=20))],
+                         ids=["cub08-small", "cub27-convnext26"])
+def test_fp32_accurate_mode_on_fp32_inputs(case):
+    """Genuine fp32 features / kernels (NOT bf16-representable): the fp32-accurate projection (3-way bf16 split,
+    six cross terms through the same tcgen05 kernel) meets the 1e-5 contract; plain bf16 operands meet 2e-2."""
+    from pipnet_b200 import ops
+    tree, C, H, B, kw = case
+    pb = Problem(tree, C, H, B, seed=13, round_bf16=False, **kw)
+    dl = ops.DeviceLayout(pb.layout, 'cuda')
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    feats = pb.features('cuda', dtype=torch.float32)
+    w_flat = pb.w_flat('cuda')
+    proto, pooled_ref, argmax_ref, _ = _oracle_forward(pb)
+    pr, ar = pb.cat_nodes(pooled_ref), pb.cat_nodes(argmax_ref)
+    masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
+    errs = {}
+    for name, prec in (("fp32", ops.PREC_FP32X3), ("bf16", ops.PREC_BF16)):
+        pooled, align, argmax = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0, prec)
+        torch.cuda.synchronize()
+        errs[name] = rel_err(pooled, pr)
+        a_err = 0.0
+        for i, n in enumerate(pb.layout.node_names):
+            if masks[n].any():
+                ref = float(ho.align_pf_term(proto[n], masks[n]))
+                a_err = max(a_err, abs(float(align[i]) - ref) / max(1.0, abs(ref)))
+        errs[name + "_align"] = a_err
+        if name == "fp32":
+            proto_flat = torch.cat([proto[n].flatten(2) for n in pb.layout.node_names], dim=1)
+            nbad, gaps = argmax_report(argmax, ar, proto_flat)
+            assert nbad == 0, f'{nbad} argmax mismatches, relative gaps {gaps[:8]}'
+    assert errs["fp32"] <= 1e-5 and errs["fp32_align"] <= 1e-5, errs
+    assert errs["bf16"] <= 2e-2 and errs["bf16_align"] <= 2e-2, errs
+    assert errs["bf16"] > errs["fp32"], errs
+
+
+def test_fp32_accurate_mode_backward_runs():
+    from pipnet_b200 import ops
+    pb = Problem("cub08", 64, 6, 3, seed=17, num_features=20, round_bf16=False)
+    dl = ops.DeviceLayout(pb.layout, 'cuda')
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    feats = pb.features('cuda', dtype=torch.float32).requires_grad_(True)
+    w_flat = pb.w_flat('cuda').requires_grad_(True)
+    g = torch.Generator().manual_seed(1)
+    G = torch.randn(pb.V, pb.layout.P, generator=g, dtype=torch.float64)
+    pooled, align, _ = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0, ops.PREC_FP32X3)
+    ((pooled.double() * G.cuda()).sum() + align.double().sum()).backward()
+    torch.cuda.synchronize()
+    x = pb.x.clone().requires_grad_(True)
+    w = {k: v.clone().requires_grad_(True) for k, v in pb.w.items()}
+    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root)
+    masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
+    ref = (pb.cat_nodes(pooled_ref) * G).sum()
+    for n in pb.layout.node_names:
+        if masks[n].any():
+            ref = ref + ho.align_pf_term(proto[n], masks[n])
+    ref.backward()
+    assert feats.grad.dtype == torch.float32
+    assert rel_err(feats.grad, x.grad) <= 2e-2
+    assert rel_err(w_flat.grad, torch.cat([w[n].grad for n in pb.layout.node_names])) <= 2e-2
