@@ -38,7 +38,7 @@ constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both
 // forward: 4 operand stages; backward: 3 operand stages + the dZ store staging
 template <bool BWD> struct PairMem {
   static constexpr int STAGES = BWD ? 3 : 4;
-  static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + 4096;
 };
 template <int S> struct PairCfg {
   static constexpr int EPI_WARPS = (S <= 20) ? 12 : 8;
@@ -75,6 +75,8 @@ struct PairSmem {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  uint32_t pad_[3];
+  uint4 pool_x[12][2][10];   // per epilogue warp: column maxima [40] and first-lane ballots [40] (forward fast path)
 };
 
 template <int S, bool MASK>
@@ -136,6 +138,39 @@ __device__ __forceinline__ void pool_segment(const float* s, bool valid, int v_r
       atomicMax(dst + 32 + lane, ((unsigned long long)m1 << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
     }
   }
+}
+
+// Fast path of pool_segment for the common case: all 32 rows of the warp are valid and belong to ONE image.
+// Per column: one REDUX.MAX on the float bits, one compare, one ballot; the per-column results (uniform across
+// lanes) are published through a 320-byte per-warp smem table so that lane c can pick column c's pair without a
+// chain of predicated selects.
+template <int S>
+__device__ __forceinline__ void pool_segment_fast(const float* s, int loc_first, int len, int lane, uint4* xch /* [2][10] */,
+                                                  unsigned long long* dst) {
+  uint32_t mx[S], bal[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) mx[i] = redux_max_u32(__float_as_uint(s[i]));
+#pragma unroll
+  for (int i = 0; i < S; ++i) bal[i] = __ballot_sync(0xffffffffu, __float_as_uint(s[i]) == mx[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i) {
+      xch[i] = make_uint4(mx[4 * i], mx[4 * i + 1], mx[4 * i + 2], mx[4 * i + 3]);
+      xch[10 + i] = make_uint4(bal[4 * i], bal[4 * i + 1], bal[4 * i + 2], bal[4 * i + 3]);
+    }
+  }
+  __syncwarp();
+  const uint32_t* xm = reinterpret_cast<const uint32_t*>(xch);
+  const uint32_t* xb = xm + 40;
+#pragma unroll
+  for (int h = 0; h < (S + 31) / 32; ++h) {
+    const int c = h * 32 + lane;
+    if (c < len) {
+      const uint32_t loc = loc_first + (__ffs(xb[c]) - 1);
+      atomicMax(dst + c, ((unsigned long long)xm[c] << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
+    }
+  }
+  __syncwarp();      // table is rewritten by the next call
 }
 
 // dZ values of one (row, segment) -> the row's slot in the 128B-swizzled staging boxes of its view
@@ -439,10 +474,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
           if constexpr (!BWD) {
             if (seg_aux[js] != 0.f) align_acc[js] = -__logf(ip + 1e-12f);
-            if (__ballot_sync(0xffffffffu, valid_a) != 0u)
+            uint4* xch = &sb->pool_x[warp - 4][0][0];
+            if (nv_a == 32 && !has_boundary)
+              pool_segment_fast<S>(s1, loc_first, len, lane, xch, p.pooled_packed + (size_t)v_first * p.P + poff);
+            else if (nv_a > 0)
               pool_segment<S>(s1, valid_a, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
                               p.pooled_packed + (size_t)v_first * p.P + poff, p.P);
-            if (__ballot_sync(0xffffffffu, valid_b) != 0u)
+            if (nv_b == 32 && !has_boundary)
+              pool_segment_fast<S>(s2, loc_first, len, lane, xch, p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff);
+            else if (nv_b > 0)
               pool_segment<S>(s2, valid_b, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
                               p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff, p.P);
           } else {
