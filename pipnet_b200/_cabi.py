@@ -54,7 +54,7 @@ SIGNATURES = {
     'hcomp_materialize_map': [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }
-EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats'] + list(SIGNATURES)
+EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats', 'hcomp_set_cta_pair'] + list(SIGNATURES)
 
 _lib = None
 
@@ -74,6 +74,8 @@ def lib():
     L.hcomp_launch_count.restype = C.c_longlong
     L.hcomp_head_losses_ws_floats.restype = C.c_longlong
     L.hcomp_head_losses_ws_floats.argtypes = [_T]
+    L.hcomp_set_cta_pair.restype = C.c_int
+    L.hcomp_set_cta_pair.argtypes = [C.c_int]
     for name, args in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = args

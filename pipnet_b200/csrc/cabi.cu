@@ -11,6 +11,7 @@
 #include <mutex>
 
 #include "gemm_tc.cuh"
+#include "gemm2_tc.cuh"
 #include "head_pair.cuh"
 #include "small_kernels.cuh"
 
@@ -18,6 +19,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+bool g_no_pair = false;               // hcomp_set_cta_pair(0): 1-CTA GEMM tiles only (A/B measurements, tests)
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -227,6 +229,23 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
   return launch_persistent(kern, "gemm_tc_kernel", 1, workers, hc::G_THREADS, SMEM, st, ta, tb, to, p);
 }
 
+template <bool A_MN, bool B_MN, int OUT>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const hc::GemmParams& p, int sms,
+                 cudaStream_t st) {
+  auto kern = hc::gemm2_tc_kernel<A_MN, B_MN, OUT>;
+  constexpr int SMEM = hc::Gemm2Cfg<OUT>::SMEM_BYTES;
+  static bool attr_done = false;
+  if (!attr_done) {
+    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    attr_done = true;
+  }
+  const int m2 = (p.M + 2 * hc::G_BM - 1) / (2 * hc::G_BM);
+  const int items = m2 * p.num_n_tiles * p.splits;
+  const int slots = sms / 2;
+  const int workers = items < slots ? items : slots;
+  return launch_persistent(kern, "gemm2_tc_kernel", 2, workers, hc::G_THREADS, SMEM, st, ta, tb, to, p);
+}
+
 // D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
 // else [N,K].  splits <= 0 picks a split-K factor that fills the GPU (only meaningful for OUT_RED_F32).
 int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool a_mn, bool b_mn, int out_mode, int splits,
@@ -237,6 +256,8 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   if (M > 0x7fffffffLL || K > 0x7fffffffLL) return fail(HCOMP_E_ARG, "GEMM dimension overflow");
   if ((out_mode == hc::OUT_BF16 && (N % 8 || ldo % 8)) || (out_mode != hc::OUT_BF16 && (N % 4 || ldo % 4)))
     return fail(HCOMP_E_ARG, "N=%d / ldo=%lld alignment", N, ldo);
+  // CTA-pair (cta_group::2, 256 x 256 tiles) variant whenever there are at least two 128-row tiles
+  const bool pair = !g_no_pair && M > hc::G_BM;
   CUtensorMap ta, tb, to;
   if (out_mode == hc::OUT_BF16) {          // bf16 output leaves through TMA stores of [128 rows x 64 cols] boxes
     if (int e = make_tmap(&to, out, N, M, ldo, 64, hc::G_BM)) return e;
@@ -246,22 +267,24 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   if (a_mn) { if (int e = make_tmap(&ta, a, M, K, M, 64, 64)) return e; }
   else      { if (int e = make_tmap(&ta, a, K, M, K, hc::G_BK, hc::G_BM)) return e; }
   if (b_mn) { if (int e = make_tmap(&tb, b, N, K, N, 64, 64)) return e; }
-  else      { if (int e = make_tmap(&tb, b, K, N, K, hc::G_BK, hc::G_BN)) return e; }
+  else      { if (int e = make_tmap(&tb, b, K, N, K, hc::G_BK, pair ? hc::G_BN / 2 : hc::G_BN)) return e; }
   hc::GemmParams p{};
   p.M = int(M); p.N = N; p.K = int(K);
   p.num_m_tiles = cdiv(M, hc::G_BM);
   p.num_n_tiles = cdiv(N, hc::G_BN);
   p.num_k_blocks = cdiv(K, hc::G_BK);
-  const int tiles_mn = p.num_m_tiles * p.num_n_tiles;
+  const int tiles_mn = (pair ? cdiv(M, 2 * hc::G_BM) : p.num_m_tiles) * p.num_n_tiles;
   if (out_mode != hc::OUT_RED_F32) splits = 1;
-  if (splits <= 0) splits = di.sms / tiles_mn;
+  if (splits <= 0) splits = (pair ? di.sms / 2 : di.sms) / tiles_mn;
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
   p.splits = cdiv(p.num_k_blocks, p.k_blocks_per_split);
   p.out = out; p.ldo = ldo; p.row_map = row_map;
-#define HC_GEMM_CASE(AM, BM, OM) \
-  if (a_mn == AM && b_mn == BM && out_mode == OM) return launch_gemm<AM, BM, OM>(ta, tb, to, p, di.sms, st);
+#define HC_GEMM_CASE(AM, BM, OM)                                         \
+  if (a_mn == AM && b_mn == BM && out_mode == OM)                        \
+    return pair ? launch_gemm2<AM, BM, OM>(ta, tb, to, p, di.sms, st)    \
+                : launch_gemm<AM, BM, OM>(ta, tb, to, p, di.sms, st);
   HC_GEMM_CASE(false, true, hc::OUT_BF16)      // dX
   HC_GEMM_CASE(true, true, hc::OUT_RED_F32)    // dW
   HC_GEMM_CASE(false, false, hc::OUT_F32)      // self-test: plain K-major GEMM
@@ -279,6 +302,11 @@ inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
 extern "C" {
 
 int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
+int hcomp_set_cta_pair(int on) {
+  const int prev = g_no_pair ? 0 : 1;
+  g_no_pair = (on == 0);
+  return prev;
+}
 int hcomp_split3_f32(const float* src, void* dst_bf16_3planes, long long n, void* stream) {
   int grid = blocks(n, 256);
   if (grid > 148 * 16) grid = 148 * 16;

@@ -6,6 +6,15 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 0], ids=["cta-pair", "single-cta"], autouse=True)
+def cta_pair_mode(request):
+    """every GEMM test runs on the cta_group::2 (256x256, CTA pair) kernels and on the 1-CTA 128x256 ones"""
+    from pipnet_b200 import _cabi
+    prev = _cabi.lib().hcomp_set_cta_pair(request.param)
+    yield request.param
+    _cabi.lib().hcomp_set_cta_pair(prev)
+
+
 def _operands(M, N, K, a_mn, b_mn, seed):
     g = torch.Generator(device='cpu').manual_seed(seed)
     a = torch.randn(M, K, generator=g).to(torch.bfloat16)
