@@ -57,8 +57,8 @@ const char* hcomp_last_error(void);
 int hcomp_num_sms(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 long long hcomp_launch_count(void);
-/* dX / dW GEMMs run as CTA pairs (tcgen05 cta_group::2, 256x256 tiles) by default; 0 selects the 1-CTA 128x256
- * kernels (same results; kept for A/B measurements).  Returns the previous setting. */
+/* K1 / K5 and the dX / dW GEMMs run as CTA pairs (tcgen05 cta_group::2, M = 256 MMAs) by default; 0 selects the
+ * 1-CTA kernels (same results; kept for A/B measurements and tests).  Returns the previous setting. */
 int hcomp_set_cta_pair(int on);
 
 /* Operand precision of the projection GEMM (K1 / K5):

@@ -122,31 +122,33 @@ int launch_persistent(Kern kern, const char* name, int cluster, int workers, int
   return 0;
 }
 
-template <int SEG, bool BWD>
+template <int SEG, bool BWD, bool CG2>
 int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& td1, const CUtensorMap& td2,
                 const hc::HeadParams& p, int sms, cudaStream_t st) {
-  auto kern = hc::head_pair_kernel<SEG, BWD>;
-  constexpr int SMEM = hc::PairMem<BWD>::SMEM_BYTES;
+  auto kern = hc::head_pair_kernel<SEG, BWD, CG2>;
+  constexpr int SMEM = hc::PairMem<BWD, CG2>::SMEM_BYTES;
   static bool attr_done = false;
   if (!attr_done) {
     HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
     attr_done = true;
   }
-  const int items = p.num_m_tiles * p.num_tiles;
-  const int workers = items < sms ? items : sms;
-  return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", 1, workers,
+  constexpr int CL = CG2 ? 2 : 1;
+  const int items = ((p.num_m_tiles + CL - 1) / CL) * p.num_tiles;
+  const int slots = sms / CL;
+  const int workers = items < slots ? items : slots;
+  return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", CL, workers,
                            hc::PairCfg<SEG>::THREADS, SMEM, st, tx, tw, td1, td2, p);
 }
 
-template <bool BWD>
+template <bool BWD, bool CG2>
 int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& td1,
                       const CUtensorMap& td2, const hc::HeadParams& p, int sms, cudaStream_t st) {
   switch (seg) {
-    case 8: return launch_pair<8, BWD>(tx, tw, td1, td2, p, sms, st);
-    case 16: return launch_pair<16, BWD>(tx, tw, td1, td2, p, sms, st);
-    case 20: return launch_pair<20, BWD>(tx, tw, td1, td2, p, sms, st);
-    case 32: return launch_pair<32, BWD>(tx, tw, td1, td2, p, sms, st);
-    case 40: return launch_pair<40, BWD>(tx, tw, td1, td2, p, sms, st);
+    case 8: return launch_pair<8, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
+    case 16: return launch_pair<16, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
+    case 20: return launch_pair<20, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
+    case 32: return launch_pair<32, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
+    case 40: return launch_pair<40, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
     default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40)", seg);
   }
 }
@@ -169,9 +171,10 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   if (M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
   const int planes = split > 1 ? 3 : 1;
   if (planes * M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
-  CUtensorMap tx, tw;
+  CUtensorMap tx, tw, tw_half;          // tw_half: 64-row boxes for the CTA-pair variant (each CTA keeps half a tile)
   if (int e = make_tmap(&tx, x, C, planes * M, C, hc::KBLK, hc::TILE_M)) return e;
   if (int e = make_tmap(&tw, wp, C, (unsigned long long)planes * P_pad, C, hc::KBLK, hc::TILE_N)) return e;
+  if (int e = make_tmap(&tw_half, wp, C, (unsigned long long)planes * P_pad, C, hc::KBLK, hc::TILE_N / 2)) return e;
   hc::HeadParams p = base;
   p.M = int(M);
   p.halfM = V_first * HW;
@@ -208,7 +211,11 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
     }
     p.tile_begin = t;
     p.num_tiles = e - t;
-    if (int err = launch_pair_class<BWD>(seg, tx, tw, td1, td2, p, di.sms, st)) return err;
+    // CTA pairs (cta_group::2) whenever there are at least two pair tiles along M
+    const bool pair = !g_no_pair && p.num_m_tiles >= 2;
+    if (int err = pair ? launch_pair_class<BWD, true>(seg, tx, tw_half, td1, td2, p, di.sms, st)
+                       : launch_pair_class<BWD, false>(seg, tx, tw, td1, td2, p, di.sms, st))
+      return err;
     t = e;
   }
   return 0;

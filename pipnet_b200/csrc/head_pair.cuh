@@ -35,10 +35,14 @@ constexpr int TILE_INTS = 4 + 3 * MAX_SEGS;   // {S, nseg, umma_n, 0, node[16], 
 constexpr int PAIR_STAGE_BYTES = 3 * TILE_M * KBLK * 2;   // A1 + A2 + W = 48 KB
 constexpr int PAIR_MAX_STAGES = 4;
 constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both views' bf16 dZ tiles staged for TMA stores (64 KB)
-// forward: 4 operand stages; backward: 3 operand stages + the dZ store staging
-template <bool BWD> struct PairMem {
+// forward: 4 operand stages; backward: 3 operand stages + the dZ store staging.
+// CG2 (CTA pair, tcgen05 cta_group::2): a cluster of two CTAs takes two neighbouring pair tiles of the same prototype
+// tile and runs M = 256 MMAs; each CTA keeps only HALF of the prototype tile (64 rows, 8 KB) in its shared memory, so
+// an MMA fetches 6 KB of operands per CTA instead of 8 KB (the kernel is bound by that fetch, ~65 B/clk).
+template <bool BWD, bool CG2> struct PairMem {
+  static constexpr int STAGE_BYTES = CG2 ? (2 * TILE_M * KBLK * 2 + (TILE_N / 2) * KBLK * 2) : PAIR_STAGE_BYTES;   // 40 / 48 KB
   static constexpr int STAGES = BWD ? 3 : 4;
-  static constexpr int SMEM_BYTES = STAGES * PAIR_STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + 4096;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + 4096;
 };
 template <int S> struct PairCfg {
   static constexpr int EPI_WARPS = (S <= 20) ? 12 : 8;
@@ -240,12 +244,14 @@ __device__ __forceinline__ void add_scatter(float* g, const ScatEntries<S>& se, 
   }
 }
 
-template <int S, bool BWD>
+template <int S, bool BWD, bool CG2>
 __global__ void __launch_bounds__(PairCfg<S>::THREADS, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_dz1, const __grid_constant__ CUtensorMap tmap_dz2,
                  const HeadParams p) {
-  constexpr int PAIR_STAGES = PairMem<BWD>::STAGES;
+  constexpr int PAIR_STAGES = PairMem<BWD, CG2>::STAGES;
+  constexpr int STAGE_BYTES = PairMem<BWD, CG2>::STAGE_BYTES;
+  constexpr int EPI_WARPS = PairCfg<S>::EPI_WARPS;
   static_assert(S % 4 == 0 && S >= 8 && S <= 40, "segment class");
   constexpr int NSEG_MAX = PairCfg<S>::NSEG_MAX;
   constexpr int SLOTS = PairCfg<S>::SLOTS;
@@ -253,14 +259,18 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* dzstage = smem + PAIR_STAGES * PAIR_STAGE_BYTES;     // backward only: view 1 boxes, then view 2 boxes
+  uint8_t* dzstage = smem + PAIR_STAGES * STAGE_BYTES;          // backward only: view 1 boxes, then view 2 boxes
   PairSmem* sb = reinterpret_cast<PairSmem*>(dzstage + (BWD ? PAIR_DZ_STAGE_BYTES : 0));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  constexpr int CL = CG2 ? 2 : 1;
+  const int crank = CG2 ? int(cluster_ctarank()) : 0;
+  const bool leader = crank == 0;
   const int n_groups = p.num_tiles;
-  const int total_items = p.num_m_tiles * n_groups;
-  const int worker = blockIdx.x, num_workers = gridDim.x;
+  const int m_groups = (p.num_m_tiles + CL - 1) / CL;          // CG2: two pair tiles per cluster item
+  const int total_items = m_groups * n_groups;
+  const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x);
@@ -268,18 +278,22 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < PAIR_STAGES; ++i) {
-      mbar_init(&sb->full[i], 1);
+      mbar_init(&sb->full[i], CL);       // CG2: leader's expect_tx arrive + the peer producer's remote arrive
       mbar_init(&sb->empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sb->tmem_full[i], 1);
-      mbar_init(&sb->tmem_empty[i], PairCfg<S>::EPI_WARPS);   // one arrive per epilogue warp
+      mbar_init(&sb->tmem_empty[i], CL * EPI_WARPS);   // one arrive per epilogue warp (of both CTAs when CG2)
     }
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(&sb->tmem_base);
+  if (warp == 2) {
+    if constexpr (CG2) tmem_alloc_2cta<512>(&sb->tmem_base);
+    else tmem_alloc<512>(&sb->tmem_base);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync();
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
 
@@ -289,16 +303,21 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int item = worker; item < total_items; item += num_workers) {
-        const int mt = item / n_groups;
-        const int nt = item - mt * n_groups;
+        const int mg = item / n_groups;
+        const int nt = item - mg * n_groups;
+        const int mt = mg * CL + crank;
         const int row_a = mt * TILE_M;
         const int row_b = p.halfM + row_a;
-        const int row_w = (p.tile_begin + nt) * TILE_N;
+        int row_w = (p.tile_begin + nt) * TILE_N;
+        if constexpr (CG2)      // my half of the prototype tile: columns [crank * umma_n/2, +umma_n/2) of the MMA's N
+          row_w += crank * (__ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2) >> 1);
         const int kb_per_term = p.num_k_blocks / p.split_terms;
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&sb->empty[stage], phase ^ 1);
-          uint8_t* st = smem + stage * PAIR_STAGE_BYTES;
-          mbar_arrive_expect_tx(&sb->full[stage], PAIR_STAGE_BYTES);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          if constexpr (!CG2) mbar_arrive_expect_tx(&sb->full[stage], STAGE_BYTES);
+          else if (leader) mbar_arrive_expect_tx(&sb->full[stage], 2 * STAGE_BYTES);
+          else mbar_arrive_cluster(&sb->full[stage], 0);
           int kc = kb, xo = 0, wo = 0;
           if (p.split_terms > 1) {            // term -> (feature split, prototype split): packed 2-bit pairs
             const int term = kb / kb_per_term;
@@ -308,15 +327,21 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             xo = ((0x001102 >> (4 * term)) & 3) * p.M;          // lo, hi, mid, mid, hi, hi
             wo = ((0x010120 >> (4 * term)) & 3) * p.P_pad;      // hi, lo, mid, hi, mid, hi
           }
-          tma_load_2d(st, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_a);
-          tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_b);
-          tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kc * KBLK, wo + row_w);
+          if constexpr (!CG2) {
+            tma_load_2d(st, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_a);
+            tma_load_2d(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_b);
+            tma_load_2d(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kc * KBLK, wo + row_w);
+          } else {        // tmap_w has a 64-row box here; completion bytes are credited to the leader's barrier
+            tma_load_2d_2cta(st, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_a);
+            tma_load_2d_2cta(st + TILE_M * KBLK * 2, &tmap_x, &sb->full[stage], kc * KBLK, xo + row_b);
+            tma_load_2d_2cta(st + 2 * TILE_M * KBLK * 2, &tmap_w, &sb->full[stage], kc * KBLK, wo + row_w);
+          }
           if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
+  } else if (warp == 1 && leader) {
+    // ------------------------------------------------------------ MMA issuer (CG2: the even CTA issues for the pair)
     // The whole warp walks the (warp-uniform) loop so that addresses and descriptors stay in uniform registers;
     // only the issue block is single-lane (elect.sync elects the same lane every time, which matters because
     // tcgen05.commit tracks the MMAs of the executing thread).
@@ -330,7 +355,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     for (int item = worker; item < total_items; item += num_workers) {
       const int nt = item % n_groups;
       const int umma_n = __ldg(p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS + 2);
-      const uint32_t idesc = make_idesc(TILE_M, umma_n, false, false);
+      const uint32_t idesc = make_idesc(CL * TILE_M, umma_n, false, false);
       mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * (2 * TILE_N);
@@ -339,18 +364,28 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         mbar_wait(&sb->full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a0 = ((smem_base + stage * PAIR_STAGE_BYTES) >> 4) | LOF;   // 16-byte units
+          const uint32_t a0 = ((smem_base + stage * STAGE_BYTES) >> 4) | LOF;   // 16-byte units
           const uint32_t a1 = a0 + (TILE_M * KBLK * 2 >> 4);
           const uint32_t b = a1 + (TILE_M * KBLK * 2 >> 4);
 #pragma unroll
           for (int k = 0; k < KBLK / 16; ++k) {
             const uint64_t bd = desc64(b + 2 * k, HI);
             const uint32_t accum = (kb | k) ? 1u : 0u;
-            umma_bf16(d0, desc64(a0 + 2 * k, HI), bd, idesc, accum);
-            umma_bf16(d1, desc64(a1 + 2 * k, HI), bd, idesc, accum);
+            if constexpr (!CG2) {
+              umma_bf16(d0, desc64(a0 + 2 * k, HI), bd, idesc, accum);
+              umma_bf16(d1, desc64(a1 + 2 * k, HI), bd, idesc, accum);
+            } else {
+              umma_bf16_2cta(d0, desc64(a0 + 2 * k, HI), bd, idesc, accum);
+              umma_bf16_2cta(d1, desc64(a1 + 2 * k, HI), bd, idesc, accum);
+            }
           }
-          umma_commit(&sb->empty[stage]);
-          if (kb == p.num_k_blocks - 1) umma_commit(&sb->tmem_full[acc]);
+          if constexpr (!CG2) {
+            umma_commit(&sb->empty[stage]);
+            if (kb == p.num_k_blocks - 1) umma_commit(&sb->tmem_full[acc]);
+          } else {
+            umma_commit_2cta(&sb->empty[stage], uint16_t(3));
+            if (kb == p.num_k_blocks - 1) umma_commit_2cta(&sb->tmem_full[acc], uint16_t(3));
+          }
         }
         __syncwarp();
         if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
@@ -366,8 +401,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = worker; item < total_items; item += num_workers) {
-      const int mt = item / n_groups;
-      const int nt = item - mt * n_groups;
+      const int mg = item / n_groups;
+      const int nt = item - mg * n_groups;
+      const int mt = mg * CL + crank;
       const int32_t* tile = p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS;
       const int nseg = __ldg(tile + 1);
 
@@ -433,13 +469,17 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * (2 * TILE_N);
       if constexpr (BWD) {
         if (warp == 4 && lane == 0) tma_store_wait_read();       // previous item's dZ has left the staging buffer
-        named_bar_sync(1, 32 * PairCfg<S>::EPI_WARPS);
+        named_bar_sync(1, 32 * EPI_WARPS);
       }
-      if (my_cnt == 0) {          // nothing to read from this stage: release it at once
+      auto release_stage = [&]() {     // accumulators of this warp are in registers: hand the TMEM stage back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
-      }
+        if (lane == 0) {
+          if constexpr (CG2) mbar_arrive_cluster(&sb->tmem_empty[acc], 0);    // the leader's MMA warp waits for both CTAs
+          else mbar_arrive(&sb->tmem_empty[acc]);
+        }
+      };
+      if (my_cnt == 0) release_stage();     // nothing to read from this stage
 
 #pragma unroll
       for (int js = 0; js < SLOTS; ++js) {
@@ -452,13 +492,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tmem_ld_cols<S>(t0 + j * S, ra);
           tmem_ld_cols<S>(t0 + TILE_N + j * S, rb);
           tmem_ld_wait();
-          if (js == my_cnt - 1) {
-            // last segment of this warp is in registers: hand the TMEM stage back to the MMA warp now, the
-            // arithmetic below overlaps the next item's MMAs
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sb->tmem_empty[acc]);
-          }
+          // last segment of this warp is in registers: release now, the arithmetic below overlaps the next MMAs
+          if (js == my_cnt - 1) release_stage();
           float s1[S], s2[S];
           if (len == S) {
             softmax_row<S, false>(ra, len, p.scale_log2, s1);
@@ -564,9 +599,11 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG2) cluster_sync();       // nobody leaves while the pair's MMAs / remote arrives may still touch this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if constexpr (CG2) tmem_dealloc_2cta<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 

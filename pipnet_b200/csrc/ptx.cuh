@@ -51,15 +51,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (-> launch error) instead of hanging the GPU box.
+// Bounded wait: a protocol bug must trap (-> launch error) instead of hanging the GPU box.  The bound is wall-clock
+// (2 s on %globaltimer): try_wait itself suspends the thread for an implementation-defined time per call.
+__device__ __forceinline__ uint64_t global_timer_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0 = 0;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
-      printf("hcomp: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
-             smem_u32(bar), parity);
-      __trap();
+    if ((++spins & 1023u) == 0u) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {
+        printf("hcomp: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
     }
   }
 }

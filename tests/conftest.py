@@ -20,3 +20,12 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=[1, 0], ids=["cta-pair", "single-cta"])
+def cta_pair_mode(request):
+    """Select the kernel family for a GPU test: tcgen05 cta_group::2 (CTA pairs; the default) or the 1-CTA kernels."""
+    from pipnet_b200 import _cabi
+    prev = _cabi.lib().hcomp_set_cta_pair(request.param)
+    yield request.param
+    _cabi.lib().hcomp_set_cta_pair(prev)

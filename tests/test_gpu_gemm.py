@@ -6,13 +6,10 @@ import torch
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[1, 0], ids=["cta-pair", "single-cta"], autouse=True)
-def cta_pair_mode(request):
-    """every GEMM test runs on the cta_group::2 (256x256, CTA pair) kernels and on the 1-CTA 128x256 ones"""
-    from pipnet_b200 import _cabi
-    prev = _cabi.lib().hcomp_set_cta_pair(request.param)
-    yield request.param
-    _cabi.lib().hcomp_set_cta_pair(prev)
+@pytest.fixture(autouse=True)
+def _both_kernel_families(cta_pair_mode):
+    """every GEMM test runs on the cta_group::2 (CTA pair) kernels and on the 1-CTA ones (fixture in conftest.py)"""
+    yield
 
 
 def _operands(M, N, K, a_mn, b_mn, seed):

@@ -10,6 +10,12 @@ from oracle.problems import Problem, rel_err, argmax_report
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True)
+def _both_kernel_families(cta_pair_mode):
+    """every head test runs on the CTA-pair (cta_group::2) kernels and on the 1-CTA ones (fixture in conftest.py)"""
+    yield
+
 FWD_CASES = [
     # tree, C, H, B, kwargs
     ("cub08", 64, 6, 4, dict(num_features=20)),
