@@ -204,9 +204,7 @@ def run_ours(a):
         step(feats[i % 2], labels_d[i % 2])
     barrier()
 
-    # ---------------- eager region: per-kernel CUDA-event timings (events cannot be timed inside a graph)
-    ops.PROFILE.reset()
-    ops.PROFILE.enabled = True
+    # ---------------- eager region: launches per step + eager step time (host-bound: ~20 small launches + autograd)
     launches0 = _cabi.lib().hcomp_launch_count()
     eager_steps = max(3, min(a.steps, 10))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -218,9 +216,38 @@ def run_ours(a):
     barrier()
     eager_ms = e0.elapsed_time(e1) / eager_steps
     launches_per_step = (_cabi.lib().hcomp_launch_count() - launches0) / eager_steps
-    ops.PROFILE.enabled = False
+
+    # ---------------- per-kernel durations: CUDA events around the C-ABI calls of the four large kernels in a
+    # GPU-saturated loop (host enqueues run ahead of the device, so a bracket holds the kernel and nothing else;
+    # inside the host-bound eager step the same brackets would also contain the host's enqueue gaps).  Inputs alternate
+    # between the two > L2 feature batches; the kernels, arguments and launch geometry are those of the step.
+    dl = net.device_layout(dev)
+    with torch.no_grad():
+        w_flat_k = net.flat_prototype_kernels().detach().contiguous()
+        wp_k = ops.pack_weights(w_flat_k, dl)
+        lab_k = [tr.make_labels(net, y) for y in labels_d]
+        xr_k = [ops.feature_rows(f) for f in feats]
+        gp_k = torch.randn(V, L.P, device=dev)
+        ga_k = torch.full((L.N,), 0.2, device=dev)
+        kern_iters = max(5, min(a.steps, 20))
+
+        def kernel_pass(i):
+            pooled, argmax, _al = ops.proj_softmax_pool_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, lab_k[i % 2])
+            ops.head_backward_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, argmax, gp_k, lab_k[i % 2], ga_k)
+
+        for i in range(3):
+            kernel_pass(i)
+        barrier()
+        ops.PROFILE.reset()
+        ops.PROFILE.enabled = True
+        saved_group, ops.GRAD_ALLREDUCE_GROUP = ops.GRAD_ALLREDUCE_GROUP, None      # kernels only, no collective here
+        for i in range(kern_iters):
+            kernel_pass(i)
+        ops.GRAD_ALLREDUCE_GROUP = saved_group
+        barrier()
+        ops.PROFILE.enabled = False
     prof = ops.PROFILE.totals_ms()
-    prof_steps = eager_steps
+    prof_steps = kern_iters
 
     # ---------------- CUDA-graph capture of the step (one graph per input batch: no copies, L2-cold inputs)
     graphs = None
@@ -317,13 +344,19 @@ def run_ours(a):
         flops = 2.0 * M * C * L.P
         achieved = flops / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
         long_region = ms > 1000.0
+        traffic = None
+        tp = os.path.join(ROOT, 'profiles', 'traffic.json')      # dram bytes of this kernel from the committed ncu --set full capture
+        if os.path.isfile(tp):
+            traffic = json.load(open(tp)).get(a.workload, {}).get('k1_dram_bytes_per_launch')
         peak = peaks['bf16_sustained'] if long_region else peaks['bf16_burst']
         kernels = {k: {'ms_per_step': v[0] / prof_steps, 'calls': v[1]} for k, v in prof.items()}
         step_flops = 4.0 * flops          # fwd + recompute + dX + dW ; algorithmic = 3 GEMMs
         roofline = {'bound': 'tensor', 'kernel': 'head_pair_kernel<20,fwd> (projection+softmax+maxpool+align)',
                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
                     'peak_kind': ('sustained' if long_region else 'burst') + ', ' + peaks['source'],
-                    'avg_launch_ms': k1_avg, 'algorithmic_flops_per_launch': flops, 'traffic': None,
+                    'avg_launch_ms': k1_avg, 'algorithmic_flops_per_launch': flops, 'traffic': traffic,
+                    'method': 'CUDA events around the C-ABI call (2 memsets + kernel) in a GPU-saturated loop of the step\'s four '
+                              'large kernels, inputs alternating between two >L2 batches',
                     'step_algorithmic_tflops': 3.0 * flops / (ms_per_step * 1e-3) / 1e12,
                     'step_executed_tflops': step_flops / (ms_per_step * 1e-3) / 1e12, 'kernels': kernels}
         cpu = None
