@@ -504,10 +504,22 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
   }
   if (do_orth) {
     if (t->p_max >= C || t->p_max > 128) return fail(HCOMP_E_ARG, "orth loss needs P_n < C and P_n <= 128 (P_max=%d, C=%d)", t->p_max, C);
-    HC_CUDA(cudaMemsetAsync(w.orth_sq, 0, sizeof(float) * t->n_nodes, S(stream)));
-    hc::orth_loss_fwd_kernel<<<t->n_protos, 128, 0, S(stream)>>>(w_flat, wc, t->proto_node, t->proto_off, t->cls_off, t->wc_off,
-                                                                C, t->p_max, w.orth_sq, w.E, rel);
-    HC_LAUNCH_CHECK("orth_loss_fwd");
+    const size_t node_smem = (size_t)t->p_max * C * sizeof(float);
+    if (node_smem <= 160 * 1024 && C % 4 == 0) {       // one block per node, W_n staged in shared memory
+      static bool attr_done = false;
+      if (!attr_done) {
+        HC_CUDA(cudaFuncSetAttribute(hc::orth_loss_fwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr_done = true;
+      }
+      hc::orth_loss_fwd_node_kernel<<<t->n_nodes, 512, node_smem, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
+                                                                              C, t->p_max, w.orth_sq, w.E, rel);
+      HC_LAUNCH_CHECK("orth_loss_fwd_node");
+    } else {
+      HC_CUDA(cudaMemsetAsync(w.orth_sq, 0, sizeof(float) * t->n_nodes, S(stream)));
+      hc::orth_loss_fwd_kernel<<<t->n_protos, 128, 0, S(stream)>>>(w_flat, wc, t->proto_node, t->proto_off, t->cls_off,
+                                                                  t->wc_off, C, t->p_max, w.orth_sq, w.E, rel);
+      HC_LAUNCH_CHECK("orth_loss_fwd");
+    }
   }
   // class kernel also produces the per-node accuracy counters, so it always runs
   hc::class_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(out, tgt, t->child_w, t->cls_off, n_desc, V, t->n_nodes,
@@ -555,9 +567,21 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
   if (g_w) {
     HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
     if (flags & HCOMP_LOSS_ORTH) {
-      hc::orth_loss_bwd_kernel<<<t->n_protos, 256, 0, S(stream)>>>(w_flat, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel,
-                                                                  gvec + 2 * N, t->proto_node, g_w);
-      HC_LAUNCH_CHECK("orth_loss_bwd");
+      const size_t node_smem = ((size_t)t->p_max * C + (size_t)t->p_max * t->p_max) * sizeof(float);
+      if (node_smem <= 170 * 1024 && C % 4 == 0) {
+        static bool attr_done = false;
+        if (!attr_done) {
+          HC_CUDA(cudaFuncSetAttribute(hc::orth_loss_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
+          attr_done = true;
+        }
+        hc::orth_loss_bwd_node_kernel<<<t->n_nodes, 256, node_smem, S(stream)>>>(w_flat, t->proto_off, C, t->p_max,
+                                                                                stats + 2 * N, w.E, rel, gvec + 2 * N, g_w);
+        HC_LAUNCH_CHECK("orth_loss_bwd_node");
+      } else {
+        hc::orth_loss_bwd_kernel<<<t->n_protos, 256, 0, S(stream)>>>(w_flat, t->proto_off, C, t->p_max, stats + 2 * N, w.E,
+                                                                    rel, gvec + 2 * N, t->proto_node, g_w);
+        HC_LAUNCH_CHECK("orth_loss_bwd");
+      }
     }
   }
   return 0;

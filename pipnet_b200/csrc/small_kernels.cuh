@@ -386,6 +386,85 @@ __global__ void orth_loss_bwd_kernel(const float* __restrict__ w, const int32_t*
   }
 }
 
+// Fast variants: one block per NODE with the node's kernels W_n [P_n, C] staged in dynamic shared memory (used when
+// P_n * C * 4 bytes fits; the per-row kernels above are the general path).  Forward: all P_n^2 Gram entries from smem,
+// one warp per entry.  Backward: dW_n = g * (2/L) * E * W_n with E and W_n in smem, one thread per channel.
+__global__ void orth_loss_fwd_node_kernel(const float* __restrict__ w, const float* __restrict__ wc,
+                                          const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
+                                          const int32_t* __restrict__ wc_off, int C, int P_max, float* __restrict__ sumsq,
+                                          float* __restrict__ E, uint8_t* __restrict__ rel) {
+  extern __shared__ float wsm[];                 // [pn][C]
+  __shared__ float sh[32];
+  __shared__ uint8_t srel[128];
+  const int n = blockIdx.x;
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const int kn = cls_off[n + 1] - cls_off[n];
+  const float4* src = reinterpret_cast<const float4*>(w + (size_t)p0 * C);
+  float4* dst = reinterpret_cast<float4*>(wsm);
+  for (int i = threadIdx.x; i < pn * C / 4; i += blockDim.x) dst[i] = src[i];
+  for (int p = threadIdx.x; p < pn; p += blockDim.x) {
+    bool r = false;
+    for (int c = 0; c < kn; ++c) r |= wc[wc_off[n] + (size_t)c * pn + p] > 0.001f;
+    srel[p] = r;
+    rel[p0 + p] = r;
+  }
+  __syncthreads();
+  float* En = E + (size_t)n * P_max * P_max;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  float acc = 0.f;
+  for (int ij = warp; ij < pn * pn; ij += nw) {
+    const int i = ij / pn, j = ij - i * pn;
+    float e = 0.f;
+    if (j >= i) {                                  // E is symmetric: compute the upper triangle, mirror it
+      if (srel[i] && srel[j]) {
+        const float* a = wsm + (size_t)i * C;
+        const float* b = wsm + (size_t)j * C;
+        float d0 = 0.f, d1 = 0.f;
+        int c = lane;
+        for (; c + 32 < C; c += 64) { d0 = fmaf(a[c], b[c], d0); d1 = fmaf(a[c + 32], b[c + 32], d1); }
+        if (c < C) d0 = fmaf(a[c], b[c], d0);
+        e = warp_sum(d0 + d1) - (i == j ? 1.f : 0.f);
+      }
+      if (lane == 0) {
+        En[i * P_max + j] = e;
+        En[j * P_max + i] = e;
+        acc += (i == j) ? e * e : 2.f * e * e;
+      }
+    }
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) sumsq[n] = acc;
+}
+__global__ void orth_loss_bwd_node_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off, int C,
+                                          int P_max, const float* __restrict__ loss, const float* __restrict__ E,
+                                          const uint8_t* __restrict__ rel, const float* __restrict__ g_loss,
+                                          float* __restrict__ g_w) {
+  extern __shared__ float wsm[];                 // [pn][C] then [pn][pn] coefficients
+  const int n = blockIdx.x;
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const float L = loss[n];
+  if (L <= 0.f || g_loss[n] == 0.f) return;       // g_w was zero-filled by the caller
+  const float s = g_loss[n] * 2.f / L;
+  float* coef = wsm + (size_t)pn * C;
+  const float4* src = reinterpret_cast<const float4*>(w + (size_t)p0 * C);
+  float4* dst = reinterpret_cast<float4*>(wsm);
+  for (int i = threadIdx.x; i < pn * C / 4; i += blockDim.x) dst[i] = src[i];
+  const float* En = E + (size_t)n * P_max * P_max;
+  for (int ij = threadIdx.x; ij < pn * pn; ij += blockDim.x) {
+    const int i = ij / pn, j = ij - i * pn;
+    coef[ij] = (rel[p0 + i] && rel[p0 + j]) ? s * En[i * P_max + j] : 0.f;
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    for (int i = 0; i < pn; ++i) {
+      float acc = 0.f;
+#pragma unroll 4
+      for (int j = 0; j < pn; ++j) acc = fmaf(coef[i * pn + j], wsm[(size_t)j * C + c], acc);
+      g_w[(size_t)(p0 + i) * C + c] = acc;
+    }
+  }
+}
+
 // ---------------------------------------------------------------- loss combination (one block)
 // stats[0..3][n] = per-node align / tanh / orth / class loss (0 for nodes without descendants or disabled terms);
 // total = sum_n sum_k weight[k] * stats[k][n]  (weights already contain the 1/N of pipnet/train.py:1071 etc.)
