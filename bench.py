@@ -36,6 +36,8 @@ WORKLOADS = {
     'cub27': dict(tree='cub27', num_features=20, batch=64, C=768, H=26),
     'cub08': dict(tree='cub08', num_features=20, batch=8, C=768, H=26),
     'cub190': dict(tree='synth190', num_features=20, batch=32, C=768, H=26),
+    # recipe B of SURVEY.md 8(d): 20 prototypes per CHILD (P_n = 20 / 40 / 60, P = 1020)
+    'cub27b': dict(tree='cub27', num_features=0, per_child=20, batch=64, C=768, H=26),
 }
 METRIC = 'train images/sec (prototype head fwd+bwd)'
 UNIT = 'images/s'
@@ -103,7 +105,8 @@ def oracle_cpu_throughput(wl, batch, steps, warmup, budget_s=25.0):
     from oracle.problems import Problem
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    pb = Problem(wl['tree'], wl['C'], wl['H'], batch, seed=1234, num_features=wl['num_features'])
+    pb = Problem(wl['tree'], wl['C'], wl['H'], batch, seed=1234, num_features=wl['num_features'],
+                 per_child=wl.get('per_child', 0))
     x = pb.x.float()
     aw = {k: v.float() for k, v in pb.w.items()}
     cw = {k: v.float() for k, v in pb.wc.items()}
@@ -162,7 +165,7 @@ def run_ours(a):
     wl = WORKLOADS[a.workload]
     B, C, H = wl['batch'], wl['C'], wl['H']
     V, HW = 2 * B, H * H
-    args = make_args(num_features=wl['num_features'])
+    args = make_args(num_features=wl['num_features'], num_protos_per_child=wl.get('per_child', 0))
     net, root = build_net(wl['tree'], C, args, seed=1)
     net = net.to(dev)
     net.train()

@@ -31,6 +31,7 @@ CASES = [
     ('cub08_A_pretrain', CUB08, 'cub08', 64, 6, 4, dict(num_features=20), (True, False)),
     ('cub18_B_train', CUB18, 'cub18', 64, 6, 6, dict(num_protos_per_child=8, num_features=0), (False, False)),
     ('cub27_A_finetune', CUB27, 'cub27', 64, 6, 6, dict(num_features=12), (False, True)),
+    ('cub27_B_train', CUB27, 'cub27', 64, 6, 4, dict(num_protos_per_child=20, num_features=0), (False, False)),
 ]
 
 

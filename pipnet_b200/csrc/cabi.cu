@@ -149,7 +149,8 @@ int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, con
     case 20: return launch_pair<20, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
     case 32: return launch_pair<32, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
     case 40: return launch_pair<40, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
-    default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40)", seg);
+    case 64: return launch_pair<64, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
+    default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40,64)", seg);
   }
 }
 

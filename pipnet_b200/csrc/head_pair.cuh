@@ -20,8 +20,8 @@
 //   warp 3   : idle
 //   warps 4..: epilogue       (warp%4 selects the TMEM lane quadrant; the EW/4 warps of a quadrant
 //                              split the tile's node segments round-robin).  EW = 12 for segment
-//                              classes <= 20 columns (register budget 128/thread), 8 otherwise (168):
-//                              the epilogue is latency-bound, more warps per scheduler hide it.
+//                              classes <= 20 columns (register budget 128/thread), 8 up to 40 (168), 4 for the
+//                              64-column class (255): the epilogue is latency-bound, more warps per scheduler hide it.
 #pragma once
 #include "ptx.cuh"
 
@@ -45,7 +45,8 @@ template <bool BWD, bool CG2> struct PairMem {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + 4096;
 };
 template <int S> struct PairCfg {
-  static constexpr int EPI_WARPS = (S <= 20) ? 12 : 8;
+  static constexpr int EPI_WARPS = (S <= 20) ? 12 : (S <= 40 ? 8 : 4);   // register budget 128 / 168 / 255 per thread
+  static constexpr int XQ = (S <= 40) ? 10 : S / 4;                       // uint4 per half of a warp's pooling table
   static constexpr int PARTS = EPI_WARPS / 4;               // epilogue warps per TMEM lane quadrant
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int NSEG_MAX = 128 / S;
@@ -80,7 +81,7 @@ struct PairSmem {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
-  uint4 pool_x[12][2][10];   // per epilogue warp: column maxima [40] and first-lane ballots [40] (forward fast path)
+  uint4 pool_x[240];         // per epilogue warp 2 * XQ: column maxima and first-lane ballots (forward fast path)
 };
 
 template <int S, bool MASK>
@@ -149,7 +150,7 @@ __device__ __forceinline__ void pool_segment(const float* s, bool valid, int v_r
 // lanes) are published through a 320-byte per-warp smem table so that lane c can pick column c's pair without a
 // chain of predicated selects.
 template <int S>
-__device__ __forceinline__ void pool_segment_fast(const float* s, int loc_first, int len, int lane, uint4* xch /* [2][10] */,
+__device__ __forceinline__ void pool_segment_fast(const float* s, int loc_first, int len, int lane, uint4* xch /* [2][XQ] */,
                                                   unsigned long long* dst) {
   uint32_t mx[S], bal[S];
 #pragma unroll
@@ -160,12 +161,12 @@ __device__ __forceinline__ void pool_segment_fast(const float* s, int loc_first,
 #pragma unroll
     for (int i = 0; i < S / 4; ++i) {
       xch[i] = make_uint4(mx[4 * i], mx[4 * i + 1], mx[4 * i + 2], mx[4 * i + 3]);
-      xch[10 + i] = make_uint4(bal[4 * i], bal[4 * i + 1], bal[4 * i + 2], bal[4 * i + 3]);
+      xch[PairCfg<S>::XQ + i] = make_uint4(bal[4 * i], bal[4 * i + 1], bal[4 * i + 2], bal[4 * i + 3]);
     }
   }
   __syncwarp();
   const uint32_t* xm = reinterpret_cast<const uint32_t*>(xch);
-  const uint32_t* xb = xm + 40;
+  const uint32_t* xb = xm + 4 * PairCfg<S>::XQ;
 #pragma unroll
   for (int h = 0; h < (S + 31) / 32; ++h) {
     const int c = h * 32 + lane;
@@ -252,7 +253,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   constexpr int PAIR_STAGES = PairMem<BWD, CG2>::STAGES;
   constexpr int STAGE_BYTES = PairMem<BWD, CG2>::STAGE_BYTES;
   constexpr int EPI_WARPS = PairCfg<S>::EPI_WARPS;
-  static_assert(S % 4 == 0 && S >= 8 && S <= 40, "segment class");
+  static_assert(S % 4 == 0 && S >= 8 && S <= 64, "segment class");
   constexpr int NSEG_MAX = PairCfg<S>::NSEG_MAX;
   constexpr int SLOTS = PairCfg<S>::SLOTS;
   constexpr int PARTS = PairCfg<S>::PARTS;
@@ -299,7 +300,11 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
+#ifdef HC_EXP_NO_MAIN      // timing experiment only (tools/k1_exp.py): no operand loads, no MMAs
+    if (false) {
+#else
     if (lane == 0) {
+#endif
       int stage = 0;
       uint32_t phase = 0;
       for (int item = worker; item < total_items; item += num_workers) {
@@ -360,7 +365,16 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       tc_fence_after();
       const uint32_t d0 = tmem_base + acc * (2 * TILE_N);
       const uint32_t d1 = d0 + TILE_N;
+#ifdef HC_EXP_NO_MAIN
+      if (elect_one()) {
+        if constexpr (!CG2) umma_commit(&sb->tmem_full[acc]);
+        else umma_commit_2cta(&sb->tmem_full[acc], uint16_t(3));
+      }
+      __syncwarp();
+      for (int kb = 0; kb < 0; ++kb) {
+#else
       for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+#endif
         mbar_wait(&sb->full[stage], phase);
         tc_fence_after();
         if (elect_one()) {
@@ -494,6 +508,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tmem_ld_wait();
           // last segment of this warp is in registers: release now, the arithmetic below overlaps the next MMAs
           if (js == my_cnt - 1) release_stage();
+#ifdef HC_EXP_NO_EPI       // timing experiment only: main loop without the epilogue arithmetic
+          continue;
+#endif
           float s1[S], s2[S];
           if (len == S) {
             softmax_row<S, false>(ra, len, p.scale_log2, s1);
@@ -509,7 +526,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 
           if constexpr (!BWD) {
             if (seg_aux[js] != 0.f) align_acc[js] = -__logf(ip + 1e-12f);
-            uint4* xch = &sb->pool_x[warp - 4][0][0];
+            uint4* xch = &sb->pool_x[(warp - 4) * 2 * PairCfg<S>::XQ];
+            static_assert(PairCfg<S>::EPI_WARPS * 2 * PairCfg<S>::XQ <= 240, "pooling table");
             if (nv_a == 32 && !has_boundary)
               pool_segment_fast<S>(s1, loc_first, len, lane, xch, p.pooled_packed + (size_t)v_first * p.P + poff);
             else if (nv_a > 0)

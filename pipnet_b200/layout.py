@@ -22,7 +22,7 @@ import numpy as np
 TILE_COLS = 128
 MAX_SEGS = 16
 TILE_INTS = 4 + 3 * MAX_SEGS
-SEG_CLASSES = (8, 16, 20, 32, 40)        # instantiated epilogues (pipnet_b200/csrc/cabi.cu)
+SEG_CLASSES = (8, 16, 20, 32, 40, 64)        # instantiated epilogues (pipnet_b200/csrc/cabi.cu)
 
 
 def seg_class(p_n: int) -> int:

@@ -46,7 +46,7 @@ def test_cuda_head_reproduces_reference_fixture(path):
     assert rel_err(pooled.flat, torch.from_numpy(d['pooled'])) <= 1e-5
     assert rel_err(out.flat, torch.from_numpy(d['out'])) <= 1e-5
     assert torch.equal(pf.argmax.flat.cpu(), torch.from_numpy(d['argmax']))
-    assert abs(float(res[0]) - float(d['loss'])) <= 1e-5 * max(1.0, abs(float(d['loss'])))
+    assert abs(float(res[0].detach()) - float(d['loss'])) <= 1e-5 * max(1.0, abs(float(d['loss'])))
     for key, idx in (('cls', 1), ('tanh', 3), ('orth', 6)):
         got = {k: v.item() for k, v in res[idx].items()}
         want = dict(zip([str(s) for s in d[key + '_nodes']], d[key + '_vals']))

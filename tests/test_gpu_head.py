@@ -24,6 +24,8 @@ FWD_CASES = [
     ("cub18", 64, 8, 4, dict(num_features=12)),          # masked tail inside the S=16 class
     ("synth12:3", 72, 6, 6, dict(per_child=16)),         # S=32 class, C not a multiple of 64
     ("cub27", 768, 26, 2, dict(num_features=20)),        # real ConvNeXt-26 geometry, image straddles tiles
+    ("cub27", 128, 7, 3, dict(per_child=20)),            # recipe B: P_n = 20 / 40 / 60 -> classes 20, 40 and 64
+    ("synth12:3", 64, 6, 4, dict(per_child=28)),         # P_n = 56: masked tail inside the 64 class
 ]
 
 
@@ -31,7 +33,7 @@ def _oracle_forward(pb, tau=1.0):
     return ho.head_forward(pb.x, pb.w, pb.wc, pb.root, softmax_tau=tau)
 
 
-@pytest.mark.parametrize("case", FWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}" for c in FWD_CASES])
+@pytest.mark.parametrize("case", FWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}-{i}" for i, c in enumerate(FWD_CASES)])
 def test_forward_pool_argmax_align(case):
     from pipnet_b200 import ops
     tree, C, H, B, kw = case
@@ -81,10 +83,12 @@ BWD_CASES = [
     ("cub08", 128, 7, 3, dict(per_child=20)),
     ("cub18", 64, 8, 4, dict(num_features=12)),
     ("cub27", 768, 26, 1, dict(num_features=20)),
+    ("cub27", 128, 7, 3, dict(per_child=20)),
+    ("synth12:3", 64, 6, 4, dict(per_child=28)),
 ]
 
 
-@pytest.mark.parametrize("case", BWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}" for c in BWD_CASES])
+@pytest.mark.parametrize("case", BWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}-{i}" for i, c in enumerate(BWD_CASES)])
 def test_backward_dx_dw(case):
     """d(sum pooled*G + sum_n a_n * align_n) w.r.t. features and prototype kernels vs oracle autograd."""
     from pipnet_b200 import ops

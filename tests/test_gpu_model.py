@@ -18,11 +18,12 @@ from oracle.problems import IdentityBackbone, make_args, build_net
 
 PHASES = [("pretrain", True, False), ("train", False, False), ("finetune", False, True)]
 CASES = [("cub08", 64, 6, 4, dict(num_features=20)), ("cub27", 96, 6, 6, dict(num_protos_per_child=10, num_features=0)),
-         ("cub18", 128, 7, 5, dict(num_features=12))]
+         ("cub18", 128, 7, 5, dict(num_features=12)),
+         ("cub27", 64, 6, 5, dict(num_protos_per_child=20, num_features=0))]     # recipe B: P_n up to 60
 
 
 @pytest.mark.parametrize("phase", PHASES, ids=[p[0] for p in PHASES])
-@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+@pytest.mark.parametrize("case", CASES, ids=[f'{c[0]}-{i}' for i, c in enumerate(CASES)])
 def test_step_matches_oracle(case, phase):
     from pipnet_b200 import train as tr
     tree, C, H, B, over = case
@@ -119,7 +120,7 @@ def test_unsupported_variants_raise():
     pp.base_architecture_to_features['identity'] = lambda pretrained=False: IdentityBackbone(64)
     with pytest.raises(Exception):
         pp.get_network(8, make_args(unitconv2d='y'), root=root)
-    root60 = make_tree("cub27", per_child=20)      # the 3-child node gets 60 prototypes > 40
+    root90 = make_tree("cub27", per_child=30)      # the 3-child node gets 90 prototypes > 64
     with pytest.raises(Exception):
-        feats, add_on, pool, cl, k = pp.get_network(27, make_args(num_protos_per_child=20, num_features=0), root=root60)
-        pp.PIPNet(27, k, feats, make_args(num_protos_per_child=20, num_features=0), add_on, pool, cl, 25, root60)
+        feats, add_on, pool, cl, k = pp.get_network(27, make_args(num_protos_per_child=30, num_features=0), root=root90)
+        pp.PIPNet(27, k, feats, make_args(num_protos_per_child=30, num_features=0), add_on, pool, cl, 25, root90)

@@ -73,7 +73,10 @@ def test_layout_tables(tree, kw):
 
 
 def test_layout_rejects_wide_nodes():
-    root = make_tree("cub27", per_child=20)                     # 3-child node -> 60 prototypes
+    root = make_tree("cub27", per_child=20)                     # 3-child node -> 60 prototypes -> the 64 class
+    L = lay.build_layout(root)
+    assert int(L.P_n.max()) == 60 and set(int(t[0]) for t in L.tiles) == {40, 64}
+    root = make_tree("cub27", per_child=30)                     # 90 prototypes: wider than any instantiated class
     with pytest.raises(Exception):
         lay.build_layout(root)
 
