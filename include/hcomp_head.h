@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HCOMP_ABI_VERSION 3
+#define HCOMP_ABI_VERSION 4
 #define HCOMP_TILE_INTS 52
 #define HCOMP_TILE_COLS 128
 #define HCOMP_MAX_SEGS 16
@@ -149,6 +149,43 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
                           const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V, int V_first, int C,
                           int flags, const float* weights_host, float eps, const float* ws, const uint8_t* rel,
                           float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream);
+
+/* ---- descendant-structured loss terms switched on by the shipped scripts ------------------------ */
+/* (run_pipnet_20protos_multi_runs_seed42.sh: --tanh_desc "y|0.05" --minimize_contrasting_set 'y'
+ *  --mask_prune_overspecific 'y|0|1.1'), batched over all nodes on the flat pooled table [V,P]:
+ *   TANH_DESC   per leaf below a node: -1/2 sum_views mean_{p in R(child)} log(tanh(sum_{rows of the leaf} pooled)+eps),
+ *               R(child) = classifier row > 1e-3; mean over the node's leaves (absent leaves give log(eps))
+ *                                                                                  pipnet/train.py:1089-1133
+ *   CONTRAST    per child: max over the node's descendants that are NOT below the child of the child's prototypes
+ *               (classifier row > 1e-5); mean over all (child, prototype) entries; TOPK = 1   pipnet/train.py:1017-1060
+ *   MASK_PRUNE  per child with a leaf in the batch: presence <- softmax((presence + gumbel) / tau) (soft Gumbel softmax,
+ *               applied to the previous child's OUTPUT, :978); overspecificity = -sum_{p in R} score[p] * presence[p,1]
+ *               with score = prod over the child's leaves in the batch of clamp(max_rows pooled * boost, max=1)
+ *               (boost <= 0: plain product; GEOMETRIC: prod of max^(1/#leaves); SG_SCORE: no gradient through the
+ *               score); mask_l1 = sum_{p in R} presence[p,1]; both / total relevant prototypes      pipnet/train.py:946-1015
+ * Nodes without a descendant in the batch contribute nothing (:941-942).
+ * ys: int64[V] leaf index per row (sorted leaf-name order); presence: float[P,2]; gumbel: float[n_welems,2] noise
+ * -log(Exp(1)) indexed like the classifier weights (node, child, prototype); weights_host: 4 HOST floats
+ * {tanh_desc_weight/N, contrast_weight/N, 2.0/N, 0.5/N}.
+ * stats[4*N]: per node {tanh_desc, contrast (unweighted means), overspecificity, mask_l1 (weighted, as the reference
+ * stores them :1006-1010)}; loss[1] = sum_n w0*stats0 + w1*stats1 + stats2 + stats3.
+ * ws: hcomp_desc_losses_ws_bytes(t, V) bytes, kept for the backward.  Halves for TANH_DESC are rows [0,V_first) and
+ * [V_first,V): equal to the reference's .chunk(2) of a leaf's rows for two-view batches ys = cat[ys, ys]. */
+#define HCOMP_DESC_TANH_DESC 1
+#define HCOMP_DESC_CONTRAST 2
+#define HCOMP_DESC_MASK_PRUNE 4
+#define HCOMP_DESC_GEOMETRIC 8
+#define HCOMP_DESC_SG_SCORE 16
+long long hcomp_desc_losses_ws_bytes(const hcomp_tables* t, int V);
+int hcomp_desc_losses_fwd(const float* pooled, const float* wc, const float* presence, const float* gumbel,
+                          const long long* ys, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
+                          int V_first, int flags, const float* weights_host, float eps, float boost, float gumbel_tau,
+                          void* ws, float* stats, float* loss, void* stream);
+/* g_loss: device scalar.  g_pooled [V,P] and g_presence [P,2] are fully written; either may be NULL. */
+int hcomp_desc_losses_bwd(const float* g_loss, const float* pooled, const float* wc, const float* presence,
+                          const float* gumbel, const long long* ys, const int8_t* tgt, const int32_t* n_desc,
+                          const hcomp_tables* t, int V, int V_first, int flags, const float* weights_host, float eps,
+                          float boost, float gumbel_tau, const void* ws, float* g_pooled, float* g_presence, void* stream);
 
 /* ---- predictions (util/node.py:300-385, pipnet/pipnet.py:173-185) ------------------------------ */
 /* probs_ws: float[V*K]; joint: float[V*L] (columns in sorted leaf-name order); pred: int64[V] argmax. */

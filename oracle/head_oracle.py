@@ -112,13 +112,105 @@ def class_term(out_node, mask, target, weights, multiplier=2.0):
     return (nll * w).mean()
 
 
+def gumbel_noise_like(logits):
+    """The noise `F.gumbel_softmax` draws internally (torch/nn/functional.py: -empty_like(logits).exponential_().log());
+    drawing it here at the same points of the loop, under the same seed, reproduces the reference's RNG stream."""
+    return -torch.empty_like(logits, memory_format=torch.legacy_contiguous_format).exponential_().log()
+
+
+def mask_prune_terms(node, pooled_node, cls_w_node, presence_node, batch_names, *, boost=None, geometric=False,
+                     sg_before_masking=False, noise=None, noise_out=None, tau=0.5):
+    """`pipnet/train.py:946-1015` for one node: overspecificity and mask-L1 terms (before their 2.0 / 0.5 weights).
+    Per child (in `node.children` order): relevant prototypes = classifier row > 1e-3 (:963); for every leaf below the
+    child that occurs in the batch, the max over its rows of `pooled` (:968-973); children without any such leaf are
+    skipped AFTER their relevant prototypes were counted (:965, :975-976); the presence logits go through a soft Gumbel
+    softmax (tau 0.5) whose OUTPUT replaces the variable, so each further child perturbs the previous child's
+    probabilities (:978); score = prod over present leaves of clamp(max * boost, max=1) (:980-985) or the plain /
+    geometric-mean product (:987-995).  Both sums are divided by the total relevant count (:1003-1004).
+    noise: {child label -> [P_n, 2]} to inject; None draws it like the reference does.  Returns (ovsp, l1)."""
+    pres = presence_node
+    ovsp, l1, total_rel = 0., 0., 0.
+    for child in node.children:
+        c = node.children_to_labels[child.name]
+        rel = torch.nonzero(cls_w_node[c, :] > 1e-3).squeeze(-1)
+        total_rel += rel.shape[0]
+        rows = []
+        for leaf in child.leaf_descendents:
+            idx = torch.tensor([n == leaf for n in batch_names])
+            if int(idx.sum()) == 0:
+                continue
+            rows.append(pooled_node[idx][:, rel].max(dim=0, keepdim=True)[0])
+        if not rows:
+            continue
+        mx = torch.cat(rows, dim=0)
+        g = gumbel_noise_like(pres) if noise is None else noise[c].to(pres.dtype)
+        if noise_out is not None:
+            noise_out[c] = g.detach().clone()
+        pres = torch.softmax((pres + g) / tau, dim=-1)
+        if boost is not None:
+            score = torch.prod(torch.clamp(mx * boost, max=1.0), dim=0)
+        elif geometric:
+            score = torch.prod(mx.pow(1 / mx.shape[0]), dim=0)
+        else:
+            score = torch.prod(mx, dim=0)
+        if sg_before_masking:
+            score = score.detach()
+        ovsp = ovsp + (-1) * (score * pres[rel, 1]).sum()
+        l1 = l1 + pres[rel, 1].sum()
+    return ovsp / total_rel, l1 / total_rel
+
+
+def contrasting_set_term(node, pooled_node, cls_w_node, mask, target):
+    """`pipnet/train.py:1017-1057` with TOPK = 1: for every child, over the node's descendants in the batch that do NOT
+    belong to that child, the max activation of the child's prototypes (classifier row > 1e-5); mean over all
+    (child, prototype) entries.  None when nothing qualifies (:1054)."""
+    vals = []
+    sub = pooled_node[mask]
+    for child in node.children:
+        c = node.children_to_labels[child.name]
+        rel = torch.nonzero(cls_w_node[c, :] > 1e-5).squeeze(-1)
+        if len(rel) == 0:
+            continue
+        rows = torch.nonzero(target != c).squeeze(-1)
+        if len(rows) == 0:
+            continue
+        vals.append(sub[rows, :][:, rel].max(dim=0)[0])
+    if not vals:
+        return None
+    return torch.cat(vals).mean()
+
+
+def tanh_desc_term(node, pooled_node, cls_w_node, batch_names, eps=1e-8):
+    """`pipnet/train.py:1089-1133`: the tanh loss of every leaf below the node, restricted to the prototypes of the
+    child the leaf hangs under (classifier row > 1e-3), on that leaf's rows split by `.chunk(2)` (:1107, :1119; an
+    absent leaf gives two empty halves -> log(tanh(0) + eps)); mean over leaves.  A child without relevant
+    prototypes is skipped (the reference asserts / raises there, :1099-1106, :1114-1117)."""
+    terms = []
+    for child in node.children:
+        c = node.children_to_labels[child.name]
+        rel = torch.nonzero(cls_w_node[c, :] > 1e-3).squeeze(-1)
+        if len(rel) == 0:
+            continue
+        leaves = [child.name] if child.is_leaf() else list(child.leaf_descendents)
+        for leaf in leaves:
+            idx = torch.tensor([n == leaf for n in batch_names])
+            p1, p2 = pooled_node[idx][:, rel].chunk(2)
+            terms.append(-(torch.log(torch.tanh(p1.sum(dim=0)) + eps).mean() + torch.log(torch.tanh(p2.sum(dim=0)) + eps).mean()) / 2.)
+    return torch.stack(terms).mean(dim=0)
+
+
 def head_losses(root, proto, pooled, out, ys, label2name, add_on_w, cls_w, *, pretrain, finetune,
                 epoch=1, nr_epochs=10, cl_weight=2.0, kernel_orth=True, tanh_during_second_phase=True,
-                multiplier=2.0):
+                multiplier=2.0, tanh_desc_weight=None, contrasting=None, mask_prune=None, presence=None,
+                gumbel=None, gumbel_out=None):
     """The head's share of `calculate_loss` (`pipnet/train.py:852-1341`) for the canonical recipe
     (align_pf + tanh + kernel_orth + class loss), with `train_pipnet`'s weights
     (`pipnet/train.py:148-177`) and the `/len(nodes)` normaliser.  Nodes with no descendant in
-    the batch are skipped (`:941-942`) but still counted in the normaliser."""
+    the batch are skipped (`:941-942`) but still counted in the normaliser.
+    Optional terms of the shipped scripts: `tanh_desc_weight` (--tanh_desc "y|w"), `contrasting` = weight of
+    --minimize_contrasting_set (TOPK 1; default 0.1), `mask_prune` = dict(start_epoch, boost, geometric, sg) for
+    --mask_prune_overspecific with `presence` {node -> [P_n, 2]} logits; `gumbel` {node -> {child label -> noise}}
+    injects the Gumbel noise (None draws it exactly where the reference does), `gumbel_out` collects what was used."""
     nodes = root.nodes_with_children()
     n_nodes = len(nodes)
     if pretrain:
@@ -127,21 +219,44 @@ def head_losses(root, proto, pooled, out, ys, label2name, add_on_w, cls_w, *, pr
         align_pf_weight, t_weight, cw = 5., 2., cl_weight
     orth_weight = 0.5
     masks, targets = node_targets(root, ys, label2name)
-    res = dict(align={}, tanh={}, orth={}, cls={}, n_desc={}, acc={})
+    batch_names = [label2name[int(y)] for y in ys]
+    res = dict(align={}, tanh={}, orth={}, cls={}, n_desc={}, acc={}, ovsp={}, mask_l1={}, contrast={}, tanh_desc={})
+    # `calculate_loss` receives EPS=1e-8 from train_pipnet (:238), but the contrasting-set block re-binds the SAME local
+    # to 1e-12 (:1025) before the tanh / tanh_desc terms of the same loop iteration read it (:1080, :1108); the root
+    # always has descendants, so with that term on every node sees 1e-12.
+    eps = 1e-12 if ((not pretrain) and (not finetune) and contrasting is not None) else 1e-8
     loss = 0.
     for node in nodes:
         m, t = masks[node.name], targets[node.name]
         if t.numel() == 0:
             continue
         res['n_desc'][node.name] = int(t.numel())
+        if (not pretrain) and mask_prune is not None and epoch >= mask_prune.get('start_epoch', 0):
+            nz_out = None if gumbel_out is None else gumbel_out.setdefault(node.name, {})
+            ov, l1 = mask_prune_terms(node, pooled[node.name], cls_w[node.name], presence[node.name], batch_names,
+                                      boost=mask_prune.get('boost'), geometric=mask_prune.get('geometric', False),
+                                      sg_before_masking=mask_prune.get('sg', False),
+                                      noise=None if gumbel is None else gumbel[node.name], noise_out=nz_out)
+            res['ovsp'][node.name] = 2.0 * ov / n_nodes             # the reference stores the weighted values (:1006-1010)
+            res['mask_l1'][node.name] = 0.5 * l1 / n_nodes
+            loss = loss + res['ovsp'][node.name] + res['mask_l1'][node.name]
+        if (not pretrain) and (not finetune) and contrasting is not None:
+            cs = contrasting_set_term(node, pooled[node.name], cls_w[node.name], m, t)
+            if cs is not None:
+                res['contrast'][node.name] = cs
+                loss = loss + contrasting * cs / n_nodes
         if not finetune:
             a = align_pf_term(proto[node.name], m)
             res['align'][node.name] = a
             loss = loss + align_pf_weight * a / n_nodes
             if pretrain or tanh_during_second_phase:
-                th = tanh_term(pooled[node.name], m)
+                th = tanh_term(pooled[node.name], m, eps)
                 res['tanh'][node.name] = th
                 loss = loss + t_weight * th / n_nodes
+        if (not finetune) and (not pretrain) and tanh_desc_weight is not None:
+            td = tanh_desc_term(node, pooled[node.name], cls_w[node.name], batch_names, eps)
+            res['tanh_desc'][node.name] = td
+            loss = loss + tanh_desc_weight * td / n_nodes
         if (not pretrain) and (not finetune) and kernel_orth:
             o = orth_term(add_on_w[node.name], cls_w[node.name])
             res['orth'][node.name] = o
@@ -185,17 +300,19 @@ def joint_distribution(root, out, softmax_tau=1.0):
 
 
 # --------------------------------------------------------------------------- convenience: one full step
-def full_step(x, add_on_w, cls_w, root, ys, label2name, *, pretrain, finetune, softmax_tau=1.0, **kw):
+def full_step(x, add_on_w, cls_w, root, ys, label2name, *, pretrain, finetune, softmax_tau=1.0, presence=None, **kw):
     """Forward + losses + autograd backward; returns outputs and gradients w.r.t. x, add-on and
     classifier weights (what `loss.backward()` at `pipnet/train.py:264` produces for the head)."""
     x = x.detach().clone().requires_grad_(True)
     aw = {k: v.detach().clone().requires_grad_(True) for k, v in add_on_w.items()}
     cw = {k: v.detach().clone().requires_grad_(True) for k, v in cls_w.items()}
     proto, pooled, argmax, out = head_forward(x, aw, cw, root, softmax_tau=softmax_tau)
-    res = head_losses(root, proto, pooled, out, ys, label2name, aw, cw, pretrain=pretrain, finetune=finetune, **kw)
+    pr = None if presence is None else {k: v.detach().clone().requires_grad_(True) for k, v in presence.items()}
+    res = head_losses(root, proto, pooled, out, ys, label2name, aw, cw, pretrain=pretrain, finetune=finetune, presence=pr, **kw)
     loss = res['loss']
     if torch.is_tensor(loss) and loss.requires_grad:
         loss.backward()
     res.update(proto=proto, pooled=pooled, argmax=argmax, out=out, grad_x=x.grad,
-               grad_w={k: v.grad for k, v in aw.items()}, grad_cls={k: v.grad for k, v in cw.items()})
+               grad_w={k: v.grad for k, v in aw.items()}, grad_cls={k: v.grad for k, v in cw.items()},
+               grad_presence=None if pr is None else {k: v.grad for k, v in pr.items()})
     return res

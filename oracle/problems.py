@@ -118,7 +118,7 @@ def make_args(**over):
     return argparse.Namespace(**a)
 
 
-def build_net(tree, C, args, seed=3):
+def build_net(tree, C, args, seed=3, device='cuda'):
     from pipnet_b200 import pipnet as pp
     root = make_tree(tree, num_features=args.num_features, per_child=args.num_protos_per_child)
     pp.base_architecture_to_features['identity'] = lambda pretrained=False: IdentityBackbone(C)
@@ -132,4 +132,43 @@ def build_net(tree, C, args, seed=3):
             w.copy_(bf16_round(w))
         net._multiplier.fill_(2.0)
         net._multiplier.requires_grad = False
-    return net.cuda(), root
+    return (net.cuda() if device == 'cuda' else net), root
+
+
+def desc_loss_kwargs(args):
+    """argparse strings of the shipped scripts' optional terms (--tanh_desc "y|w", --minimize_contrasting_set 'y|k|w',
+    --mask_prune_overspecific 'y|epoch|boost') -> keyword arguments of `head_oracle.head_losses`"""
+    kw = {}
+    if 'y' in getattr(args, 'tanh_desc', 'n'):
+        kw['tanh_desc_weight'] = float(args.tanh_desc.split('|')[1])
+    if 'y' in getattr(args, 'minimize_contrasting_set', 'n'):
+        f = args.minimize_contrasting_set.split('|')
+        assert len(f) < 2 or int(f[1]) == 1, 'TOPK 1 only'
+        kw['contrasting'] = float(f[2]) if len(f) > 2 else 0.1
+    if 'y' in getattr(args, 'mask_prune_overspecific', 'n'):
+        f = args.mask_prune_overspecific.split('|')
+        kw['mask_prune'] = dict(start_epoch=int(f[1]) if len(f) > 1 else 0, boost=float(f[2]) if len(f) > 2 else None,
+                                geometric='y' in getattr(args, 'geometric_mean_overspecificity_score', 'n'),
+                                sg='y' in getattr(args, 'sg_before_masking', 'n'))
+    return kw
+
+
+def flat_gumbel(noise_by_node, nodes):
+    """{node name -> {child label -> [P_n, 2]}} -> [sum C_n*P_n, 2] indexed like the flat classifier weights"""
+    total = sum(n.num_protos * n.num_children() for n in nodes)
+    out = torch.zeros(total, 2, dtype=torch.float64)
+    off = 0
+    for n in nodes:
+        for c, g in noise_by_node.get(n.name, {}).items():
+            out[off + c * n.num_protos: off + (c + 1) * n.num_protos] = g.double()
+        off += n.num_protos * n.num_children()
+    return out
+
+
+def split_gumbel(flat, nodes):
+    """inverse of `flat_gumbel` (all children present; unused entries are simply never read)"""
+    out, off = {}, 0
+    for n in nodes:
+        out[n.name] = {c: flat[off + c * n.num_protos: off + (c + 1) * n.num_protos] for c in range(n.num_children())}
+        off += n.num_protos * n.num_children()
+    return out

@@ -137,7 +137,7 @@ def build_reference_net(tree_edges, channels, args, seed=1):
 
 
 def run_reference(net, root, x, ys, args, *, pretrain, finetune, epoch=1, nr_epochs=10, dtype=torch.float32,
-                  kernel_orth=True, inference=False):
+                  kernel_orth=True, inference=False, rng_seed=None):
     """One reference step: `PIPNet.forward` (`pipnet/pipnet.py:111-171`) + `calculate_loss`
     (`pipnet/train.py:852`) with the loss weights of `train_pipnet` (`pipnet/train.py:148-177`)
     + backward.  Returns plain tensors keyed by node name."""
@@ -159,6 +159,8 @@ def run_reference(net, root, x, ys, args, *, pretrain, finetune, epoch=1, nr_epo
     else:
         w = dict(align_pf_weight=5., t_weight=2., cl_weight=args.cl_weight)
     criterion = ref_losses.WeightedNLLLoss(device='cpu')
+    if rng_seed is not None:          # the only RNG consumer on this path is the Gumbel softmax of the mask-prune term
+        torch.manual_seed(rng_seed)
     res = ref_train.calculate_loss(
         epoch, _Wrap(net), {}, features, proto_features, pooled, out, ys,
         align_weight=0.5, align_pf_weight=w['align_pf_weight'], t_weight=w['t_weight'], mm_weight=0., unif_weight=3.,
@@ -166,7 +168,7 @@ def run_reference(net, root, x, ys, args, *, pretrain, finetune, epoch=1, nr_epo
         subspace_sep_weight=1e-2, byol_weight=0.5, net_normalization_multiplier=net._multiplier,
         pretrain=pretrain, finetune=finetune, criterion=criterion, train_iter=_Iter(), print=True, EPS=1e-8,
         root=root, label2name=label2name, node_accuracy=node_accuracy, OOD_loss_required=False,
-        kernel_orth=kernel_orth, tanh_desc=False, align=False, uni=False, align_pf=True, tanh=True,
+        kernel_orth=kernel_orth, tanh_desc=('y' in args.tanh_desc), align=False, uni=False, align_pf=True, tanh=True,
         minmaximize=False, cluster_desc=False, sep_desc=False, subspace_sep=False, byol=False, args=args, device='cpu')
     loss, class_loss, _a, tanh_loss, _mm, _ood, orth_loss = res[:7]
     loss.backward()
@@ -177,6 +179,10 @@ def run_reference(net, root, x, ys, args, *, pretrain, finetune, epoch=1, nr_epo
         cls = getattr(net, '_' + node.name + '_classification')
         g[node.name] = (None if conv.weight.grad is None else conv.weight.grad.detach().flatten(1).clone(),
                         None if cls.weight.grad is None else cls.weight.grad.detach().clone())
+    g_presence = {}
+    for node in nodes:
+        pp = getattr(net, '_' + node.name + '_proto_presence')
+        g_presence[node.name] = None if pp.grad is None else pp.grad.detach().clone()
     H, W = x.shape[-2:]
     argmax = {}
     for node in nodes:
@@ -187,5 +193,6 @@ def run_reference(net, root, x, ys, args, *, pretrain, finetune, epoch=1, nr_epo
                 orth_loss={k: torch.as_tensor(v).detach() for k, v in orth_loss.items()},
                 pooled={k: v.detach() for k, v in pooled.items()}, out={k: v.detach() for k, v in out.items()},
                 proto_features={k: v.detach() for k, v in proto_features.items()}, argmax=argmax,
-                grad_x=None if x.grad is None else x.grad.detach().clone(), grads=g,
+                grad_x=None if x.grad is None else x.grad.detach().clone(), grads=g, grad_presence=g_presence,
+                avg_tanh_desc=float(res[17]),
                 node_accuracy={k: (v['n_examples'], v['n_correct']) for k, v in node_accuracy.items()})

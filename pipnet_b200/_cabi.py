@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhcomp_head.so')
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class HcompError(RuntimeError):
@@ -50,11 +50,14 @@ SIGNATURES = {
     'hcomp_classifier_bwd': [_p, _p, _p, _T, _i, _p, _i, _p, _p, _p],
     'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p],
     'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_desc_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
+    'hcomp_desc_losses_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p],
     'hcomp_materialize_map': [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }
-EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats', 'hcomp_set_cta_pair'] + list(SIGNATURES)
+EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats',
+           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair'] + list(SIGNATURES)
 
 _lib = None
 
@@ -74,6 +77,8 @@ def lib():
     L.hcomp_launch_count.restype = C.c_longlong
     L.hcomp_head_losses_ws_floats.restype = C.c_longlong
     L.hcomp_head_losses_ws_floats.argtypes = [_T]
+    L.hcomp_desc_losses_ws_bytes.restype = C.c_longlong
+    L.hcomp_desc_losses_ws_bytes.argtypes = [_T, C.c_int]
     L.hcomp_set_cta_pair.restype = C.c_int
     L.hcomp_set_cta_pair.argtypes = [C.c_int]
     for name, args in SIGNATURES.items():

@@ -171,6 +171,7 @@ class LabelTables:
         ys = ys.to(torch.int64).contiguous()
         V = ys.numel()
         self.V, self.V_first = V, V_first
+        self.ys = ys                      # leaf index per row (the descendant-structured loss terms group rows by leaf)
         self.tgt = torch.empty(V, dl.N, device=ys.device, dtype=torch.int8)
         self.desc = torch.empty(V_first, dl.N, device=ys.device, dtype=torch.uint8)
         self.n_desc = torch.empty(dl.N, device=ys.device, dtype=torch.int32)
@@ -386,6 +387,63 @@ class HeadLosses(torch.autograd.Function):
              V, labels.V_first, Cc, flags, wts, eps, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out), ptr(g_w),
              _stream())
         return g_pooled, g_out, (gvec[0] if need_align else None), g_w, None, None, None, None, None, None
+
+DESC_TANH_DESC, DESC_CONTRAST, DESC_MASK_PRUNE, DESC_GEOMETRIC, DESC_SG_SCORE = 1, 2, 4, 8, 16
+
+
+def gumbel_noise(dl: DeviceLayout, device) -> torch.Tensor:
+    """Gumbel(0,1) noise for the mask-pruning term, one pair per classifier weight element (node, child, prototype):
+    the same distribution `F.gumbel_softmax` draws from inside the reference's child loop (pipnet/train.py:978)."""
+    return -torch.empty(dl.layout.n_welems, 2, device=device, dtype=torch.float32).exponential_().log()
+
+
+class DescLosses(torch.autograd.Function):
+    """tanh_desc + minimize_contrasting_set + mask-prune overspecificity (pipnet/train.py:946-1060, 1089-1133) for
+    all nodes in one forward / one backward call.  weights = (tanh_desc_w/N, contrast_w/N, 2.0/N, 0.5/N).
+    Returns (loss, stats[4,N]); gradients flow to `pooled` and the presence logits only (the classifier weights
+    enter through index selections in the reference and get none)."""
+
+    @staticmethod
+    def forward(ctx, pooled, wc_flat, presence, gumbel, labels: LabelTables, dl: DeviceLayout, flags, weights, eps,
+                boost, tau):
+        pooled = pooled.contiguous()
+        V, dev = pooled.shape[0], pooled.device
+        wc = wc_flat.detach().contiguous()
+        pres = presence.detach().contiguous().float() if presence is not None else None
+        gum = gumbel.detach().contiguous().float() if gumbel is not None else None
+        if (flags & DESC_MASK_PRUNE) and (pres is None or gum is None or tuple(pres.shape) != (dl.P, 2)
+                                         or tuple(gum.shape) != (dl.layout.n_welems, 2)):
+            raise _cabi.HcompError('mask pruning needs presence [P,2] and gumbel noise [n_welems,2]')
+        wts = (C.c_float * 4)(*[float(x) for x in weights])
+        ws = torch.empty(int(_cabi.lib().hcomp_desc_losses_ws_bytes(dl.tref, V)), device=dev, dtype=torch.uint8)
+        stats = torch.empty(4, dl.N, device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        boost = float(boost) if boost else 0.0
+        call('hcomp_desc_losses_fwd', ptr(pooled), ptr(wc), ptr(pres), ptr(gum), ptr(labels.ys), ptr(labels.tgt),
+             ptr(labels.n_desc), dl.tref, V, labels.V_first, int(flags), wts, float(eps), boost, float(tau), ptr(ws),
+             ptr(stats), ptr(loss), _stream())
+        ctx.dl, ctx.labels = dl, labels
+        ctx.cfg = (int(flags), [float(x) for x in weights], float(eps), boost, float(tau), V)
+        ctx.has_presence = presence is not None
+        ctx.save_for_backward(pooled, wc, pres, gum, ws)
+        ctx.mark_non_differentiable(stats)
+        return loss, stats
+
+    @staticmethod
+    def backward(ctx, g_loss, _gs):
+        pooled, wc, pres, gum, ws = ctx.saved_tensors
+        dl, labels = ctx.dl, ctx.labels
+        flags, weights, eps, boost, tau, V = ctx.cfg
+        dev = pooled.device
+        wts = (C.c_float * 4)(*weights)
+        g_loss = g_loss.contiguous().float()
+        g_pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        g_pres = (torch.empty(dl.P, 2, device=dev, dtype=torch.float32)
+                  if (ctx.has_presence and ctx.needs_input_grad[2]) else None)
+        call('hcomp_desc_losses_bwd', ptr(g_loss), ptr(pooled), ptr(wc), ptr(pres), ptr(gum), ptr(labels.ys), ptr(labels.tgt),
+             ptr(labels.n_desc), dl.tref, V, labels.V_first, flags, wts, eps, boost, tau, ptr(ws), ptr(g_pooled), ptr(g_pres),
+             _stream())
+        return g_pooled, None, g_pres, None, None, None, None, None, None, None, None
 
 
 def joint_leaf_distribution(out_flat: torch.Tensor, dl: DeviceLayout, tau=1.0):

@@ -239,6 +239,7 @@ class PIPNet(nn.Module):
         self._wc_group = _FlatGroup([getattr(self, '_' + n + '_classification').weight for n in names])
         self._bias_group = (_FlatGroup([getattr(self, '_' + n + '_classification').bias for n in names])
                             if self._has_cls_bias else None)
+        self._pp_group = _FlatGroup([getattr(self, '_' + n + '_proto_presence') for n in names])
         self._dl: Optional[ops.DeviceLayout] = None
         # 'bf16': bf16 GEMM operands (default, the benchmarked path); 'fp32': fp32-accurate projection (3-way bf16 split
         # operands, six cross terms through the same tcgen05 kernel) for the <= 1e-5 contract on fp32 inputs
@@ -279,6 +280,10 @@ class PIPNet(nn.Module):
     def flat_classifier_weights(self) -> Tensor:
         return self._wc_group.gather()
 
+    def flat_proto_presence(self) -> Tensor:
+        """[P, 2] view of all `_<node>_proto_presence` logits with autograd edges to the per-node parameters."""
+        return self._pp_group.gather().view(self.layout.P, 2)
+
     # ------------------------------------------------------------------ forward
     def head(self, features: Tensor, *, inference=False, labels: Optional[ops.LabelTables] = None,
              V_first: Optional[int] = None):
@@ -300,14 +305,14 @@ class PIPNet(nn.Module):
         return ops.NonNegClassifier.apply(pooled_flat, self.flat_classifier_weights(), bias, dl)
 
     def forward(self, xs, inference=False, apply_overspecificity_mask=False, labels: Optional[ops.LabelTables] = None):
-        for grp in (self._w_group, self._wc_group, self._bias_group):
+        for grp in (self._w_group, self._wc_group, self._bias_group, self._pp_group):
             if grp is not None:
                 grp.invalidate()
         features = self._net(xs)
         pooled_flat, align, argmax, dl = self.head(features, inference=inference, labels=labels)
         if apply_overspecificity_mask:
             # Gumbel hard sample on proto_presence (pipnet/pipnet.py:164-166), one draw for the whole flat axis
-            pres = torch.cat([getattr(self, '_' + n + '_proto_presence') for n in self.layout.node_names])
+            pres = self.flat_proto_presence()
             mask = F.gumbel_softmax(pres, tau=0.5, hard=True, dim=-1)[:, 1].unsqueeze(0)
             pooled_flat = mask * pooled_flat
         out_flat = self.classify(pooled_flat, dl)

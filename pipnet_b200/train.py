@@ -10,8 +10,9 @@ Differences that matter for speed, not for results:
   * the per-step `barrier` + broadcast of every parameter (`pipnet/train.py:54-65`) is dropped: its rank-0
     mutation tests `name.endswith('_classification')` on *parameter* names and never fires.
 
-Loss terms implemented as kernels: align_pf, tanh, kernel_orth, class (the shipped recipe).  Terms marked
-"next" in SURVEY 8f (tanh_desc, minimize_contrasting_set, mask-prune, OOD, BYOL, align/uni) raise.
+Loss terms implemented as kernels: align_pf, tanh, kernel_orth, class, and the three extra terms the shipped
+scripts switch on -- tanh_desc, minimize_contrasting_set (TOPK 1), mask-prune overspecificity (`ops.DescLosses`,
+pipnet/train.py:946-1060, 1089-1133).  OOD, BYOL, feature-level align/uni and the research-only terms raise.
 """
 from __future__ import annotations
 
@@ -116,7 +117,8 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
                    pretrain, finetune, criterion, train_iter, print=True, EPS=1e-10, root=None, label2name=None,
                    node_accuracy=None, OOD_loss_required=False, kernel_orth=False, tanh_desc=False, align=True, uni=True,
                    align_pf=False, tanh=False, minmaximize=False, cluster_desc=False, sep_desc=False, subspace_sep=False,
-                   byol=False, train=True, args=None, device=None, labels: Optional[ops.LabelTables] = None):
+                   byol=False, train=True, args=None, device=None, labels: Optional[ops.LabelTables] = None,
+                   gumbel_noise: Optional[torch.Tensor] = None):
     """Same positional contract and 21-tuple as `pipnet/train.py:852-1341`.  `pooled` / `out` are the
     `NodeDict`s returned by `PIPNet.forward`; `labels` are the device label tables of this batch (built here
     from `ys` when not given).  `criterion` is accepted for signature parity: the class term is always the
@@ -124,12 +126,9 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
     m: PIPNet = _unwrap(net)
     _reject('align/uni', (not finetune) and (align or uni))
     _reject('byol', (not finetune) and byol)
-    _reject('tanh_desc', (not finetune) and (not pretrain) and tanh_desc)
     _reject('minmaximize / cluster_desc / sep_desc / subspace_sep', minmaximize or cluster_desc or sep_desc or subspace_sep)
     _reject('OOD loss', OOD_loss_required)
     if args is not None:
-        _reject('--mask_prune_overspecific', (not pretrain) and 'y' in getattr(args, 'mask_prune_overspecific', 'n'))
-        _reject('--minimize_contrasting_set', (not pretrain) and (not finetune) and 'y' in getattr(args, 'minimize_contrasting_set', 'n'))
         _reject('--OOD_ent', 'y' in getattr(args, 'OOD_ent', 'n'))
     if not isinstance(pooled, NodeDict) or not isinstance(out, NodeDict):
         raise Exception('calculate_loss expects the outputs of pipnet_b200.PIPNet.forward')
@@ -152,6 +151,33 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
             raise Exception('align_pf needs the per-node align loss of the fused forward: call net(xs, labels=...)')
         wts[0] = align_pf_weight / N
         losses_used.append('AL_PF')
+    # ---- descendant-structured terms of the shipped scripts (tanh_desc, contrasting set, mask pruning)
+    dflags, dw, boost = 0, [0.0, 0.0, 2.0 / N, 0.5 / N], 0.0
+    mp_arg = getattr(args, 'mask_prune_overspecific', 'n') if args is not None else 'n'
+    cs_arg = getattr(args, 'minimize_contrasting_set', 'n') if args is not None else 'n'
+    if (not pretrain) and 'y' in mp_arg:                                           # pipnet/train.py:946-1015
+        if getattr(args, 'protopool', 'n') == 'y':
+            raise Exception('--mask_prune_overspecific cannot be combined with --protopool y (pipnet/train.py:947)')
+        f = mp_arg.split('|')
+        if not (len(f) > 1 and epoch < int(f[1])):
+            dflags |= ops.DESC_MASK_PRUNE
+            if len(f) > 2:
+                boost = float(f[2])
+            elif 'y' in getattr(args, 'geometric_mean_overspecificity_score', 'n'):
+                dflags |= ops.DESC_GEOMETRIC
+            if 'y' in getattr(args, 'sg_before_masking', 'n'):
+                dflags |= ops.DESC_SG_SCORE
+            losses_used.append('MASK_PRUNING')
+    if (not pretrain) and (not finetune) and 'y' in cs_arg:                        # pipnet/train.py:1017-1060
+        f = cs_arg.split('|')
+        if len(f) > 1 and int(f[1]) != 1:
+            raise Exception('--minimize_contrasting_set with TOPK != 1 is not supported by the B200 head')
+        dflags |= ops.DESC_CONTRAST
+        dw[1] = (float(f[2]) if len(f) > 2 else 0.1) / N
+        losses_used.append('MIN_CONT')
+        # the reference re-binds its local EPS to 1e-12 inside this block (:1025), BEFORE the tanh / tanh_desc terms of
+        # the same loop iteration read it (:1080, :1108): with the term on they all see 1e-12
+        EPS = 1e-12
     use_tanh = (not finetune) and tanh and not (getattr(args, 'tanh_during_second_phase', 'y') == 'n' and not pretrain)
     if use_tanh:
         flags |= ops.LOSS_TANH
@@ -171,6 +197,19 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         flags |= ops.LOSS_SPARSITY
     loss, stats, n_correct = ops.HeadLosses.apply(pooled.flat, out.flat, align_vec, m.flat_prototype_kernels() if use_orth else None,
                                                   m.flat_classifier_weights(), labels, dl, flags, wts, EPS)
+    if (not finetune) and (not pretrain) and tanh_desc:                             # pipnet/train.py:1089-1133
+        dflags |= ops.DESC_TANH_DESC
+        dw[0] = float(args.tanh_desc.split('|')[1]) / N
+        losses_used.append('TANH_DESC')
+    desc_stats = None
+    if dflags:
+        use_mp = bool(dflags & ops.DESC_MASK_PRUNE)
+        if use_mp and gumbel_noise is None:
+            gumbel_noise = ops.gumbel_noise(dl, pooled.flat.device)
+        dloss, desc_stats = ops.DescLosses.apply(pooled.flat, m.flat_classifier_weights(),
+                                                 m.flat_proto_presence() if use_mp else None,
+                                                 gumbel_noise if use_mp else None, labels, dl, dflags, dw, EPS, boost, 0.5)
+        loss = loss + dloss
 
     if node_accuracy is not None:
         acc = node_accuracy.setdefault('__device__', {'n_examples': torch.zeros(N, device=zero.device, dtype=torch.int64),
@@ -189,9 +228,13 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         train_iter.lazy_postfix = (loss.detach(), avg_class_loss, avg_a_loss_pf, avg_tanh_loss, avg_orth, '+'.join(losses_used))
     a_loss = torch.tensor(-5)
     uni_loss = torch.tensor(-5)
+    use_td = bool(dflags & ops.DESC_TANH_DESC)
+    avg_tanh_desc = LazyMean(LazyNodeLosses(desc_stats[0], labels.n_desc, names)) if use_td else -5
     res = (loss, class_loss, a_loss, tanh_loss, {}, {}, orth_loss, uni_loss, avg_class_loss, avg_a_loss_pf, avg_tanh_loss,
-           placeholder, (placeholder if pretrain else -5), avg_orth, -5, -5, -5, -5, -5, -5, 0.)
-    return _LossResult(res, stats, labels.n_desc)
+           placeholder, (placeholder if pretrain else -5), avg_orth, -5, -5, -5, avg_tanh_desc, -5, -5, 0.)
+    out_res = _LossResult(res, stats, labels.n_desc)
+    out_res.desc_stats = desc_stats          # [4,N] tanh_desc, contrast, overspecificity, mask_l1 (None when all are off)
+    return out_res
 
 
 # --------------------------------------------------------------------------- epoch drivers

@@ -19,7 +19,9 @@ def test_cuda_head_reproduces_reference_fixture(path):
     d = np.load(path, allow_pickle=False)
     C, H, B = int(d['C']), int(d['H']), int(d['B'])
     pretrain, finetune = bool(d['pretrain']), bool(d['finetune'])
-    args = make_args(num_features=int(d['num_features']), num_protos_per_child=int(d['per_child']))
+    shipped = 'gumbel' in d.files         # fixture of the shipped scripts' full recipe (extra terms + recorded Gumbel noise)
+    extra_args = {k[4:]: str(d[k]) for k in d.files if k.startswith('arg_')}
+    args = make_args(num_features=int(d['num_features']), num_protos_per_child=int(d['per_child']), **extra_args)
     net, root = build_net(str(d['tree']), C, args)
     names = net.layout.node_names
     assert names == [str(n) for n in d['node_names']]
@@ -32,6 +34,11 @@ def test_cuda_head_reproduces_reference_fixture(path):
             p.copy_(w[o1:o1 + p.shape[0]].view_as(p)); o1 += p.shape[0]
             q = getattr(net, '_' + n + '_classification').weight
             q.copy_(wc[o2:o2 + q.numel()].view_as(q)); o2 += q.numel()
+        if shipped:
+            pres, o3 = torch.from_numpy(d['presence']).float().cuda(), 0
+            for n in names:
+                pp = getattr(net, '_' + n + '_proto_presence')
+                pp.copy_(pres[o3:o3 + pp.shape[0]]); o3 += pp.shape[0]
     xs = torch.from_numpy(d['x']).cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last).requires_grad_(True)
     ys = torch.from_numpy(d['ys']).cuda()
     labels = tr.make_labels(net, ys)
@@ -39,8 +46,9 @@ def test_cuda_head_reproduces_reference_fixture(path):
     w_ = tr._phase_weights(pretrain, 3, 10, args)
     res = tr.calculate_loss(3, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
                             pretrain=pretrain, finetune=finetune, criterion=None, train_iter=None, print=False, EPS=1e-8,
-                            root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
-                            device='cuda', labels=labels, **w_)
+                            root=root, kernel_orth=True, tanh_desc='y' in args.tanh_desc, align=False, uni=False,
+                            align_pf=True, tanh=True, args=args, device='cuda', labels=labels,
+                            gumbel_noise=torch.from_numpy(d['gumbel']).float().cuda() if shipped else None, **w_)
     res[0].backward()
     torch.cuda.synchronize()
     assert rel_err(pooled.flat, torch.from_numpy(d['pooled'])) <= 1e-5
@@ -57,6 +65,12 @@ def test_cuda_head_reproduces_reference_fixture(path):
         assert rel_err(xs.grad, torch.from_numpy(d['grad_x'])) <= 2e-2
     gw = torch.cat([getattr(net, '_' + n + '_add_on').weight.grad.flatten(1) for n in names])
     assert rel_err(gw, torch.from_numpy(d['grad_w'])) <= 2e-2
+    if shipped:
+        gp = torch.cat([getattr(net, '_' + n + '_proto_presence').grad for n in names]).double().cpu()
+        want = torch.from_numpy(d['grad_presence'])
+        assert (gp - want).abs().max() <= 2e-4 * float(want.abs().max()) + 1e-9
+        if 'y' in args.tanh_desc and not finetune:
+            assert abs(float(res[17]) - float(d['avg_tanh_desc'])) <= 2e-5 * max(1.0, abs(float(d['avg_tanh_desc'])))
     _, joint = net.get_joint_distribution(out)
     ref_joint = torch.from_numpy(d['joint'])
     assert rel_err(joint, ref_joint) <= 1e-5

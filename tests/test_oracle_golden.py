@@ -49,8 +49,19 @@ def test_oracle_reproduces_reference_fixture(path):
     x = torch.from_numpy(d['x']).double()
     ys = torch.from_numpy(d['ys'])
     label2name = {i: n for i, n in enumerate(sorted(root.leaf_descendents))}
+    extra = {}
+    if 'gumbel' in d.files:               # shipped-recipe fixture: optional terms + the Gumbel noise the reference drew
+        import argparse
+        from oracle.problems import desc_loss_kwargs, split_gumbel
+        args = argparse.Namespace(**{k[4:]: str(d[k]) for k in d.files if k.startswith('arg_')})
+        pres_flat = torch.from_numpy(d['presence']).double()
+        pres, off = {}, 0
+        for n, k in zip(names, pn):
+            pres[n] = pres_flat[off:off + k]
+            off += k
+        extra = dict(presence=pres, gumbel=split_gumbel(torch.from_numpy(d['gumbel']).double(), nodes), **desc_loss_kwargs(args))
     res = ho.full_step(x, aw, wc, root, ys, label2name, pretrain=bool(d['pretrain']), finetune=bool(d['finetune']),
-                       epoch=3, nr_epochs=10)
+                       epoch=3, nr_epochs=10, **extra)
     tol = dict(rtol=1e-10, atol=1e-12)
     torch.testing.assert_close(torch.cat([res['pooled'][n] for n in names], 1), torch.from_numpy(d['pooled']), **tol)
     torch.testing.assert_close(torch.cat([res['out'][n] for n in names], 1), torch.from_numpy(d['out']), **tol)
@@ -66,6 +77,12 @@ def test_oracle_reproduces_reference_fixture(path):
         torch.testing.assert_close(res['grad_x'], torch.from_numpy(d['grad_x']), rtol=1e-8, atol=1e-12)
     gw = torch.cat([res['grad_w'][n] if res['grad_w'][n] is not None else torch.zeros_like(aw[n]) for n in names])
     torch.testing.assert_close(gw, torch.from_numpy(d['grad_w']), rtol=1e-8, atol=1e-12)
+    if 'gumbel' in d.files:
+        gp = torch.cat([res['grad_presence'][n] if res['grad_presence'][n] is not None else torch.zeros_like(pres[n]) for n in names])
+        torch.testing.assert_close(gp, torch.from_numpy(d['grad_presence']), rtol=1e-8, atol=1e-12)
+        if res['tanh_desc']:
+            mean_td = sum(float(v.detach()) for v in res['tanh_desc'].values()) / len(res['tanh_desc'])
+            assert abs(mean_td - float(d['avg_tanh_desc'])) <= 1e-10 * max(1.0, abs(mean_td))
     joint = ho.joint_distribution(root, res['out'], 1.0)
     torch.testing.assert_close(joint, torch.from_numpy(d['joint']), rtol=1e-10, atol=1e-14)
 

@@ -5,6 +5,7 @@ import torch
 
 from oracle import head_oracle as ho
 from oracle import ref_harness as rh
+from oracle.problems import desc_loss_kwargs
 from pipnet_b200.trees import CUB08, CUB18, CUB27, synthetic_edges
 
 pytestmark = pytest.mark.skipif(not rh.available(), reason="reference checkout not present")
@@ -17,6 +18,14 @@ CASES = [
     ("cub18-A-finetune", CUB18, 16, 3, 5, dict(num_features=10), (False, True)),
     ("cub27-B-train", CUB27, 16, 3, 6, dict(num_protos_per_child=4), (False, False)),
     ("synth12-tau2", synthetic_edges(12, 3), 16, 4, 4, dict(num_features=6, softmax='y|2'), (False, False)),
+    # the shipped scripts' extra terms (run_pipnet_20protos_multi_runs_seed42.sh): tanh_desc, contrasting set, mask pruning
+    ("cub27-B-shipped", CUB27, 16, 3, 8, dict(num_protos_per_child=4, tanh_desc='y|0.05', minimize_contrasting_set='y',
+                                              mask_prune_overspecific='y|0|1.1'), (False, False)),
+    ("cub18-A-shipped", CUB18, 16, 3, 6, dict(num_features=10, tanh_desc='y|0.05', minimize_contrasting_set='y|1|0.1',
+                                              mask_prune_overspecific='y|0'), (False, False)),
+    ("cub18-A-shipped-finetune", CUB18, 16, 3, 6, dict(num_features=10, tanh_desc='y|0.05', minimize_contrasting_set='y',
+                                                       mask_prune_overspecific='y|0|1.1'), (False, True)),
+    ("cub08-B-maskprune-late", CUB08, 16, 3, 4, dict(num_protos_per_child=6, mask_prune_overspecific='y|5|1.1'), (False, False)),
 ]
 
 
@@ -29,14 +38,20 @@ def _run(case, dtype):
     L = len(root.leaf_descendents)
     ys = torch.randint(0, L, (B,), generator=g)
     ys = torch.cat([ys, ys])
-    ref = rh.run_reference(net, root, x, ys, args, pretrain=pretrain, finetune=finetune, dtype=dtype)
     nodes = root.nodes_with_children()
+    with torch.no_grad():          # break the symmetric zero init of the presence logits
+        for n in nodes:
+            pp = getattr(net, '_' + n.name + '_proto_presence')
+            pp.copy_(torch.randn(pp.shape, generator=g, dtype=torch.float64).to(pp.dtype))
+    ref = rh.run_reference(net, root, x, ys, args, pretrain=pretrain, finetune=finetune, dtype=dtype, rng_seed=77)
     aw = {n.name: getattr(net, '_' + n.name + '_add_on').weight.detach().flatten(1).to(dtype) for n in nodes}
     cw = {n.name: getattr(net, '_' + n.name + '_classification').weight.detach().to(dtype) for n in nodes}
     tau = float(args.softmax.split('|')[1])
     label2name = {i: n for i, n in enumerate(sorted(root.leaf_descendents))}
+    presence = {n.name: getattr(net, '_' + n.name + '_proto_presence').detach().to(dtype) for n in nodes}
+    torch.manual_seed(77)          # same seed, same draw order -> the oracle sees the reference's Gumbel noise
     ours = ho.full_step(x, aw, cw, root, ys, label2name, pretrain=pretrain, finetune=finetune, softmax_tau=tau,
-                        cl_weight=args.cl_weight)
+                        cl_weight=args.cl_weight, presence=presence, **desc_loss_kwargs(args))
     return ref, ours, nodes
 
 
@@ -60,6 +75,14 @@ def test_oracle_matches_reference_fp64(case):
             torch.testing.assert_close(ours['grad_w'][k], gw, rtol=1e-9, atol=1e-12)
         if gc is not None:
             torch.testing.assert_close(ours['grad_cls'][k], gc, rtol=1e-9, atol=1e-12)
+        gp = ref['grad_presence'][k]
+        if gp is not None:
+            torch.testing.assert_close(ours['grad_presence'][k], gp, rtol=1e-9, atol=1e-12)
+        else:
+            assert ours['grad_presence'][k] is None or float(ours['grad_presence'][k].abs().max()) == 0.0
+    if ours['tanh_desc']:
+        mean_td = sum(float(v) for v in ours['tanh_desc'].values()) / len(ours['tanh_desc'])
+        assert abs(mean_td - ref['avg_tanh_desc']) <= 1e-9 * max(1.0, abs(mean_td))
     torch.testing.assert_close(ours['loss'].detach(), ref['loss'], **tol)
     if ref['grad_x'] is not None:
         torch.testing.assert_close(ours['grad_x'], ref['grad_x'], rtol=1e-9, atol=1e-12)
