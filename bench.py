@@ -166,6 +166,9 @@ def run_ours(a):
     B, C, H = wl['batch'], wl['C'], wl['H']
     V, HW = 2 * B, H * H
     args = make_args(num_features=wl['num_features'], num_protos_per_child=wl.get('per_child', 0))
+    if a.recipe == 'shipped':        # + the three extra terms of run_pipnet_20protos_multi_runs_seed42.sh:72-94
+        args.tanh_desc, args.minimize_contrasting_set, args.mask_prune_overspecific = 'y|0.05', 'y', 'y|0|1.1'
+    use_td = 'y' in args.tanh_desc
     net, root = build_net(wl['tree'], C, args, seed=1)
     net = net.to(dev)
     net.train()
@@ -192,8 +195,8 @@ def run_ours(a):
         features, pf, pooled, out = net(x, labels=labels)
         res = tr.calculate_loss(1, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
                                 pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8,
-                                root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
-                                device=dev, labels=labels, **w)
+                                root=root, kernel_orth=True, tanh_desc=use_td, align=False, uni=False, align_pf=True,
+                                tanh=True, args=args, device=dev, labels=labels, **w)
         loss = res[0]
         loss.backward()        # N > 1: both flat gradient buffers are mean all-reduced inside backward (ops.GRAD_ALLREDUCE_GROUP)
         return loss, x.grad
@@ -263,8 +266,8 @@ def run_ours(a):
                 features, pf, pooled, out = net(x, labels=labels)
                 res = tr.calculate_loss(1, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
                                         pretrain=False, finetune=False, criterion=None, train_iter=None, print=False,
-                                        EPS=1e-8, root=root, kernel_orth=True, align=False, uni=False, align_pf=True,
-                                        tanh=True, args=args, device=dev, labels=labels, **w)
+                                        EPS=1e-8, root=root, kernel_orth=True, tanh_desc=use_td, align=False, uni=False,
+                                        align_pf=True, tanh=True, args=args, device=dev, labels=labels, **w)
                 return res[0]
 
             graphs = [GraphedHeadStep(loss_fn, list(net.parameters()), feats[i], labels_d[i]) for i in range(2)]
@@ -354,7 +357,8 @@ def run_ours(a):
         peak = peaks['bf16_sustained'] if long_region else peaks['bf16_burst']
         kernels = {k: {'ms_per_step': v[0] / prof_steps, 'calls': v[1]} for k, v in prof.items()}
         step_flops = 4.0 * flops          # fwd + recompute + dX + dW ; algorithmic = 3 GEMMs
-        roofline = {'bound': 'tensor', 'kernel': 'head_pair_kernel<20,fwd> (projection+softmax+maxpool+align)',
+        seg_classes = sorted(set(int(t[0]) for t in L.tiles))
+        roofline = {'bound': 'tensor', 'kernel': f'head_pair_kernel<{"/".join(map(str, seg_classes))},fwd> (projection+softmax+maxpool+align)',
                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
                     'peak_kind': ('sustained' if long_region else 'burst') + ', ' + peaks['source'],
                     'avg_launch_ms': k1_avg, 'algorithmic_flops_per_launch': flops, 'traffic': traffic,
@@ -369,9 +373,11 @@ def run_ours(a):
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
                 'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
                 'data': 'synthetic',
-                'config': {'workload': f'{a.workload}: tree {wl["tree"]} ({L.N} nodes), {wl["num_features"]} protos/node '
-                                       f'(P={L.P}), batch {B}/GPU = {V} views of {H}x{H}x{C} bf16 features, full-training '
-                                       f'phase losses (align_pf+tanh+kernel_orth+class), fwd+bwd',
+                'config': {'workload': f'{a.workload}: tree {wl["tree"]} ({L.N} nodes), '
+                                       + (f'{wl["per_child"]} protos/child' if wl.get('per_child') else f'{wl["num_features"]} protos/node')
+                                       + f' (P={L.P}), batch {B}/GPU = {V} views of {H}x{H}x{C} bf16 features, full-training '
+                                       f'phase losses (align_pf+tanh+kernel_orth+class'
+                                       + ('+tanh_desc+contrasting_set+mask_prune' if a.recipe == 'shipped' else '') + '), fwd+bwd',
                            'global_batch': world * B, 'parallelism': f'dp{world}',
                            'launch': ('one CUDA graph replay per step' if graphs is not None else 'eager'),
                            'eager_ms_per_step': eager_ms,
@@ -396,6 +402,8 @@ def main():
     ap.add_argument('--workload', default='cub27', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'])
+    ap.add_argument('--recipe', default='core', choices=['core', 'shipped'],
+                    help="core: align_pf+tanh+kernel_orth+class (BASELINE.json); shipped: + tanh_desc, contrasting set, mask pruning")
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)

@@ -50,6 +50,7 @@ typedef struct hcomp_tables {
   const int32_t* path_off;     /* [L+1] root->leaf path of leaf l (leaves in sorted-name order)*/
   const int32_t* path_col;     /* [..]  flat child column taken at each step of the path      */
   const int8_t* anc;           /* [L,N] child label of leaf l at node n, -1 if not below n     */
+  const int32_t* col_nleaves;  /* [K]   number of leaves below child column k (descendant-structured losses) */
 } hcomp_tables;
 
 int hcomp_abi_version(void);

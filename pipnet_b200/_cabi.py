@@ -25,7 +25,7 @@ class Tables(C.Structure):
         ('n_welems', C.c_int32), ('p_max', C.c_int32),
         ('proto_off', C.c_void_p), ('cls_off', C.c_void_p), ('wc_off', C.c_void_p), ('proto_node', C.c_void_p),
         ('col_node', C.c_void_p), ('welem_col', C.c_void_p), ('welem_proto', C.c_void_p), ('child_w', C.c_void_p),
-        ('path_off', C.c_void_p), ('path_col', C.c_void_p), ('anc', C.c_void_p),
+        ('path_off', C.c_void_p), ('path_col', C.c_void_p), ('anc', C.c_void_p), ('col_nleaves', C.c_void_p),
     ]
 
 

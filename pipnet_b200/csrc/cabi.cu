@@ -591,16 +591,29 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
 
 // ---------------------------------------------------------------- descendant-structured loss terms
 namespace {
-hc::DescWs desc_ws(void* ws, const hcomp_tables* t, int V) {
+size_t align16(size_t x) { return (x + 15) & ~size_t(15); }
+
+hc::DescWs desc_ws(void* ws, const hcomp_tables* t, int V, size_t* total = nullptr) {
   hc::DescWs w;
   uint8_t* b = static_cast<uint8_t*>(ws);
-  w.acc = reinterpret_cast<double*>(b);
-  b += sizeof(double) * 7 * (size_t)t->n_nodes;
-  w.leafmax = reinterpret_cast<float*>(b);
-  b += sizeof(float) * (size_t)V * t->n_protos;
-  w.leafarg = reinterpret_cast<int32_t*>(b);
-  b += sizeof(int32_t) * (size_t)V * t->n_protos;
-  w.leader = reinterpret_cast<int32_t*>(b);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { uint8_t* p = b + off; off += align16(bytes); return p; };
+  const size_t N = t->n_nodes, P = t->n_protos, K = t->n_cols, E = t->n_welems, VP = (size_t)V * P;
+  w.acc = reinterpret_cast<double*>(take(sizeof(double) * 5 * N));
+  w.leader = reinterpret_cast<int32_t*>(take(4 * (size_t)V));
+  w.next = reinterpret_cast<int32_t*>(take(4 * (size_t)V));
+  w.leaf_s1 = reinterpret_cast<float*>(take(4 * VP));
+  w.leaf_s2 = reinterpret_cast<float*>(take(4 * VP));
+  w.leaf_max = reinterpret_cast<float*>(take(4 * VP));
+  w.leaf_arg = reinterpret_cast<int32_t*>(take(4 * VP));
+  w.col_rel = reinterpret_cast<int32_t*>(take(4 * K));
+  w.col_present = reinterpret_cast<int32_t*>(take(4 * K));
+  w.cs_arg = reinterpret_cast<int32_t*>(take(4 * E));
+  w.score = reinterpret_cast<float*>(take(4 * E));
+  w.nz_prod = reinterpret_cast<float*>(take(4 * E));
+  w.zeros = reinterpret_cast<int32_t*>(take(4 * E));
+  w.y1_at = reinterpret_cast<float*>(take(4 * E));
+  if (total) *total = off;
   return w;
 }
 
@@ -610,17 +623,17 @@ hc::DescParams desc_params(const float* pooled, const float* wc, const float* pr
   hc::DescParams q;
   q.pooled = pooled; q.wc = wc; q.presence = presence; q.gumbel = gumbel; q.ys = ys; q.tgt = tgt; q.n_desc = n_desc;
   q.proto_off = t->proto_off; q.cls_off = t->cls_off; q.wc_off = t->wc_off; q.proto_node = t->proto_node;
-  q.col_node = t->col_node; q.welem_col = t->welem_col; q.welem_proto = t->welem_proto; q.path_off = t->path_off;
-  q.path_col = t->path_col;
-  q.V = V; q.V_first = V_first; q.N = t->n_nodes; q.P = t->n_protos; q.L = t->n_leaves; q.n_welems = t->n_welems;
+  q.col_node = t->col_node; q.welem_col = t->welem_col; q.welem_proto = t->welem_proto; q.col_nleaves = t->col_nleaves;
+  q.V = V; q.V_first = V_first; q.N = t->n_nodes; q.P = t->n_protos; q.K = t->n_cols; q.E = t->n_welems;
   q.flags = flags;
   q.w_td = weights_host[0]; q.w_cs = weights_host[1]; q.w_ov = weights_host[2]; q.w_l1 = weights_host[3];
   q.eps = eps; q.boost = boost; q.inv_tau = 1.0f / gumbel_tau;
   return q;
 }
 
-int desc_check(const float* presence, const float* gumbel, int V, int flags, float gumbel_tau) {
-  if (V <= 0) return fail(HCOMP_E_ARG, "desc losses: empty batch");
+int desc_check(const float* presence, const float* gumbel, const hcomp_tables* t, int V, int flags, float gumbel_tau) {
+  if (V <= 0 || V > 4096) return fail(HCOMP_E_ARG, "desc losses: batch of %d rows (supported: 1..4096)", V);
+  if (t->col_nleaves == nullptr) return fail(HCOMP_E_ARG, "desc losses: hcomp_tables.col_nleaves missing");
   if ((flags & HCOMP_DESC_MASK_PRUNE) && (presence == nullptr || gumbel == nullptr || !(gumbel_tau > 0.f)))
     return fail(HCOMP_E_ARG, "mask pruning needs the presence logits, the Gumbel noise and tau > 0");
   return 0;
@@ -628,36 +641,42 @@ int desc_check(const float* presence, const float* gumbel, int V, int flags, flo
 }  // namespace
 
 long long hcomp_desc_losses_ws_bytes(const hcomp_tables* t, int V) {
-  return 8LL * 7 * t->n_nodes + 8LL * V * t->n_protos + 4LL * V + 64;
+  size_t total = 0;
+  desc_ws(nullptr, t, V, &total);
+  return (long long)total;
 }
 
 int hcomp_desc_losses_fwd(const float* pooled, const float* wc, const float* presence, const float* gumbel,
                           const long long* ys, const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V,
                           int V_first, int flags, const float* weights_host, float eps, float boost, float gumbel_tau,
                           void* ws, float* stats, float* loss, void* stream) {
-  if (int rc = desc_check(presence, gumbel, V, flags, gumbel_tau)) return rc;
+  if (int rc = desc_check(presence, gumbel, t, V, flags, gumbel_tau)) return rc;
   const hc::DescWs w = desc_ws(ws, t, V);
   const hc::DescParams q = desc_params(pooled, wc, presence, gumbel, ys, tgt, n_desc, t, V, V_first, flags, weights_host,
                                        eps, boost, gumbel_tau > 0.f ? gumbel_tau : 1.f);
-  HC_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 7 * (size_t)t->n_nodes, S(stream)));
-  if (flags & HCOMP_DESC_MASK_PRUNE) {
-    hc::desc_leader_kernel<<<(V + 127) / 128, 128, 0, S(stream)>>>(ys, V, w.leader);
-    HC_LAUNCH_CHECK("desc_leader");
-    hc::desc_leafmax_kernel<<<dim3((t->n_protos + 127) / 128, V), 128, 0, S(stream)>>>(pooled, ys, w.leader, V, t->n_protos,
-                                                                                     w.leafmax, w.leafarg);
-    HC_LAUNCH_CHECK("desc_leafmax");
+  const bool td = flags & HCOMP_DESC_TANH_DESC, cs = flags & HCOMP_DESC_CONTRAST, mp = flags & HCOMP_DESC_MASK_PRUNE;
+  HC_CUDA(cudaMemsetAsync(w.acc, 0, sizeof(double) * 5 * (size_t)t->n_nodes, S(stream)));
+  hc::desc_prep_kernel<<<1, 256, sizeof(long long) * V, S(stream)>>>(ys, V, w.leader, w.next);
+  HC_LAUNCH_CHECK("desc_prep");
+  if (td || mp) {
+    hc::desc_leaf_stats_kernel<<<dim3((t->n_protos + 127) / 128, V), 128, 0, S(stream)>>>(q, w);
+    HC_LAUNCH_CHECK("desc_leaf_stats");
+  }
+  hc::desc_col_stats_kernel<<<(t->n_cols * 32 + 127) / 128, 128, 0, S(stream)>>>(q, w);
+  HC_LAUNCH_CHECK("desc_col_stats");
+  if (cs || mp) {
+    hc::desc_elem_reduce_kernel<<<(int)(((long long)t->n_welems * 32 + 127) / 128), 128, 0, S(stream)>>>(q, w);
+    HC_LAUNCH_CHECK("desc_elem_reduce");
+  }
+  if (td) {
+    hc::tanh_desc_fwd_kernel<<<dim3((t->n_nodes + 63) / 64, V), 64, 0, S(stream)>>>(q, w);
+    HC_LAUNCH_CHECK("tanh_desc_fwd");
+  }
+  if (mp) {
     hc::mask_prune_fwd_kernel<<<(t->n_protos + 127) / 128, 128, 0, S(stream)>>>(q, w);
     HC_LAUNCH_CHECK("mask_prune_fwd");
   }
-  if (flags & HCOMP_DESC_TANH_DESC) {
-    hc::tanh_desc_fwd_kernel<<<t->n_leaves, 64, 0, S(stream)>>>(q, w.acc);
-    HC_LAUNCH_CHECK("tanh_desc_fwd");
-  }
-  if (flags & HCOMP_DESC_CONTRAST) {
-    hc::contrast_fwd_kernel<<<(t->n_welems + 127) / 128, 128, 0, S(stream)>>>(q, w.acc);
-    HC_LAUNCH_CHECK("contrast_fwd");
-  }
-  hc::desc_combine_kernel<<<1, 256, 0, S(stream)>>>(q, w.acc, stats, loss);
+  hc::desc_combine_kernel<<<1, 256, 0, S(stream)>>>(q, w, stats, loss);
   HC_LAUNCH_CHECK("desc_combine");
   return 0;
 }
@@ -666,7 +685,7 @@ int hcomp_desc_losses_bwd(const float* g_loss, const float* pooled, const float*
                           const float* gumbel, const long long* ys, const int8_t* tgt, const int32_t* n_desc,
                           const hcomp_tables* t, int V, int V_first, int flags, const float* weights_host, float eps,
                           float boost, float gumbel_tau, const void* ws, float* g_pooled, float* g_presence, void* stream) {
-  if (int rc = desc_check(presence, gumbel, V, flags, gumbel_tau)) return rc;
+  if (int rc = desc_check(presence, gumbel, t, V, flags, gumbel_tau)) return rc;
   const hc::DescWs w = desc_ws(const_cast<void*>(ws), t, V);
   const hc::DescParams q = desc_params(pooled, wc, presence, gumbel, ys, tgt, n_desc, t, V, V_first, flags, weights_host,
                                        eps, boost, gumbel_tau > 0.f ? gumbel_tau : 1.f);
@@ -684,7 +703,6 @@ int hcomp_desc_losses_bwd(const float* g_loss, const float* pooled, const float*
   }
   return 0;
 }
-
 
 int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, float* probs_ws, float* joint,
                      long long* pred, void* stream) {

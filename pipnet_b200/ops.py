@@ -87,6 +87,13 @@ class DeviceLayout:
         self.child_w = up(L.child_w, torch.float32)
         self.path_off, self.path_col = up(L.path_off, torch.int32), up(L.path_col, torch.int32)
         self.anc = up(L.anc, torch.int8)
+        # leaves below every child column (static; the descendant-structured loss terms count absent leaves with it)
+        col_nleaves = np.zeros(L.K, dtype=np.int32)
+        for n in range(L.N):
+            a = L.anc[:, n]
+            for c in range(int(L.cls_off[n + 1] - L.cls_off[n])):
+                col_nleaves[L.cls_off[n] + c] = int((a == c).sum())
+        self.col_nleaves = up(col_nleaves, torch.int32)
         self.tiles_host = torch.from_numpy(np.ascontiguousarray(L.tiles)).to(torch.int32)
         self.tiles_dev = self.tiles_host.to(d)
         self.row_map = up(L.row_map, torch.int32)
@@ -94,7 +101,7 @@ class DeviceLayout:
                              self.proto_off.data_ptr(), self.cls_off.data_ptr(), self.wc_off.data_ptr(),
                              self.proto_node.data_ptr(), self.col_node.data_ptr(), self.welem_col.data_ptr(),
                              self.welem_proto.data_ptr(), self.child_w.data_ptr(), self.path_off.data_ptr(),
-                             self.path_col.data_ptr(), self.anc.data_ptr())
+                             self.path_col.data_ptr(), self.anc.data_ptr(), self.col_nleaves.data_ptr())
         self.tref = C.byref(self.tables)
         self.n_tiles = int(L.tiles.shape[0])
 
