@@ -314,24 +314,53 @@ def run_ours(a):
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(a.steps, 20))
 
-    def e2e_step(i):
-        if graphs is not None:
-            gs = graphs[i % 2]
-            gs.static_x.detach().permute(0, 2, 3, 1).copy_(host_x[i % 2], non_blocking=True)
-            gs.static_y.copy_(host_y[i % 2], non_blocking=True)
-            loss, _ = gs.replay()
-        else:
-            dev_x.copy_(host_x[i % 2], non_blocking=True)
-            dev_y.copy_(host_y[i % 2], non_blocking=True)
-            loss, _ = step(dev_x.permute(0, 3, 1, 2), dev_y)
-        host_loss.copy_(loss.detach(), non_blocking=True)
+    # Double-buffered like a prefetching loader (pin_memory + non_blocking): the H2D copy of step i+1 runs on a copy stream
+    # into the OTHER graph's static inputs while step i computes; every step's inputs still cross PCIe inside the timed
+    # region and every step's loss is read back to the host.
+    copy_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream(dev)
+    ready = [torch.cuda.Event() for _ in range(2)]
+    done = [torch.cuda.Event() for _ in range(2)]
 
+    def e2e_prefetch(i):
+        j = i % 2
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[j])                  # the previous step that read this buffer has finished
+            if graphs is not None:
+                graphs[j].static_x.detach().permute(0, 2, 3, 1).copy_(host_x[j], non_blocking=True)
+                graphs[j].static_y.copy_(host_y[j], non_blocking=True)
+            else:
+                dev_xs[j].copy_(host_x[j], non_blocking=True)
+                dev_ys[j].copy_(host_y[j], non_blocking=True)
+            ready[j].record(copy_stream)
+
+    def e2e_step(i, last):
+        j = i % 2
+        if not last:
+            e2e_prefetch(i + 1)
+        main_stream.wait_event(ready[j])
+        if graphs is not None:
+            loss, _ = graphs[j].replay()
+        else:
+            loss, _ = step(dev_xs[j].permute(0, 3, 1, 2), dev_ys[j])
+        host_loss.copy_(loss.detach(), non_blocking=True)
+        done[j].record(main_stream)
+
+    dev_xs = [dev_x, torch.empty_like(dev_x)] if graphs is None else None
+    dev_ys = [dev_y, torch.empty_like(dev_y)] if graphs is None else None
+    for j in range(2):
+        done[j].record(main_stream)
+    e2e_prefetch(0)
     for i in range(2):
-        e2e_step(i)
+        e2e_step(i, last=False)
     barrier()
+    copy_stream.synchronize()
+    for j in range(2):
+        done[j].record(main_stream)
     e0.record()
+    e2e_prefetch(0)                                          # step 0's copy is inside the timed region too
     for i in range(e2e_steps):
-        e2e_step(i)
+        e2e_step(i, last=(i == e2e_steps - 1))
     e1.record()
     barrier()
     t = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -339,7 +368,8 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t) / e2e_steps
     e2e = {'value': world * B / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_x[0].numel() * 2 + V * 8),
-           'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms}
+           'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms,
+           'pipeline': 'H2D of step i+1 on a copy stream overlaps the compute of step i (two device input buffers)'}
 
     if rank == 0:
         peaks = load_peaks()

@@ -35,14 +35,17 @@ constexpr int TILE_INTS = 4 + 3 * MAX_SEGS;   // {S, nseg, umma_n, 0, node[16], 
 constexpr int PAIR_STAGE_BYTES = 3 * TILE_M * KBLK * 2;   // A1 + A2 + W = 48 KB
 constexpr int PAIR_MAX_STAGES = 4;
 constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both views' bf16 dZ tiles staged for TMA stores (64 KB)
-// forward: 4 operand stages; backward: 3 operand stages + the dZ store staging.
+// forward: 4 operand stages; backward: the dZ store staging + 3 operand stages (1-CTA, 48 KB each) or 4 (CTA pair, 40 KB
+// each; fits because the backward does not carry the forward's pooling exchange table).  Ring depth matters: operand
+// delivery is latency-bound per SM (profiles/r1_k1_analysis.md), 160 KB in flight deliver ~25 % more than 120 KB.
 // CG2 (CTA pair, tcgen05 cta_group::2): a cluster of two CTAs takes two neighbouring pair tiles of the same prototype
 // tile and runs M = 256 MMAs; each CTA keeps only HALF of the prototype tile (64 rows, 8 KB) in its shared memory, so
 // an MMA fetches 6 KB of operands per CTA instead of 8 KB (the kernel is bound by that fetch, ~65 B/clk).
 template <bool BWD, bool CG2> struct PairMem {
   static constexpr int STAGE_BYTES = CG2 ? (2 * TILE_M * KBLK * 2 + (TILE_N / 2) * KBLK * 2) : PAIR_STAGE_BYTES;   // 40 / 48 KB
-  static constexpr int STAGES = BWD ? 3 : 4;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + 4096;
+  static constexpr int STAGES = BWD ? (CG2 ? 4 : 3) : 4;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + (BWD ? 256 : 4096);
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 template <int S> struct PairCfg {
   static constexpr int EPI_WARPS = (S <= 20) ? 12 : (S <= 40 ? 8 : 4);   // register budget 128 / 168 / 255 per thread
@@ -74,14 +77,14 @@ struct HeadParams {
   __nv_bfloat16* dz;                   // [M, P_pad]
 };
 
-struct PairSmem {
+template <bool BWD> struct PairSmemT {
   uint64_t full[PAIR_MAX_STAGES];
   uint64_t empty[PAIR_MAX_STAGES];
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
-  uint4 pool_x[240];         // per epilogue warp 2 * XQ: column maxima and first-lane ballots (forward fast path)
+  uint4 pool_x[BWD ? 1 : 240];   // forward: per epilogue warp 2 * XQ column maxima and first-lane ballots (pooling fast path)
 };
 
 template <int S, bool MASK>
@@ -261,6 +264,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* dzstage = smem + PAIR_STAGES * STAGE_BYTES;          // backward only: view 1 boxes, then view 2 boxes
+  using PairSmem = PairSmemT<BWD>;
+  static_assert(sizeof(PairSmem) <= (BWD ? 256 : 4096), "barrier block");
   PairSmem* sb = reinterpret_cast<PairSmem*>(dzstage + (BWD ? PAIR_DZ_STAGE_BYTES : 0));
 
   const int warp = threadIdx.x >> 5;
