@@ -160,6 +160,10 @@ def run_ours(a):
         if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
             os.environ.pop('NCCL_DEBUG')                 # NCCL prints its version banner on stdout: keep it to the JSON line
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        # the gradient all-reduce (1.5 MB, latency-bound) is meant to run BESIDE the persistent dX GEMM: keep NCCL to as
+        # many CTAs as the GEMM leaves SMs free (ops.COLLECTIVE_SMS), otherwise its surplus CTAs queue behind the GEMM
+        os.environ.setdefault('NCCL_MAX_CTAS', str(ops.COLLECTIVE_SMS))
+        os.environ.setdefault('NCCL_MAX_NCHANNELS', str(ops.COLLECTIVE_SMS))
         dist.init_process_group('nccl', device_id=dev)
         ops.GRAD_ALLREDUCE_GROUP = dist.group.WORLD
     wl = WORKLOADS[a.workload]
@@ -305,6 +309,24 @@ def run_ours(a):
     ms = float(t)
     ms_per_step = ms / a.steps
     value = world * B / (ms_per_step * 1e-3)
+
+    if os.environ.get('HC_TRACE') and graphs is not None:      # debugging aid: kernel timeline of two replays (rank 0)
+        from torch.profiler import profile, ProfilerActivity
+        import contextlib
+        barrier()
+        ctxm = profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) if rank == 0 else contextlib.nullcontext()
+        with ctxm as prof:
+            for i in range(2):                 # every rank replays: the step contains collectives
+                run_step(i)
+            torch.cuda.synchronize()
+        barrier()
+        if rank == 0:
+            evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+            t0 = evs[0].time_range.start if evs else 0
+            os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
+            with open(os.path.join(ROOT, 'gpurun_out', 'trace_rank0.txt'), 'w') as f:
+                for e in evs:
+                    f.write(f'{e.time_range.start - t0:10.1f} {e.time_range.end - e.time_range.start:8.1f}  {e.name[:90]}\n')
 
     # ---------------- end-to-end from pinned host buffers
     host_x = [f.permute(0, 2, 3, 1).contiguous().cpu().pin_memory() for f in feats]

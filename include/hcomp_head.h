@@ -61,6 +61,10 @@ long long hcomp_launch_count(void);
 /* K1 / K5 and the dX / dW GEMMs run as CTA pairs (tcgen05 cta_group::2, M = 256 MMAs) by default; 0 selects the
  * 1-CTA kernels (same results; kept for A/B measurements and tests).  Returns the previous setting. */
 int hcomp_set_cta_pair(int on);
+/* Data-parallel training: the dW all-reduce (NCCL, side stream) is meant to overlap the dX GEMM, but a persistent GEMM
+ * that owns every SM leaves the collective's CTAs nowhere to run.  n > 0 makes hcomp_head_bwd_dx launch on (SMs - n)
+ * SMs.  Returns the previous setting (default 0). */
+int hcomp_set_reserved_sms(int n);
 
 /* Operand precision of the projection GEMM (K1 / K5):
  *   HCOMP_PREC_BF16   bf16 operands, fp32 accumulate (<= 2e-2 relative on pooled scores / losses for fp32 inputs)

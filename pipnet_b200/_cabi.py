@@ -57,7 +57,7 @@ SIGNATURES = {
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }
 EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats',
-           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair'] + list(SIGNATURES)
+           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_reserved_sms'] + list(SIGNATURES)
 
 _lib = None
 
@@ -81,6 +81,8 @@ def lib():
     L.hcomp_desc_losses_ws_bytes.argtypes = [_T, C.c_int]
     L.hcomp_set_cta_pair.restype = C.c_int
     L.hcomp_set_cta_pair.argtypes = [C.c_int]
+    L.hcomp_set_reserved_sms.restype = C.c_int
+    L.hcomp_set_reserved_sms.argtypes = [C.c_int]
     for name, args in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = args

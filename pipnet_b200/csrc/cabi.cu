@@ -21,6 +21,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 bool g_no_pair = false;               // hcomp_set_cta_pair(0): 1-CTA GEMM tiles only (A/B measurements, tests)
+int g_reserved_sms = 0;               // hcomp_set_reserved_sms(n): SMs the dX GEMM leaves free for a concurrent collective
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -258,7 +259,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 // D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
 // else [N,K].  splits <= 0 picks a split-K factor that fills the GPU (only meaningful for OUT_RED_F32).
 int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool a_mn, bool b_mn, int out_mode, int splits,
-             void* out, long long ldo, const int32_t* row_map, cudaStream_t st) {
+             void* out, long long ldo, const int32_t* row_map, cudaStream_t st, int reserve_sms = 0) {
   DevInfo di;
   if (int e = dev_info(&di)) return e;
   if (M <= 0 || N <= 0 || K <= 0) return fail(HCOMP_E_ARG, "empty GEMM");
@@ -284,7 +285,9 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   p.num_k_blocks = cdiv(K, hc::G_BK);
   const int tiles_mn = (pair ? cdiv(M, 2 * hc::G_BM) : p.num_m_tiles) * p.num_n_tiles;
   if (out_mode != hc::OUT_RED_F32) splits = 1;
-  if (splits <= 0) splits = (pair ? di.sms / 2 : di.sms) / tiles_mn;
+  int sms = di.sms - reserve_sms;       // persistent grid; a reserve leaves whole SMs to kernels of other streams
+  if (sms < 2) sms = 2;
+  if (splits <= 0) splits = (pair ? sms / 2 : sms) / tiles_mn;
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
@@ -292,8 +295,8 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   p.out = out; p.ldo = ldo; p.row_map = row_map;
 #define HC_GEMM_CASE(AM, BM, OM)                                         \
   if (a_mn == AM && b_mn == BM && out_mode == OM)                        \
-    return pair ? launch_gemm2<AM, BM, OM>(ta, tb, to, p, di.sms, st)    \
-                : launch_gemm<AM, BM, OM>(ta, tb, to, p, di.sms, st);
+    return pair ? launch_gemm2<AM, BM, OM>(ta, tb, to, p, sms, st)       \
+                : launch_gemm<AM, BM, OM>(ta, tb, to, p, sms, st);
   HC_GEMM_CASE(false, true, hc::OUT_BF16)      // dX
   HC_GEMM_CASE(true, true, hc::OUT_RED_F32)    // dW
   HC_GEMM_CASE(false, false, hc::OUT_F32)      // self-test: plain K-major GEMM
@@ -314,6 +317,11 @@ int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
 int hcomp_set_cta_pair(int on) {
   const int prev = g_no_pair ? 0 : 1;
   g_no_pair = (on == 0);
+  return prev;
+}
+int hcomp_set_reserved_sms(int n) {
+  const int prev = g_reserved_sms;
+  g_reserved_sms = n < 0 ? 0 : n;
   return prev;
 }
 int hcomp_split3_f32(const float* src, void* dst_bf16_3planes, long long n, void* stream) {
@@ -432,7 +440,8 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
 
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wp_bf16, long long rows, int P_pad, int C, void* dx_bf16,
                       void* stream) {
-  return run_gemm(dz_bf16, wp_bf16, rows, C, P_pad, false, true, hc::OUT_BF16, 1, dx_bf16, C, nullptr, S(stream));
+  return run_gemm(dz_bf16, wp_bf16, rows, C, P_pad, false, true, hc::OUT_BF16, 1, dx_bf16, C, nullptr, S(stream),
+                  g_reserved_sms);
 }
 
 int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map, long long rows, int P_pad, int C,
@@ -505,23 +514,14 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
     HC_LAUNCH_CHECK("tanh_loss_fwd");
   }
   if (do_orth) {
-    if (t->p_max >= C || t->p_max > 128) return fail(HCOMP_E_ARG, "orth loss needs P_n < C and P_n <= 128 (P_max=%d, C=%d)", t->p_max, C);
-    const size_t node_smem = (size_t)t->p_max * C * sizeof(float);
-    if (node_smem <= 160 * 1024 && C % 4 == 0) {       // one block per node, W_n staged in shared memory
-      static bool attr_done = false;
-      if (!attr_done) {
-        HC_CUDA(cudaFuncSetAttribute(hc::orth_loss_fwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        attr_done = true;
-      }
-      hc::orth_loss_fwd_node_kernel<<<t->n_nodes, 512, node_smem, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
-                                                                              C, t->p_max, w.orth_sq, w.E, rel);
-      HC_LAUNCH_CHECK("orth_loss_fwd_node");
-    } else {
-      HC_CUDA(cudaMemsetAsync(w.orth_sq, 0, sizeof(float) * t->n_nodes, S(stream)));
-      hc::orth_loss_fwd_kernel<<<t->n_protos, 128, 0, S(stream)>>>(w_flat, wc, t->proto_node, t->proto_off, t->cls_off,
-                                                                  t->wc_off, C, t->p_max, w.orth_sq, w.E, rel);
-      HC_LAUNCH_CHECK("orth_loss_fwd");
-    }
+    if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
+    const long long warps = (long long)t->n_nodes * t->p_max * t->p_max;
+    hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
+                                                                        t->n_nodes, C, t->p_max, w.E, rel);
+    HC_LAUNCH_CHECK("orth_gram");
+    hc::orth_sumsq_kernel<<<blocks((long long)t->n_nodes * 32, 128), 128, 0, S(stream)>>>(w.E, t->proto_off, t->n_nodes,
+                                                                                         t->p_max, w.orth_sq);
+    HC_LAUNCH_CHECK("orth_sumsq");
   }
   // class kernel also produces the per-node accuracy counters, so it always runs
   hc::class_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(out, tgt, t->child_w, t->cls_off, n_desc, V, t->n_nodes,
@@ -567,23 +567,13 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
     }
   }
   if (g_w) {
-    HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
     if (flags & HCOMP_LOSS_ORTH) {
-      const size_t node_smem = ((size_t)t->p_max * C + (size_t)t->p_max * t->p_max) * sizeof(float);
-      if (node_smem <= 170 * 1024 && C % 4 == 0) {
-        static bool attr_done = false;
-        if (!attr_done) {
-          HC_CUDA(cudaFuncSetAttribute(hc::orth_loss_bwd_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024));
-          attr_done = true;
-        }
-        hc::orth_loss_bwd_node_kernel<<<t->n_nodes, 256, node_smem, S(stream)>>>(w_flat, t->proto_off, C, t->p_max,
-                                                                                stats + 2 * N, w.E, rel, gvec + 2 * N, g_w);
-        HC_LAUNCH_CHECK("orth_loss_bwd_node");
-      } else {
-        hc::orth_loss_bwd_kernel<<<t->n_protos, 256, 0, S(stream)>>>(w_flat, t->proto_off, C, t->p_max, stats + 2 * N, w.E,
-                                                                    rel, gvec + 2 * N, t->proto_node, g_w);
-        HC_LAUNCH_CHECK("orth_loss_bwd");
-      }
+      hc::orth_bwd_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, S(stream)>>>(w_flat, t->proto_node, t->proto_off, C,
+                                                                                    t->p_max, stats + 2 * N, w.E, rel,
+                                                                                    gvec + 2 * N, g_w);
+      HC_LAUNCH_CHECK("orth_bwd");
+    } else {
+      HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
     }
   }
   return 0;

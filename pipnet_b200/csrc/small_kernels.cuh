@@ -321,148 +321,89 @@ __global__ void tanh_loss_bwd_kernel(const float* __restrict__ colsum, const int
 
 // ---------------------------------------------------------------- kernel-orthogonality loss (pipnet/train.py:1136-1151, orth_dist :1408-1412)
 // Per node: rows of W whose classifier column has any weight > 1e-3; E = W_rel W_rel^T - I (P_rel < C);
-// loss = ||E||_F.  One block per prototype ROW (row i of its node's Gram matrix): warps stride over the columns
-// j, lanes over channels.  E is kept in a [N, P_max, P_max] slab for the backward; sumsq[n] (zeroed by the caller)
-// collects the squared norm.
-__global__ void orth_loss_fwd_kernel(const float* __restrict__ w, const float* __restrict__ wc,
-                                     const int32_t* __restrict__ proto_node, const int32_t* __restrict__ proto_off,
-                                     const int32_t* __restrict__ cls_off, const int32_t* __restrict__ wc_off, int C,
-                                     int P_max, float* __restrict__ sumsq, float* __restrict__ E,
-                                     uint8_t* __restrict__ rel) {
-  __shared__ float sh[32];
-  __shared__ uint8_t srel[128];
+// loss = ||E||_F.  The Gram matrix is tiny (P_n^2 dots of length C) but latency-critical inside the step, so it is
+// spread over the whole GPU: ONE WARP per entry (n, i, j >= i) of the [N, P_max, P_max] slab, operands read straight from
+// L2 (all prototype kernels are 1.5 MB) with independent coalesced loads; the slab is kept for the backward.
+// A block-per-node version that staged W_n in shared memory spent 10 of its 17 us in the serial copy loop.
+__global__ void orth_gram_kernel(const float* __restrict__ w, const float* __restrict__ wc,
+                                 const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
+                                 const int32_t* __restrict__ wc_off, int N, int C, int P_max, float* __restrict__ E,
+                                 uint8_t* __restrict__ rel) {
+  const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int slots = P_max * P_max;
+  const int n = int(wid / slots);
+  if (n >= N) return;
+  const int ij = int(wid - (long long)n * slots);
+  const int i = ij / P_max, j = ij - i * P_max;
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  if (i >= pn || j >= pn || j < i) return;            // E is symmetric: upper triangle computed, mirrored below
+  const int kn = cls_off[n + 1] - cls_off[n];
+  const float* wcn = wc + wc_off[n];
+  bool ri = false, rj = false;                        // relevant = some classifier weight > 1e-3 (pipnet/train.py:1140)
+  for (int c = 0; c < kn; ++c) {
+    ri |= wcn[(size_t)c * pn + i] > 0.001f;
+    rj |= wcn[(size_t)c * pn + j] > 0.001f;
+  }
+  if (i == j && lane == 0) rel[p0 + i] = ri;
+  float e = 0.f;
+  if (ri && rj) {
+    const float* a = w + (size_t)(p0 + i) * C;
+    const float* b = w + (size_t)(p0 + j) * C;
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    int c = lane;
+    for (; c + 96 < C; c += 128) {
+      d0 = fmaf(a[c], b[c], d0);
+      d1 = fmaf(a[c + 32], b[c + 32], d1);
+      d2 = fmaf(a[c + 64], b[c + 64], d2);
+      d3 = fmaf(a[c + 96], b[c + 96], d3);
+    }
+    for (; c < C; c += 32) d0 = fmaf(a[c], b[c], d0);
+    e = warp_sum((d0 + d1) + (d2 + d3)) - (i == j ? 1.f : 0.f);
+  }
+  if (lane == 0) {
+    float* En = E + (size_t)n * slots;
+    En[i * P_max + j] = e;
+    En[j * P_max + i] = e;
+  }
+}
+// sumsq[n] = ||E_n||_F^2 in a fixed order (one warp per node): deterministic, unlike per-entry atomics
+__global__ void orth_sumsq_kernel(const float* __restrict__ E, const int32_t* __restrict__ proto_off, int N, int P_max,
+                                  float* __restrict__ sumsq) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const int pn = proto_off[n + 1] - proto_off[n];
+  const float* En = E + (size_t)n * P_max * P_max;
+  float acc = 0.f;
+  for (int ij = lane; ij < pn * pn; ij += 32) {
+    const float e = En[(ij / pn) * P_max + (ij % pn)];
+    acc = fmaf(e, e, acc);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) sumsq[n] = acc;
+}
+// dW[i,:] = g[n] * (2/L) * sum_j E[i,j] W[j,:]   (E symmetric, zero outside the relevant rows): one thread per
+// (prototype row, channel); writes every element (zeros where the term is off), so the caller does not clear g_w.
+__global__ void orth_bwd_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_node,
+                                const int32_t* __restrict__ proto_off, int C, int P_max, const float* __restrict__ loss,
+                                const float* __restrict__ E, const uint8_t* __restrict__ rel,
+                                const float* __restrict__ g_loss, float* __restrict__ g_w) {
   const int row = blockIdx.x;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
   const int n = proto_node[row];
   const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
-  const int kn = cls_off[n + 1] - cls_off[n];
-  const int i = row - p0;
-  for (int p = threadIdx.x; p < pn; p += blockDim.x) {
-    bool r = false;
-    for (int c = 0; c < kn; ++c) r |= wc[wc_off[n] + (size_t)c * pn + p] > 0.001f;
-    srel[p] = r;
-    if (p == i) rel[row] = r;
-  }
-  __syncthreads();
-  float* Er = E + ((size_t)n * P_max + i) * P_max;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float L = loss[n], g = g_loss[n];
   float acc = 0.f;
-  const float* a = w + (size_t)row * C;
-  for (int j = warp; j < pn; j += nw) {
-    float e = 0.f;
-    if (srel[i] && srel[j]) {
-      const float* b = w + (size_t)(p0 + j) * C;
-      float d0 = 0.f, d1 = 0.f;
-      int c = lane;
-      for (; c + 32 < C; c += 64) { d0 = fmaf(a[c], b[c], d0); d1 = fmaf(a[c + 32], b[c + 32], d1); }
-      if (c < C) d0 = fmaf(a[c], b[c], d0);
-      e = warp_sum(d0 + d1) - (i == j ? 1.f : 0.f);
-    }
-    if (lane == 0) { Er[j] = e; acc += e * e; }
-  }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0 && acc != 0.f) atomicAdd(sumsq + n, acc);
-}
-// dW[i,:] += g[n] * (2/L) * sum_j E[i,j] W[j,:]   (E symmetric, zero outside the relevant rows); one block per row.
-__global__ void orth_loss_bwd_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off, int C, int P_max,
-                                     const float* __restrict__ loss, const float* __restrict__ E,
-                                     const uint8_t* __restrict__ rel, const float* __restrict__ g_loss,
-                                     const int32_t* __restrict__ row_node, float* __restrict__ g_w) {
-  __shared__ float coef[128];
-  const int row = blockIdx.x;
-  const int n = row_node[row];
-  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
-  const int i = row - p0;
-  const float L = loss[n];
-  if (!rel[row] || L <= 0.f || g_loss[n] == 0.f) return;
-  const float s = g_loss[n] * 2.f / L;
-  const float* En = E + ((size_t)n * P_max + i) * P_max;
-  for (int j = threadIdx.x; j < pn; j += blockDim.x) coef[j] = s * En[j];
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float acc = 0.f;
+  if (rel[row] && L > 0.f && g != 0.f) {
+    const float* Er = E + ((size_t)n * P_max + (row - p0)) * P_max;
+    const float* wn = w + (size_t)p0 * C + c;
 #pragma unroll 4
-    for (int j = 0; j < pn; ++j) acc = fmaf(coef[j], w[(size_t)(p0 + j) * C + c], acc);
-    g_w[(size_t)row * C + c] += acc;
+    for (int j = 0; j < pn; ++j) acc = fmaf(Er[j], wn[(size_t)j * C], acc);
+    acc *= g * 2.f / L;
   }
-}
-
-// Fast variants: one block per NODE with the node's kernels W_n [P_n, C] staged in dynamic shared memory (used when
-// P_n * C * 4 bytes fits; the per-row kernels above are the general path).  Forward: all P_n^2 Gram entries from smem,
-// one warp per entry.  Backward: dW_n = g * (2/L) * E * W_n with E and W_n in smem, one thread per channel.
-__global__ void orth_loss_fwd_node_kernel(const float* __restrict__ w, const float* __restrict__ wc,
-                                          const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
-                                          const int32_t* __restrict__ wc_off, int C, int P_max, float* __restrict__ sumsq,
-                                          float* __restrict__ E, uint8_t* __restrict__ rel) {
-  extern __shared__ float wsm[];                 // [pn][C]
-  __shared__ float sh[32];
-  __shared__ uint8_t srel[128];
-  const int n = blockIdx.x;
-  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
-  const int kn = cls_off[n + 1] - cls_off[n];
-  const float4* src = reinterpret_cast<const float4*>(w + (size_t)p0 * C);
-  float4* dst = reinterpret_cast<float4*>(wsm);
-  for (int i = threadIdx.x; i < pn * C / 4; i += blockDim.x) dst[i] = src[i];
-  for (int p = threadIdx.x; p < pn; p += blockDim.x) {
-    bool r = false;
-    for (int c = 0; c < kn; ++c) r |= wc[wc_off[n] + (size_t)c * pn + p] > 0.001f;
-    srel[p] = r;
-    rel[p0 + p] = r;
-  }
-  __syncthreads();
-  float* En = E + (size_t)n * P_max * P_max;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  float acc = 0.f;
-  for (int ij = warp; ij < pn * pn; ij += nw) {
-    const int i = ij / pn, j = ij - i * pn;
-    float e = 0.f;
-    if (j >= i) {                                  // E is symmetric: compute the upper triangle, mirror it
-      if (srel[i] && srel[j]) {
-        const float* a = wsm + (size_t)i * C;
-        const float* b = wsm + (size_t)j * C;
-        float d0 = 0.f, d1 = 0.f;
-        int c = lane;
-        for (; c + 32 < C; c += 64) { d0 = fmaf(a[c], b[c], d0); d1 = fmaf(a[c + 32], b[c + 32], d1); }
-        if (c < C) d0 = fmaf(a[c], b[c], d0);
-        e = warp_sum(d0 + d1) - (i == j ? 1.f : 0.f);
-      }
-      if (lane == 0) {
-        En[i * P_max + j] = e;
-        En[j * P_max + i] = e;
-        acc += (i == j) ? e * e : 2.f * e * e;
-      }
-    }
-  }
-  acc = block_sum(acc, sh);
-  if (threadIdx.x == 0) sumsq[n] = acc;
-}
-__global__ void orth_loss_bwd_node_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off, int C,
-                                          int P_max, const float* __restrict__ loss, const float* __restrict__ E,
-                                          const uint8_t* __restrict__ rel, const float* __restrict__ g_loss,
-                                          float* __restrict__ g_w) {
-  extern __shared__ float wsm[];                 // [pn][C] then [pn][pn] coefficients
-  const int n = blockIdx.x;
-  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
-  const float L = loss[n];
-  if (L <= 0.f || g_loss[n] == 0.f) return;       // g_w was zero-filled by the caller
-  const float s = g_loss[n] * 2.f / L;
-  float* coef = wsm + (size_t)pn * C;
-  const float4* src = reinterpret_cast<const float4*>(w + (size_t)p0 * C);
-  float4* dst = reinterpret_cast<float4*>(wsm);
-  for (int i = threadIdx.x; i < pn * C / 4; i += blockDim.x) dst[i] = src[i];
-  const float* En = E + (size_t)n * P_max * P_max;
-  for (int ij = threadIdx.x; ij < pn * pn; ij += blockDim.x) {
-    const int i = ij / pn, j = ij - i * pn;
-    coef[ij] = (rel[p0 + i] && rel[p0 + j]) ? s * En[i * P_max + j] : 0.f;
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    for (int i = 0; i < pn; ++i) {
-      float acc = 0.f;
-#pragma unroll 4
-      for (int j = 0; j < pn; ++j) acc = fmaf(coef[i * pn + j], wsm[(size_t)j * C + c], acc);
-      g_w[(size_t)(p0 + i) * C + c] = acc;
-    }
-  }
+  g_w[(size_t)row * C + c] = acc;
 }
 
 // ---------------------------------------------------------------- loss combination (one block)

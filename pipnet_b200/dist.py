@@ -35,10 +35,17 @@ def flat_allreduce_mean_(tensors: Iterable[torch.Tensor], group=None) -> None:
         off += n
 
 
-def enable_overlapped_allreduce(group=None) -> None:
-    """Reduce the flat prototype-kernel gradient inside the head's backward, overlapped with the dX GEMM."""
+def enable_overlapped_allreduce(group=None, fresh_grads: bool = True) -> None:
+    """Data parallelism handled by the head itself (instead of DistributedDataParallel): mean all-reduce of its gradients
+    (prototype kernels, classifiers, presence logits) inside the backward, on a side stream over NCCL.
+    fresh_grads=True: all producers write into ONE flat bucket, ONE all-reduce is issued right after the dW GEMM and is
+    joined at the end of the backward pass, so it overlaps the dX GEMM and the backbone backward; `param.grad` is set
+    (or accumulated into) by the head, not by autograd.  False: gradients travel through autograd and every all-reduce
+    is joined before its tensor is returned (dW still overlaps the dX GEMM).
+    Do not combine with DistributedDataParallel on the same parameters (they would be reduced twice)."""
     from . import ops
     ops.GRAD_ALLREDUCE_GROUP = group if group is not None else dist.group.WORLD
+    ops.ASYNC_GRAD_ALLREDUCE = bool(fresh_grads)
 
 
 def disable_overlapped_allreduce() -> None:

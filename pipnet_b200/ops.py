@@ -6,6 +6,7 @@ arithmetic of the path runs in libhcomp_head.so.  There is no fallback path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -54,6 +55,9 @@ PROFILE = _Profile()
 # is all-reduced (mean) on a side stream right after the dW GEMM so it overlaps the dX GEMM and whatever
 # backbone backward follows.
 GRAD_ALLREDUCE_GROUP = None
+# SMs the dX GEMM leaves free while the dW all-reduce is in flight: a persistent GEMM that owns every SM (1 CTA/SM, ~198 KB
+# of shared memory) would otherwise keep NCCL's CTAs waiting until it drains and the "overlap" would serialise.
+COLLECTIVE_SMS = int(os.environ.get('HC_COLLECTIVE_SMS', '8'))
 _side_stream = None
 
 
@@ -62,6 +66,100 @@ def _side():
     if _side_stream is None:
         _side_stream = torch.cuda.Stream()
     return _side_stream
+
+
+# ---- data-parallel gradient bucket ---------------------------------------------------------------------------------
+# With GRAD_ALLREDUCE_GROUP set (the head's own data parallelism, not DistributedDataParallel) and ASYNC_GRAD_ALLREDUCE,
+# the head's parameter gradients never travel through autograd: every producer (orth loss, classifier, presence logits,
+# dW GEMM) writes into its segment of ONE zero-initialised flat buffer, ONE mean all-reduce of that buffer is issued on
+# the side stream right after the dW GEMM (so it overlaps the dX GEMM and the backbone backward), and a callback at the
+# END of the backward pass (the autograd-engine hook DDP's reducer uses) re-joins the stream and hands `param.grad` views
+# out.  Handing the tensors to autograd instead would let it read them on the main stream while the collective is still
+# in flight (input-buffer accumulation of dW + orth gradient, AccumulateGrad clones) -- tests/test_gpu_multi.py.
+# ASYNC_GRAD_ALLREDUCE = False: gradients go through autograd; each all-reduce is joined before its tensor is returned
+# (the dW one still overlaps the dX GEMM).
+ASYNC_GRAD_ALLREDUCE = True
+
+
+class _GradBucket:
+    def __init__(self, family, device):
+        self.family = family
+        self.offsets, self.sizes, off = {}, {}, 0
+        for grp in family:              # groups that were not used in this step (e.g. presence logits) get an idle segment
+            n = sum(p_.numel() for p_ in grp.params)
+            self.offsets[id(grp)], self.sizes[id(grp)] = off, n
+            off += n
+        self.flat = torch.zeros(off, device=device, dtype=torch.float32)
+        self.produced = []
+        self.reduced = False
+
+    def segment(self, grp):
+        o = self.offsets[id(grp)]
+        if grp not in self.produced:
+            self.produced.append(grp)
+        return self.flat[o:o + self.sizes[id(grp)]]
+
+
+_bucket: Optional[_GradBucket] = None
+
+
+def _bucket_mode(grp) -> bool:
+    return (GRAD_ALLREDUCE_GROUP is not None and ASYNC_GRAD_ALLREDUCE and grp is not None
+            and getattr(grp, 'family', None) is not None)
+
+
+def _bucket_segment(grp, device) -> torch.Tensor:
+    """This step's gradient segment of parameter group `grp` (zero-initialised; producers write or accumulate)."""
+    global _bucket
+    if _bucket is None:
+        _bucket = _GradBucket(grp.family, device)
+        torch.autograd.Variable._execution_engine.queue_callback(_bucket_finalize)
+    return _bucket.segment(grp)
+
+
+def _bucket_allreduce():
+    import torch.distributed as dist
+    b = _bucket
+    side = _side()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
+    b.flat.record_stream(side)
+    b.reduced = True
+
+
+def _bucket_finalize():
+    """end of the backward pass: make sure the bucket was reduced, re-join the side stream, deliver param.grad"""
+    global _bucket
+    b, _bucket = _bucket, None
+    if b is None:
+        return
+    if not b.reduced:                       # the dW GEMM did not run in this pass (frozen prototypes): reduce now
+        _bucket = b
+        _bucket_allreduce()
+        _bucket = None
+    torch.cuda.current_stream().wait_stream(_side())
+    for grp in b.produced:
+        seg = b.segment(grp)
+        for p_, (off, numel, shape) in zip(grp.params, grp.meta):
+            if not p_.requires_grad:
+                continue
+            g = seg[off:off + numel].view(shape)
+            if p_.grad is None:
+                p_.grad = g
+            else:
+                p_.grad.add_(g)
+
+
+def _allreduce_grad_sync_(t: torch.Tensor):
+    """autograd path: mean all-reduce on the side stream; returns the stream to wait on before `t` is handed on"""
+    import torch.distributed as dist
+    side = _side()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        dist.all_reduce(t, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
+    t.record_stream(side)
+    return side
 
 
 def _require_cuda(t: torch.Tensor, what: str):
@@ -208,7 +306,7 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
 
 
 def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
-                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16):
+                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None):
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
@@ -224,23 +322,28 @@ def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax,
     PROFILE.stop(tok)
     dx = dw = None
     pending = None
+    bucketed = need_dw and _bucket_mode(w_group)
     if need_dw:
-        dw = torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32)
+        # bucket mode: the segment already holds the orth-loss gradient (or zeros) and K7 accumulates on top of it
+        dw = (_bucket_segment(w_group, dev).view(dl.P, Cc) if bucketed
+              else torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32))
         tok = PROFILE.start('k7_bwd_dw')
         call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map), C.c_longlong(M), dl.P_pad, Cc, ptr(dw), _stream())
         PROFILE.stop(tok)
-        if GRAD_ALLREDUCE_GROUP is not None:
-            import torch.distributed as dist
-            side = _side()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                dist.all_reduce(dw, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
-            dw.record_stream(side)
-            pending = side
+        if bucketed:
+            _bucket_allreduce()             # everything the head produces is in the bucket by now; overlaps K6
+            dw = None                       # delivered to param.grad at the end of the backward pass
+        elif GRAD_ALLREDUCE_GROUP is not None:
+            pending = _allreduce_grad_sync_(dw)      # overlaps K6, joined before dW is returned to autograd
     if need_dx:
         dx = torch.empty(M, Cc, device=dev, dtype=torch.bfloat16)
         tok = PROFILE.start('k6_bwd_dx')
-        call('hcomp_head_bwd_dx', ptr(dz), ptr(wp), C.c_longlong(M), dl.P_pad, Cc, ptr(dx), _stream())
+        prev = _cabi.lib().hcomp_set_reserved_sms(COLLECTIVE_SMS) if (pending is not None or bucketed) else None
+        try:
+            call('hcomp_head_bwd_dx', ptr(dz), ptr(wp), C.c_longlong(M), dl.P_pad, Cc, ptr(dx), _stream())
+        finally:
+            if prev is not None:
+                _cabi.lib().hcomp_set_reserved_sms(prev)
         PROFILE.stop(tok)
     if pending is not None:
         torch.cuda.current_stream().wait_stream(pending)      # dW is consumed by autograd on this stream
@@ -276,6 +379,7 @@ class HeadProjPool(torch.autograd.Function):
         wp = pack_weights(w_flat.detach().contiguous(), dl, precision)
         pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision)
         ctx.dl, ctx.geom, ctx.labels, ctx.thresh, ctx.precision = dl, (V, V_first, H, W, Cc, tau), labels, thresh, precision
+        ctx.w_group = getattr(w_flat, '_hc_group', None)
         ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
         ctx.save_for_backward(x_rows, wp, argmax, pooled)
         ctx.mark_non_differentiable(argmax)
@@ -296,7 +400,7 @@ class HeadProjPool(torch.autograd.Function):
             g_align = g_align.contiguous().float()
         dx, dw, _ = head_backward_raw(x_rows, wp, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
                                       pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw,
-                                      precision=ctx.precision)
+                                      precision=ctx.precision, w_group=ctx.w_group)
         d_feat = None
         if need_dx:
             dtype, _cl = ctx.feat_meta
@@ -319,6 +423,7 @@ class NonNegClassifier(torch.autograd.Function):
         ctx.dl = dl
         ctx.save_for_backward(pooled, wc_flat)
         ctx.has_bias = bias is not None
+        ctx.groups = (getattr(wc_flat, '_hc_group', None), getattr(bias, '_hc_group', None) if bias is not None else None)
         return out
 
     @staticmethod
@@ -328,15 +433,25 @@ class NonNegClassifier(torch.autograd.Function):
         V = pooled.shape[0]
         g_out = g_out.contiguous()
         g_pooled = torch.empty_like(pooled) if ctx.needs_input_grad[0] else None
-        g_wc = torch.empty_like(wc_flat) if ctx.needs_input_grad[1] else None
-        g_bias = torch.empty(dl.K, device=pooled.device, dtype=torch.float32) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        need_wc, need_bias = ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2]
+        wc_grp, bias_grp = ctx.groups
+        b_wc, b_bias = need_wc and _bucket_mode(wc_grp), need_bias and _bucket_mode(bias_grp)
+        g_wc = g_bias = None
+        if need_wc:
+            g_wc = _bucket_segment(wc_grp, pooled.device) if b_wc else torch.empty_like(wc_flat)
+        if need_bias:
+            g_bias = (_bucket_segment(bias_grp, pooled.device) if b_bias
+                      else torch.empty(dl.K, device=pooled.device, dtype=torch.float32))
         call('hcomp_classifier_bwd', ptr(g_out), ptr(pooled), ptr(wc_flat), dl.tref, V, ptr(g_pooled), 0, ptr(g_wc),
              ptr(g_bias), _stream())
-        if GRAD_ALLREDUCE_GROUP is not None:        # data-parallel: ONE flat mean all-reduce for all nodes' classifiers
-            import torch.distributed as dist
+        if b_wc:
+            g_wc = None                     # reduced with the bucket, delivered at the end of the backward pass
+        if b_bias:
+            g_bias = None
+        if GRAD_ALLREDUCE_GROUP is not None:        # autograd path: one flat mean all-reduce for all nodes' classifiers
             for g in (g_wc, g_bias):
                 if g is not None:
-                    dist.all_reduce(g, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
+                    torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g))
         return g_pooled, g_wc, g_bias, None
 
 
@@ -371,6 +486,7 @@ class HeadLosses(torch.autograd.Function):
              ptr(rel), _stream())
         ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc)
         ctx.has = (align is not None, w_flat is not None and use_orth)
+        ctx.w_group = getattr(w_flat, '_hc_group', None) if w_flat is not None else None
         ctx.save_for_backward(out, wf if use_orth else None, stats, ws, rel)
         ctx.mark_non_differentiable(stats, n_correct)
         return total, stats, n_correct
@@ -389,10 +505,20 @@ class HeadLosses(torch.autograd.Function):
                                                      ctx.needs_input_grad[3] and ctx.has[1])
         g_pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32) if need_pooled else None
         g_out = torch.empty(V, dl.K, device=dev, dtype=torch.float32) if need_out else None
-        g_w = torch.empty(dl.P, Cc, device=dev, dtype=torch.float32) if need_w else None
+        bucketed = need_w and _bucket_mode(ctx.w_group)
+        g_w = None
+        if need_w:      # bucket mode: the orth gradient (identical on every rank) lands where K7 will accumulate dW
+            g_w = (_bucket_segment(ctx.w_group, dev).view(dl.P, Cc) if bucketed
+                   else torch.empty(dl.P, Cc, device=dev, dtype=torch.float32))
         call('hcomp_head_losses_bwd', ptr(g_total), ptr(out), ptr(wf), ptr(labels.tgt), ptr(labels.n_desc), ptr(stats), dl.tref,
              V, labels.V_first, Cc, flags, wts, eps, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out), ptr(g_w),
              _stream())
+        if bucketed:
+            g_w = None
+        elif g_w is not None and GRAD_ALLREDUCE_GROUP is not None:
+            # the orth term is skipped for nodes without a descendant in the LOCAL batch (pipnet/train.py:941-942), so
+            # its gradient differs across ranks like any other and needs the mean too
+            torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g_w))
         return g_pooled, g_out, (gvec[0] if need_align else None), g_w, None, None, None, None, None, None
 
 DESC_TANH_DESC, DESC_CONTRAST, DESC_MASK_PRUNE, DESC_GEOMETRIC, DESC_SG_SCORE = 1, 2, 4, 8, 16
@@ -432,6 +558,7 @@ class DescLosses(torch.autograd.Function):
         ctx.dl, ctx.labels = dl, labels
         ctx.cfg = (int(flags), [float(x) for x in weights], float(eps), boost, float(tau), V)
         ctx.has_presence = presence is not None
+        ctx.pp_group = getattr(presence, '_hc_group', None) if presence is not None else None
         ctx.save_for_backward(pooled, wc, pres, gum, ws)
         ctx.mark_non_differentiable(stats)
         return loss, stats
@@ -445,11 +572,19 @@ class DescLosses(torch.autograd.Function):
         wts = (C.c_float * 4)(*weights)
         g_loss = g_loss.contiguous().float()
         g_pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
-        g_pres = (torch.empty(dl.P, 2, device=dev, dtype=torch.float32)
-                  if (ctx.has_presence and ctx.needs_input_grad[2]) else None)
+        need_pres = ctx.has_presence and ctx.needs_input_grad[2]
+        bucketed = need_pres and _bucket_mode(ctx.pp_group)
+        g_pres = None
+        if need_pres:
+            g_pres = (_bucket_segment(ctx.pp_group, dev).view(dl.P, 2) if bucketed
+                      else torch.empty(dl.P, 2, device=dev, dtype=torch.float32))
         call('hcomp_desc_losses_bwd', ptr(g_loss), ptr(pooled), ptr(wc), ptr(pres), ptr(gum), ptr(labels.ys), ptr(labels.tgt),
              ptr(labels.n_desc), dl.tref, V, labels.V_first, flags, wts, eps, boost, tau, ptr(ws), ptr(g_pooled), ptr(g_pres),
              _stream())
+        if bucketed:
+            g_pres = None
+        elif GRAD_ALLREDUCE_GROUP is not None and g_pres is not None:
+            torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g_pres))
         return g_pooled, None, g_pres, None, None, None, None, None, None, None, None
 
 

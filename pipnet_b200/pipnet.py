@@ -64,10 +64,15 @@ class _GatherParams(torch.autograd.Function):
     @staticmethod
     def forward(ctx, holder, *params):
         ctx.meta = holder.meta
+        ctx.n_params = len(params)
+        # no zero-filled gradients when every consumer delivered its gradient out of band (ops._GradBucket)
+        ctx.set_materialize_grads(False)
         return holder.flat.detach()
 
     @staticmethod
     def backward(ctx, g):
+        if g is None:
+            return (None,) * (1 + ctx.n_params)
         g = g.contiguous()
         flat = g.view(-1)
         grads = []
@@ -86,6 +91,7 @@ class _FlatGroup:
         self.meta = []
         self._gathered: Optional[Tensor] = None
         self._gathered_grad = None
+        self.family = None       # all flat groups of the model (set by PIPNet): layout of the data-parallel gradient bucket
 
     def ensure(self):
         p0 = self.params[0]
@@ -117,6 +123,7 @@ class _FlatGroup:
         self.ensure()
         if self._gathered is None or not torch.is_grad_enabled() or self._gathered_grad != torch.is_grad_enabled():
             self._gathered = _GatherParams.apply(self, *self.params)
+            self._gathered._hc_group = self      # lets the kernels' autograd functions find the parameters (ops._GradBucket)
             self._gathered_grad = torch.is_grad_enabled()
         return self._gathered
 
@@ -240,6 +247,9 @@ class PIPNet(nn.Module):
         self._bias_group = (_FlatGroup([getattr(self, '_' + n + '_classification').bias for n in names])
                             if self._has_cls_bias else None)
         self._pp_group = _FlatGroup([getattr(self, '_' + n + '_proto_presence') for n in names])
+        family = [g for g in (self._w_group, self._wc_group, self._bias_group, self._pp_group) if g is not None]
+        for g in family:
+            g.family = family
         self._dl: Optional[ops.DeviceLayout] = None
         # 'bf16': bf16 GEMM operands (default, the benchmarked path); 'fp32': fp32-accurate projection (3-way bf16 split
         # operands, six cross terms through the same tcgen05 kernel) for the <= 1e-5 contract on fp32 inputs
@@ -275,14 +285,18 @@ class PIPNet(nn.Module):
     def flat_prototype_kernels(self) -> Tensor:
         """[P, C] view of all add-on kernels with autograd edges to the per-node parameters."""
         C = self._w_group.params[0].shape[1]
-        return self._w_group.gather().view(self.layout.P, C)
+        v = self._w_group.gather().view(self.layout.P, C)
+        v._hc_group = self._w_group
+        return v
 
     def flat_classifier_weights(self) -> Tensor:
         return self._wc_group.gather()
 
     def flat_proto_presence(self) -> Tensor:
         """[P, 2] view of all `_<node>_proto_presence` logits with autograd edges to the per-node parameters."""
-        return self._pp_group.gather().view(self.layout.P, 2)
+        v = self._pp_group.gather().view(self.layout.P, 2)
+        v._hc_group = self._pp_group
+        return v
 
     # ------------------------------------------------------------------ forward
     def head(self, features: Tensor, *, inference=False, labels: Optional[ops.LabelTables] = None,
