@@ -160,10 +160,6 @@ def run_ours(a):
         if os.environ.get('NCCL_DEBUG', '').upper() in ('VERSION', 'WARN'):
             os.environ.pop('NCCL_DEBUG')                 # NCCL prints its version banner on stdout: keep it to the JSON line
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        # the gradient all-reduce (1.5 MB, latency-bound) is meant to run BESIDE the persistent dX GEMM: keep NCCL to as
-        # many CTAs as the GEMM leaves SMs free (ops.COLLECTIVE_SMS), otherwise its surplus CTAs queue behind the GEMM
-        os.environ.setdefault('NCCL_MAX_CTAS', str(ops.COLLECTIVE_SMS))
-        os.environ.setdefault('NCCL_MAX_NCHANNELS', str(ops.COLLECTIVE_SMS))
         dist.init_process_group('nccl', device_id=dev)
         ops.GRAD_ALLREDUCE_GROUP = dist.group.WORLD
     wl = WORKLOADS[a.workload]
@@ -310,7 +306,7 @@ def run_ours(a):
     ms_per_step = ms / a.steps
     value = world * B / (ms_per_step * 1e-3)
 
-    if os.environ.get('HC_TRACE') and graphs is not None:      # debugging aid: kernel timeline of two replays (rank 0)
+    if os.environ.get('HC_TRACE') and graphs is not None:      # debugging aid (never set by the driver): kernel timeline
         from torch.profiler import profile, ProfilerActivity
         import contextlib
         barrier()

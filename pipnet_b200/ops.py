@@ -55,9 +55,11 @@ PROFILE = _Profile()
 # is all-reduced (mean) on a side stream right after the dW GEMM so it overlaps the dX GEMM and whatever
 # backbone backward follows.
 GRAD_ALLREDUCE_GROUP = None
-# SMs the dX GEMM leaves free while the dW all-reduce is in flight: a persistent GEMM that owns every SM (1 CTA/SM, ~198 KB
-# of shared memory) would otherwise keep NCCL's CTAs waiting until it drains and the "overlap" would serialise.
-COLLECTIVE_SMS = int(os.environ.get('HC_COLLECTIVE_SMS', '8'))
+# SMs the dX GEMM leaves free while the gradient all-reduce is in flight (hcomp_set_reserved_sms).  Measured on 2xB200: the
+# NCCL kernel does not make progress beside the persistent GEMM whether 0, 8 or 32 SMs are left free (its tail after the
+# GEMM stays ~20 us), and capping NCCL to 8 CTAs makes the tail longer, so the default is 0; the collective is hidden
+# behind the backbone backward instead (its join is at the end of the backward pass).
+COLLECTIVE_SMS = int(os.environ.get('HC_COLLECTIVE_SMS', '0'))
 _side_stream = None
 
 
