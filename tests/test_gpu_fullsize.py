@@ -114,3 +114,52 @@ def test_backward_linearity_and_spot_checks(name):
     got = gxo.permute(0, 2, 3, 1).reshape(V, HW, C).double()
     err = float((got - dx_ref).abs().max() / dx_ref.abs().max())
     assert err <= 2e-2, err
+
+
+def test_large_tree_inference_sweep_shape():
+    """BASELINE.json configs[4] (iNat-bird-like tree, inference only): 1486 leaves => 1485 nodes, P = 29 700, single-view
+    batch through the reference-facing API (`PIPNet.forward(inference=True)` + `get_joint_distribution`).  Sized down in the
+    batch dimension only (the reference could not even materialise its 82 GB map at batch 1024)."""
+    from oracle.problems import build_net, make_args
+    from pipnet_b200 import ops
+    args = make_args(num_features=20)
+    net, root = build_net('synth1486', 768, args)
+    L = net.layout
+    assert (L.N, L.P) == (1485, 29700)
+    V, H = 24, 26
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randn(V, H, H, 768, generator=g, device='cuda').to(torch.bfloat16).permute(0, 3, 1, 2)   # channels-last view
+    with torch.no_grad():
+        _, pf, pooled, out = net(x, inference=True)
+        _, joint = net.get_joint_distribution(out)
+        pred = joint.argmax(dim=1)
+    torch.cuda.synchronize()
+    assert tuple(pooled.flat.shape) == (V, L.P) and tuple(out.flat.shape) == (V, L.K) and tuple(joint.shape) == (V, L.L)
+    # inference threshold (pipnet/pipnet.py:168-169): nothing in (0, 0.1)
+    pv = pooled.flat
+    assert bool(((pv == 0) | (pv >= 0.1)).all()) and float(pv.max()) <= 1.0 + 1e-6
+    torch.testing.assert_close(joint.sum(dim=1), torch.ones(V, device='cuda'), rtol=1e-4, atol=1e-5)
+    # spot-check nodes across the tile range against the plain SIMT map kernel (incl. the argmax the visualisers use)
+    w = net.flat_prototype_kernels().detach()
+    for ni in (0, 1, L.N // 3, L.N // 2, L.N - 2, L.N - 1):
+        p0, p1 = int(L.proto_off[ni]), int(L.proto_off[ni + 1])
+        m = ops.materialize_map(x, w[p0:p1], 1.0).flatten(2)
+        mv, mi = m.max(dim=2)
+        want = torch.where(mv < 0.1, torch.zeros_like(mv), mv)
+        torch.testing.assert_close(pv[:, p0:p1], want, rtol=2e-5, atol=1e-7)
+        am = pf.argmax.flat[:, p0:p1].long()
+        torch.testing.assert_close(m.gather(2, am.unsqueeze(-1)).squeeze(-1), mv, rtol=2e-5, atol=1e-7)
+    # the fine prediction is the leaf whose root->leaf path has the largest probability product: check two samples by hand
+    names = L.node_names
+    node_by_name = {n.name: n for n in root.nodes_with_children()}
+    for v in (0, V - 1):
+        leaf = L.leaf_names[int(pred[v])]
+        prob, node = 1.0, root
+        while not node.is_leaf():
+            i = names.index(node.name)
+            o = out.flat[v, int(L.cls_off[i]):int(L.cls_off[i + 1])].double()
+            pr = torch.softmax(torch.log1p(o * o), dim=0)
+            child = node.closest_descendent_for(leaf)
+            prob *= float(pr[node.children_to_labels[child.name]])
+            node = child
+        assert abs(prob - float(joint[v, pred[v]])) <= 1e-4 * max(prob, 1e-12)
