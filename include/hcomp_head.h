@@ -95,11 +95,12 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
 /* Replaces conv1x1 -> /tau -> softmax(dim=1) -> AdaptiveMaxPool2d for every node
  * (pipnet/pipnet.py:124-159) and the align_pf reduction (pipnet/train.py:1063-1069).
  * x: bf16 [V*HW, C]; views [0,V_first) are paired with views [V_first, V) (train: V_first = V/2).
- * pooled_packed[V,P] and align_sum[N] are cleared by the call.  desc/align_sum may be NULL. */
+ * pooled_packed[V,P] and align_sum[N] are cleared by the call unless outputs_zeroed != 0 (the caller already did).
+ * desc/align_sum may be NULL. */
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
-                                int P_pad, int n_nodes, float tau, int precision, const uint8_t* desc,
-                                unsigned long long* pooled_packed, double* align_sum, void* stream);
+                                int P_pad, int n_nodes, float tau, int precision, int outputs_zeroed,
+                                const uint8_t* desc, unsigned long long* pooled_packed, double* align_sum, void* stream);
 /* packed -> pooled fp32 [V,P] + argmax int32 [V,P] (flat h*W+w, first occurrence; pipnet/pipnet.py:24-25);
  * thresh > 0 applies the inference rule pooled < thresh -> 0 (pipnet/pipnet.py:168-169). */
 int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,

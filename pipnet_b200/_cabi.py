@@ -40,7 +40,7 @@ SIGNATURES = {
     'hcomp_label_tables': [_p, _T, _i, _i, _p, _p, _p, _p],
     'hcomp_split3_f32': [_p, _p, _ll, _p],
     'hcomp_pack_weights_split3': [_p, _p, _i, _i, _p, _p],
-    'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _p],
+    'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p],
     'hcomp_unpack_pool': [_p, _ll, _f, _p, _p, _p],
     'hcomp_align_finalize': [_p, _p, _i, _i, _p, _p],
     'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],

@@ -80,6 +80,37 @@ int dev_info(DevInfo* out) {
   return 0;
 }
 
+// Internal side branch: independent small kernels of one call run beside each other (fork/join with events on the
+// caller's stream: no host synchronisation, capturable into a CUDA graph).
+struct SideBranch {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+int side_branch(SideBranch** out) {
+  int dev = 0;
+  HC_CUDA(cudaGetDevice(&dev));
+  static SideBranch cache[64];
+  if (dev >= 64) return fail(HCOMP_E_ARG, "device index %d", dev);
+  SideBranch& b = cache[dev];
+  if (b.stream == nullptr) {
+    HC_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
+    HC_CUDA(cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming));
+    HC_CUDA(cudaEventCreateWithFlags(&b.join, cudaEventDisableTiming));
+  }
+  *out = &b;
+  return 0;
+}
+#define HC_FORK(b, main)                               \
+  do {                                                 \
+    HC_CUDA(cudaEventRecord((b)->fork, (main)));       \
+    HC_CUDA(cudaStreamWaitEvent((b)->stream, (b)->fork, 0)); \
+  } while (0)
+#define HC_JOIN(b, main)                               \
+  do {                                                 \
+    HC_CUDA(cudaEventRecord((b)->join, (b)->stream));  \
+    HC_CUDA(cudaStreamWaitEvent((main), (b)->join, 0)); \
+  } while (0)
+
 // 2D bf16 row-major tensor [outer, inner] (inner contiguous, pitch in elements), 128B-swizzled boxes.
 int make_tmap(CUtensorMap* m, const void* base, unsigned long long inner, unsigned long long outer,
               unsigned long long pitch_elems, unsigned box_inner, unsigned box_outer) {
@@ -391,14 +422,16 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
 
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
-                                int P_pad, int n_nodes, float tau, int precision, const uint8_t* desc,
-                                unsigned long long* pooled_packed, double* align_sum, void* stream) {
+                                int P_pad, int n_nodes, float tau, int precision, int outputs_zeroed,
+                                const uint8_t* desc, unsigned long long* pooled_packed, double* align_sum, void* stream) {
   hc::HeadParams p{};
   p.pooled_packed = pooled_packed;
   p.align_sum = align_sum;
   p.desc = (align_sum != nullptr) ? desc : nullptr;
-  HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
-  if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
+  if (!outputs_zeroed) {
+    HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
+    if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
+  }
   return run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
                          precision, p, S(stream));
 }
@@ -507,26 +540,30 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
   const LossWs w = loss_ws(ws, t);
   const bool do_tanh = flags & HCOMP_LOSS_TANH, do_orth = flags & HCOMP_LOSS_ORTH, do_cls = flags & HCOMP_LOSS_CLASS;
   const int sparsity = (flags & HCOMP_LOSS_SPARSITY) ? 1 : 0;
+  SideBranch* sb = nullptr;
+  if (do_orth) {        // depends on the weights only: runs on the side branch beside the tanh / class kernels
+    if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
+    if (int e = side_branch(&sb)) return e;
+    HC_FORK(sb, S(stream));
+    const long long warps = (long long)t->n_nodes * t->p_max * t->p_max;
+    hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, sb->stream>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
+                                                                         t->n_nodes, C, t->p_max, w.E, rel);
+    HC_LAUNCH_CHECK("orth_gram");
+    hc::orth_sumsq_kernel<<<blocks((long long)t->n_nodes * 32, 128), 128, 0, sb->stream>>>(w.E, t->proto_off, t->n_nodes,
+                                                                                          t->p_max, w.orth_sq);
+    HC_LAUNCH_CHECK("orth_sumsq");
+  }
   if (do_tanh) {
     if (t->p_max > 64 * 1024) return fail(HCOMP_E_ARG, "P_max too large");
     hc::tanh_loss_fwd_kernel<<<dim3(t->n_nodes, 2), 256, 0, S(stream)>>>(pooled, tgt, t->proto_off, n_desc, V, V_first,
                                                                         t->n_nodes, t->n_protos, eps, w.tanh_part, w.colsum);
     HC_LAUNCH_CHECK("tanh_loss_fwd");
   }
-  if (do_orth) {
-    if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
-    const long long warps = (long long)t->n_nodes * t->p_max * t->p_max;
-    hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
-                                                                        t->n_nodes, C, t->p_max, w.E, rel);
-    HC_LAUNCH_CHECK("orth_gram");
-    hc::orth_sumsq_kernel<<<blocks((long long)t->n_nodes * 32, 128), 128, 0, S(stream)>>>(w.E, t->proto_off, t->n_nodes,
-                                                                                         t->p_max, w.orth_sq);
-    HC_LAUNCH_CHECK("orth_sumsq");
-  }
   // class kernel also produces the per-node accuracy counters, so it always runs
   hc::class_loss_fwd_kernel<<<t->n_nodes, 128, 0, S(stream)>>>(out, tgt, t->child_w, t->cls_off, n_desc, V, t->n_nodes,
                                                               t->n_cols, sparsity, w.cls, n_correct);
   HC_LAUNCH_CHECK("class_loss_fwd");
+  if (sb) HC_JOIN(sb, S(stream));
   hc::LossWeights lw;
   for (int i = 0; i < 4; ++i) lw.w[i] = weights_host[i];
   hc::loss_combine_kernel<<<1, 256, 0, S(stream)>>>(align, do_tanh ? w.tanh_part : nullptr, do_orth ? w.orth_sq : nullptr,
@@ -546,6 +583,18 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
   for (int i = 0; i < 4; ++i) lw.w[i] = weights_host[i];
   hc::loss_grads_kernel<<<blocks(4 * N, 128), 128, 0, S(stream)>>>(g_total, N, lw, gvec);   // gvec[0..N) is g_align
   HC_LAUNCH_CHECK("loss_grads");
+  SideBranch* sb_bwd = nullptr;
+  if (g_w) {
+    if (flags & HCOMP_LOSS_ORTH) {      // weights-only term: beside the tanh / class backward kernels
+      if (int e = side_branch(&sb_bwd)) return e;
+      HC_FORK(sb_bwd, S(stream));
+      hc::orth_bwd_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb_bwd->stream>>>(
+          w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, gvec + 2 * N, g_w);
+      HC_LAUNCH_CHECK("orth_bwd");
+    } else {
+      HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
+    }
+  }
   if (g_pooled) {
     if (flags & HCOMP_LOSS_TANH) {
       const long long n = (long long)V * t->n_protos;
@@ -566,16 +615,7 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
       HC_CUDA(cudaMemsetAsync(g_out, 0, sizeof(float) * (size_t)V * t->n_cols, S(stream)));
     }
   }
-  if (g_w) {
-    if (flags & HCOMP_LOSS_ORTH) {
-      hc::orth_bwd_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, S(stream)>>>(w_flat, t->proto_node, t->proto_off, C,
-                                                                                    t->p_max, stats + 2 * N, w.E, rel,
-                                                                                    gvec + 2 * N, g_w);
-      HC_LAUNCH_CHECK("orth_bwd");
-    } else {
-      HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
-    }
-  }
+  if (sb_bwd) HC_JOIN(sb_bwd, S(stream));
   return 0;
 }
 

@@ -290,11 +290,12 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
                           precision=PREC_BF16):
     Cc = x_rows.shape[1]
     dev = x_rows.device
-    packed = torch.empty(V * dl.P, device=dev, dtype=torch.int64)
-    align_sum = torch.empty(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
+    # the packed max table and the align accumulators are merged into with atomics: cleared here (outputs_zeroed = 1)
+    packed = torch.zeros(V * dl.P, device=dev, dtype=torch.int64)
+    align_sum = torch.zeros(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
     tok = PROFILE.start('k1_proj_softmax_pool_fwd')
     call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
-         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), ptr(labels.desc) if labels is not None else None,
+         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), 1, ptr(labels.desc) if labels is not None else None,
          ptr(packed), ptr(align_sum), _stream())
     PROFILE.stop(tok)
     pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)

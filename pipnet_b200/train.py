@@ -137,8 +137,7 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         labels = make_labels(net, ys)
     N = dl.N
     names = m.layout.node_names
-    zero = torch.zeros((), device=pooled.flat.device)
-    loss = zero
+    out_device = pooled.flat.device
     losses_used = []
 
     flags = 0
@@ -212,8 +211,8 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         loss = loss + dloss
 
     if node_accuracy is not None:
-        acc = node_accuracy.setdefault('__device__', {'n_examples': torch.zeros(N, device=zero.device, dtype=torch.int64),
-                                                      'n_correct': torch.zeros(N, device=zero.device, dtype=torch.int64)})
+        acc = node_accuracy.setdefault('__device__', {'n_examples': torch.zeros(N, device=out_device, dtype=torch.int64),
+                                                      'n_correct': torch.zeros(N, device=out_device, dtype=torch.int64)})
         acc['n_examples'] += labels.n_desc
         acc['n_correct'] += n_correct
 
