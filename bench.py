@@ -230,7 +230,7 @@ def run_ours(a):
     dl = net.device_layout(dev)
     with torch.no_grad():
         w_flat_k = net.flat_prototype_kernels().detach().contiguous()
-        wp_k = ops.pack_weights(w_flat_k, dl)
+        wp_k, wpc_k = ops.pack_weights(w_flat_k, dl)
         lab_k = [tr.make_labels(net, y) for y in labels_d]
         xr_k = [ops.feature_rows(f) for f in feats]
         gp_k = torch.randn(V, L.P, device=dev)
@@ -239,7 +239,7 @@ def run_ours(a):
 
         def kernel_pass(i):
             pooled, argmax, _al = ops.proj_softmax_pool_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, lab_k[i % 2])
-            ops.head_backward_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, argmax, gp_k, lab_k[i % 2], ga_k)
+            ops.head_backward_raw(xr_k[i % 2], wp_k, wpc_k, dl, V, B, HW, net.softmax_tau, argmax, gp_k, lab_k[i % 2], ga_k)
 
         for i in range(3):
             kernel_pass(i)

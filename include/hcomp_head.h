@@ -15,7 +15,7 @@
  *   K          total child logits = sum of C_n; flat logit axis, same order
  *   rows       one row per (view, location): M = V*HW rows of C channels, bf16, channels-last
  *   tiles      the padded prototype axis: 128-column tiles of equal-length node segments
- *              (int32 records of HCOMP_TILE_INTS words: {S, nseg, umma_n, 0, node[16], len[16], poff[16]})
+ *              (int32 records of HCOMP_TILE_INTS words: {S, nseg, umma_n, dz_col, node[16], len[16], poff[16]})
  *   P_pad      128 * number of tiles
  */
 #ifndef HCOMP_HEAD_H
@@ -110,17 +110,20 @@ int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, 
 /* ---- K5-K7: backward -------------------------------------------------------------------------- */
 /* dZ = S * (G - sum_p G*S) / tau with G = align gradient + g_pooled scattered at argmax; recomputes the
  * logits tile (same GEMM as K1).  scat_ws: int2[V*P], coef_ws: float[V_first*N] workspaces.
- * g_align (per node upstream gradient), desc may be NULL.  dz: bf16 [V*HW, P_pad], fully written. */
+ * g_align (per node upstream gradient), desc may be NULL.
+ * dz: bf16 [V*HW, P_c] on the COMPACT column axis: tile t owns columns [tiles[t][3], + used width), used width =
+ * segments * S rounded up to 8; within a segment class the full tiles are contiguous (layout.py builds the table,
+ * row_map_c[P_c] maps a compact column to its flat prototype or -1).  Every column of dz is written. */
 int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host, const int32_t* tiles_dev,
-                      int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau,
+                      int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int P_c, int n_nodes, float tau,
                       int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
                       void* dz_bf16, void* stream);
-/* dX[rows,C] (bf16) = dZ[rows,P_pad] * Wp[P_pad,C]. */
-int hcomp_head_bwd_dx(const void* dz_bf16, const void* wp_bf16, long long rows, int P_pad, int C, void* dx_bf16,
+/* dX[rows,C] (bf16) = dZ[rows,P_c] * Wpc[P_c,C]  (Wpc: bf16 kernels packed on the compact axis with row_map_c). */
+int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,
                       void* stream);
-/* dW[P,C] (fp32, ACCUMULATED into; clear it first) += dZ^T * X, padded rows dropped via row_map. */
-int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map, long long rows, int P_pad, int C,
+/* dW[P,C] (fp32, ACCUMULATED into; clear it first) += dZ^T * X, padding columns dropped via row_map_c. */
+int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map_c, long long rows, int P_c, int C,
                       float* dw_flat, void* stream);
 
 /* ---- K2: per-node non-negative classifier (pipnet/pipnet.py:1035-1036) ------------------------- */

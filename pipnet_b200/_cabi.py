@@ -43,7 +43,7 @@ SIGNATURES = {
     'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p],
     'hcomp_unpack_pool': [_p, _ll, _f, _p, _p, _p],
     'hcomp_align_finalize': [_p, _p, _i, _i, _p, _p],
-    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_head_bwd_dx': [_p, _p, _ll, _i, _i, _p, _p],
     'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p],
     'hcomp_classifier_fwd': [_p, _p, _p, _T, _i, _p, _p],

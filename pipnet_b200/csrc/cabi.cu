@@ -130,6 +130,26 @@ int make_tmap(CUtensorMap* m, const void* base, unsigned long long inner, unsign
   return 0;
 }
 
+// 3D bf16 store map over the compact dZ matrix: {w columns of a tile, n_tiles tiles at `w`-column pitch, rows}; boxes
+// are [64 cols x 1 tile x box_rows rows], 128B-swizzled in shared memory like the 2D maps.
+int make_tmap_dz(CUtensorMap* m, const void* base, unsigned w, unsigned n_tiles, unsigned long long rows,
+                 unsigned long long pitch_elems, unsigned box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(HCOMP_E_ARG, "dZ tile base not 16-byte aligned");
+  if ((pitch_elems * 2) % 16 != 0 || (w * 2) % 16 != 0 || w == 0 || n_tiles == 0 || rows == 0)
+    return fail(HCOMP_E_ARG, "bad compact dZ geometry (w %u, tiles %u, rows %llu, pitch %llu)", w, n_tiles, rows, pitch_elems);
+  cuuint64_t gdim[3] = {w, n_tiles, rows};
+  cuuint64_t gstr[2] = {(cuuint64_t)w * 2, pitch_elems * 2};
+  cuuint32_t box[3] = {64, 1, box_rows};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled (dZ) failed with %d (w %u tiles %u rows %llu)", int(r), w, n_tiles, rows);
+  return 0;
+}
+
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 
@@ -156,7 +176,7 @@ int launch_persistent(Kern kern, const char* name, int cluster, int workers, int
 }
 
 template <int SEG, bool BWD, bool CG2>
-int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& td1, const CUtensorMap& td2,
+int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap* td /* [4]: dz1, dz2, dz1 partial, dz2 partial */,
                 const hc::HeadParams& p, int sms, cudaStream_t st) {
   auto kern = hc::head_pair_kernel<SEG, BWD, CG2>;
   constexpr int SMEM = hc::PairMem<BWD, CG2>::SMEM_BYTES;
@@ -170,19 +190,19 @@ int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap&
   const int slots = sms / CL;
   const int workers = items < slots ? items : slots;
   return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", CL, workers,
-                           hc::PairCfg<SEG>::THREADS, SMEM, st, tx, tw, td1, td2, p);
+                           hc::PairCfg<SEG>::THREADS, SMEM, st, tx, tw, td[0], td[1], td[2], td[3], p);
 }
 
 template <bool BWD, bool CG2>
-int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap& td1,
-                      const CUtensorMap& td2, const hc::HeadParams& p, int sms, cudaStream_t st) {
+int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap* td,
+                      const hc::HeadParams& p, int sms, cudaStream_t st) {
   switch (seg) {
-    case 8: return launch_pair<8, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
-    case 16: return launch_pair<16, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
-    case 20: return launch_pair<20, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
-    case 32: return launch_pair<32, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
-    case 40: return launch_pair<40, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
-    case 64: return launch_pair<64, BWD, CG2>(tx, tw, td1, td2, p, sms, st);
+    case 8: return launch_pair<8, BWD, CG2>(tx, tw, td, p, sms, st);
+    case 16: return launch_pair<16, BWD, CG2>(tx, tw, td, p, sms, st);
+    case 20: return launch_pair<20, BWD, CG2>(tx, tw, td, p, sms, st);
+    case 32: return launch_pair<32, BWD, CG2>(tx, tw, td, p, sms, st);
+    case 40: return launch_pair<40, BWD, CG2>(tx, tw, td, p, sms, st);
+    case 64: return launch_pair<64, BWD, CG2>(tx, tw, td, p, sms, st);
     default: return fail(HCOMP_E_ARG, "unsupported segment class %d (supported: 8,16,20,32,40,64)", seg);
   }
 }
@@ -213,17 +233,8 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   p.M = int(M);
   p.halfM = V_first * HW;
   p.rowsB = int(M) - p.halfM;
-  CUtensorMap td1, td2;                 // backward: dZ leaves through TMA stores, one map per view half (row clipping)
-  memset(&td1, 0, sizeof(td1));
-  memset(&td2, 0, sizeof(td2));
-  if (BWD) {
-    if (int e = make_tmap(&td1, p.dz, P_pad, p.halfM, P_pad, 64, hc::TILE_M)) return e;
-    if (p.rowsB > 0) {
-      if (int e = make_tmap(&td2, p.dz + (size_t)p.halfM * P_pad, P_pad, p.rowsB, P_pad, 64, hc::TILE_M)) return e;
-    } else {
-      td2 = td1;                        // no second half: every store of it would be fully clipped; keep a valid map
-    }
-  }
+  CUtensorMap td[4];                    // backward: dZ leaves through TMA stores (per class: full tiles / partial tile x view half)
+  memset(td, 0, sizeof(td));
   p.HW = HW; p.C = C; p.P = P; p.P_pad = P_pad;
   p.split_terms = split;
   p.num_k_blocks = cdiv(C, hc::KBLK) * split;
@@ -245,10 +256,42 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
     }
     p.tile_begin = t;
     p.num_tiles = e - t;
+    if (BWD) {
+      // compact dZ columns of this class: full tiles (all segments used) are contiguous at one pitch, then at most one
+      // partial tile; widths are the used columns rounded up to 8 (layout.py)
+      const int per_tile = hc::TILE_N / seg;
+      const int32_t* last = tiles_host + (size_t)(e - 1) * hc::TILE_INTS;
+      const bool has_partial = last[1] < per_tile;
+      p.n_full_tiles = p.num_tiles - (has_partial ? 1 : 0);
+      p.w_full = ((per_tile * seg + 7) / 8) * 8;
+      p.w_partial = has_partial ? ((last[1] * seg + 7) / 8) * 8 : 0;
+      const int c_full = tiles_host[(size_t)t * hc::TILE_INTS + 3];
+      for (int i = t; i < e; ++i) {
+        const int want = (i - t) < p.n_full_tiles ? c_full + (i - t) * p.w_full : c_full + p.n_full_tiles * p.w_full;
+        if (tiles_host[(size_t)i * hc::TILE_INTS + 3] != want || want % 8 != 0)
+          return fail(HCOMP_E_ARG, "tile %d: compact dZ column %d, expected %d", i, tiles_host[(size_t)i * hc::TILE_INTS + 3], want);
+      }
+      if (c_full + p.n_full_tiles * p.w_full + p.w_partial > p.P_c) return fail(HCOMP_E_ARG, "compact dZ columns exceed P_c=%d", p.P_c);
+      __nv_bfloat16* h1 = p.dz;
+      __nv_bfloat16* h2 = p.dz + (size_t)p.halfM * p.P_c;
+      const unsigned long long rows2 = p.rowsB > 0 ? p.rowsB : p.halfM;      // no second half: keep valid (unused) maps
+      if (p.rowsB <= 0) h2 = h1;
+      if (p.n_full_tiles > 0) {
+        if (int er = make_tmap_dz(&td[0], h1 + c_full, p.w_full, p.n_full_tiles, p.halfM, p.P_c, hc::TILE_M)) return er;
+        if (int er = make_tmap_dz(&td[1], h2 + c_full, p.w_full, p.n_full_tiles, rows2, p.P_c, hc::TILE_M)) return er;
+      }
+      if (has_partial) {
+        const int c_part = c_full + p.n_full_tiles * p.w_full;
+        if (int er = make_tmap_dz(&td[2], h1 + c_part, p.w_partial, 1, p.halfM, p.P_c, hc::TILE_M)) return er;
+        if (int er = make_tmap_dz(&td[3], h2 + c_part, p.w_partial, 1, rows2, p.P_c, hc::TILE_M)) return er;
+      }
+      if (p.n_full_tiles == 0) { td[0] = td[2]; td[1] = td[3]; }
+      if (!has_partial) { td[2] = td[0]; td[3] = td[1]; }
+    }
     // CTA pairs (cta_group::2) whenever there are at least two pair tiles along M
     const bool pair = !g_no_pair && p.num_m_tiles >= 2;
-    if (int err = pair ? launch_pair_class<BWD, true>(seg, tx, tw_half, td1, td2, p, di.sms, st)
-                       : launch_pair_class<BWD, false>(seg, tx, tw, td1, td2, p, di.sms, st))
+    if (int err = pair ? launch_pair_class<BWD, true>(seg, tx, tw_half, td, p, di.sms, st)
+                       : launch_pair_class<BWD, false>(seg, tx, tw, td, p, di.sms, st))
       return err;
     t = e;
   }
@@ -450,10 +493,11 @@ int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, 
 }
 
 int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host, const int32_t* tiles_dev,
-                      int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau,
+                      int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int P_c, int n_nodes, float tau,
                       int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
                       void* dz_bf16, void* stream) {
+  if (P_c <= 0 || P_c % 8 != 0 || P_c > P_pad) return fail(HCOMP_E_ARG, "P_c=%d must be a positive multiple of 8, <= P_pad", P_c);
   const long long n = (long long)V * P;
   hc::make_scat_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
                                                                reinterpret_cast<int2*>(scat_ws));
@@ -461,6 +505,7 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
   hc::HeadParams p{};
   p.scat = reinterpret_cast<const int2*>(scat_ws);
   p.dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
+  p.P_c = P_c;
   if (g_align != nullptr && desc != nullptr && n_desc != nullptr) {
     hc::align_coef_kernel<<<blocks((long long)V_first * n_nodes, 256), 256, 0, S(stream)>>>(desc, n_desc, g_align, V_first,
                                                                                            n_nodes, HW, coef_ws);
@@ -471,15 +516,15 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                         precision, p, S(stream));
 }
 
-int hcomp_head_bwd_dx(const void* dz_bf16, const void* wp_bf16, long long rows, int P_pad, int C, void* dx_bf16,
+int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,
                       void* stream) {
-  return run_gemm(dz_bf16, wp_bf16, rows, C, P_pad, false, true, hc::OUT_BF16, 1, dx_bf16, C, nullptr, S(stream),
+  return run_gemm(dz_bf16, wpc_bf16, rows, C, P_c, false, true, hc::OUT_BF16, 1, dx_bf16, C, nullptr, S(stream),
                   g_reserved_sms);
 }
 
-int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map, long long rows, int P_pad, int C,
+int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map_c, long long rows, int P_c, int C,
                       float* dw_flat, void* stream) {
-  return run_gemm(dz_bf16, x_bf16, P_pad, C, rows, true, true, hc::OUT_RED_F32, 0, dw_flat, C, row_map, S(stream));
+  return run_gemm(dz_bf16, x_bf16, P_c, C, rows, true, true, hc::OUT_RED_F32, 0, dw_flat, C, row_map_c, S(stream));
 }
 
 int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias, const hcomp_tables* t, int V,

@@ -74,7 +74,10 @@ struct HeadParams {
   // backward
   const int2* scat;                    // [V,P] {argmax location, g_pooled bits}
   const float* coef_align;             // [imgs_first, n_nodes] upstream * 0.5 / (n_desc * HW) (0 if masked); may be null
-  __nv_bfloat16* dz;                   // [M, P_pad]
+  __nv_bfloat16* dz;                   // [M, P_c]: COMPACT column axis (tile t starts at column tiles[t][3], used columns only)
+  int P_c;                             // columns of dz
+  int n_full_tiles;                    // tiles of this launch that hold the class's full segment count (the rest: <= 1 partial tile)
+  int w_full, w_partial;               // compact widths (multiples of 8) of a full tile / of the partial last tile
 };
 
 template <bool BWD> struct PairSmemT {
@@ -252,6 +255,7 @@ template <int S, bool BWD, bool CG2>
 __global__ void __launch_bounds__(PairCfg<S>::THREADS, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                  const __grid_constant__ CUtensorMap tmap_dz1, const __grid_constant__ CUtensorMap tmap_dz2,
+                 const __grid_constant__ CUtensorMap tmap_dz1p, const __grid_constant__ CUtensorMap tmap_dz2p,
                  const HeadParams p) {
   constexpr int PAIR_STAGES = PairMem<BWD, CG2>::STAGES;
   constexpr int STAGE_BYTES = PairMem<BWD, CG2>::STAGE_BYTES;
@@ -601,13 +605,19 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         fence_proxy_async();
         named_bar_sync(1, 32 * PairCfg<S>::EPI_WARPS);
         if (warp == 4 && lane == 0) {
-          const int col0 = (p.tile_begin + nt) * TILE_N;
+          // compact dZ: 3-D maps {column inside the tile, tile of this class, row}; the tensor's inner extent (the
+          // tile's used width) clips the second 64-column box, the row extent clips the end of the view half
+          const bool partial = nt >= p.n_full_tiles;
+          const int width = partial ? p.w_partial : p.w_full;
+          const int tc = partial ? 0 : nt;
           const int row0 = mt * TILE_M;
 #pragma unroll
           for (int b = 0; b < 2; ++b) {
-            tma_store_2d(&tmap_dz1, dzstage + b * (TILE_M * 128), col0 + 64 * b, row0);
+            if (64 * b >= width) break;
+            tma_store_3d(partial ? &tmap_dz1p : &tmap_dz1, dzstage + b * (TILE_M * 128), 64 * b, tc, row0);
             if (p.rowsB > 0)
-              tma_store_2d(&tmap_dz2, dzstage + PAIR_DZ_STAGE_BYTES / 2 + b * (TILE_M * 128), col0 + 64 * b, row0);
+              tma_store_3d(partial ? &tmap_dz2p : &tmap_dz2, dzstage + PAIR_DZ_STAGE_BYTES / 2 + b * (TILE_M * 128), 64 * b,
+                           tc, row0);
           }
           tma_store_commit();
         }

@@ -54,7 +54,10 @@ class HeadLayout:
     tiles: np.ndarray                     # [T, TILE_INTS] int32
     row_map: np.ndarray                   # [P_pad] int32 -> flat prototype or -1
     child_proto_slices: Dict[str, List[tuple]] = field(default_factory=dict)
+    row_map_c: np.ndarray = None          # [P_c] int32: compact dZ column -> flat prototype or -1
 
+    @property
+    def P_c(self): return int(self.row_map_c.shape[0])     # columns of the compact dZ axis (multiple of 8)
     @property
     def N(self): return len(self.node_names)
     @property
@@ -127,7 +130,12 @@ def build_layout(root) -> HeadLayout:
     by_class: Dict[int, List[int]] = {}
     for i in range(N):
         by_class.setdefault(seg_class(int(P_n[i])), []).append(i)
-    recs, row_map = [], []
+    # The padded axis (128 columns per tile) is what the MMAs of the fused kernels see.  The backward's dZ matrix and the
+    # dX / dW GEMMs use a COMPACT column axis instead: a tile contributes only its used columns (segments * S rounded up
+    # to 8 columns = 16 bytes), e.g. 120 instead of 128 for six 20-prototype nodes and 24 instead of 128 for a lone one.
+    # rec[3] = first compact column of the tile; within a class all full tiles have the same width and are contiguous.
+    recs, row_map, row_map_c = [], [], []
+    col_c = 0
     for s in sorted(by_class):
         per_tile = TILE_COLS // s
         ids = by_class[s]
@@ -136,6 +144,8 @@ def build_layout(root) -> HeadLayout:
             rec = np.zeros(TILE_INTS, dtype=np.int32)
             rec[0], rec[1] = s, len(chunk)
             rec[2] = min(TILE_COLS, ((len(chunk) * s + 15) // 16) * 16)
+            rec[3] = col_c
+            width = ((len(chunk) * s + 7) // 8) * 8
             rows = np.full(TILE_COLS, -1, dtype=np.int32)
             for j, ni in enumerate(chunk):
                 rec[4 + j] = ni
@@ -144,8 +154,11 @@ def build_layout(root) -> HeadLayout:
                 rows[j * s: j * s + P_n[ni]] = np.arange(proto_off[ni], proto_off[ni] + P_n[ni])
             recs.append(rec)
             row_map.append(rows)
+            row_map_c.append(rows[:width])
+            col_c += width
     tiles = np.stack(recs).astype(np.int32)
     row_map = np.concatenate(row_map).astype(np.int32)
+    row_map_c = np.concatenate(row_map_c).astype(np.int32)
 
     slices = {}
     for n in nodes:
@@ -157,4 +170,4 @@ def build_layout(root) -> HeadLayout:
                 start += k
             slices[n.name] = sl
     return HeadLayout([n.name for n in nodes], leaf_names, P_n, C_n, proto_off, cls_off, wc_off, proto_node, col_node,
-                      welem_col, welem_proto, child_w, path_off, path_col, anc, tiles, row_map, slices)
+                      welem_col, welem_proto, child_w, path_off, path_col, anc, tiles, row_map, slices, row_map_c)

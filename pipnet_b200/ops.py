@@ -197,6 +197,8 @@ class DeviceLayout:
         self.tiles_host = torch.from_numpy(np.ascontiguousarray(L.tiles)).to(torch.int32)
         self.tiles_dev = self.tiles_host.to(d)
         self.row_map = up(L.row_map, torch.int32)
+        self.row_map_c = up(L.row_map_c, torch.int32)                # compact dZ axis (backward GEMMs)
+        self.row_map_all = torch.cat([self.row_map, self.row_map_c])  # one pack launch writes both weight layouts
         self.tables = Tables(L.N, L.P, L.K, L.L, L.n_welems, L.p_max,
                              self.proto_off.data_ptr(), self.cls_off.data_ptr(), self.wc_off.data_ptr(),
                              self.proto_node.data_ptr(), self.col_node.data_ptr(), self.welem_col.data_ptr(),
@@ -216,6 +218,8 @@ class DeviceLayout:
     def L(self): return self.layout.L
     @property
     def P_pad(self): return self.layout.P_pad
+    @property
+    def P_c(self): return self.layout.P_c
 
 
 # --------------------------------------------------------------------------- operand preparation
@@ -245,18 +249,21 @@ def feature_rows(features: torch.Tensor):
 PREC_BF16, PREC_FP32X3 = 0, 1
 
 
-def pack_weights(w_flat: torch.Tensor, dl: DeviceLayout, precision=PREC_BF16) -> torch.Tensor:
-    """fp32 flat kernels [P,C] -> tile-padded bf16 [P_pad,C] (or 3 stacked split planes in fp32-accurate mode)"""
+def pack_weights(w_flat: torch.Tensor, dl: DeviceLayout, precision=PREC_BF16):
+    """fp32 flat kernels [P,C] -> (wp, wpc): wp = tile-padded bf16 [P_pad,C] for the fused projection kernels (3 stacked
+    split planes in fp32-accurate mode), wpc = bf16 [P_c,C] on the compact dZ axis for the dX GEMM."""
     _require_cuda(w_flat, 'prototype kernels')
     assert w_flat.dtype == torch.float32 and w_flat.is_contiguous() and w_flat.shape[0] == dl.P
     Cc = w_flat.shape[1]
     if precision == PREC_FP32X3:
         wp = torch.empty(3 * dl.P_pad, Cc, device=w_flat.device, dtype=torch.bfloat16)
         call('hcomp_pack_weights_split3', ptr(w_flat), ptr(dl.row_map), dl.P_pad, Cc, ptr(wp), _stream())
-        return wp
-    wp = torch.empty(dl.P_pad, Cc, device=w_flat.device, dtype=torch.bfloat16)
-    call('hcomp_pack_weights', ptr(w_flat), ptr(dl.row_map), dl.P_pad, Cc, ptr(wp), _stream())
-    return wp
+        wpc = torch.empty(dl.P_c, Cc, device=w_flat.device, dtype=torch.bfloat16)
+        call('hcomp_pack_weights', ptr(w_flat), ptr(dl.row_map_c), dl.P_c, Cc, ptr(wpc), _stream())
+        return wp, wpc
+    both = torch.empty(dl.P_pad + dl.P_c, Cc, device=w_flat.device, dtype=torch.bfloat16)
+    call('hcomp_pack_weights', ptr(w_flat), ptr(dl.row_map_all), dl.P_pad + dl.P_c, Cc, ptr(both), _stream())
+    return both[:dl.P_pad], both[dl.P_pad:]
 
 
 def feature_rows_split3(features: torch.Tensor) -> torch.Tensor:
@@ -308,18 +315,18 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
     return pooled, argmax, align
 
 
-def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
+def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
                       pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None):
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
-    dz = torch.empty(M, dl.P_pad, device=dev, dtype=torch.bfloat16)
+    dz = torch.empty(M, dl.P_c, device=dev, dtype=torch.bfloat16)       # compact column axis (layout.row_map_c)
     scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
     coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
     use_align = labels is not None and g_align is not None
     tok = PROFILE.start('k5_bwd_dz')
     call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
-         dl.P, dl.P_pad, dl.N, float(tau), int(precision), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
+         dl.P, dl.P_pad, dl.P_c, dl.N, float(tau), int(precision), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
          ptr(labels.desc) if use_align else None, ptr(labels.n_desc) if use_align else None,
          ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), _stream())
     PROFILE.stop(tok)
@@ -331,7 +338,7 @@ def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax,
         dw = (_bucket_segment(w_group, dev).view(dl.P, Cc) if bucketed
               else torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32))
         tok = PROFILE.start('k7_bwd_dw')
-        call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map), C.c_longlong(M), dl.P_pad, Cc, ptr(dw), _stream())
+        call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map_c), C.c_longlong(M), dl.P_c, Cc, ptr(dw), _stream())
         PROFILE.stop(tok)
         if bucketed:
             _bucket_allreduce()             # everything the head produces is in the bucket by now; overlaps K6
@@ -343,7 +350,7 @@ def head_backward_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, argmax,
         tok = PROFILE.start('k6_bwd_dx')
         prev = _cabi.lib().hcomp_set_reserved_sms(COLLECTIVE_SMS) if (pending is not None or bucketed) else None
         try:
-            call('hcomp_head_bwd_dx', ptr(dz), ptr(wp), C.c_longlong(M), dl.P_pad, Cc, ptr(dx), _stream())
+            call('hcomp_head_bwd_dx', ptr(dz), ptr(wpc), C.c_longlong(M), dl.P_c, Cc, ptr(dx), _stream())
         finally:
             if prev is not None:
                 _cabi.lib().hcomp_set_reserved_sms(prev)
@@ -379,12 +386,12 @@ class HeadProjPool(torch.autograd.Function):
             x_rows = feature_rows_split3(features.detach())
         else:
             x_rows = feature_rows(features.detach())
-        wp = pack_weights(w_flat.detach().contiguous(), dl, precision)
+        wp, wpc = pack_weights(w_flat.detach().contiguous(), dl, precision)
         pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision)
         ctx.dl, ctx.geom, ctx.labels, ctx.thresh, ctx.precision = dl, (V, V_first, H, W, Cc, tau), labels, thresh, precision
         ctx.w_group = getattr(w_flat, '_hc_group', None)
         ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
-        ctx.save_for_backward(x_rows, wp, argmax, pooled)
+        ctx.save_for_backward(x_rows, wp, wpc, argmax, pooled)
         ctx.mark_non_differentiable(argmax)
         if align is None:
             align = torch.zeros(dl.N, device=features.device, dtype=torch.float32)
@@ -392,7 +399,7 @@ class HeadProjPool(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_pooled, g_align, _g_argmax):
-        x_rows, wp, argmax, pooled = ctx.saved_tensors
+        x_rows, wp, wpc, argmax, pooled = ctx.saved_tensors
         V, V_first, H, W, Cc, tau = ctx.geom
         dl = ctx.dl
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
@@ -401,7 +408,7 @@ class HeadProjPool(torch.autograd.Function):
         g_pooled = g_pooled.contiguous().float()
         if g_align is not None:
             g_align = g_align.contiguous().float()
-        dx, dw, _ = head_backward_raw(x_rows, wp, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
+        dx, dw, _ = head_backward_raw(x_rows, wp, wpc, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
                                       pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw,
                                       precision=ctx.precision, w_group=ctx.w_group)
         d_feat = None

@@ -42,7 +42,7 @@ def test_forward_pool_argmax_align(case):
     feats = pb.features('cuda')
     labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
     x_rows = ops.feature_rows(feats)
-    wp = ops.pack_weights(pb.w_flat('cuda'), dl)
+    wp, _wpc = ops.pack_weights(pb.w_flat('cuda'), dl)
     pooled, argmax, align = ops.proj_softmax_pool_raw(x_rows, wp, dl, pb.V, pb.V_first, H * H, 1.0, labels)
     torch.cuda.synchronize()
 
@@ -70,7 +70,7 @@ def test_forward_unpaired_inference(V):
     pb = Problem("cub08", 64, 6, 0, seed=3, num_features=20, paired=False, V=V)
     dl = ops.DeviceLayout(pb.layout, 'cuda')
     x_rows = ops.feature_rows(pb.features('cuda'))
-    wp = ops.pack_weights(pb.w_flat('cuda'), dl)
+    wp, _wpc = ops.pack_weights(pb.w_flat('cuda'), dl)
     pooled, argmax, _ = ops.proj_softmax_pool_raw(x_rows, wp, dl, pb.V, pb.V_first, 36, 1.0, None, thresh=0.1)
     torch.cuda.synchronize()
     _, pooled_ref, argmax_ref, _ = ho.head_forward(pb.x, pb.w, pb.wc, pb.root, inference=True)

@@ -14,7 +14,7 @@ pb = Problem('cub27', 768, 26, 64, seed=1, num_features=20)
 dl = ops.DeviceLayout(pb.layout, dev)
 V, B, HW = pb.V, pb.V_first, 26 * 26
 xr = ops.feature_rows(pb.features(dev))
-wp = ops.pack_weights(pb.w_flat(dev).contiguous(), dl, ops.PREC_BF16)
+wp, _wpc = ops.pack_weights(pb.w_flat(dev).contiguous(), dl, ops.PREC_BF16)
 lab = ops.LabelTables(pb.ys.to(dev), dl, B)
 for mode in (0, 1):
     _cabi.lib().hcomp_set_cta_pair(mode)
