@@ -86,12 +86,12 @@ struct SideBranch {
   cudaStream_t stream = nullptr;
   cudaEvent_t fork = nullptr, join = nullptr;
 };
-int side_branch(SideBranch** out) {
+int side_branch(SideBranch** out, int which = 0) {
   int dev = 0;
   HC_CUDA(cudaGetDevice(&dev));
-  static SideBranch cache[64];
-  if (dev >= 64) return fail(HCOMP_E_ARG, "device index %d", dev);
-  SideBranch& b = cache[dev];
+  static SideBranch cache[64][2];
+  if (dev >= 64 || which < 0 || which > 1) return fail(HCOMP_E_ARG, "device index %d / branch %d", dev, which);
+  SideBranch& b = cache[dev][which];
   if (b.stream == nullptr) {
     HC_CUDA(cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking));
     HC_CUDA(cudaEventCreateWithFlags(&b.fork, cudaEventDisableTiming));
@@ -499,19 +499,23 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                       void* dz_bf16, void* stream) {
   if (P_c <= 0 || P_c % 8 != 0 || P_c > P_pad) return fail(HCOMP_E_ARG, "P_c=%d must be a positive multiple of 8, <= P_pad", P_c);
   const long long n = (long long)V * P;
-  hc::make_scat_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
-                                                               reinterpret_cast<int2*>(scat_ws));
-  HC_LAUNCH_CHECK("make_scat");
   hc::HeadParams p{};
   p.scat = reinterpret_cast<const int2*>(scat_ws);
   p.dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
   p.P_c = P_c;
-  if (g_align != nullptr && desc != nullptr && n_desc != nullptr) {
-    hc::align_coef_kernel<<<blocks((long long)V_first * n_nodes, 256), 256, 0, S(stream)>>>(desc, n_desc, g_align, V_first,
-                                                                                           n_nodes, HW, coef_ws);
+  SideBranch* sb = nullptr;
+  if (g_align != nullptr && desc != nullptr && n_desc != nullptr) {       // beside make_scat
+    if (int e = side_branch(&sb, 0)) return e;
+    HC_FORK(sb, S(stream));
+    hc::align_coef_kernel<<<blocks((long long)V_first * n_nodes, 256), 256, 0, sb->stream>>>(desc, n_desc, g_align, V_first,
+                                                                                            n_nodes, HW, coef_ws);
     HC_LAUNCH_CHECK("align_coef");
     p.coef_align = coef_ws;
   }
+  hc::make_scat_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
+                                                               reinterpret_cast<int2*>(scat_ws));
+  HC_LAUNCH_CHECK("make_scat");
+  if (sb) HC_JOIN(sb, S(stream));
   return run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
                         precision, p, S(stream));
 }
@@ -538,6 +542,23 @@ int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias
 
 int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* wc, const hcomp_tables* t, int V,
                          float* g_pooled, int accumulate, float* g_wc, float* g_bias, void* stream) {
+  SideBranch* sb = nullptr;             // the weight / bias gradients are independent of g_pooled: side branch
+  cudaStream_t ws = S(stream);
+  if (g_pooled && (g_wc || g_bias)) {
+    if (int e = side_branch(&sb, 0)) return e;
+    HC_FORK(sb, S(stream));
+    ws = sb->stream;
+  }
+  if (g_wc) {
+    const long long n = (long long)t->n_welems * 32;
+    hc::classifier_bwd_weight_kernel<<<blocks(n, 256), 256, 0, ws>>>(g_out, pooled, wc, t->welem_col, t->welem_proto, V,
+                                                                    t->n_protos, t->n_cols, t->n_welems, g_wc, nullptr);
+    HC_LAUNCH_CHECK("classifier_bwd_weight");
+  }
+  if (g_bias) {
+    hc::classifier_bwd_bias_kernel<<<blocks(t->n_cols, 128), 128, 0, ws>>>(g_out, V, t->n_cols, g_bias);
+    HC_LAUNCH_CHECK("classifier_bwd_bias");
+  }
   if (g_pooled) {
     const long long n = (long long)V * t->n_protos;
     hc::classifier_bwd_pooled_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(g_out, wc, t->proto_node, t->proto_off,
@@ -545,17 +566,7 @@ int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* w
                                                                            t->n_cols, g_pooled, accumulate);
     HC_LAUNCH_CHECK("classifier_bwd_pooled");
   }
-  if (g_wc) {
-    const long long n = (long long)t->n_welems * 32;
-    hc::classifier_bwd_weight_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(g_out, pooled, wc, t->welem_col, t->welem_proto,
-                                                                           V, t->n_protos, t->n_cols, t->n_welems, g_wc,
-                                                                           nullptr);
-    HC_LAUNCH_CHECK("classifier_bwd_weight");
-  }
-  if (g_bias) {
-    hc::classifier_bwd_bias_kernel<<<blocks(t->n_cols, 128), 128, 0, S(stream)>>>(g_out, V, t->n_cols, g_bias);
-    HC_LAUNCH_CHECK("classifier_bwd_bias");
-  }
+  if (sb) HC_JOIN(sb, S(stream));
   return 0;
 }
 
@@ -598,10 +609,13 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
                                                                                           t->p_max, w.orth_sq);
     HC_LAUNCH_CHECK("orth_sumsq");
   }
-  if (do_tanh) {
+  SideBranch* sb_t = nullptr;
+  if (do_tanh) {        // second side branch: the class kernel below stays on the caller's stream
     if (t->p_max > 64 * 1024) return fail(HCOMP_E_ARG, "P_max too large");
-    hc::tanh_loss_fwd_kernel<<<dim3(t->n_nodes, 2), 256, 0, S(stream)>>>(pooled, tgt, t->proto_off, n_desc, V, V_first,
-                                                                        t->n_nodes, t->n_protos, eps, w.tanh_part, w.colsum);
+    if (int e = side_branch(&sb_t, 1)) return e;
+    HC_FORK(sb_t, S(stream));
+    hc::tanh_loss_fwd_kernel<<<dim3(t->n_nodes, 2), 256, 0, sb_t->stream>>>(pooled, tgt, t->proto_off, n_desc, V, V_first,
+                                                                           t->n_nodes, t->n_protos, eps, w.tanh_part, w.colsum);
     HC_LAUNCH_CHECK("tanh_loss_fwd");
   }
   // class kernel also produces the per-node accuracy counters, so it always runs
@@ -609,6 +623,7 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
                                                               t->n_cols, sparsity, w.cls, n_correct);
   HC_LAUNCH_CHECK("class_loss_fwd");
   if (sb) HC_JOIN(sb, S(stream));
+  if (sb_t) HC_JOIN(sb_t, S(stream));
   hc::LossWeights lw;
   for (int i = 0; i < 4; ++i) lw.w[i] = weights_host[i];
   hc::loss_combine_kernel<<<1, 256, 0, S(stream)>>>(align, do_tanh ? w.tanh_part : nullptr, do_orth ? w.orth_sq : nullptr,
@@ -640,11 +655,14 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
       HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
     }
   }
+  SideBranch* sb_tb = nullptr;
   if (g_pooled) {
     if (flags & HCOMP_LOSS_TANH) {
       const long long n = (long long)V * t->n_protos;
-      hc::tanh_loss_bwd_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(w.colsum, tgt, t->proto_node, t->proto_off, gvec + N, V,
-                                                                     V_first, N, t->n_protos, eps, g_pooled, 0);
+      if (int e = side_branch(&sb_tb, 1)) return e;
+      HC_FORK(sb_tb, S(stream));
+      hc::tanh_loss_bwd_kernel<<<blocks(n, 256), 256, 0, sb_tb->stream>>>(w.colsum, tgt, t->proto_node, t->proto_off, gvec + N,
+                                                                         V, V_first, N, t->n_protos, eps, g_pooled, 0);
       HC_LAUNCH_CHECK("tanh_loss_bwd");
     } else {
       HC_CUDA(cudaMemsetAsync(g_pooled, 0, sizeof(float) * (size_t)V * t->n_protos, S(stream)));
@@ -661,6 +679,7 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
     }
   }
   if (sb_bwd) HC_JOIN(sb_bwd, S(stream));
+  if (sb_tb) HC_JOIN(sb_tb, S(stream));
   return 0;
 }
 
