@@ -55,3 +55,48 @@ def test_train_and_test_epochs_run_and_learn():
                     align=False, uni=False, align_pf=True, tanh=True, args=args)
     after = torch.cat([getattr(net, '_' + n + '_classification').weight.detach().flatten() for n in names])
     assert torch.equal(before, after)
+
+
+def test_convnext26_backbone_handoff_step():
+    """The real hand-off: torchvision ConvNeXt-tiny with the reference's stride relaxation
+    (`features/convnext_features.py:7-25`, random init -- no weights on the box) feeds 768x26x26 maps into the fused head;
+    one full training-phase step with the shipped scripts' loss set runs, is finite, reaches the backbone's parameters,
+    and the head's pooled scores / argmax agree with the plain map kernel on the backbone's actual output."""
+    from oracle.problems import make_tree
+    from pipnet_b200 import ops, pipnet as pp, train as tr
+    torch.manual_seed(0)
+    root = make_tree("cub08", num_features=20)
+    args = make_args(net='convnext_tiny_26', num_features=20, tanh_desc='y|0.05', minimize_contrasting_set='y',
+                     mask_prune_overspecific='y|0|1.1')
+    feats, add_on, pool, cls_layers, k = pp.get_network(8, args, root=root)
+    net = pp.PIPNet(8, k, feats, args, add_on, pool, cls_layers, len(root.nodes_with_children()), root).cuda()
+    net.train()
+    B = 2
+    x = torch.randn(2 * B, 3, 224, 224, device='cuda')
+    ys = torch.tensor([1, 5, 1, 5], device='cuda')
+    labels = tr.make_labels(net, ys)
+    features, pf, pooled, out = net(x, labels=labels)
+    assert tuple(features.shape) == (2 * B, 768, 26, 26)
+    w = tr._phase_weights(False, 1, 10, args)
+    res = tr.calculate_loss(1, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                            pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8, root=root,
+                            kernel_orth=True, tanh_desc=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                            device='cuda', labels=labels, **w)
+    res[0].backward()
+    torch.cuda.synchronize()
+    assert torch.isfinite(res[0]).item()
+    stem = next(net._net.parameters())
+    assert stem.grad is not None and torch.isfinite(stem.grad).all() and float(stem.grad.abs().max()) > 0
+    for n in net.layout.node_names:
+        for suffix in ('_add_on', '_classification'):
+            g = getattr(net, '_' + n + suffix).weight.grad
+            assert g is not None and torch.isfinite(g).all()
+    # head output vs the SIMT map kernel on the same features
+    L = net.layout
+    wflat = net.flat_prototype_kernels().detach()
+    p0, p1 = int(L.proto_off[1]), int(L.proto_off[2])
+    m = ops.materialize_map(features.detach(), wflat[p0:p1], 1.0).flatten(2)
+    mv, _ = m.max(dim=2)
+    torch.testing.assert_close(pooled.flat[:, p0:p1].detach(), mv, rtol=2e-2, atol=1e-4)     # fp32 features -> bf16 operands
+    am = pf.argmax.flat[:, p0:p1].long()
+    torch.testing.assert_close(m.gather(2, am.unsqueeze(-1)).squeeze(-1), mv, rtol=2e-2, atol=1e-4)
