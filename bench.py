@@ -97,6 +97,70 @@ class ClockSampler:
         return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': mx, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+# --------------------------------------------------------------------------- optional image-level number
+def image_level_throughput(a, wl, dev, steps=5):
+    """ConvNeXt-tiny-26 (torchvision, the reference's stride relaxation, random init, bf16 autocast, channels-last) -> fused
+    head -> loss -> backward through the backbone, on synthetic 224x224 images copied from pinned host memory each step.
+    The backbone is library code (cuDNN / cuBLAS via PyTorch) and dominates the time; reported for context only."""
+    from oracle.problems import make_args, make_tree
+    from pipnet_b200 import pipnet as pp, train as tr
+    args = make_args(net='convnext_tiny_26', num_features=wl['num_features'], num_protos_per_child=wl.get('per_child', 0))
+    root = make_tree(wl['tree'], num_features=wl['num_features'], per_child=wl.get('per_child', 0))
+    torch.manual_seed(1)
+    feats, add_on, pool, cls_layers, k = pp.get_network(len(root.leaf_descendents), args, root=root)
+    net = pp.PIPNet(len(root.leaf_descendents), k, feats, args, add_on, pool, cls_layers, len(root.nodes_with_children()), root)
+    net = net.to(dev).to(memory_format=torch.channels_last)
+    net.train()
+    B = wl['batch']
+    g = torch.Generator().manual_seed(3)
+    host_x = torch.rand(2 * B, 3, 224, 224, generator=g).pin_memory()
+    y = torch.randint(0, net.layout.L, (B,), generator=g)
+    host_y = torch.cat([y, y]).pin_memory()
+    w = tr._phase_weights(False, 1, 10, args)
+    host_loss = torch.empty((), dtype=torch.float32).pin_memory()
+
+    def one():
+        x = host_x.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+        ys = host_y.to(dev, non_blocking=True)
+        for p in net.parameters():
+            p.grad = None
+        labels = tr.make_labels(net, ys)
+        with torch.autocast('cuda', dtype=torch.bfloat16):
+            feats_ = net._net(x)
+        features, pf, pooled, out = net.forward_from_features(feats_, labels=labels) if hasattr(net, 'forward_from_features') \
+            else _head_only(net, feats_, labels)
+        res = tr.calculate_loss(1, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                                device=dev, labels=labels, **w)
+        res[0].backward()
+        host_loss.copy_(res[0].detach(), non_blocking=True)
+
+    for _ in range(2):
+        one()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    return {'value': B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+            'what': 'ConvNeXt-tiny-26 (torchvision, random init, bf16 autocast) + fused head, fwd+bwd, 224x224 synthetic images '
+                    'from pinned host memory; backbone = PyTorch library kernels'}
+
+
+def _head_only(net, features, labels):
+    """PIPNet.forward without re-running the backbone (features already computed under autocast)"""
+    saved = net._net
+    try:
+        net._net = torch.nn.Identity()
+        return net(features, labels=labels)
+    finally:
+        net._net = saved
+
+
 # --------------------------------------------------------------------------- reference arm / cpu baseline
 def oracle_cpu_throughput(wl, batch, steps, warmup, budget_s=25.0):
     """The reference algorithm (oracle port, fp32, all host threads) on a bounded sample of the workload:
@@ -389,6 +453,11 @@ def run_ours(a):
            'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms,
            'pipeline': 'H2D of step i+1 on a copy stream overlaps the compute of step i (two device input buffers)'}
 
+    # ---------------- optional: the same step behind a real backbone on synthetic 224x224 images (N = 1 only)
+    image_level = None
+    if a.with_backbone and world == 1:
+        image_level = image_level_throughput(a, wl, dev)
+
     if rank == 0:
         peaks = load_peaks()
         # roofline of the dominant fused kernel (K1): algorithmic flops = 2 * M * C * P per launch
@@ -431,6 +500,8 @@ def run_ours(a):
                            'eager_ms_per_step': eager_ms,
                            'l2_policy': f'two alternating input batches of {feats[0].numel() * 2 / 1e6:.0f} MB each (> 126 MB L2)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
+        if image_level is not None:
+            line['image_level'] = image_level
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:
@@ -449,6 +520,8 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cub27', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--with-backbone', action='store_true',
+                    help='also report images/s of ConvNeXt-tiny-26 (torchvision, random init, bf16 autocast) + head on 224x224 images')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'])
     ap.add_argument('--recipe', default='core', choices=['core', 'shipped'],
                     help="core: align_pf+tanh+kernel_orth+class (BASELINE.json); shipped: + tanh_desc, contrasting set, mask pruning")
