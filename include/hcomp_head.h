@@ -197,9 +197,12 @@ int hcomp_desc_losses_bwd(const float* g_loss, const float* pooled, const float*
                           float boost, float gumbel_tau, const void* ws, float* g_pooled, float* g_presence, void* stream);
 
 /* ---- predictions (util/node.py:300-385, pipnet/pipnet.py:173-185) ------------------------------ */
-/* probs_ws: float[V*K]; joint: float[V*L] (columns in sorted leaf-name order); pred: int64[V] argmax. */
-int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, float* probs_ws, float* joint,
-                     long long* pred, void* stream);
+/* probs_ws: float[V*K]; joint: float[V*L] (columns in sorted leaf-name order); pred: int64[V] argmax.
+ * prob_override: float[K] or NULL; a node whose first column holds a value >= 0 uses these child probabilities for every
+ * sample instead of the softmax (leave_out_classes util/node.py:319-323, fully masked class under
+ * apply_overspecificity_mask :335-359; pipnet_b200/pipnet.py builds the table). */
+int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, const float* prob_override,
+                     float* probs_ws, float* joint, long long* pred, void* stream);
 
 /* ---- visualisation feed (util/vis_hpipnet.py:62-127) ------------------------------------------- */
 /* full softmax map of ONE node, fp32 [V, P_n, HW]; w_node: fp32 [P_n, C]. */

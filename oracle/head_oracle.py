@@ -272,16 +272,45 @@ def head_losses(root, proto, pooled, out, ys, label2name, add_on_w, cls_w, *, pr
 
 
 # --------------------------------------------------------------------------- joint leaf distribution
-def joint_distribution(root, out, softmax_tau=1.0):
+def joint_distribution(root, out, softmax_tau=1.0, *, leave_out_classes=None, mask=None, cls_w=None, presence=None,
+                       mask_out=None):
     """`PIPNet.get_joint_distribution` (`pipnet/pipnet.py:173-185`) -> `Node.distribution_over_furthest_descendents`
-    (`util/node.py:383-385`): product along each root->leaf path of
-    softmax(log1p(out[node]**2)/tau)[:, child]; columns re-ordered by sorted leaf name."""
+    (`util/node.py:300-385`): product along each root->leaf path of softmax(log1p(out[node]**2)/tau)[:, child];
+    columns re-ordered by sorted leaf name.  Two test-time switches change the child probabilities of a node:
+      leave_out_classes  a node with a child whose leaves are ALL left out puts probability 1 on its left-out LEAF child
+                         for every sample (`:319-323`; the reference indexes `[0]` of that list and fails without one);
+      overspecificity mask (`apply_overspecificity_mask`): a hard Gumbel sample of the node's presence logits masks the
+                         classifier weights; if some class row is then entirely <= 1e-3 the node falls back to the
+                         leaf-count fractions num_leaves(child) / num_leaves(node) (`:335-359`).
+    mask: {node name -> [P_n] 0/1} to inject; otherwise, with `presence` given, drawn like the reference does (same
+    recursion order, so the same seed gives the same draws); `mask_out` collects what was used."""
+    import torch.nn.functional as Fn
     V = out[root.name].shape[0]
+    dt = out[root.name].dtype
+    lo = set(leave_out_classes or [])
+    use_mask = mask is not None or presence is not None
 
     def rec(node):
+        if lo and any(set(c.leaf_descendents).issubset(lo) for c in node.children):
+            left = [c for c in node.children if c.is_leaf() and c.name in lo][0].name
+            names = node.unwrap_names_of_joint(node.names_of_joint_distribution())
+            row = torch.tensor([1.0 if n == left else 0.0 for n in names], dtype=dt)
+            return row.reshape(1, -1).repeat(V, 1), list(names)
         if node.is_leaf():
-            return torch.ones(V, 1, dtype=out[root.name].dtype), [node.name]
+            return torch.ones(V, 1, dtype=dt), [node.name]
         p = torch.softmax(torch.log1p(out[node.name] ** 2) / softmax_tau, dim=1)
+        if use_mask:
+            if mask is not None:
+                m = mask[node.name].to(dt)
+            else:
+                m = Fn.gumbel_softmax(presence[node.name], tau=0.5, hard=True, dim=-1)[:, 1].to(dt)
+            if mask_out is not None:
+                mask_out[node.name] = m.detach().clone()
+            mw = m.unsqueeze(0) * cls_w[node.name].to(dt)
+            if any(bool((mw[c, :] <= 1e-3).all()) for c in range(mw.shape[0])):
+                frac = [c.num_leaf_descendents() / node.num_leaf_descendents() for c in node.children]
+                # the reference builds these with torch.tensor([float(...)]) = float32 (util/node.py:359)
+                p = torch.tensor(frac, dtype=torch.float32).to(dt).reshape(1, -1).repeat(V, 1)
         cols, names = [], []
         for i, c in enumerate(node.children):
             sub, nm = rec(c)

@@ -798,10 +798,12 @@ int hcomp_desc_losses_bwd(const float* g_loss, const float* pooled, const float*
   return 0;
 }
 
-int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, float* probs_ws, float* joint,
-                     long long* pred, void* stream) {
+int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, const float* prob_override,
+                     float* probs_ws, float* joint, long long* pred, void* stream) {
+  if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "path-probability tau must be > 0");
   hc::node_probs_kernel<<<blocks((long long)V * t->n_nodes, 128), 128, 0, S(stream)>>>(out, t->cls_off, V, t->n_nodes,
-                                                                                      t->n_cols, 1.f / tau, probs_ws);
+                                                                                      t->n_cols, 1.f / tau, prob_override,
+                                                                                      probs_ws);
   HC_LAUNCH_CHECK("node_probs");
   hc::leaf_joint_kernel<<<blocks((long long)V * t->n_leaves, 128), 128, 0, S(stream)>>>(probs_ws, t->path_off, t->path_col,
                                                                                        V, t->n_leaves, t->n_cols, joint);

@@ -465,12 +465,19 @@ __global__ void make_scat_kernel(const int32_t* __restrict__ argmax, const float
 
 // ---------------------------------------------------------------- joint leaf distribution (util/node.py:383-385, pipnet/pipnet.py:173-185)
 // probs[v,k] = softmax_c(log1p(out^2)/tau) within each node; leaf[v,l] = product of probs along the path.
+// override[k] >= 0 forces the probability of child column k for every sample (leave-out classes: 1 on the left-out leaf
+// child, 0 on its siblings, util/node.py:319-323; fully masked class under the overspecificity mask: leaf-count
+// fractions, :335-359); a node is overridden as a whole.
 __global__ void node_probs_kernel(const float* __restrict__ out, const int32_t* __restrict__ cls_off, int V, int N, int K,
-                                  float inv_tau, float* __restrict__ probs) {
+                                  float inv_tau, const float* __restrict__ override, float* __restrict__ probs) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= V * N) return;
   const int v = idx / N, n = idx - v * N;
   const int k0 = cls_off[n], kn = cls_off[n + 1] - k0;
+  if (override != nullptr && override[k0] >= 0.f) {
+    for (int c = 0; c < kn; ++c) probs[(size_t)v * K + k0 + c] = override[k0 + c];
+    return;
+  }
   const float* o = out + (size_t)v * K + k0;
   float mx = -INFINITY;
   for (int c = 0; c < kn; ++c) mx = fmaxf(mx, log1pf(o[c] * o[c]) * inv_tau);

@@ -598,16 +598,20 @@ class DescLosses(torch.autograd.Function):
         return g_pooled, None, g_pres, None, None, None, None, None, None, None, None
 
 
-def joint_leaf_distribution(out_flat: torch.Tensor, dl: DeviceLayout, tau=1.0):
+def joint_leaf_distribution(out_flat: torch.Tensor, dl: DeviceLayout, tau=1.0, override: Optional[torch.Tensor] = None):
     """[V,K] child logits -> ([V,L] joint leaf probabilities in sorted-leaf order, [V] argmax)
-    (util/node.py:300-385 + pipnet/pipnet.py:173-185 as one pass over a flattened path table)."""
+    (util/node.py:300-385 + pipnet/pipnet.py:173-185 as one pass over a flattened path table).
+    override: optional float [K]; nodes whose first column is >= 0 use these child probabilities for every sample."""
     out_flat = out_flat.detach().contiguous()
+    if override is not None:
+        override = override.detach().to(device=out_flat.device, dtype=torch.float32).contiguous()
+        assert override.numel() == dl.K
     V = out_flat.shape[0]
     dev = out_flat.device
     probs = torch.empty(V, dl.K, device=dev, dtype=torch.float32)
     joint = torch.empty(V, dl.L, device=dev, dtype=torch.float32)
     pred = torch.empty(V, device=dev, dtype=torch.int64)
-    call('hcomp_joint_leaf', ptr(out_flat), dl.tref, V, float(tau), ptr(probs), ptr(joint), ptr(pred), _stream())
+    call('hcomp_joint_leaf', ptr(out_flat), dl.tref, V, float(tau), ptr(override), ptr(probs), ptr(joint), ptr(pred), _stream())
     return joint, pred
 
 

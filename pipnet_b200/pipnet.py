@@ -339,15 +339,59 @@ class PIPNet(nn.Module):
         return features, proto_features, pooled, out
 
     def get_joint_distribution(self, out, leave_out_classes=None, apply_overspecificity_mask=False, device='cuda',
-                               softmax_tau=1):
-        """(`pipnet/pipnet.py:173-185`) -> (out['root'], [V, L] joint leaf probabilities, sorted-leaf columns)."""
-        if leave_out_classes or apply_overspecificity_mask:
-            raise Exception('leave_out_classes / overspecificity mask are outside the fused joint-distribution path')
+                               softmax_tau=1, presence_mask: Optional[Tensor] = None):
+        """(`pipnet/pipnet.py:173-185`) -> (out['root'], [V, L] joint leaf probabilities, sorted-leaf columns).
+        `leave_out_classes` / `apply_overspecificity_mask` follow `util/node.py:300-385`: they replace the child
+        probabilities of whole nodes (one-hot at a left-out leaf child / leaf-count fractions when the hard Gumbel
+        presence mask wipes out a class), which the kernel takes as a [K] override table.  `presence_mask` ([P] 0/1)
+        injects the mask instead of drawing it (one flat Gumbel draw here, one per node in the reference)."""
         flat = out.flat if isinstance(out, NodeDict) else torch.cat([out[n] for n in self.layout.node_names], dim=1)
-        joint, _ = ops.joint_leaf_distribution(flat, self.device_layout(flat.device), float(softmax_tau))
+        dl = self.device_layout(flat.device)
+        override = None
+        if leave_out_classes:
+            override = self._leave_out_override(tuple(leave_out_classes)).to(flat.device)
+        if apply_overspecificity_mask or presence_mask is not None:
+            m_ovr = self._mask_override(dl, presence_mask)
+            # the leave-out rule is checked first in the reference (util/node.py:319), the mask only below it
+            override = m_ovr if override is None else torch.where(override >= 0, override, m_ovr)
+        joint, _ = ops.joint_leaf_distribution(flat, dl, float(softmax_tau), override)
         if self._joint_cols is not None:
             joint = joint[:, torch.as_tensor(self._joint_cols, device=joint.device)]
         return out['root'], joint
+
+    def _leave_out_override(self, leave_out: tuple) -> Tensor:
+        cache = self.__dict__.setdefault('_leave_out_cache', {})
+        if leave_out not in cache:
+            lo = set(leave_out)
+            L = self.layout
+            ovr = np.full(L.K, -1.0, dtype=np.float32)
+            for i, node in enumerate(self.root.nodes_with_children()):
+                if any(set(c.leaf_descendents).issubset(lo) for c in node.children):
+                    left = [c for c in node.children if c.is_leaf() and c.name in lo]
+                    if not left:
+                        raise Exception(f'node {node.name}: a whole non-leaf child is left out; the reference indexes an '
+                                        f'empty list there (util/node.py:321)')
+                    k0, k1 = int(L.cls_off[i]), int(L.cls_off[i + 1])
+                    ovr[k0:k1] = 0.0
+                    ovr[k0 + node.children_to_labels[left[0].name]] = 1.0
+            cache[leave_out] = torch.from_numpy(ovr)
+        return cache[leave_out]
+
+    def _mask_override(self, dl, presence_mask: Optional[Tensor]) -> Tensor:
+        """[K] override: leaf-count fractions for nodes where the masked classifier has an all-<=1e-3 class row."""
+        with torch.no_grad():
+            dev = dl.device
+            if presence_mask is None:
+                presence_mask = F.gumbel_softmax(self.flat_proto_presence().detach(), tau=0.5, hard=True, dim=-1)[:, 1]
+            m = presence_mask.to(device=dev, dtype=torch.float32)
+            wc = self.flat_classifier_weights().detach()
+            alive = ((m[dl.welem_proto.long()] * wc) > 1e-3).float()                       # [n_welems]
+            col_alive = torch.zeros(dl.K, device=dev).scatter_reduce_(0, dl.welem_col.long(), alive, reduce='amax')
+            node_dead = torch.zeros(dl.N, device=dev).scatter_reduce_(0, dl.col_node.long(), 1.0 - col_alive, reduce='amax')
+            nl = dl.col_nleaves.float()
+            node_leaves = torch.zeros(dl.N, device=dev).scatter_add_(0, dl.col_node.long(), nl)
+            frac = nl / node_leaves[dl.col_node.long()]
+            return torch.where(node_dead[dl.col_node.long()] > 0, frac, torch.full_like(frac, -1.0))
 
     def get_classification_layers(self):
         return [getattr(self, attr) for attr in dir(self) if attr.endswith('_classification')]

@@ -355,7 +355,12 @@ def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, 
                 node_cnt += act
                 stat_sums += res.stats                       # [4,N]: align, tanh, orth, class (0 where absent)
                 step_means += res.stats.sum(dim=1) / act.sum().clamp_min(1.0)
-                _, joint = m.get_joint_distribution(out, softmax_tau=kw.get('path_prob_softmax_tau', 1))
+                if train:                                     # pipnet/train.py:363 (plain) vs :713 (test-time switches)
+                    _, joint = m.get_joint_distribution(out)
+                else:
+                    _, joint = m.get_joint_distribution(out, leave_out_classes=kw.get('leave_out_classes'),
+                                                        apply_overspecificity_mask=kw.get('apply_overspecificity_mask', False),
+                                                        softmax_tau=kw.get('path_prob_softmax_tau', 1))
                 n_fine_correct += (joint.argmax(dim=1) == ys).sum()                      # pipnet/train.py:363-369
                 n_samples += ys.numel()
             steps += 1
@@ -459,11 +464,10 @@ def test_pipnet(net, test_loader, optimizer_net, optimizer_classifier, scheduler
     """One evaluation epoch (`pipnet/train.py:525-849`): the test batch is duplicated like the reference does
     (`:652-653`) so the same paired kernels and losses apply.  Returns (test_info, log_dict)."""
     net.eval()
-    _reject('leave_out_classes', bool(leave_out_classes))
     kw = dict(wandb_logging=wandb_logging, test_loader_OOD=test_loader_OOD, kernel_orth=kernel_orth, tanh_desc=tanh_desc,
               align=align, uni=uni, align_pf=align_pf, tanh=tanh, minmaximize=minmaximize, cluster_desc=cluster_desc,
               sep_desc=sep_desc, subspace_sep=subspace_sep, byol=byol, wandb_run=wandb_run, pretrain_epochs=pretrain_epochs,
-              log=log, args=args, apply_overspecificity_mask=apply_overspecificity_mask,
+              log=log, args=args, apply_overspecificity_mask=apply_overspecificity_mask, leave_out_classes=leave_out_classes,
               path_prob_softmax_tau=path_prob_softmax_tau)
     return _run_epoch(net, test_loader, optimizer_net, optimizer_classifier, scheduler_net, scheduler_classifier, criterion,
                       epoch, nr_epochs, device, pretrain, finetune, progress_prefix, kw, train=False)

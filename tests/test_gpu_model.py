@@ -124,3 +124,42 @@ def test_unsupported_variants_raise():
     with pytest.raises(Exception):
         feats, add_on, pool, cl, k = pp.get_network(27, make_args(num_protos_per_child=30, num_features=0), root=root90)
         pp.PIPNet(27, k, feats, make_args(num_protos_per_child=30, num_features=0), add_on, pool, cl, 25, root90)
+
+
+@pytest.mark.parametrize("mode", ["leave_out", "mask", "both"])
+def test_joint_distribution_switches(mode):
+    """leave_out_classes / apply_overspecificity_mask of get_joint_distribution (util/node.py:300-385) vs the oracle
+    (pinned to the reference in tests/test_oracle_vs_reference.py); the hard presence mask is injected on both sides."""
+    args = make_args(num_features=6)
+    net, root = build_net("cub27", 64, args)
+    L = net.layout
+    nodes = root.nodes_with_children()
+    g = torch.Generator().manual_seed(4)
+    V = 7
+    out_flat = (torch.rand(V, L.K, generator=g) * 3).cuda()
+    with torch.no_grad():
+        for n in L.node_names:
+            w = getattr(net, '_' + n + '_classification').weight
+            w.mul_((torch.rand(w.shape, generator=g) < 0.5).float().cuda())     # sparse rows: masking can wipe a class
+    from pipnet_b200.pipnet import NodeDict
+    out = NodeDict(out_flat, L.node_names, L.cls_off)
+    leave_out = None
+    if mode in ("leave_out", "both"):
+        cands = [c.name for n in nodes for c in n.children if c.is_leaf()]
+        leave_out = [cands[1], cands[-1]]
+    mask_flat = None
+    kw = {}
+    if mode in ("mask", "both"):
+        mask_flat = (torch.rand(L.P, generator=g) < 0.5).float()
+        kw = dict(mask={n: mask_flat[int(L.proto_off[i]):int(L.proto_off[i + 1])].double() for i, n in enumerate(L.node_names)},
+                  cls_w={n: getattr(net, '_' + n + '_classification').weight.detach().double().cpu() for n in L.node_names})
+    ref = ho.joint_distribution(root, {n: out[n].double().cpu() for n in L.node_names}, 1.0, leave_out_classes=leave_out, **kw)
+    _, joint = net.get_joint_distribution(out, leave_out_classes=leave_out,
+                                          presence_mask=None if mask_flat is None else mask_flat.cuda())
+    assert rel_err(joint, ref) <= 1e-5
+    assert torch.equal(joint.argmax(1).cpu(), ref.argmax(1))
+    plain = ho.joint_distribution(root, {n: out[n].double().cpu() for n in L.node_names}, 1.0)
+    assert not torch.allclose(ref, plain)
+    if mode != "leave_out":      # drawing the mask on the device works too and still yields a distribution
+        _, j2 = net.get_joint_distribution(out, leave_out_classes=leave_out, apply_overspecificity_mask=True)
+        torch.testing.assert_close(j2.sum(1), torch.ones(V, device='cuda'), rtol=1e-4, atol=1e-5)

@@ -112,3 +112,41 @@ def test_joint_distribution_matches_reference():
     ours = ho.joint_distribution(root, out, 1.0)
     torch.testing.assert_close(ours, ref, rtol=1e-12, atol=1e-14)
     assert torch.equal(ours.argmax(1), ref.argmax(1))
+
+
+@pytest.mark.parametrize("mode", ["leave_out", "mask", "both"])
+def test_joint_distribution_switches_match_reference(mode):
+    """leave_out_classes and the test-time overspecificity mask of `distribution_over_furthest_descendents`
+    (`util/node.py:300-385`); the hard Gumbel draws coincide under the same seed (same recursion order)."""
+    import numpy as np
+    args = rh.make_args(num_features=6)
+    net, root = rh.build_reference_net(CUB27, 8, args, seed=2)
+    g = torch.Generator().manual_seed(3)
+    nodes = root.nodes_with_children()
+    out = {n.name: torch.rand(5, n.num_children(), generator=g, dtype=torch.float64) * 3 for n in nodes}
+    with torch.no_grad():
+        for n in nodes:
+            pp = getattr(net, '_' + n.name + '_proto_presence')
+            pp.copy_(3 * torch.randn(pp.shape, generator=g))
+            w = getattr(net, '_' + n.name + '_classification').weight
+            w.mul_((torch.rand(w.shape, generator=g) < 0.5).float())          # sparse classifier: masked rows do happen
+    leaves = sorted(root.leaf_descendents)
+    leave_out = None
+    if mode in ("leave_out", "both"):      # two leaf children of different parents
+        cands = [c.name for n in nodes for c in n.children if c.is_leaf()]
+        leave_out = [cands[0], cands[len(cands) // 2]]
+    use_mask = mode in ("mask", "both")
+    torch.manual_seed(21)
+    ref = root.distribution_over_furthest_descendents(net=net, batch_size=5, out=out, leave_out_classes=leave_out,
+                                                      apply_overspecificity_mask=use_mask, device='cpu', softmax_tau=1)
+    names = root.unwrap_names_of_joint(root.names_of_joint_distribution())
+    ref = ref[:, np.argsort(names)].to(torch.float64)
+    torch.manual_seed(21)
+    kw = {}
+    if use_mask:
+        kw = dict(presence={n.name: getattr(net, '_' + n.name + '_proto_presence').detach() for n in nodes},
+                  cls_w={n.name: getattr(net, '_' + n.name + '_classification').weight.detach() for n in nodes})
+    ours = ho.joint_distribution(root, out, 1.0, leave_out_classes=leave_out, **kw)
+    torch.testing.assert_close(ours, ref, rtol=1e-12, atol=1e-14)
+    plain = ho.joint_distribution(root, out, 1.0)
+    assert not torch.allclose(ours, plain)                                      # the switches did something
