@@ -18,13 +18,14 @@ wp, _wpc = ops.pack_weights(pb.w_flat(dev).contiguous(), dl, ops.PREC_BF16)
 lab = ops.LabelTables(pb.ys.to(dev), dl, B)
 for mode in (0, 1):
     _cabi.lib().hcomp_set_cta_pair(mode)
-    for _ in range(3):
-        ops.proj_softmax_pool_raw(xr, wp, dl, V, B, HW, 1.0, lab)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 30
-    e0.record()
-    for _ in range(n):
-        ops.proj_softmax_pool_raw(xr, wp, dl, V, B, HW, 1.0, lab)
-    e1.record(); torch.cuda.synchronize()
-    print(f'cta_pair={mode}: K1 call {e0.elapsed_time(e1) / n * 1e3:.1f} us (incl. memsets + unpack)')
+    for use_lab in (lab, None):
+        for _ in range(3):
+            ops.proj_softmax_pool_raw(xr, wp, dl, V, B, HW, 1.0, use_lab)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 30
+        e0.record()
+        for _ in range(n):
+            ops.proj_softmax_pool_raw(xr, wp, dl, V, B, HW, 1.0, use_lab)
+        e1.record(); torch.cuda.synchronize()
+        print(f'cta_pair={mode} align={"on" if use_lab is not None else "off"}: K1 call {e0.elapsed_time(e1) / n * 1e3:.1f} us (incl. memsets + unpack)')
