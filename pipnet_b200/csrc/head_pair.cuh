@@ -521,6 +521,12 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           continue;
 #endif
           float s1[S], s2[S];
+#ifdef HC_EXP_NO_SOFTMAX   // timing experiment only: raw accumulators instead of the softmax
+          if (true) {
+#pragma unroll
+            for (int i = 0; i < S; ++i) { s1[i] = fabsf(__uint_as_float(ra[i])); s2[i] = fabsf(__uint_as_float(rb[i])); }
+          } else
+#endif
           if (len == S) {
             softmax_row<S, false>(ra, len, p.scale_log2, s1);
             softmax_row<S, false>(rb, len, p.scale_log2, s2);
@@ -537,6 +543,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             if (seg_aux[js] != 0.f) align_acc[js] = -__logf(ip + 1e-12f);
             uint4* xch = &sb->pool_x[(warp - 4) * 2 * PairCfg<S>::XQ];
             static_assert(PairCfg<S>::EPI_WARPS * 2 * PairCfg<S>::XQ <= 240, "pooling table");
+#ifdef HC_EXP_NO_POOL      // timing experiment only: no column reduction (the softmax stays alive through ip / the align term)
+            align_acc[js] += ip * 1e-30f;
+            continue;
+#endif
             if (nv_a == 32 && !has_boundary)
               pool_segment_fast<S>(s1, loc_first, len, lane, xch, p.pooled_packed + (size_t)v_first * p.P + poff);
             else if (nv_a > 0)
