@@ -204,7 +204,15 @@ int hcomp_desc_losses_bwd(const float* g_loss, const float* pooled, const float*
 int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, const float* prob_override,
                      float* probs_ws, float* joint, long long* pred, void* stream);
 
-/* ---- visualisation feed (util/vis_hpipnet.py:62-127) ------------------------------------------- */
+/* ---- visualisation feed (util/vis_hpipnet.py:62-127, :184-290) ---------------------------------- */
+/* Top-k activations per (prototype, leaf) over a pass through the data, from the pooled scores / argmax of the fused
+ * forward (replaces save_images_topk's per-node, batch-1 loop with Python heaps).  Tables [P, L, k]: t_score descending,
+ * t_img = caller's image id (-1 = empty slot; initialise to -1), t_loc = flat argmax location h*W+w.  An image enters the
+ * list of (p, its leaf) if the leaf is below p's node, p has a relevant class (classifier column > 1e-3) and the image's
+ * child class at that node is relevant to p (or is NOT, with find_non_descendants).  k <= 32.  ws_2v: int32[2*V]. */
+int hcomp_topk_update(const float* pooled, const int32_t* argmax, const long long* ys, const long long* img_ids,
+                      const float* wc, const hcomp_tables* t, int V, int k, int find_non_descendants, int32_t* ws_2v,
+                      float* t_score, long long* t_img, int32_t* t_loc, void* stream);
 /* full softmax map of ONE node, fp32 [V, P_n, HW]; w_node: fp32 [P_n, C]. */
 int hcomp_materialize_map(const void* x_bf16, const float* w_node, int V, int HW, int C, int P_n, float tau, float* map,
                           void* stream);

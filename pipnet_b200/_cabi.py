@@ -53,6 +53,7 @@ SIGNATURES = {
     'hcomp_desc_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_desc_losses_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p, _p],
+    'hcomp_topk_update': [_p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _p, _p, _p, _p],
     'hcomp_materialize_map': [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }

@@ -15,6 +15,7 @@
 #include "head_pair.cuh"
 #include "small_kernels.cuh"
 #include "desc_losses.cuh"
+#include "topk.cuh"
 
 namespace {
 
@@ -812,6 +813,22 @@ int hcomp_joint_leaf(const float* out, const hcomp_tables* t, int V, float tau, 
     hc::row_argmax_kernel<<<blocks(V, 128), 128, 0, S(stream)>>>(joint, V, t->n_leaves, pred);
     HC_LAUNCH_CHECK("row_argmax");
   }
+  return 0;
+}
+
+int hcomp_topk_update(const float* pooled, const int32_t* argmax, const long long* ys, const long long* img_ids,
+                      const float* wc, const hcomp_tables* t, int V, int k, int find_non_descendants, int32_t* ws_2v,
+                      float* t_score, long long* t_img, int32_t* t_loc, void* stream) {
+  if (k <= 0 || k > hc::TOPK_MAX) return fail(HCOMP_E_ARG, "topk=%d (supported: 1..%d)", k, hc::TOPK_MAX);
+  if (V <= 0 || V > 4096) return fail(HCOMP_E_ARG, "topk update: batch of %d rows (supported: 1..4096)", V);
+  int32_t* leader = ws_2v;
+  int32_t* next = ws_2v + V;
+  hc::desc_prep_kernel<<<1, 256, sizeof(long long) * V, S(stream)>>>(ys, V, leader, next);
+  HC_LAUNCH_CHECK("desc_prep");
+  hc::topk_update_kernel<<<dim3((t->n_protos + 127) / 128, V), 128, 0, S(stream)>>>(
+      pooled, argmax, ys, img_ids, leader, next, t->anc, t->proto_node, t->proto_off, t->cls_off, t->wc_off, wc,
+      find_non_descendants, V, t->n_protos, t->n_nodes, t->n_leaves, k, t_score, t_img, t_loc);
+  HC_LAUNCH_CHECK("topk_update");
   return 0;
 }
 
