@@ -1,9 +1,10 @@
 // cta_group::2 variant of the tcgen05 GEMM (see gemm_tc.cuh for the operand conventions).
 //
-// Why: in SS mode a CTA fetches both MMA operands from its own shared memory at ~64-72 B/clk (measured: a
-// 128x256x16 MMA takes ~168 cycles instead of 128, a 128x128x16 one ~140 instead of 64), so 1-CTA tiles are
-// operand-fetch-bound at 60-75 % of the tensor peak.  A CTA pair running ONE M=256 x N=256 MMA halves the B traffic
-// per CTA: each CTA supplies its 128 rows of A and HALF of B (8 KB per 128-cycle instruction = 64 B/clk).
+// Why: what limits these GEMMs is operand DELIVERY into the SM, not the tensor pipe: a single SM ingests ~54.5 B/clk
+// through TMA (tools/tma_bench.cu; the same for L2- and HBM-resident sources, for 18 or 148 active SMs), while
+// back-to-back 128x256x16 MMAs on resident operands run at their nominal 128 cycles (tools/mma_bench.cu).  A 1-CTA
+// 128 x 256 tile needs 48 KB per 64-element k-block (512 MMA cycles) = 880 cycles of ingest; a CTA pair running ONE
+// M=256 x N=256 MMA needs each CTA's 128 rows of A and only HALF of B: 32 KB = 590 cycles, ~87 % of the tensor peak.
 //
 // Cluster of 2 CTAs = one 256 x 256 output tile; CTA r owns rows [128r, 128r+128) (accumulator in its own TMEM).
 //   producer (warp 0, both CTAs): own A tile + own half of B; completion bytes go to the LEADER's `full` barrier

@@ -1,8 +1,8 @@
 // Warp-specialised tcgen05 GEMM, D[M,N] (+)= A[M,K] * B[K,N], bf16 in / fp32 accumulate in TMEM.
 // Used for the head's two backward contractions (reference: autograd of the per-node 1x1 convs,
 // pipnet/train.py:264 -> cuDNN dgrad/wgrad per node):
-//   dX[rows, C]   = dZ[rows, P_pad] * Wp[P_pad, C]      A K-major , B MN-major
-//   dW[P_pad, C] += dZ^T[P_pad, rows] * X[rows, C]      A MN-major, B MN-major, split-K + fp32 red.add
+//   dX[rows, C]  = dZ[rows, P_c] * Wpc[P_c, C]        A K-major , B MN-major      (P_c: compact dZ column axis)
+//   dW[P_c, C]  += dZ^T[P_c, rows] * X[rows, C]       A MN-major, B MN-major, split-K + fp32 red.add (rows -> flat via row_map_c)
 // Tile 128 x 256 x 64, 4-stage TMA ring (48 KB / stage), 2 accumulator stages of 256 TMEM columns.
 // "MN-major" operands are consumed straight from row-major storage whose contiguous axis is the
 // M (or N) dimension -- no transposed copies in HBM.

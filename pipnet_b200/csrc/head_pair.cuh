@@ -40,7 +40,8 @@ constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both
 // delivery is latency-bound per SM (profiles/r1_k1_analysis.md), 160 KB in flight deliver ~25 % more than 120 KB.
 // CG2 (CTA pair, tcgen05 cta_group::2): a cluster of two CTAs takes two neighbouring pair tiles of the same prototype
 // tile and runs M = 256 MMAs; each CTA keeps only HALF of the prototype tile (64 rows, 8 KB) in its shared memory, so
-// an MMA fetches 6 KB of operands per CTA instead of 8 KB (the kernel is bound by that fetch, ~65 B/clk).
+// a k-block needs 40 KB of operands per CTA instead of 48 KB -- the main loop is bound by operand delivery into the SM
+// (~54.5 B/clk through TMA, tools/tma_bench.cu), not by the tensor pipe (profiles/r1_k1_analysis.md).
 template <bool BWD, bool CG2> struct PairMem {
   static constexpr int STAGE_BYTES = CG2 ? (2 * TILE_M * KBLK * 2 + (TILE_N / 2) * KBLK * 2) : PAIR_STAGE_BYTES;   // 40 / 48 KB
   static constexpr int STAGES = BWD ? (CG2 ? 4 : 3) : 4;
@@ -601,9 +602,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
         }
       } else {
-        // zero the padding columns [nseg*S, 128) of the staged rows (the dX GEMM reads all P_pad columns), then
-        // one elected thread writes both views' tiles with TMA bulk stores: full 128-byte lines, rows clipped at
-        // the end of each view half by the two tensor maps
+        // zero the padding columns [nseg*S, 128) of the staged rows (the first few of them are inside the tile's
+        // compact width, which the dX / dW GEMMs read), then one elected thread writes both views' tiles with TMA
+        // bulk stores, columns and rows clipped by the tensor maps
         if (part == 0) {
           const int r = quad * 32 + lane;
           for (int byte = 2 * nseg * S; byte < 2 * TILE_N; byte += 8) {
