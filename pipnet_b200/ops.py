@@ -390,6 +390,7 @@ class HeadProjPool(torch.autograd.Function):
         pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision)
         ctx.dl, ctx.geom, ctx.labels, ctx.thresh, ctx.precision = dl, (V, V_first, H, W, Cc, tau), labels, thresh, precision
         ctx.w_group = getattr(w_flat, '_hc_group', None)
+        ctx.set_materialize_grads(False)      # unused outputs (argmax, align without the loss) get None, not zero fills
         ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
         ctx.save_for_backward(x_rows, wp, wpc, argmax, pooled)
         ctx.mark_non_differentiable(argmax)
@@ -497,12 +498,15 @@ class HeadLosses(torch.autograd.Function):
         ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc)
         ctx.has = (align is not None, w_flat is not None and use_orth)
         ctx.w_group = getattr(w_flat, '_hc_group', None) if w_flat is not None else None
+        ctx.set_materialize_grads(False)      # stats / n_correct are not differentiable: no zero-filled grads for them
         ctx.save_for_backward(out, wf if use_orth else None, stats, ws, rel)
         ctx.mark_non_differentiable(stats, n_correct)
         return total, stats, n_correct
 
     @staticmethod
     def backward(ctx, g_total, _gs, _gc):
+        if g_total is None:
+            return (None,) * 10
         out, wf, stats, ws, rel = ctx.saved_tensors
         dl, labels = ctx.dl, ctx.labels
         flags, weights, eps, V, Cc = ctx.cfg
@@ -567,6 +571,7 @@ class DescLosses(torch.autograd.Function):
              ptr(stats), ptr(loss), _stream())
         ctx.dl, ctx.labels = dl, labels
         ctx.cfg = (int(flags), [float(x) for x in weights], float(eps), boost, float(tau), V)
+        ctx.set_materialize_grads(False)
         ctx.has_presence = presence is not None
         ctx.pp_group = getattr(presence, '_hc_group', None) if presence is not None else None
         ctx.save_for_backward(pooled, wc, pres, gum, ws)
@@ -575,6 +580,8 @@ class DescLosses(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_loss, _gs):
+        if g_loss is None:
+            return (None,) * 11
         pooled, wc, pres, gum, ws = ctx.saved_tensors
         dl, labels = ctx.dl, ctx.labels
         flags, weights, eps, boost, tau, V = ctx.cfg
