@@ -491,9 +491,19 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       mbar_wait(&sb->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * (2 * TILE_N);
+      // backward: the staging buffer may be rewritten only after the previous item's TMA stores have read it.  That wait
+      // (one thread) + the barrier that publishes it sit right before this warp's FIRST write into the buffer, so the
+      // TMEM loads and the softmax / gradient arithmetic of the first segment overlap the store's shared-memory reads.
+      [[maybe_unused]] bool staging_free = false;
+      [[maybe_unused]] auto wait_staging = [&]() {
+        if (!staging_free) {
+          if (warp == 4 && lane == 0) tma_store_wait_read();
+          named_bar_sync(1, 32 * EPI_WARPS);
+          staging_free = true;
+        }
+      };
       if constexpr (BWD) {
-        if (warp == 4 && lane == 0) tma_store_wait_read();       // previous item's dZ has left the staging buffer
-        named_bar_sync(1, 32 * EPI_WARPS);
+        if (my_cnt == 0) wait_staging();     // warps without a segment still take part in the barrier
       }
       auto release_stage = [&]() {     // accumulators of this warp are in registers: hand the TMEM stage back
         tc_fence_before();
@@ -571,6 +581,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
               for (int i = 0; i < S; ++i) g[i] = s1[i] * (g[i] - dot) * p.inv_tau;
+              wait_staging();
               stage_dz<S>(dzstage, quad * 32 + lane, 2 * j * S, g);
             }
             {
