@@ -100,3 +100,33 @@ def test_convnext26_backbone_handoff_step():
     torch.testing.assert_close(pooled.flat[:, p0:p1].detach(), mv, rtol=2e-2, atol=1e-4)     # fp32 features -> bf16 operands
     am = pf.argmax.flat[:, p0:p1].long()
     torch.testing.assert_close(m.gather(2, am.unsqueeze(-1)).squeeze(-1), mv, rtol=2e-2, atol=1e-4)
+
+
+def test_shipped_script_flags_through_epoch_drivers():
+    """`train_pipnet` / `test_pipnet` with the flag set of run_pipnet_20protos_multi_runs_seed42.sh:72-94 (tanh_desc,
+    minimize_contrasting_set, mask pruning) in the training and fine-tuning phases, then the leave-out evaluation
+    (`main_dist.py:727-735`) with the test-time overspecificity mask."""
+    from pipnet_b200 import train as tr
+    args = make_args(num_features=20, tanh_desc='y|0.05', minimize_contrasting_set='y', mask_prune_overspecific='y|0|1.1')
+    net, root = build_net("cub08", 64, args)
+    names = net.layout.node_names
+    params = [getattr(net, '_' + n + '_add_on').weight for n in names] + [getattr(net, '_' + n + '_proto_presence') for n in names]
+    opt_net = torch.optim.AdamW(params, lr=5e-3)
+    opt_cls = torch.optim.AdamW([getattr(net, '_' + n + '_classification').weight for n in names], lr=5e-2)
+    sch_net = torch.optim.lr_scheduler.CosineAnnealingLR(opt_net, T_max=40)
+    sch_cls = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt_cls, T_0=5)
+    pres_before = torch.cat([getattr(net, '_' + n + '_proto_presence').detach().flatten() for n in names]).clone()
+    common = dict(kernel_orth=True, tanh_desc=True, align=False, uni=False, align_pf=True, tanh=True, wandb_logging=True, args=args)
+    info, log = tr.train_pipnet(net, _loader(net, True), opt_net, opt_cls, sch_net, sch_cls, None, 1, 3, 'cuda', pretrain=False,
+                                finetune=False, **common)
+    assert info['loss'] == info['loss'] and 'train/epoch loss' in log
+    pres_after = torch.cat([getattr(net, '_' + n + '_proto_presence').detach().flatten() for n in names])
+    assert not torch.equal(pres_before, pres_after)              # the mask-pruning term trains the presence logits
+    info, _ = tr.train_pipnet(net, _loader(net, True), opt_net, opt_cls, sch_net, sch_cls, None, 2, 3, 'cuda', pretrain=False,
+                              finetune=True, **common)
+    assert info['loss'] == info['loss']
+    leaf_children = [c.name for n in root.nodes_with_children() for c in n.children if c.is_leaf()]
+    info, _ = tr.test_pipnet(net, _loader(net, False), opt_net, opt_cls, sch_net, sch_cls, None, 1, 3, 'cuda',
+                             kernel_orth=True, tanh_desc=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                             leave_out_classes=[leaf_children[0]], apply_overspecificity_mask=True)
+    assert 0.0 <= info['fine_accuracy'] <= 1.0
