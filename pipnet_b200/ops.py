@@ -316,11 +316,13 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
 
 
 def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
-                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None):
+                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None, dz_out=None):
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
-    dz = torch.empty(M, dl.P_c, device=dev, dtype=torch.bfloat16)       # compact column axis (layout.row_map_c)
+    # compact column axis (layout.row_map_c); `dz_out` lets tests supply a guarded buffer
+    dz = dz_out if dz_out is not None else torch.empty(M, dl.P_c, device=dev, dtype=torch.bfloat16)
+    assert dz.shape == (M, dl.P_c) and dz.dtype == torch.bfloat16 and dz.is_contiguous()
     scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
     coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
     use_align = labels is not None and g_align is not None

@@ -51,3 +51,27 @@ def test_gemm_splitk_red(splits):
     torch.cuda.synchronize()
     err = (out.double().cpu() - ref).abs().max().item()
     assert err <= 1e-3 * max(1.0, ref.abs().max().item()), f'max abs err {err}'
+
+
+@pytest.mark.parametrize("out_mode", [0, 1, 2])
+@pytest.mark.parametrize("M,N,K", [(1352, 768, 504), (136, 264, 72)])
+def test_gemm_writes_exactly_its_output(M, N, K, out_mode):
+    """guard rows around the output (sanitizer stand-in): ragged M / K (compact dZ: K = 504) must neither leave holes nor
+    write past row M -- TMA-store epilogue (bf16), plain fp32 stores and the split-K red.add path."""
+    import ctypes as C
+    from pipnet_b200._cabi import call, ptr
+    a_mn, b_mn = (0, 1) if out_mode != 2 else (1, 1)
+    a, b, ref = _operands(M, N, K, a_mn, b_mn, seed=9)
+    dt = torch.bfloat16 if out_mode == 0 else torch.float32
+    guard = 300
+    big = torch.full((M + guard, N), float('nan'), device='cuda', dtype=dt)
+    if out_mode == 2:
+        big[:M].zero_()                                    # the reduction path accumulates into its output
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call('hcomp_gemm_bf16', ptr(a), ptr(b), M, N, K, a_mn, b_mn, out_mode, 0 if out_mode == 2 else 1, ptr(big), C.c_longlong(N), stream)
+    torch.cuda.synchronize()
+    assert torch.isnan(big[M:].float()).all(), "GEMM wrote past its last row"
+    got = big[:M].double().cpu()
+    assert not torch.isnan(got).any()
+    tol = 1e-2 if out_mode == 0 else 2e-4
+    assert (got - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item()) + (1e-1 if out_mode == 0 else 0)

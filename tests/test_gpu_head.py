@@ -182,3 +182,35 @@ def test_fp32_accurate_mode_backward_runs():
     assert feats.grad.dtype == torch.float32
     assert rel_err(feats.grad, x.grad) <= 2e-2
     assert rel_err(w_flat.grad, torch.cat([w[n].grad for n in pb.layout.node_names])) <= 2e-2
+
+
+@pytest.mark.parametrize("case", [("cub08", 64, 6, 3, dict(per_child=20)), ("cub18", 64, 8, 4, dict(num_features=12)),
+                                  ("cub27", 64, 7, 3, dict(per_child=20)), ("cub27", 64, 26, 1, dict(num_features=20))],
+                         ids=["cub08-B", "cub18-12", "cub27-B", "cub27-26x26"])
+def test_dz_store_writes_exactly_its_buffer(case):
+    """compute-sanitizer stand-in for the TMA stores into the compact dZ matrix: the buffer is pre-filled with NaN and
+    followed by NaN guard rows; after K5 every element inside is a number (padding columns are zeros) and no guard
+    element was touched -- ragged tiles, partial last tiles and view halves that end inside a 128-row tile included."""
+    from pipnet_b200 import ops
+    tree, C, H, B, kw = case
+    pb = Problem(tree, C, H, B, seed=11, **kw)
+    dl = ops.DeviceLayout(pb.layout, 'cuda')
+    V, HW = pb.V, H * H
+    M = V * HW
+    xr = ops.feature_rows(pb.features('cuda'))
+    wp, wpc = ops.pack_weights(pb.w_flat('cuda'), dl)
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    pooled, argmax, _ = ops.proj_softmax_pool_raw(xr, wp, dl, V, pb.V_first, HW, 1.0, labels)
+    g = torch.Generator(device='cuda').manual_seed(1)
+    gp = torch.randn(V, dl.P, device='cuda', generator=g)
+    ga = torch.full((dl.N,), 0.3, device='cuda')
+    guard = 256
+    big = torch.full((M + guard, dl.P_c), float('nan'), device='cuda', dtype=torch.bfloat16)
+    ops.head_backward_raw(xr, wp, wpc, dl, V, pb.V_first, HW, 1.0, argmax, gp, labels, ga, dz_out=big[:M])
+    torch.cuda.synchronize()
+    inside, outside = big[:M].float(), big[M:].float()
+    assert not torch.isnan(inside).any(), f"{int(torch.isnan(inside).sum())} dZ elements were never written"
+    assert torch.isnan(outside).all(), "K5 wrote past the end of the dZ matrix"
+    pad_cols = torch.from_numpy(pb.layout.row_map_c < 0).cuda()
+    assert float(inside[:, pad_cols].abs().max() if bool(pad_cols.any()) else 0.0) == 0.0       # padding columns are zeros
+    assert float(inside[:, ~pad_cols].abs().max()) > 0.0
