@@ -262,10 +262,16 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
       // partial tile; widths are the used columns rounded up to 8 (layout.py)
       const int per_tile = hc::TILE_N / seg;
       const int32_t* last = tiles_host + (size_t)(e - 1) * hc::TILE_INTS;
-      const bool has_partial = last[1] < per_tile;
-      p.n_full_tiles = p.num_tiles - (has_partial ? 1 : 0);
       p.w_full = ((per_tile * seg + 7) / 8) * 8;
-      p.w_partial = has_partial ? ((last[1] * seg + 7) / 8) * 8 : 0;
+      // the last tile of the class is "partial" (own store map) if it has fewer segments, or if it is the globally last
+      // tile and owns the alignment padding of the dZ pitch (layout.py rounds P_c up to 64 columns when that fits)
+      int last_w = ((last[1] * seg + 7) / 8) * 8;
+      if (e == n_tiles) last_w = p.P_c - last[3];
+      const bool has_partial = last_w != p.w_full;
+      p.n_full_tiles = p.num_tiles - (has_partial ? 1 : 0);
+      p.w_partial = has_partial ? last_w : 0;
+      if (has_partial && (last_w <= 0 || last_w > hc::TILE_N || last_w % 8 != 0 || last_w < last[1] * seg))
+        return fail(HCOMP_E_ARG, "last tile of class %d: compact width %d", seg, last_w);
       const int c_full = tiles_host[(size_t)t * hc::TILE_INTS + 3];
       for (int i = t; i < e; ++i) {
         const int want = (i - t) < p.n_full_tiles ? c_full + (i - t) * p.w_full : c_full + p.n_full_tiles * p.w_full;

@@ -159,6 +159,13 @@ def build_layout(root) -> HeadLayout:
     tiles = np.stack(recs).astype(np.int32)
     row_map = np.concatenate(row_map).astype(np.int32)
     row_map_c = np.concatenate(row_map_c).astype(np.int32)
+    # Row pitch of dZ: a multiple of 64 columns (128 bytes) keeps every 128-byte row segment of a TMA box inside one
+    # cache line (pitch 1008 B measured ~15 % slower per k-block in the dX GEMM than 1024 B).  The extra columns belong to
+    # the LAST tile (it stores zeros there), which works as long as that tile stays within 128 columns.
+    last_width = len(row_map_c) - int(tiles[-1][3])
+    pad = (-len(row_map_c)) % 64
+    if pad and last_width + pad <= TILE_COLS:
+        row_map_c = np.concatenate([row_map_c, np.full(pad, -1, dtype=np.int32)])
 
     slices = {}
     for n in nodes:

@@ -64,7 +64,7 @@ def test_layout_tables(tree, kw):
             assert L.row_map[t * 128 + j * S: t * 128 + j * S + ln].tolist() == list(range(po, po + ln))
     assert (np.diff(L.tiles[:, 0]) >= 0).all()                # tiles sorted by class: one launch per class
     # compact dZ axis: tile t owns [dz_col, dz_col + round8(nseg*S)); same prototypes in the same order, padding -1
-    assert L.P_c % 8 == 0 and L.P <= L.P_c <= L.P_pad
+    assert L.P_c % 8 == 0 and L.P <= L.P_c <= L.P_pad + 63
     col = 0
     for t, rec in enumerate(L.tiles):
         S, nseg, dz_col = int(rec[0]), int(rec[1]), int(rec[3])
@@ -73,7 +73,8 @@ def test_layout_tables(tree, kw):
         assert L.row_map_c[col:col + width].tolist() == L.row_map[t * 128: t * 128 + width].tolist()
         assert (L.row_map[t * 128 + width: (t + 1) * 128] == -1).all()
         col += width
-    assert col == L.P_c
+    assert col <= L.P_c < col + 64 and (L.row_map_c[col:] == -1).all()      # pitch padding owned by the last tile
+    assert L.P_c % 64 == 0 or (L.P_c == col and L.P_c - int(L.tiles[-1][3]) + (-col) % 64 > 128)
     usedc = L.row_map_c[L.row_map_c >= 0]
     assert sorted(usedc.tolist()) == list(range(L.P))
     # anc / path tables agree with the tree
