@@ -50,3 +50,41 @@ def test_product_fails_loudly_without_cuda():
         pytest.skip('CPU-only check')
     with pytest.raises(_cabi.HcompError):
         ops.feature_rows(torch.zeros(1, 8, 6, 6))
+
+
+def _header_prototypes():
+    """{name: [parameter type strings]} for every `int hcomp_*(...)` prototype of the header"""
+    text = open(os.path.join(ROOT, 'include', 'hcomp_head.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    protos = {}
+    for m in re.finditer(r'\bint\s+(hcomp_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;', text, flags=re.S):
+        params = [p.strip() for p in m.group(2).replace('\n', ' ').split(',')]
+        protos[m.group(1)] = [] if params == ['void'] else params
+    return protos
+
+
+def test_ctypes_signatures_match_header_prototypes():
+    """argument count and kind (pointer / float / 64-bit / int) of every bound entry point follow the header"""
+    import ctypes as C
+    from pipnet_b200 import _cabi
+    protos = _header_prototypes()
+
+    def kind_of_decl(p):
+        if '*' in p:
+            return 'ptr'
+        if re.match(r'(const\s+)?float\b', p):
+            return 'float'
+        if re.match(r'(const\s+)?long long\b', p):
+            return 'i64'
+        return 'int'
+
+    def kind_of_ctype(t):
+        if t in (C.c_void_p,) or (isinstance(t, type) and issubclass(t, C._Pointer)):
+            return 'ptr'
+        return {C.c_float: 'float', C.c_longlong: 'i64', C.c_int: 'int'}[t]
+
+    for name, argtypes in _cabi.SIGNATURES.items():
+        assert name in protos, name
+        want = [kind_of_decl(p) for p in protos[name]]
+        got = [kind_of_ctype(t) for t in argtypes]
+        assert got == want, f'{name}: binding {got} vs header {want}'
