@@ -103,15 +103,19 @@ __device__ __forceinline__ void softmax_row(uint32_t* raw, int len, float scale_
   }
   const float m = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
   const float mk = m * scale_log2;
+  // packed pairs (FFMA2 / FADD2 / FMUL2): same operations and association order as the scalar loops, half the issue slots
   float l4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < S; ++i) {
-    s[i] = ex2(fmaf(s[i], scale_log2, -mk));
-    l4[i & 3] += s[i];
+  for (int i = 0; i < S; i += 2) {
+    float t0, t1;
+    fma2(t0, t1, s[i], s[i + 1], scale_log2, scale_log2, -mk, -mk);
+    s[i] = ex2(t0);
+    s[i + 1] = ex2(t1);
+    add2(l4[i & 3], l4[(i & 3) + 1], l4[i & 3], l4[(i & 3) + 1], s[i], s[i + 1]);
   }
   const float inv = __frcp_rn((l4[0] + l4[1]) + (l4[2] + l4[3]));
 #pragma unroll
-  for (int i = 0; i < S; ++i) s[i] *= inv;
+  for (int i = 0; i < S; i += 2) mul2(s[i], s[i + 1], s[i], s[i + 1], inv, inv);
 }
 
 // Max over the warp's rows (per column) with first-row tie break, merged into the packed
@@ -547,7 +551,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           }
           float ip4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < S; ++i) ip4[i & 3] = fmaf(s1[i], s2[i], ip4[i & 3]);
+          for (int i = 0; i < S; i += 2)
+            fma2(ip4[i & 3], ip4[(i & 3) + 1], s1[i], s1[i + 1], s2[i], s2[i + 1], ip4[i & 3], ip4[(i & 3) + 1]);
           const float ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
 
           if constexpr (!BWD) {
@@ -573,28 +578,38 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
             {
               float g[S];
 #pragma unroll
-              for (int i = 0; i < S; ++i) g[i] = -ca * s2[i];
+              for (int i = 0; i < S; i += 2) mul2(g[i], g[i + 1], -ca, -ca, s2[i], s2[i + 1]);
               if (nv_a > 0) add_scatter<S>(g, scat_e[js][0], lane, loc_first, lane_b, nv_a);
               float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int i = 0; i < S; ++i) d4[i & 3] = fmaf(g[i], s1[i], d4[i & 3]);
+              for (int i = 0; i < S; i += 2)
+                fma2(d4[i & 3], d4[(i & 3) + 1], g[i], g[i + 1], s1[i], s1[i + 1], d4[i & 3], d4[(i & 3) + 1]);
               const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-              for (int i = 0; i < S; ++i) g[i] = s1[i] * (g[i] - dot) * p.inv_tau;
+              for (int i = 0; i < S; i += 2) {        // g = s1 * (g - dot) * inv_tau, left to right
+                add2(g[i], g[i + 1], g[i], g[i + 1], -dot, -dot);
+                mul2(g[i], g[i + 1], s1[i], s1[i + 1], g[i], g[i + 1]);
+                mul2(g[i], g[i + 1], g[i], g[i + 1], p.inv_tau, p.inv_tau);
+              }
               wait_staging();
               stage_dz<S>(dzstage, quad * 32 + lane, 2 * j * S, g);
             }
             {
               float g[S];
 #pragma unroll
-              for (int i = 0; i < S; ++i) g[i] = -ca * s1[i];
+              for (int i = 0; i < S; i += 2) mul2(g[i], g[i + 1], -ca, -ca, s1[i], s1[i + 1]);
               if (nv_b > 0) add_scatter<S>(g, scat_e[js][1], lane, loc_first, lane_b, nv_b);
               float d4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-              for (int i = 0; i < S; ++i) d4[i & 3] = fmaf(g[i], s2[i], d4[i & 3]);
+              for (int i = 0; i < S; i += 2)
+                fma2(d4[i & 3], d4[(i & 3) + 1], g[i], g[i + 1], s2[i], s2[i + 1], d4[i & 3], d4[(i & 3) + 1]);
               const float dot = (d4[0] + d4[1]) + (d4[2] + d4[3]);
 #pragma unroll
-              for (int i = 0; i < S; ++i) g[i] = s2[i] * (g[i] - dot) * p.inv_tau;
+              for (int i = 0; i < S; i += 2) {
+                add2(g[i], g[i + 1], g[i], g[i + 1], -dot, -dot);
+                mul2(g[i], g[i + 1], s2[i], s2[i + 1], g[i], g[i + 1]);
+                mul2(g[i], g[i + 1], g[i], g[i + 1], p.inv_tau, p.inv_tau);
+              }
               stage_dz<S>(dzstage + PAIR_DZ_STAGE_BYTES / 2, quad * 32 + lane, 2 * j * S, g);
             }
           }

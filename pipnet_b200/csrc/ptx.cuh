@@ -313,6 +313,30 @@ __device__ __forceinline__ uint32_t redux_max_u32(uint32_t v) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): two IEEE operations per issue slot, same rounding as the scalar
+// forms, so results are bit-identical to an unpacked loop with the same association order.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{ .reg .b64 ra, rb, rc, rd;\n"
+      "  mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5}; mov.b64 rc, {%6, %7};\n"
+      "  fma.rn.f32x2 rd, ra, rb, rc;\n"
+      "  mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd;\n"
+      "  mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+      "  mul.rn.f32x2 rd, ra, rb;\n"
+      "  mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{ .reg .b64 ra, rb, rd;\n"
+      "  mov.b64 ra, {%2, %3}; mov.b64 rb, {%4, %5};\n"
+      "  add.rn.f32x2 rd, ra, rb;\n"
+      "  mov.b64 {%0, %1}, rd; }"
+      : "=f"(d0), "=f"(d1) : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
