@@ -128,3 +128,46 @@ def test_flat_allreduce_mean_world2_gloo():
         p.join(timeout=60)
     assert all(r[1] for r in res)
     assert (res[0][2], res[0][3], res[1][2], res[1][3]) == (0, 6, 6, 11)     # shards cover the batch exactly once
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_layout_invariants_on_random_trees(seed):
+    """random trees with arbitrary per-node prototype counts (1..64): every segment class, ragged partial tiles, the
+    compact-axis rules the kernels rely on (run_pair checks the same conditions on the device side of the ABI)."""
+    rng = np.random.default_rng(seed)
+    leaves = int(rng.integers(3, 60))
+    root = build_tree(synthetic_edges(leaves, seed), Node)
+    nodes = root.nodes_with_children()
+    choices = [1, 5, 8, 9, 16, 17, 20, 21, 32, 33, 40, 41, 60, 64] if seed % 2 else [20, 40, 60]
+    for n in nodes:
+        n.num_protos = int(rng.choice(choices))
+        n.num_protos_per_child = {}
+    L = lay.build_layout(root)
+    assert L.P == sum(n.num_protos for n in nodes)
+    # padded axis: every prototype exactly once, inside a segment of its class
+    used = L.row_map[L.row_map >= 0]
+    assert sorted(used.tolist()) == list(range(L.P))
+    classes = [int(t[0]) for t in L.tiles]
+    assert classes == sorted(classes)
+    col = 0
+    for t, rec in enumerate(L.tiles):
+        S, nseg, umma_n, dz_col = (int(x) for x in rec[:4])
+        assert S in lay.SEG_CLASSES and 1 <= nseg <= 128 // S and umma_n % 16 == 0 and nseg * S <= umma_n <= 128
+        assert dz_col == col and dz_col % 8 == 0
+        width = (nseg * S + 7) // 8 * 8
+        for j in range(nseg):
+            ni, ln, po = int(rec[4 + j]), int(rec[4 + 16 + j]), int(rec[4 + 32 + j])
+            assert lay.seg_class(nodes[ni].num_protos) == S and ln == nodes[ni].num_protos and po == int(L.proto_off[ni])
+        # within a class only the LAST tile may be partial (the store maps assume full tiles are contiguous)
+        same = [i for i, c in enumerate(classes) if c == S]
+        if t != same[-1]:
+            assert nseg == 128 // S
+        assert L.row_map_c[col:col + width].tolist() == L.row_map[t * 128: t * 128 + width].tolist()
+        col += width
+    # compact axis: multiple of 8, padded to 64 when the last tile can absorb it, padding = -1
+    assert L.P_c % 8 == 0 and col <= L.P_c and (L.row_map_c[col:] == -1).all()
+    last_w = L.P_c - int(L.tiles[-1][3])
+    assert 0 < last_w <= 128
+    if L.P_c % 64:
+        assert L.P_c == col and (col - int(L.tiles[-1][3])) + (-col) % 64 > 128
+    assert sorted(L.row_map_c[L.row_map_c >= 0].tolist()) == list(range(L.P))
