@@ -214,3 +214,50 @@ def test_dz_store_writes_exactly_its_buffer(case):
     pad_cols = torch.from_numpy(pb.layout.row_map_c < 0).cuda()
     assert float(inside[:, pad_cols].abs().max() if bool(pad_cols.any()) else 0.0) == 0.0       # padding columns are zeros
     assert float(inside[:, ~pad_cols].abs().max()) > 0.0
+
+
+@pytest.mark.parametrize("seed", [1, 4])
+def test_all_segment_classes_in_one_model(seed):
+    """random tree whose nodes have arbitrary prototype counts (1..64): all six segment classes, masked tails and ragged
+    partial tiles in ONE launch sequence -- forward (pooled, argmax, align) and backward (dX, dW) vs the oracle."""
+    import numpy as np
+    from pipnet_b200 import ops
+    from pipnet_b200.node import Node
+    from pipnet_b200.trees import build_tree, synthetic_edges
+    rng = np.random.default_rng(seed)
+    root = build_tree(synthetic_edges(14, seed), Node)
+    for n in root.nodes_with_children():
+        n.num_protos = int(rng.choice([3, 8, 13, 16, 20, 27, 32, 40, 49, 64]))
+        n.num_protos_per_child = {}
+        n.set_loss_weightage_using_descendants_count()
+    pb = Problem("custom", 64, 7, 3, seed=seed, root=root)
+    L = pb.layout
+    assert len(set(int(t[0]) for t in L.tiles)) >= 4
+    dl = ops.DeviceLayout(L, 'cuda')
+    g = torch.Generator().manual_seed(5)
+    G = torch.randn(pb.V, L.P, generator=g, dtype=torch.float64)
+    a = torch.rand(L.N, generator=g, dtype=torch.float64) + 0.5
+    feats = pb.features('cuda').requires_grad_(True)
+    w_flat = pb.w_flat('cuda').requires_grad_(True)
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    pooled, align, argmax = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0)
+    loss = (pooled.double() * G.cuda()).sum() + (align.double() * a.cuda()).sum()
+    loss.backward()
+    torch.cuda.synchronize()
+
+    x = pb.x.clone().requires_grad_(True)
+    w = {k: v.clone().requires_grad_(True) for k, v in pb.w.items()}
+    proto, pooled_ref, argmax_ref, _ = ho.head_forward(x, w, pb.wc, pb.root)
+    assert rel_err(pooled, pb.cat_nodes(pooled_ref)) <= 1e-5
+    assert torch.equal(argmax.cpu().long(), pb.cat_nodes(argmax_ref))
+    masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
+    ref = (pb.cat_nodes(pooled_ref) * G).sum()
+    for i, name in enumerate(L.node_names):
+        if masks[name].any():
+            t = ho.align_pf_term(proto[name], masks[name])
+            assert abs(float(align[i].detach()) - float(t.detach())) <= 1e-5 * max(1.0, abs(float(t.detach())))
+            ref = ref + a[i] * t
+    ref.backward()
+    gw_ref = torch.cat([w[n].grad for n in L.node_names])
+    assert rel_err(feats.grad, x.grad) <= 2e-2, f'dX rel err {rel_err(feats.grad, x.grad)}'
+    assert rel_err(w_flat.grad, gw_ref) <= 2e-2, f'dW rel err {rel_err(w_flat.grad, gw_ref)}'
