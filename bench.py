@@ -102,7 +102,7 @@ def image_level_throughput(a, wl, dev, steps=5):
     """ConvNeXt-tiny-26 (torchvision, the reference's stride relaxation, random init, bf16 autocast, channels-last) -> fused
     head -> loss -> backward through the backbone, on synthetic 224x224 images copied from pinned host memory each step.
     The backbone is library code (cuDNN / cuBLAS via PyTorch) and dominates the time; reported for context only."""
-    from oracle.problems import make_args, make_tree
+    from pipnet_b200.fixtures import make_args, make_tree
     from pipnet_b200 import pipnet as pp, train as tr
     args = make_args(net='convnext_tiny_26', num_features=wl['num_features'], num_protos_per_child=wl.get('per_child', 0))
     root = make_tree(wl['tree'], num_features=wl['num_features'], per_child=wl.get('per_child', 0))
@@ -211,7 +211,7 @@ def run_ours(a):
     import torch.distributed as dist
     from pipnet_b200 import _cabi, ops
     from pipnet_b200 import train as tr
-    from oracle.problems import build_net, make_args      # builders only (identity backbone, seeded weights)
+    from pipnet_b200.fixtures import build_net, make_args      # product-side builders (identity backbone, seeded weights)
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define HCOMP_ABI_VERSION 4
+#define HCOMP_ABI_VERSION 5
 #define HCOMP_TILE_INTS 52
 #define HCOMP_TILE_COLS 128
 #define HCOMP_MAX_SEGS 16
@@ -56,6 +56,13 @@ typedef struct hcomp_tables {
 int hcomp_abi_version(void);
 const char* hcomp_last_error(void);
 int hcomp_num_sms(void);
+/* Creates the library's per-device helper objects for the CURRENT device up front: two non-blocking side streams and
+ * their fork/join events (independent small kernels of one fused call run beside each other on them; event fork/join
+ * on the caller's stream, capturable into a CUDA graph).  Optional: the first call that needs them creates them lazily,
+ * which is the only allocation-like side effect a compute entry point can have -- call this once per device (and before
+ * stream capture) to keep the compute calls free of it.  The helper objects belong to the device, not to a host
+ * thread: drive one device from one host thread at a time. */
+int hcomp_init(void);
 /* number of kernels this library has launched in this process (bench.py reports it as gpu_launches) */
 long long hcomp_launch_count(void);
 /* K1 / K5 and the dX / dW GEMMs run as CTA pairs (tcgen05 cta_group::2, M = 256 MMAs) by default; 0 selects the
@@ -138,7 +145,7 @@ int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* w
  *   align  [N] as produced by hcomp_align_finalize (NULL = term off)              pipnet/train.py:1063-1074
  *   tanh   -1/2 sum_views mean_p log(tanh(sum_desc pooled)+eps)                   pipnet/train.py:1076-1087
  *   orth   ||W_rel W_rel^T - I||_F over prototypes with a classifier weight > 1e-3 pipnet/train.py:1136-1151, :1408-1412
- *   class  weighted NLL(log_softmax(log1p(out^2)))                                pipnet/train.py:1153-1163, util/custom_losses.py:22-34
+ *   class  weighted NLL(log_softmax(log1p(out^m)))   m = `multiplier` (net._multiplier) pipnet/train.py:1153-1163, util/custom_losses.py:22-34
  * Nodes without a descendant in the batch contribute nothing (pipnet/train.py:941-942).
  * stats[4*N] = per-node {align, tanh, orth, class}; total = sum_k weights[k] * sum_n stats[k][n]
  * (weights_host: 4 floats on the HOST, already divided by N); n_correct[N] = argmax accuracy counters.
@@ -146,18 +153,18 @@ int hcomp_classifier_bwd(const float* g_out, const float* pooled, const float* w
 #define HCOMP_LOSS_TANH 1
 #define HCOMP_LOSS_ORTH 2
 #define HCOMP_LOSS_CLASS 4
-#define HCOMP_LOSS_SPARSITY 8   /* class term on log1p(out^2) (default recipe) instead of out */
+#define HCOMP_LOSS_SPARSITY 8   /* class term on log1p(out^multiplier) (default recipe, multiplier = 2) instead of out */
 long long hcomp_head_losses_ws_floats(const hcomp_tables* t);
 int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* align, const float* w_flat, const float* wc,
                           const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V, int V_first, int C,
-                          int flags, const float* weights_host, float eps, float* total, float* stats,
+                          int flags, const float* weights_host, float eps, float multiplier, float* total, float* stats,
                           int32_t* n_correct, float* ws, uint8_t* rel, void* stream);
 /* g_total: device scalar.  gvec: float[4*N] workspace; on return gvec[0..N) is the gradient w.r.t. align.
  * g_pooled [V,P], g_out [V,K], g_w [P,C] are fully written (zero where a term is off); any may be NULL. */
 int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w_flat, const int8_t* tgt,
                           const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V, int V_first, int C,
-                          int flags, const float* weights_host, float eps, const float* ws, const uint8_t* rel,
-                          float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream);
+                          int flags, const float* weights_host, float eps, float multiplier, const float* ws,
+                          const uint8_t* rel, float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream);
 
 /* ---- descendant-structured loss terms switched on by the shipped scripts ------------------------ */
 /* (run_pipnet_20protos_multi_runs_seed42.sh: --tanh_desc "y|0.05" --minimize_contrasting_set 'y'

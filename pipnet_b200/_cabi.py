@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhcomp_head.so')
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 
 class HcompError(RuntimeError):
@@ -48,8 +48,8 @@ SIGNATURES = {
     'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p],
     'hcomp_classifier_fwd': [_p, _p, _p, _T, _i, _p, _p],
     'hcomp_classifier_bwd': [_p, _p, _p, _T, _i, _p, _i, _p, _p, _p],
-    'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p],
-    'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_desc_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_desc_losses_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p, _p],
@@ -58,7 +58,7 @@ SIGNATURES = {
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
 }
 EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats',
-           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_reserved_sms'] + list(SIGNATURES)
+           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_reserved_sms', 'hcomp_init'] + list(SIGNATURES)
 
 _lib = None
 
@@ -84,6 +84,8 @@ def lib():
     L.hcomp_set_cta_pair.argtypes = [C.c_int]
     L.hcomp_set_reserved_sms.restype = C.c_int
     L.hcomp_set_reserved_sms.argtypes = [C.c_int]
+    L.hcomp_init.restype = C.c_int
+    L.hcomp_init.argtypes = []
     for name, args in SIGNATURES.items():
         fn = getattr(L, name)
         fn.argtypes = args

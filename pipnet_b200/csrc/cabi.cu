@@ -151,6 +151,19 @@ int make_tmap_dz(CUtensorMap* m, const void* base, unsigned w, unsigned n_tiles,
   return 0;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is per (function, device): one bit per device index, set once.  A process
+// that drives several GPUs (or several host threads racing here) at worst sets the attribute twice.
+template <typename Kern>
+int ensure_dyn_smem(Kern kern, int smem, std::atomic<unsigned long long>& done) {
+  int dev = 0;
+  HC_CUDA(cudaGetDevice(&dev));
+  const bool tracked = dev >= 0 && dev < 64;
+  if (tracked && ((done.load(std::memory_order_acquire) >> dev) & 1ull)) return 0;
+  HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  if (tracked) done.fetch_or(1ull << dev, std::memory_order_release);
+  return 0;
+}
+
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 inline int cdiv(long long a, long long b) { return int((a + b - 1) / b); }
 
@@ -181,11 +194,8 @@ int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap*
                 const hc::HeadParams& p, int sms, cudaStream_t st) {
   auto kern = hc::head_pair_kernel<SEG, BWD, CG2>;
   constexpr int SMEM = hc::PairMem<BWD, CG2>::SMEM_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int e = ensure_dyn_smem(kern, SMEM, attr_done)) return e;
   constexpr int CL = CG2 ? 2 : 1;
   const int items = ((p.num_m_tiles + CL - 1) / CL) * p.num_tiles;
   const int slots = sms / CL;
@@ -244,6 +254,7 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   p.imgs_first = V_first;
   p.scale_log2 = 1.4426950408889634f / tau;
   p.inv_tau = 1.f / tau;
+  p.inv_HW = 1.f / float(HW);
   p.tiles = tiles_dev;
   int t = 0;
   while (t < n_tiles) {
@@ -310,11 +321,8 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap&
                 cudaStream_t st) {
   auto kern = hc::gemm_tc_kernel<A_MN, B_MN, OUT>;
   constexpr int SMEM = hc::GemmCfg<OUT>::SMEM_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int e = ensure_dyn_smem(kern, SMEM, attr_done)) return e;
   const int items = p.num_m_tiles * p.num_n_tiles * p.splits;
   const int workers = items < sms ? items : sms;
   return launch_persistent(kern, "gemm_tc_kernel", 1, workers, hc::G_THREADS, SMEM, st, ta, tb, to, p);
@@ -325,11 +333,8 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
                  cudaStream_t st) {
   auto kern = hc::gemm2_tc_kernel<A_MN, B_MN, OUT>;
   constexpr int SMEM = hc::Gemm2Cfg<OUT>::SMEM_BYTES;
-  static bool attr_done = false;
-  if (!attr_done) {
-    HC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    attr_done = true;
-  }
+  static std::atomic<unsigned long long> attr_done{0};
+  if (int e = ensure_dyn_smem(kern, SMEM, attr_done)) return e;
   const int m2 = (p.M + 2 * hc::G_BM - 1) / (2 * hc::G_BM);
   const int items = m2 * p.num_n_tiles * p.splits;
   const int slots = sms / 2;
@@ -427,6 +432,14 @@ int hcomp_num_sms(void) {
   DevInfo di;
   if (int e = dev_info(&di)) return e;
   return di.sms;
+}
+int hcomp_init(void) {
+  DevInfo di;
+  if (int e = dev_info(&di)) return e;
+  SideBranch* b = nullptr;
+  for (int which = 0; which < 2; ++which)
+    if (int e = side_branch(&b, which)) return e;
+  return 0;
 }
 
 int hcomp_pack_weights(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp_bf16, void* stream) {
@@ -598,11 +611,12 @@ long long hcomp_head_losses_ws_floats(const hcomp_tables* t) {
 
 int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* align, const float* w_flat, const float* wc,
                           const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V, int V_first, int C,
-                          int flags, const float* weights_host, float eps, float* total, float* stats,
+                          int flags, const float* weights_host, float eps, float multiplier, float* total, float* stats,
                           int32_t* n_correct, float* ws, uint8_t* rel, void* stream) {
   const LossWs w = loss_ws(ws, t);
   const bool do_tanh = flags & HCOMP_LOSS_TANH, do_orth = flags & HCOMP_LOSS_ORTH, do_cls = flags & HCOMP_LOSS_CLASS;
-  const int sparsity = (flags & HCOMP_LOSS_SPARSITY) ? 1 : 0;
+  if ((flags & HCOMP_LOSS_SPARSITY) && !(multiplier > 0.f)) return fail(HCOMP_E_ARG, "class loss: log1p(out**m) needs m > 0 (got %g)", multiplier);
+  const float sparsity = (flags & HCOMP_LOSS_SPARSITY) ? multiplier : 0.f;
   SideBranch* sb = nullptr;
   if (do_orth) {        // depends on the weights only: runs on the side branch beside the tanh / class kernels
     if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
@@ -641,11 +655,12 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
 
 int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w_flat, const int8_t* tgt,
                           const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V, int V_first, int C,
-                          int flags, const float* weights_host, float eps, const float* ws, const uint8_t* rel,
-                          float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream) {
+                          int flags, const float* weights_host, float eps, float multiplier, const float* ws,
+                          const uint8_t* rel, float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream) {
   const LossWs w = loss_ws(const_cast<float*>(ws), t);
   const int N = t->n_nodes;
-  const int sparsity = (flags & HCOMP_LOSS_SPARSITY) ? 1 : 0;
+  if ((flags & HCOMP_LOSS_SPARSITY) && !(multiplier > 0.f)) return fail(HCOMP_E_ARG, "class loss: log1p(out**m) needs m > 0 (got %g)", multiplier);
+  const float sparsity = (flags & HCOMP_LOSS_SPARSITY) ? multiplier : 0.f;
   hc::LossWeights lw;
   for (int i = 0; i < 4; ++i) lw.w[i] = weights_host[i];
   hc::loss_grads_kernel<<<blocks(4 * N, 128), 128, 0, S(stream)>>>(g_total, N, lw, gvec);   // gvec[0..N) is g_align
@@ -847,6 +862,23 @@ int hcomp_materialize_map(const void* x_bf16, const float* w_node, int V, int HW
   HC_LAUNCH_CHECK("materialize_map");
   return 0;
 }
+
+#ifdef HC_EXP_TIMING
+/* timing experiment only: read and clear the per-role cycle counters of the fused pair kernels */
+int hcomp_debug_pair_counters(unsigned long long* out16) {
+  HC_CUDA(cudaDeviceSynchronize());
+  HC_CUDA(cudaMemcpyFromSymbol(out16, hc::g_pair_dbg, sizeof(unsigned long long) * 16));
+  unsigned long long z[16] = {0};
+  HC_CUDA(cudaMemcpyToSymbol(hc::g_pair_dbg, z, sizeof(z)));
+  return 0;
+}
+/* per-CTA wall-clock stamps of the LAST pair-kernel launch: out[160*4] ns */
+int hcomp_debug_pair_stamps(unsigned long long* out640) {
+  HC_CUDA(cudaDeviceSynchronize());
+  HC_CUDA(cudaMemcpyFromSymbol(out640, hc::g_pair_stamps, sizeof(unsigned long long) * 640));
+  return 0;
+}
+#endif
 
 int hcomp_gemm_bf16(const void* a, const void* b, int M, int N, int K, int a_mn, int b_mn, int out_mode, int splits,
                     void* out, long long ldo, void* stream) {

@@ -75,6 +75,35 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Polling wait (mbarrier.test_wait never suspends the thread): for the single-thread service roles (TMA producer, MMA
+// issuer) whose wake-up latency is on the critical path of the operand ring.  Same wall-clock watchdog.
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_poll(uint64_t* bar, uint32_t parity) {
+  uint64_t t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if ((++spins & 0xFFFFu) == 0u) {
+      const uint64_t now = global_timer_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 2000000000ull) {
+        printf("hcomp: mbarrier poll timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+               smem_u32(bar), parity);
+        __trap();
+      }
+    }
+  }
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -194,11 +194,20 @@ __global__ void classifier_bwd_bias_kernel(const float* __restrict__ g_out, int 
 }
 
 // ---------------------------------------------------------------- class loss (pipnet/train.py:1153-1163, util/custom_losses.py:22-34)
-// One block per node.  x = log1p(out^2) (multiplier 2, main_dist.py:426) or out (pipnet_sparsity n);
+// x = log1p(out ** mult) with mult = net._multiplier (pipnet/train.py:1158; main_dist.py:426 initialises it to 2 and
+// freezes it -- that value takes the exact out*out path), or x = out when mult == 0 (pipnet_sparsity n).
+__device__ __forceinline__ float sparsity_x(float o, float mult) {
+  return mult == 2.f ? log1pf(o * o) : (mult > 0.f ? log1pf(powf(o, mult)) : o);
+}
+__device__ __forceinline__ float sparsity_dx(float o, float mult) {
+  if (mult == 2.f) return 2.f * o / (1.f + o * o);
+  return mult > 0.f ? mult * powf(o, mult - 1.f) / (1.f + powf(o, mult)) : 1.f;
+}
+// One block per node.
 // loss[n] = mean over descendants of w[t] * (logsumexp(x) - x[t]); also per-node accuracy counts.
 __global__ void class_loss_fwd_kernel(const float* __restrict__ out, const int8_t* __restrict__ tgt,
                                       const float* __restrict__ child_w, const int32_t* __restrict__ cls_off,
-                                      const int32_t* __restrict__ n_desc, int V, int N, int K, int sparsity,
+                                      const int32_t* __restrict__ n_desc, int V, int N, int K, float mult,
                                       float* __restrict__ loss, int32_t* __restrict__ n_correct) {
   __shared__ float sh[32];
   const int n = blockIdx.x;
@@ -211,13 +220,13 @@ __global__ void class_loss_fwd_kernel(const float* __restrict__ out, const int8_
     float mx = -INFINITY, best = -INFINITY;
     int arg = 0;
     for (int c = 0; c < kn; ++c) {
-      const float x = sparsity ? log1pf(o[c] * o[c]) : o[c];
+      const float x = sparsity_x(o[c], mult);
       mx = fmaxf(mx, x);
       if (o[c] > best) { best = o[c]; arg = c; }     // torch.max(node_logits, 1): first max (pipnet/train.py:1189)
     }
     float se = 0.f, xt = 0.f;
     for (int c = 0; c < kn; ++c) {
-      const float x = sparsity ? log1pf(o[c] * o[c]) : o[c];
+      const float x = sparsity_x(o[c], mult);
       se += expf(x - mx);
       if (c == t) xt = x;
     }
@@ -236,7 +245,7 @@ __global__ void class_loss_fwd_kernel(const float* __restrict__ out, const int8_
 __global__ void class_loss_bwd_kernel(const float* __restrict__ out, const int8_t* __restrict__ tgt,
                                       const float* __restrict__ child_w, const int32_t* __restrict__ col_node,
                                       const int32_t* __restrict__ cls_off, const int32_t* __restrict__ n_desc,
-                                      const float* __restrict__ g_loss, int V, int N, int K, int sparsity,
+                                      const float* __restrict__ g_loss, int V, int N, int K, float mult,
                                       float* __restrict__ g_out) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= V * K) return;
@@ -248,13 +257,13 @@ __global__ void class_loss_bwd_kernel(const float* __restrict__ out, const int8_
     const int k0 = cls_off[n], kn = cls_off[n + 1] - k0;
     const float* o = out + (size_t)v * K + k0;
     float mx = -INFINITY;
-    for (int c = 0; c < kn; ++c) mx = fmaxf(mx, sparsity ? log1pf(o[c] * o[c]) : o[c]);
+    for (int c = 0; c < kn; ++c) mx = fmaxf(mx, sparsity_x(o[c], mult));
     float se = 0.f;
-    for (int c = 0; c < kn; ++c) se += expf((sparsity ? log1pf(o[c] * o[c]) : o[c]) - mx);
+    for (int c = 0; c < kn; ++c) se += expf(sparsity_x(o[c], mult) - mx);
     const float ok = o[k - k0];
-    const float xk = sparsity ? log1pf(ok * ok) : ok;
+    const float xk = sparsity_x(ok, mult);
     const float sm = expf(xk - mx) / se;
-    const float dx = sparsity ? (2.f * ok / (1.f + ok * ok)) : 1.f;
+    const float dx = sparsity_dx(ok, mult);
     g = g_loss[n] / float(n_desc[n]) * child_w[k0 + t] * (sm - ((k - k0) == t ? 1.f : 0.f)) * dx;
   }
   g_out[idx] = g;

@@ -479,7 +479,9 @@ class HeadLosses(torch.autograd.Function):
     gradient from it (boolean indexing in the reference, `pipnet/train.py:1140`)."""
 
     @staticmethod
-    def forward(ctx, pooled, out, align, w_flat, wc_flat, labels: LabelTables, dl: DeviceLayout, flags, weights, eps):
+    def forward(ctx, pooled, out, align, w_flat, wc_flat, labels: LabelTables, dl: DeviceLayout, flags, weights, eps,
+                multiplier=2.0):
+        # multiplier: exponent of the class term's log1p(out ** m) (net._multiplier, pipnet/train.py:1158)
         pooled, out = pooled.contiguous(), out.contiguous()
         V = pooled.shape[0]
         dev = pooled.device
@@ -495,9 +497,9 @@ class HeadLosses(torch.autograd.Function):
         wc = wc_flat.detach().contiguous() if wc_flat is not None else None
         al = align.detach().contiguous() if align is not None else None
         call('hcomp_head_losses_fwd', ptr(pooled), ptr(out), ptr(al), ptr(wf), ptr(wc), ptr(labels.tgt), ptr(labels.n_desc),
-             dl.tref, V, labels.V_first, Cc, int(flags), wts, float(eps), ptr(total), ptr(stats), ptr(n_correct), ptr(ws),
-             ptr(rel), _stream())
-        ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc)
+             dl.tref, V, labels.V_first, Cc, int(flags), wts, float(eps), float(multiplier), ptr(total), ptr(stats),
+             ptr(n_correct), ptr(ws), ptr(rel), _stream())
+        ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc, float(multiplier))
         ctx.has = (align is not None, w_flat is not None and use_orth)
         ctx.w_group = getattr(w_flat, '_hc_group', None) if w_flat is not None else None
         ctx.set_materialize_grads(False)      # stats / n_correct are not differentiable: no zero-filled grads for them
@@ -508,10 +510,10 @@ class HeadLosses(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g_total, _gs, _gc):
         if g_total is None:
-            return (None,) * 10
+            return (None,) * 11
         out, wf, stats, ws, rel = ctx.saved_tensors
         dl, labels = ctx.dl, ctx.labels
-        flags, weights, eps, V, Cc = ctx.cfg
+        flags, weights, eps, V, Cc, multiplier = ctx.cfg
         dev = out.device
         wts = (C.c_float * 4)(*weights)
         g_total = g_total.contiguous().float()
@@ -527,15 +529,15 @@ class HeadLosses(torch.autograd.Function):
             g_w = (_bucket_segment(ctx.w_group, dev).view(dl.P, Cc) if bucketed
                    else torch.empty(dl.P, Cc, device=dev, dtype=torch.float32))
         call('hcomp_head_losses_bwd', ptr(g_total), ptr(out), ptr(wf), ptr(labels.tgt), ptr(labels.n_desc), ptr(stats), dl.tref,
-             V, labels.V_first, Cc, flags, wts, eps, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out), ptr(g_w),
-             _stream())
+             V, labels.V_first, Cc, flags, wts, eps, multiplier, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out),
+             ptr(g_w), _stream())
         if bucketed:
             g_w = None
         elif g_w is not None and GRAD_ALLREDUCE_GROUP is not None:
             # the orth term is skipped for nodes without a descendant in the LOCAL batch (pipnet/train.py:941-942), so
             # its gradient differs across ranks like any other and needs the mean too
             torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g_w))
-        return g_pooled, g_out, (gvec[0] if need_align else None), g_w, None, None, None, None, None, None
+        return g_pooled, g_out, (gvec[0] if need_align else None), g_w, None, None, None, None, None, None, None
 
 DESC_TANH_DESC, DESC_CONTRAST, DESC_MASK_PRUNE, DESC_GEOMETRIC, DESC_SG_SCORE = 1, 2, 4, 8, 16
 

@@ -131,11 +131,16 @@ class _FlatGroup:
         self._gathered = None
 
 
-class NodeDict:
+class NodeDict(dict):
     """Read-only mapping node name -> column slice of a flat [V, total] tensor, shaped like the dicts the
-    reference returns (`pipnet/pipnet.py:115-116`).  `.flat` is what the fused losses consume."""
+    reference returns (`pipnet/pipnet.py:115-116`).  `.flat` is what the fused losses consume.
+    It IS a `dict` (its own storage stays empty, the slices are made on demand): `DistributedDataParallel(...,
+    find_unused_parameters=True)` -- how main_dist.py:330 wraps the model -- walks the forward outputs looking for
+    tensors and only descends into tuples / lists / dicts; an opaque object would hide every output from its reducer
+    and all parameters would be declared unused (tests/test_gpu_ddp.py)."""
 
     def __init__(self, flat: Tensor, names: List[str], offsets: np.ndarray):
+        super().__init__()
         self.flat, self._names, self._off = flat, names, offsets
         self._idx = {n: i for i, n in enumerate(names)}
         self._cache: Dict[str, Tensor] = {}
@@ -151,9 +156,15 @@ class NodeDict:
     def __contains__(self, name): return name in self._idx
     def __iter__(self): return iter(self._names)
     def __len__(self): return len(self._names)
+    def __bool__(self): return len(self._names) > 0
     def keys(self): return list(self._names)
     def values(self): return [self[n] for n in self._names]
     def items(self): return [(n, self[n]) for n in self._names]
+    def get(self, name, default=None): return self[name] if name in self._idx else default
+
+    def _read_only(self, *a, **k):
+        raise TypeError('NodeDict is a read-only view of the flat head outputs')
+    __setitem__ = __delitem__ = pop = popitem = clear = update = setdefault = _read_only
 
 
 class LazyProtoFeatures:
@@ -292,8 +303,10 @@ class PIPNet(nn.Module):
     def flat_classifier_weights(self) -> Tensor:
         return self._wc_group.gather()
 
-    def flat_proto_presence(self) -> Tensor:
-        """[P, 2] view of all `_<node>_proto_presence` logits with autograd edges to the per-node parameters."""
+    def flat_presence_logits(self) -> Tensor:
+        """[P, 2] view of all `_<node>_proto_presence` logits with autograd edges to the per-node parameters.
+        (The name must NOT end in `_proto_presence` / `_add_on` / `_classification`: the reference discovers parameters
+        with `dir(net.module)` + suffix matching, util/args.py:528-556, main_dist.py:474-481 -- tests/test_reference_optimizer.py.)"""
         v = self._pp_group.gather().view(self.layout.P, 2)
         v._hc_group = self._pp_group
         return v
@@ -326,7 +339,7 @@ class PIPNet(nn.Module):
         pooled_flat, align, argmax, dl = self.head(features, inference=inference, labels=labels)
         if apply_overspecificity_mask:
             # Gumbel hard sample on proto_presence (pipnet/pipnet.py:164-166), one draw for the whole flat axis
-            pres = self.flat_proto_presence()
+            pres = self.flat_presence_logits()
             mask = F.gumbel_softmax(pres, tau=0.5, hard=True, dim=-1)[:, 1].unsqueeze(0)
             pooled_flat = mask * pooled_flat
         out_flat = self.classify(pooled_flat, dl)
@@ -382,7 +395,7 @@ class PIPNet(nn.Module):
         with torch.no_grad():
             dev = dl.device
             if presence_mask is None:
-                presence_mask = F.gumbel_softmax(self.flat_proto_presence().detach(), tau=0.5, hard=True, dim=-1)[:, 1]
+                presence_mask = F.gumbel_softmax(self.flat_presence_logits().detach(), tau=0.5, hard=True, dim=-1)[:, 1]
             m = presence_mask.to(device=dev, dtype=torch.float32)
             wc = self.flat_classifier_weights().detach()
             alive = ((m[dl.welem_proto.long()] * wc) > 1e-3).float()                       # [n_welems]

@@ -111,6 +111,28 @@ def make_labels(net, ys: torch.Tensor, V_first: Optional[int] = None) -> ops.Lab
 
 
 # --------------------------------------------------------------------------- the loss
+_MULT_CACHE = {}
+
+
+def _multiplier_value(m) -> float:
+    """`net._multiplier` as a host float (exponent of log1p(out ** m), pipnet/train.py:1158).  The reference keeps it in a
+    frozen nn.Parameter; reading it costs a device sync, so the value is cached per tensor and re-read only when the
+    tensor's version counter says it was written (optimizer step, load_state_dict, .fill_)."""
+    if m is None:
+        return 2.0
+    if not torch.is_tensor(m):
+        return float(m)
+    key = id(m)
+    ver = m._version
+    hit = _MULT_CACHE.get(key)
+    if hit is not None and hit[0] == ver and hit[2]() is m:
+        return hit[1]
+    import weakref
+    val = float(m.detach().reshape(-1)[0])          # no gradient flows to it: every driver path of the reference freezes
+    _MULT_CACHE[key] = (ver, val, weakref.ref(m))   # it at 2 (main_dist.py:344, :381-382, :402-403, :426-427)
+    return val
+
+
 def calculate_loss(epoch, net, additional_network_outputs, features, proto_features, pooled, out, ys, align_weight,
                    align_pf_weight, t_weight, mm_weight, unif_weight, cl_weight, OOD_loss_weight, orth_weight,
                    cluster_desc_weight, sep_desc_weight, subspace_sep_weight, byol_weight, net_normalization_multiplier,
@@ -194,8 +216,9 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         losses_used.append('CL')
     if not (args is not None and getattr(args, 'pipnet_sparsity', 'y') == 'n'):
         flags |= ops.LOSS_SPARSITY
+    mult = _multiplier_value(net_normalization_multiplier) if (use_cls and (flags & ops.LOSS_SPARSITY)) else 2.0
     loss, stats, n_correct = ops.HeadLosses.apply(pooled.flat, out.flat, align_vec, m.flat_prototype_kernels() if use_orth else None,
-                                                  m.flat_classifier_weights(), labels, dl, flags, wts, EPS)
+                                                  m.flat_classifier_weights(), labels, dl, flags, wts, EPS, mult)
     if (not finetune) and (not pretrain) and tanh_desc:                             # pipnet/train.py:1089-1133
         dflags |= ops.DESC_TANH_DESC
         dw[0] = float(args.tanh_desc.split('|')[1]) / N
@@ -206,7 +229,7 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
         if use_mp and gumbel_noise is None:
             gumbel_noise = ops.gumbel_noise(dl, pooled.flat.device)
         dloss, desc_stats = ops.DescLosses.apply(pooled.flat, m.flat_classifier_weights(),
-                                                 m.flat_proto_presence() if use_mp else None,
+                                                 m.flat_presence_logits() if use_mp else None,
                                                  gumbel_noise if use_mp else None, labels, dl, dflags, dw, EPS, boost, 0.5)
         loss = loss + dloss
 

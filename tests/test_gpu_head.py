@@ -33,26 +33,36 @@ def _oracle_forward(pb, tau=1.0):
     return ho.head_forward(pb.x, pb.w, pb.wc, pb.root, softmax_tau=tau)
 
 
+# softmax temperatures the reference can run (pipnet/pipnet.py:130-136): "y|1" (shipped scripts), "y|2" (int(tau)) and the
+# 0.2 default of a bare "y"
+TAUS = [1.0, 2.0, 0.2]
+
+
+@pytest.mark.parametrize("tau", TAUS, ids=[f"tau{t}" for t in TAUS])
 @pytest.mark.parametrize("case", FWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}-{i}" for i, c in enumerate(FWD_CASES)])
-def test_forward_pool_argmax_align(case):
+def test_forward_pool_argmax_align(case, tau):
     from pipnet_b200 import ops
     tree, C, H, B, kw = case
+    if tau != 1.0 and (C, H) == (768, 26) and B > 1:
+        B = 1                       # the real-geometry oracle run is the slow one: one image pair for the extra temperatures
     pb = Problem(tree, C, H, B, seed=7, **kw)
     dl = ops.DeviceLayout(pb.layout, 'cuda')
     feats = pb.features('cuda')
     labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
     x_rows = ops.feature_rows(feats)
     wp, _wpc = ops.pack_weights(pb.w_flat('cuda'), dl)
-    pooled, argmax, align = ops.proj_softmax_pool_raw(x_rows, wp, dl, pb.V, pb.V_first, H * H, 1.0, labels)
+    pooled, argmax, align = ops.proj_softmax_pool_raw(x_rows, wp, dl, pb.V, pb.V_first, H * H, tau, labels)
     torch.cuda.synchronize()
 
-    proto, pooled_ref, argmax_ref, _ = _oracle_forward(pb)
+    proto, pooled_ref, argmax_ref, _ = _oracle_forward(pb, tau)
     pr = pb.cat_nodes(pooled_ref)
     ar = pb.cat_nodes(argmax_ref)
     assert rel_err(pooled, pr) <= 1e-5, f'pooled rel err {rel_err(pooled, pr)}'
     proto_flat = torch.cat([proto[n].flatten(2) for n in pb.layout.node_names], dim=1)
+    # bit-exact argmax, except where the fp64 oracle separates two locations by less than fp32 can resolve (relative gap
+    # below 2^-23 = 1.2e-7: the same number in fp32, so "first occurrence" legitimately picks the earlier one)
     nbad, gaps = argmax_report(argmax, ar, proto_flat)
-    assert nbad == 0, f'{nbad} argmax mismatches, relative gaps {gaps[:8]}'
+    assert all(abs(g) <= 1.2e-7 for g in gaps) and nbad <= 2, f'{nbad} argmax mismatches, relative gaps {gaps[:8]}'
 
     masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
     for i, name in enumerate(pb.layout.node_names):
@@ -88,8 +98,9 @@ BWD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("tau", TAUS, ids=[f"tau{t}" for t in TAUS])
 @pytest.mark.parametrize("case", BWD_CASES, ids=[f"{c[0]}-C{c[1]}-H{c[2]}-B{c[3]}-{i}" for i, c in enumerate(BWD_CASES)])
-def test_backward_dx_dw(case):
+def test_backward_dx_dw(case, tau):
     """d(sum pooled*G + sum_n a_n * align_n) w.r.t. features and prototype kernels vs oracle autograd."""
     from pipnet_b200 import ops
     tree, C, H, B, kw = case
@@ -103,14 +114,14 @@ def test_backward_dx_dw(case):
     feats = pb.features('cuda').requires_grad_(True)
     w_flat = pb.w_flat('cuda').requires_grad_(True)
     labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
-    pooled, align, _ = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0)
+    pooled, align, _ = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, tau, labels, 0.0)
     loss = (pooled.double() * G.cuda()).sum() + (align.double() * a.cuda()).sum()
     loss.backward()
     torch.cuda.synchronize()
 
     x = pb.x.clone().requires_grad_(True)
     w = {k: v.clone().requires_grad_(True) for k, v in pb.w.items()}
-    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root)
+    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root, softmax_tau=tau)
     masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
     ref = (pb.cat_nodes(pooled_ref) * G).sum()
     for i, name in enumerate(L.node_names):
@@ -172,7 +183,7 @@ def test_fp32_accurate_mode_backward_runs():
     torch.cuda.synchronize()
     x = pb.x.clone().requires_grad_(True)
     w = {k: v.clone().requires_grad_(True) for k, v in pb.w.items()}
-    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root)
+    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root, softmax_tau=tau)
     masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
     ref = (pb.cat_nodes(pooled_ref) * G).sum()
     for n in pb.layout.node_names:

@@ -13,7 +13,7 @@ from oracle.problems import make_tree, bf16_round, rel_err
 pytestmark = pytest.mark.gpu
 
 
-from oracle.problems import IdentityBackbone, make_args, build_net
+from pipnet_b200.fixtures import IdentityBackbone, make_args, build_net
 
 
 PHASES = [("pretrain", True, False), ("train", False, False), ("finetune", False, True)]
@@ -22,13 +22,19 @@ CASES = [("cub08", 64, 6, 4, dict(num_features=20)), ("cub27", 96, 6, 6, dict(nu
          ("cub27", 64, 6, 5, dict(num_protos_per_child=20, num_features=0))]     # recipe B: P_n up to 60
 
 
+# --softmax values the reference parses (pipnet/pipnet.py:130-136): "y|1" (shipped scripts), "y|2", and a bare "y" = 0.2
+SOFTMAX_ARGS = [("y|1", 1.0), ("y|2", 2.0), ("y", 0.2)]
+
+
+@pytest.mark.parametrize("softmax", SOFTMAX_ARGS, ids=[f"softmax-{s[0]}" for s in SOFTMAX_ARGS])
 @pytest.mark.parametrize("phase", PHASES, ids=[p[0] for p in PHASES])
 @pytest.mark.parametrize("case", CASES, ids=[f'{c[0]}-{i}' for i, c in enumerate(CASES)])
-def test_step_matches_oracle(case, phase):
+def test_step_matches_oracle(case, phase, softmax):
     from pipnet_b200 import train as tr
     tree, C, H, B, over = case
     _, pretrain, finetune = phase
-    args = make_args(**over)
+    softmax_arg, tau = softmax
+    args = make_args(softmax=softmax_arg, **over)
     net, root = build_net(tree, C, args)
     names = net.layout.node_names
     g = torch.Generator().manual_seed(17)
@@ -50,7 +56,8 @@ def test_step_matches_oracle(case, phase):
     aw = {n: getattr(net, '_' + n + '_add_on').weight.detach().flatten(1).double().cpu() for n in names}
     cw = {n: getattr(net, '_' + n + '_classification').weight.detach().double().cpu() for n in names}
     label2name = {i: n for i, n in enumerate(net.layout.leaf_names)}
-    ref = ho.full_step(x.double(), aw, cw, root, ys, label2name, pretrain=pretrain, finetune=finetune, softmax_tau=1.0,
+    assert net.softmax_tau == tau
+    ref = ho.full_step(x.double(), aw, cw, root, ys, label2name, pretrain=pretrain, finetune=finetune, softmax_tau=tau,
                        epoch=3, nr_epochs=10, cl_weight=args.cl_weight)
 
     assert rel_err(pooled.flat, torch.cat([ref['pooled'][n] for n in names], 1)) <= 1e-5

@@ -1,0 +1,96 @@
+"""A/B timing of the fused forward (K1) and backward-recompute (K5) kernels for several builds of the library:
+    python tools/k1_ab.py lib_a.so lib_b.so ...        (each build runs in its own process)
+Prints kernel-only times (CUDA events around the C-ABI call in a back-to-back loop, inputs alternating between two
+> L2 batches) and a checksum of pooled / argmax / dZ so that variants can be compared bit for bit."""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def one(path, workload):
+    import ctypes as C
+    import hashlib
+    import torch
+    from pipnet_b200 import _cabi
+    if path != 'default':
+        _cabi.LIB_PATH = os.path.abspath(path)
+    from pipnet_b200 import ops
+    from oracle.problems import Problem
+    tree, nf, batch = {'cub27': ('cub27', 20, 64), 'cub190': ('synth190', 20, 32)}[workload]
+    dev = torch.device('cuda:0')
+    pb = Problem(tree, 768, 26, batch, seed=1, num_features=nf)
+    dl = ops.DeviceLayout(pb.layout, dev)
+    V, B, HW = pb.V, pb.V_first, 26 * 26
+    xs = [ops.feature_rows(pb.features(dev)), None]
+    xs[1] = (xs[0].float().roll(1, 0) * 0.97).to(torch.bfloat16)
+    wp, wpc = ops.pack_weights(pb.w_flat(dev).contiguous(), dl, ops.PREC_BF16)
+    lab = ops.LabelTables(pb.ys.to(dev), dl, B)
+    gp = torch.randn(V, dl.P, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
+    ga = torch.full((dl.N,), 0.2, device=dev)
+    pooled, argmax, align = ops.proj_softmax_pool_raw(xs[0], wp, dl, V, B, HW, 1.0, lab)
+    _, _, dz = ops.head_backward_raw(xs[0], wp, wpc, dl, V, B, HW, 1.0, argmax, gp, lab, ga, pooled=pooled, need_dx=False,
+                                     need_dw=False)
+    torch.cuda.synchronize()
+    h = hashlib.sha1()
+    for t in (pooled, argmax, align, dz):
+        h.update(t.detach().cpu().contiguous().view(torch.uint8).numpy().tobytes())
+    ops.PROFILE.enabled = True
+    n = 20
+    for it in range(3 + n):
+        if it == 3:
+            torch.cuda.synchronize()
+            ops.PROFILE.reset()
+        p_, a_, _ = ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab)
+        ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, a_, gp, lab, ga, pooled=p_, need_dx=False, need_dw=False)
+    torch.cuda.synchronize()
+    tot = ops.PROFILE.totals_ms()
+    k1 = tot['k1_proj_softmax_pool_fwd'][0] / n * 1e3
+    k5 = tot['k5_bwd_dz'][0] / n * 1e3
+    print(f'{os.path.basename(path):14s} {workload:7s} K1 {k1:7.1f} us   K5(+scat) {k5:7.1f} us   sha1 {h.hexdigest()[:12]}', flush=True)
+    L = _cabi.lib()
+    if hasattr(L, 'hcomp_debug_pair_counters'):          # library built with -DHC_EXP_TIMING: per-role cycle counters
+        ops.PROFILE.enabled = False
+        buf = (C.c_ulonglong * 16)()
+
+        def report(tag):
+            L.hcomp_debug_pair_counters(buf)
+            c = list(buf)
+            pk, mk, it = max(c[2], 1), max(c[6], 1), max(c[9], 1)
+            print(f'   {tag}: producer/k-block: wait(empty) {c[0] / pk:7.0f}  issue {c[1] / pk:5.0f} | MMA/k-block: wait(full) {c[3] / mk:7.0f}  '
+                  f'issue {c[5] / mk:5.0f}  wait(tmem_empty)/item {c[4] / max(c[6] // 12, 1):7.0f} | epilogue warp/item: wait(tmem_full) '
+                  f'{c[7] / it:7.0f}  work {c[8] / it:7.0f} | SM clock {c[10] / max(c[11], 1):.3f} GHz', flush=True)
+
+        def stamps(tag, nblk):
+            sb = (C.c_ulonglong * 640)()
+            L.hcomp_debug_pair_stamps(sb)
+            import numpy as np
+            a = np.array(list(sb), dtype=np.int64).reshape(160, 4)[:nblk]
+            t0 = a[:, 0].min()
+            a = (a - t0) / 1e3
+            print(f'   {tag} stamps (us, {nblk} CTAs): entry {a[:,0].min():.1f}..{a[:,0].max():.1f} | setup done {a[:,1].min():.1f}..{a[:,1].max():.1f} '
+                  f'| epilogue loop end {a[:,2].min():.1f}..{a[:,2].max():.1f} (median {np.median(a[:,2]):.1f}) | exit {a[:,3].min():.1f}..{a[:,3].max():.1f}',
+                  flush=True)
+
+        L.hcomp_debug_pair_counters(buf)
+        for it in range(6):
+            ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab)
+        report('K1')
+        stamps('K1', 148)
+        for it in range(6):
+            ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, argmax, gp, lab, ga, pooled=pooled, need_dx=False, need_dw=False)
+        report('K5')
+        stamps('K5', 148)
+
+
+if __name__ == '__main__':
+    if len(sys.argv) >= 3 and sys.argv[1] == '--one':
+        one(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else 'cub27')
+    else:
+        wls = os.environ.get('HC_AB_WORKLOADS', 'cub27').split(',')
+        for path in sys.argv[1:] or ['default']:
+            for wl in wls:
+                r = subprocess.run([sys.executable, os.path.abspath(__file__), '--one', path, wl], capture_output=True, text=True)
+                sys.stdout.write(r.stdout)
+                if r.returncode != 0:
+                    sys.stdout.write(f'{path} {wl}: FAILED\n{r.stderr[-1500:]}\n')
+                sys.stdout.flush()
