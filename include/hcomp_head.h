@@ -229,6 +229,21 @@ int hcomp_materialize_map(const void* x_bf16, const float* w_node, int V, int HW
 int hcomp_gemm_bf16(const void* a, const void* b, int M, int N, int K, int a_mn, int b_mn, int out_mode, int splits,
                     void* out, long long ldo, void* stream);
 
+/* ---- data-parallel gradient exchange (reference: DistributedDataParallel's mean of the per-rank
+ *      gradients, main_dist.py:330) ---------------------------------------------------------------------------- */
+/* In-place MEAN all-reduce of one flat fp32 buffer that every rank of one NVSwitch box allocated symmetrically (same
+ * size, mapped into every peer; torch.distributed._symmetric_memory or cuMem* + cuMulticast*).  `ctas` CTAs (the SMs
+ * the concurrent dX GEMM leaves free, hcomp_set_reserved_sms) run: cross-rank barrier -> each rank reduces its 1/world
+ * shard (mc != NULL: in the switch, multimem.ld_reduce at the multicast address `mc`; else peer loads through
+ * `peers_dev`, a DEVICE array of `world` buffer pointers) and scales it by 1/world -> broadcasts it (multimem.st / peer
+ * stores) -> cross-rank barrier.  `pads_dev`: DEVICE array of `world` pointers to the ranks' zero-initialised 32-bit
+ * signal pads; this call uses channels [channel_base, channel_base + ctas), i.e. words
+ * [channel_base * world, (channel_base + ctas) * world) of every pad, and leaves them zero.  Every rank must make the
+ * same call (same n, ctas, channel_base) in the same stream order; the buffer must not be written by the caller between
+ * the producers' completion and the end of this call.  n: floats, a multiple of 4. */
+int hcomp_allreduce_mean_symm(float* local, float* mc, const void* peers_dev, const void* pads_dev, int rank, int world,
+                              long long n, int channel_base, int ctas, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -56,6 +56,7 @@ SIGNATURES = {
     'hcomp_topk_update': [_p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _p, _p, _p, _p],
     'hcomp_materialize_map': [_p, _p, _i, _i, _i, _i, _f, _p, _p],
     'hcomp_gemm_bf16': [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p, _ll, _p],
+    'hcomp_allreduce_mean_symm': [_p, _p, _p, _p, _i, _i, _ll, _i, _i, _p],
 }
 EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats',
            'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_reserved_sms', 'hcomp_init'] + list(SIGNATURES)

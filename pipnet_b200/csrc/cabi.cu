@@ -16,6 +16,7 @@
 #include "small_kernels.cuh"
 #include "desc_losses.cuh"
 #include "topk.cuh"
+#include "allreduce_mc.cuh"
 
 namespace {
 
@@ -879,6 +880,23 @@ int hcomp_debug_pair_stamps(unsigned long long* out640) {
   return 0;
 }
 #endif
+
+int hcomp_allreduce_mean_symm(float* local, float* mc, const void* peers_dev, const void* pads_dev, int rank, int world,
+                              long long n, int channel_base, int ctas, void* stream) {
+  if (world < 2 || rank < 0 || rank >= world) return fail(HCOMP_E_ARG, "all-reduce: rank %d of %d", rank, world);
+  if (n <= 0 || n % 4 != 0 || (reinterpret_cast<uintptr_t>(local) & 15) != 0)
+    return fail(HCOMP_E_ARG, "all-reduce: n=%lld floats must be a positive multiple of 4 and the buffer 16-byte aligned", n);
+  if (pads_dev == nullptr || (mc == nullptr && peers_dev == nullptr)) return fail(HCOMP_E_ARG, "all-reduce: missing signal pads / peer pointers");
+  if (ctas < 1 || ctas > 64 || world > 256) return fail(HCOMP_E_ARG, "all-reduce: ctas=%d world=%d", ctas, world);
+  hc::AllreduceParams p;
+  p.local = local; p.mc = mc;
+  p.peers = reinterpret_cast<float* const*>(peers_dev);
+  p.pads = reinterpret_cast<uint32_t* const*>(pads_dev);
+  p.rank = rank; p.world = world; p.n = n; p.channel_base = channel_base; p.scale = 1.f / float(world);
+  hc::allreduce_mean_kernel<<<ctas, 256, 0, S(stream)>>>(p);
+  HC_LAUNCH_CHECK("allreduce_mean");
+  return 0;
+}
 
 int hcomp_gemm_bf16(const void* a, const void* b, int M, int N, int K, int a_mn, int b_mn, int out_mode, int splits,
                     void* out, long long ldo, void* stream) {

@@ -247,6 +247,28 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta)
       : "memory");
 }
 
+// Publish one 32-bit word into the shared memory of CTA `cta` of the cluster: the store travels through the async proxy
+// and credits 4 bytes to the mbarrier at `bar`'s offset in THAT CTA, so a thread that observes the barrier phase
+// complete also observes the word (same guarantee as a TMA load) -- no cluster-scope fences needed.
+__device__ __forceinline__ void st_async_u32_cluster(void* dst, uint64_t* bar, uint32_t cta, uint32_t value) {
+  asm volatile(
+      "{\n\t.reg .b32 rd, rb;\n\t"
+      "mapa.shared::cluster.u32 rd, %0, %2;\n\t"
+      "mapa.shared::cluster.u32 rb, %1, %2;\n\t"
+      "st.async.shared::cluster.mbarrier::complete_tx::bytes.b32 [rd], %3, [rb];\n\t}\n"
+      ::"r"(smem_u32(dst)), "r"(smem_u32(bar)), "r"(cta), "r"(value)
+      : "memory");
+}
+// arrive + expect `bytes` of async transactions on the barrier at this offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint64_t* bar, uint32_t cta, uint32_t bytes) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.expect_tx.shared::cluster.b64 _, [ra], %2;\n\t}\n"
+      ::"r"(smem_u32(bar)), "r"(cta), "r"(bytes)
+      : "memory");
+}
+
 // TMEM -> registers: 32 lanes x 32-bit, N consecutive columns per thread (thread i <-> lane base+i).
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"

@@ -83,6 +83,77 @@ def _side():
 ASYNC_GRAD_ALLREDUCE = True
 
 
+# How the bucket is reduced.  'symm' (default when available): the bucket lives in symmetric memory (every rank's buffer
+# mapped into every peer, plus one multicast address over the NVSwitch) and the library's own kernel
+# (hcomp_allreduce_mean_symm: barrier -> in-switch reduce of my shard -> broadcast -> barrier) runs on the side stream on
+# the few SMs the dX GEMM is told to leave free.  'nccl': one NCCL all-reduce (the fallback when symmetric memory or the
+# group's peer mapping is not available, e.g. ranks on different nodes).  Env HC_GRAD_EXCHANGE=nccl forces the fallback.
+GRAD_EXCHANGE = os.environ.get('HC_GRAD_EXCHANGE', 'symm')
+SYMM_CTAS = int(os.environ.get('HC_SYMM_CTAS', '8'))          # CTAs of the all-reduce kernel = SMs reserved from the dX GEMM
+
+
+class _SymmBuffers:
+    """Two persistent symmetric-memory gradient buckets per (bucket layout, device, group): step i reduces into one while
+    `param.grad` of step i-1 may still alias the other.  Created collectively (every rank at the same point of its first
+    backward pass)."""
+
+    _cache = {}
+
+    def __init__(self, numel, device, group):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.numel = numel
+        self.padded = (numel + 3) // 4 * 4
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.bufs, self.hdls = [], []
+        for _ in range(2):
+            t = symm.empty(self.padded, dtype=torch.float32, device=device)
+            h = symm.rendezvous(t, group)
+            t.zero_()
+            self.bufs.append(t)
+            self.hdls.append(h)
+        self.turn = 0
+        h = self.hdls[0]
+        pad_words = int(h.signal_pad_size) // 4
+        if SYMM_CTAS * self.world > pad_words:
+            raise RuntimeError('signal pad too small for the all-reduce channels')
+        self.multicast = all(int(getattr(x, 'multicast_ptr', 0) or 0) != 0 for x in self.hdls)
+
+    @classmethod
+    def get(cls, numel, device, group):
+        key = (numel, str(device), id(group))
+        if key not in cls._cache:
+            cls._cache[key] = cls(numel, device, group)
+        return cls._cache[key]
+
+    def next(self):
+        self.turn ^= 1
+        return self.turn
+
+
+def _symm_buffers(numel, device):
+    """symmetric buckets for the current group or None (-> NCCL fallback); the decision is made once per layout"""
+    if GRAD_EXCHANGE != 'symm' or GRAD_ALLREDUCE_GROUP is None:
+        return None
+    key = (numel, str(device), id(GRAD_ALLREDUCE_GROUP))
+    if key in _SymmBuffers._cache:
+        return _SymmBuffers._cache[key]
+    import torch.distributed as dist
+    ok = 1
+    try:
+        sb = _SymmBuffers.get(numel, device, GRAD_ALLREDUCE_GROUP)
+    except Exception as ex:             # no symmetric memory on this system / group: every rank must fall back together
+        import warnings
+        warnings.warn(f'symmetric-memory gradient bucket unavailable ({ex!r}); using the NCCL all-reduce')
+        sb, ok = None, 0
+    flag = torch.tensor([ok], device=device, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=GRAD_ALLREDUCE_GROUP)
+    if int(flag) == 0:
+        sb = None
+    _SymmBuffers._cache[key] = sb
+    return sb
+
+
 class _GradBucket:
     def __init__(self, family, device):
         self.family = family
@@ -91,7 +162,23 @@ class _GradBucket:
             n = sum(p_.numel() for p_ in grp.params)
             self.offsets[id(grp)], self.sizes[id(grp)] = off, n
             off += n
-        self.flat = torch.zeros(off, device=device, dtype=torch.float32)
+        self.numel = off
+        self.symm = _symm_buffers(off, device)
+        self.symm_turn = None
+        if self.symm is not None:
+            # persistent bucket: make sure no live param.grad still aliases the buffer about to be cleared (gradient
+            # accumulation without zero_grad between steps), then clear it
+            self.symm_turn = self.symm.next()
+            buf = self.symm.bufs[self.symm_turn]
+            lo, hi = buf.data_ptr(), buf.data_ptr() + buf.numel() * 4
+            for grp in family:
+                for p_ in grp.params:
+                    if p_.grad is not None and lo <= p_.grad.data_ptr() < hi:
+                        p_.grad = p_.grad.clone()
+            buf.zero_()
+            self.flat = buf[:off]
+        else:
+            self.flat = torch.zeros(off, device=device, dtype=torch.float32)
         self.produced = []
         self.reduced = False
 
@@ -113,6 +200,12 @@ def _bucket_mode(grp) -> bool:
 def _bucket_segment(grp, device) -> torch.Tensor:
     """This step's gradient segment of parameter group `grp` (zero-initialised; producers write or accumulate)."""
     global _bucket
+    if _bucket is not None and _bucket.reduced:
+        # a second head forward contributed to the same loss and its backward runs after the exchange was issued: the
+        # in-flight all-reduce reads the bucket on the side stream -- writing into it now would be a race (ADVICE r1)
+        raise _cabi.HcompError('a gradient producer ran after the head\'s gradient all-reduce of this backward pass was issued '
+                               '(two head forwards in one loss?): use DistributedDataParallel or '
+                               'enable_overlapped_allreduce(fresh_grads=False) for that pattern')
     if _bucket is None:
         _bucket = _GradBucket(grp.family, device)
         torch.autograd.Variable._execution_engine.queue_callback(_bucket_finalize)
@@ -125,32 +218,54 @@ def _bucket_allreduce():
     side = _side()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
-        dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
+        if b.symm is not None:
+            sb, h = b.symm, b.symm.hdls[b.symm_turn]
+            mc = int(h.multicast_ptr) if sb.multicast else 0
+            call('hcomp_allreduce_mean_symm', ptr(sb.bufs[b.symm_turn]), C.c_void_p(mc) if mc else None,
+                 C.c_void_p(int(h.buffer_ptrs_dev)), C.c_void_p(int(h.signal_pad_ptrs_dev)), sb.rank, sb.world,
+                 C.c_longlong(sb.padded), 0, SYMM_CTAS, C.c_void_p(side.cuda_stream))
+        else:
+            dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
     b.flat.record_stream(side)
     b.reduced = True
+
+
+def collective_sms() -> int:
+    """SMs the dX GEMM leaves free while the gradient exchange is in flight"""
+    if _bucket is not None and _bucket.symm is not None:
+        return max(COLLECTIVE_SMS, SYMM_CTAS)
+    return COLLECTIVE_SMS
 
 
 def _bucket_finalize():
     """end of the backward pass: make sure the bucket was reduced, re-join the side stream, deliver param.grad"""
     global _bucket
-    b, _bucket = _bucket, None
+    b = _bucket
     if b is None:
         return
-    if not b.reduced:                       # the dW GEMM did not run in this pass (frozen prototypes): reduce now
-        _bucket = b
-        _bucket_allreduce()
-        _bucket = None
-    torch.cuda.current_stream().wait_stream(_side())
-    for grp in b.produced:
-        seg = b.segment(grp)
-        for p_, (off, numel, shape) in zip(grp.params, grp.meta):
-            if not p_.requires_grad:
-                continue
-            g = seg[off:off + numel].view(shape)
-            if p_.grad is None:
-                p_.grad = g
-            else:
-                p_.grad.add_(g)
+    try:
+        if not b.reduced:                       # the dW GEMM did not run in this pass (frozen prototypes): reduce now
+            _bucket_allreduce()
+        torch.cuda.current_stream().wait_stream(_side())
+        for grp in b.produced:
+            seg = b.segment(grp)
+            for p_, (off, numel, shape) in zip(grp.params, grp.meta):
+                if not p_.requires_grad:
+                    continue
+                g = seg[off:off + numel].view(shape)
+                if p_.grad is None:
+                    p_.grad = g
+                else:
+                    p_.grad.add_(g)
+    finally:
+        _bucket = None                          # never leave a stale bucket behind (an exception above would otherwise
+                                                # make the next backward pass write into it and deliver nothing)
+
+
+def reset_grad_bucket():
+    """Drop a half-built gradient bucket (call after an exception escaped a backward pass in bucket mode)."""
+    global _bucket
+    _bucket = None
 
 
 def _allreduce_grad_sync_(t: torch.Tensor):
@@ -350,7 +465,7 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
     if need_dx:
         dx = torch.empty(M, Cc, device=dev, dtype=torch.bfloat16)
         tok = PROFILE.start('k6_bwd_dx')
-        prev = _cabi.lib().hcomp_set_reserved_sms(COLLECTIVE_SMS) if (pending is not None or bucketed) else None
+        prev = _cabi.lib().hcomp_set_reserved_sms(collective_sms()) if (pending is not None or bucketed) else None
         try:
             call('hcomp_head_bwd_dx', ptr(dz), ptr(wpc), C.c_longlong(M), dl.P_c, Cc, ptr(dx), _stream())
         finally:

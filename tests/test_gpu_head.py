@@ -183,7 +183,7 @@ def test_fp32_accurate_mode_backward_runs():
     torch.cuda.synchronize()
     x = pb.x.clone().requires_grad_(True)
     w = {k: v.clone().requires_grad_(True) for k, v in pb.w.items()}
-    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root, softmax_tau=tau)
+    proto, pooled_ref, _, _ = ho.head_forward(x, w, pb.wc, pb.root, softmax_tau=1.0)
     masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
     ref = (pb.cat_nodes(pooled_ref) * G).sum()
     for n in pb.layout.node_names:
