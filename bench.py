@@ -302,8 +302,11 @@ def run_ours(a):
         kern_iters = max(5, min(a.steps, 20))
 
         def kernel_pass(i):
-            pooled, argmax, _al = ops.proj_softmax_pool_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, lab_k[i % 2])
-            ops.head_backward_raw(xr_k[i % 2], wp_k, wpc_k, dl, V, B, HW, net.softmax_tau, argmax, gp_k, lab_k[i % 2], ga_k)
+            sp = []
+            pooled, argmax, _al = ops.proj_softmax_pool_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, lab_k[i % 2],
+                                                            spill_out=sp)
+            ops.head_backward_raw(xr_k[i % 2], wp_k, wpc_k, dl, V, B, HW, net.softmax_tau, argmax, gp_k, lab_k[i % 2], ga_k,
+                                  spill=sp)
 
         for i in range(3):
             kernel_pass(i)

@@ -15,7 +15,12 @@
  *   K          total child logits = sum of C_n; flat logit axis, same order
  *   rows       one row per (view, location): M = V*HW rows of C channels, bf16, channels-last
  *   tiles      the padded prototype axis: 128-column tiles of equal-length node segments
- *              (int32 records of HCOMP_TILE_INTS words: {S, nseg, umma_n, dz_col, node[16], len[16], poff[16]})
+ *              (int32 records of HCOMP_TILE_INTS words:
+ *               {S, nseg, umma_n, dz_col, spill_n, spill_col0, spill_dst, 0, node[16], len[16], poff[16]})
+ *   spill      nodes whose softmax does not run in the GEMM epilogue: wide nodes (P_n > 64) and nodes moved out of a
+ *              nearly empty last tile into spare pad columns.  K1 writes their raw logits to a scratch matrix
+ *              zs[V*HW, ldz] (tile record: spill_n columns from tile column spill_col0 -> zs columns spill_dst..);
+ *              row kernels inside the same entry points finish them (forward) and produce their dZ (backward)
  *   P_pad      128 * number of tiles
  */
 #ifndef HCOMP_HEAD_H
@@ -28,7 +33,7 @@ extern "C" {
 #endif
 
 #define HCOMP_ABI_VERSION 5
-#define HCOMP_TILE_INTS 52
+#define HCOMP_TILE_INTS 56
 #define HCOMP_TILE_COLS 128
 #define HCOMP_MAX_SEGS 16
 
@@ -52,6 +57,16 @@ typedef struct hcomp_tables {
   const int8_t* anc;           /* [L,N] child label of leaf l at node n, -1 if not below n     */
   const int32_t* col_nleaves;  /* [K]   number of leaves below child column k (descendant-structured losses) */
 } hcomp_tables;
+
+/* Spill nodes of a layout (host-built, pipnet_b200/layout.py); pass NULL when the layout has none. */
+typedef struct hcomp_spill {
+  int32_t n_spill;            /* number of spill nodes                                                        */
+  int32_t ldz;                /* columns of zs (multiple of 4)                                                */
+  const int32_t* recs_host;   /* HOST [n_spill,8] {node, P_n, poff, zoff, dz_col, S class (0 = wide), dz_width, 0} */
+  float* zs;                  /* DEVICE [V*HW, ldz] raw logits: the forward writes, the backward reads        */
+  float* stats;               /* DEVICE [n_wide, V*HW, 2] row max / 1 over row sum of the wide nodes (same lifetime);
+                                 NULL without wide nodes                                                      */
+} hcomp_spill;
 
 int hcomp_abi_version(void);
 const char* hcomp_last_error(void);
@@ -107,7 +122,8 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
                                 int P_pad, int n_nodes, float tau, int precision, int outputs_zeroed,
-                                const uint8_t* desc, unsigned long long* pooled_packed, double* align_sum, void* stream);
+                                const uint8_t* desc, unsigned long long* pooled_packed, double* align_sum,
+                                const hcomp_spill* spill, void* stream);
 /* packed -> pooled fp32 [V,P] + argmax int32 [V,P] (flat h*W+w, first occurrence; pipnet/pipnet.py:24-25);
  * thresh > 0 applies the inference rule pooled < thresh -> 0 (pipnet/pipnet.py:168-169). */
 int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
@@ -125,7 +141,7 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                       int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int P_c, int n_nodes, float tau,
                       int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
-                      void* dz_bf16, void* stream);
+                      void* dz_bf16, const hcomp_spill* spill, void* stream);
 /* dX[rows,C] (bf16) = dZ[rows,P_c] * Wpc[P_c,C]  (Wpc: bf16 kernels packed on the compact axis with row_map_c). */
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,
                       void* stream);

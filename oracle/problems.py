@@ -17,10 +17,11 @@ class Problem:
     classifier weights N(1, 0.1) on each child's own prototype slice and -0.5 elsewhere
     (pipnet/pipnet.py:1026, :1235-1248), features N(0,1) rounded to bf16 (the GEMM operand type)."""
 
-    def __init__(self, tree, C, H, B, *, seed=0, num_features=0, per_child=0, paired=True, V=None, feat_scale=1.0,
-                 round_bf16=True, root=None):
+    def __init__(self, tree, C, H, B, *, seed=0, num_features=0, per_child=0, per_desc=0, paired=True, V=None,
+                 feat_scale=1.0, round_bf16=True, root=None):
         # `root`: a ready tree whose internal nodes already carry num_protos (arbitrary per-node counts)
-        self.root = root if root is not None else make_tree(tree, num_features=num_features, per_child=per_child)
+        self.root = root if root is not None else make_tree(tree, num_features=num_features, per_child=per_child,
+                                                            per_desc=per_desc)
         self.layout = build_layout(self.root)
         L = self.layout
         g = torch.Generator().manual_seed(seed)

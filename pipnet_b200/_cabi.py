@@ -29,6 +29,12 @@ class Tables(C.Structure):
     ]
 
 
+class Spill(C.Structure):
+    """mirror of `struct hcomp_spill`"""
+    _fields_ = [('n_spill', C.c_int32), ('ldz', C.c_int32), ('recs_host', C.c_void_p), ('zs', C.c_void_p),
+                ('stats', C.c_void_p)]
+
+
 _p, _i, _f, _ll = C.c_void_p, C.c_int, C.c_float, C.c_longlong
 _T = C.POINTER(Tables)
 
@@ -40,10 +46,10 @@ SIGNATURES = {
     'hcomp_label_tables': [_p, _T, _i, _i, _p, _p, _p, _p],
     'hcomp_split3_f32': [_p, _p, _ll, _p],
     'hcomp_pack_weights_split3': [_p, _p, _i, _i, _p, _p],
-    'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p],
+    'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p],
     'hcomp_unpack_pool': [_p, _ll, _f, _p, _p, _p],
     'hcomp_align_finalize': [_p, _p, _i, _i, _p, _p],
-    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_head_bwd_dx': [_p, _p, _ll, _i, _i, _p, _p],
     'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p],
     'hcomp_classifier_fwd': [_p, _p, _p, _T, _i, _p, _p],

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, 'csrc', 'cabi.cu')
 OUT = os.path.join(HERE, 'libhcomp_head.so')
-DEPS = [os.path.join(HERE, 'csrc', f) for f in ('cabi.cu', 'ptx.cuh', 'head_pair.cuh', 'gemm_tc.cuh', 'gemm2_tc.cuh', 'small_kernels.cuh', 'desc_losses.cuh', 'topk.cuh')]
+DEPS = sorted(os.path.join(HERE, 'csrc', f) for f in os.listdir(os.path.join(HERE, 'csrc')) if f.endswith(('.cu', '.cuh')))
 DEPS.append(os.path.join(os.path.dirname(HERE), 'include', 'hcomp_head.h'))
 
 NVCC_FLAGS = ['-shared', '-Xcompiler', '-fPIC', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',

@@ -17,6 +17,7 @@
 #include "desc_losses.cuh"
 #include "topk.cuh"
 #include "allreduce_mc.cuh"
+#include "spill_nodes.cuh"
 
 namespace {
 
@@ -257,35 +258,49 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   p.inv_tau = 1.f / tau;
   p.inv_HW = 1.f / float(HW);
   p.tiles = tiles_dev;
+  int last_fused_global = -1;             // the last tile with segments owns the pitch padding of the compact dZ axis
+  for (int i = 0; i < n_tiles; ++i)
+    if (tiles_host[(size_t)i * hc::TILE_INTS + 1] > 0) last_fused_global = i;
   int t = 0;
   while (t < n_tiles) {
     const int seg = tiles_host[(size_t)t * hc::TILE_INTS];
     int e = t;
     while (e < n_tiles && tiles_host[(size_t)e * hc::TILE_INTS] == seg) {
       const int32_t* rec = tiles_host + (size_t)e * hc::TILE_INTS;
-      if (rec[1] <= 0 || rec[1] * seg > hc::TILE_N || rec[2] % 16 != 0 || rec[2] < rec[1] * seg || rec[2] > hc::TILE_N)
+      if (rec[1] < 0 || rec[1] * seg > hc::TILE_N || rec[2] % 16 != 0 || rec[2] < rec[1] * seg || rec[2] > hc::TILE_N ||
+          rec[4] < 0 || rec[4] % 4 != 0 || (rec[4] > 0 && (rec[5] % 4 != 0 || rec[5] < rec[1] * seg || rec[5] + rec[4] > rec[2])) ||
+          (rec[1] == 0 && rec[4] == 0))
         return fail(HCOMP_E_ARG, "malformed tile record %d", e);
+      if (!BWD && rec[4] > 0 && (p.zs == nullptr || rec[6] < 0 || rec[6] + rec[4] > p.ldz))
+        return fail(HCOMP_E_ARG, "tile %d spills %d columns but the scratch matrix is missing or too narrow", e, rec[4]);
       ++e;
     }
     p.tile_begin = t;
     p.num_tiles = e - t;
     if (BWD) {
+      // dedicated spill tiles (no segments) sit at the end of the group: their dZ comes from the row kernels, the
+      // recompute GEMM skips them
+      while (p.num_tiles > 0 && tiles_host[(size_t)(t + p.num_tiles - 1) * hc::TILE_INTS + 1] == 0) --p.num_tiles;
+      if (p.num_tiles == 0) { t = e; continue; }
+    }
+    const int e_fused = t + p.num_tiles;
+    if (BWD) {
       // compact dZ columns of this class: full tiles (all segments used) are contiguous at one pitch, then at most one
       // partial tile; widths are the used columns rounded up to 8 (layout.py)
       const int per_tile = hc::TILE_N / seg;
-      const int32_t* last = tiles_host + (size_t)(e - 1) * hc::TILE_INTS;
+      const int32_t* last = tiles_host + (size_t)(e_fused - 1) * hc::TILE_INTS;
       p.w_full = ((per_tile * seg + 7) / 8) * 8;
       // the last tile of the class is "partial" (own store map) if it has fewer segments, or if it is the globally last
       // tile and owns the alignment padding of the dZ pitch (layout.py rounds P_c up to 64 columns when that fits)
       int last_w = ((last[1] * seg + 7) / 8) * 8;
-      if (e == n_tiles) last_w = p.P_c - last[3];
+      if (last_fused_global == e_fused - 1) last_w = p.P_c - last[3];
       const bool has_partial = last_w != p.w_full;
       p.n_full_tiles = p.num_tiles - (has_partial ? 1 : 0);
       p.w_partial = has_partial ? last_w : 0;
       if (has_partial && (last_w <= 0 || last_w > hc::TILE_N || last_w % 8 != 0 || last_w < last[1] * seg))
         return fail(HCOMP_E_ARG, "last tile of class %d: compact width %d", seg, last_w);
       const int c_full = tiles_host[(size_t)t * hc::TILE_INTS + 3];
-      for (int i = t; i < e; ++i) {
+      for (int i = t; i < e_fused; ++i) {
         const int want = (i - t) < p.n_full_tiles ? c_full + (i - t) * p.w_full : c_full + p.n_full_tiles * p.w_full;
         if (tiles_host[(size_t)i * hc::TILE_INTS + 3] != want || want % 8 != 0)
           return fail(HCOMP_E_ARG, "tile %d: compact dZ column %d, expected %d", i, tiles_host[(size_t)i * hc::TILE_INTS + 3], want);
@@ -394,6 +409,63 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   return fail(HCOMP_E_ARG, "GEMM variant (a_mn=%d b_mn=%d out=%d) not instantiated", int(a_mn), int(b_mn), out_mode);
 }
 
+// Row kernels of the spill nodes (csrc/spill_nodes.cuh): forward = softmax / max-pool / align from the raw logits K1 wrote
+// to zs; backward = their dZ columns (no GEMM recompute).
+template <bool BWD>
+int run_spill(const hcomp_spill* sp, const hc::SpillParams& base, int V, cudaStream_t st) {
+  if (sp == nullptr || sp->n_spill <= 0) return 0;
+  if (sp->recs_host == nullptr || sp->zs == nullptr || sp->ldz <= 0 || sp->ldz % 4 != 0)
+    return fail(HCOMP_E_ARG, "spill nodes: records / scratch matrix missing (ldz=%d)", sp->ldz);
+  int wide_idx = 0;
+  for (int i = 0; i < sp->n_spill; ++i) {
+    const int32_t* r = sp->recs_host + (size_t)i * 8;
+    hc::SpillParams p = base;
+    p.zs = sp->zs; p.ldz = sp->ldz;
+    p.node = r[0]; p.P_n = r[1]; p.poff = r[2]; p.zoff = r[3]; p.dz_col = r[4]; p.dz_width = r[6];
+    const int cls = r[5];
+    if (p.P_n <= 0 || p.zoff < 0 || p.zoff + p.P_n > p.ldz || p.node < 0 || p.node >= p.n_nodes || p.poff < 0 || p.poff + p.P_n > p.P)
+      return fail(HCOMP_E_ARG, "malformed spill record %d", i);
+    if (BWD && (p.dz_col < 0 || p.dz_col % 8 != 0 || p.dz_width < p.P_n || p.dz_width % 2 != 0 || p.dz_col + p.dz_width > p.P_c))
+      return fail(HCOMP_E_ARG, "spill record %d: dZ columns [%d, +%d) outside P_c=%d", i, p.dz_col, p.dz_width, p.P_c);
+    if (cls == 0) {                       // wide node
+      if (sp->stats == nullptr) return fail(HCOMP_E_ARG, "spill nodes: statistics workspace missing");
+      p.stats = sp->stats + (size_t)wide_idx * 2 * (size_t)p.M;
+      ++wide_idx;
+      if (!BWD) {
+        hc::spill_wide_stats_kernel<<<cdiv(p.halfM, 8), 256, 0, st>>>(p);
+        HC_LAUNCH_CHECK("spill_wide_stats");
+        hc::spill_wide_pool_kernel<<<dim3(cdiv(p.P_n, 128), V), 128, 0, st>>>(p);
+        HC_LAUNCH_CHECK("spill_wide_pool");
+      } else {
+        hc::spill_wide_bwd_kernel<<<cdiv(p.halfM, 8), 256, 0, st>>>(p);
+        HC_LAUNCH_CHECK("spill_wide_bwd");
+      }
+      continue;
+    }
+    if (p.P_n > cls) return fail(HCOMP_E_ARG, "spill record %d: %d prototypes in class %d", i, p.P_n, cls);
+#define HC_SPILL_CASE(SEG)                                                                    \
+    case SEG:                                                                                 \
+      if (!BWD) hc::spill_narrow_fwd_kernel<SEG><<<cdiv(cdiv(p.halfM, 32), 8), 256, 0, st>>>(p); \
+      else hc::spill_narrow_bwd_kernel<SEG><<<cdiv(p.halfM, 256), 256, 0, st>>>(p);           \
+      break;
+    switch (cls) {
+      HC_SPILL_CASE(8) HC_SPILL_CASE(16) HC_SPILL_CASE(20) HC_SPILL_CASE(32) HC_SPILL_CASE(40) HC_SPILL_CASE(64)
+      default: return fail(HCOMP_E_ARG, "spill record %d: unsupported segment class %d", i, cls);
+    }
+#undef HC_SPILL_CASE
+    HC_LAUNCH_CHECK(BWD ? "spill_narrow_bwd" : "spill_narrow_fwd");
+  }
+  return 0;
+}
+
+hc::SpillParams spill_base(int V, int V_first, int HW, int P, int n_nodes, float tau) {
+  hc::SpillParams q{};
+  q.M = V * HW; q.halfM = V_first * HW; q.rowsB = q.M - q.halfM; q.HW = HW; q.P = P; q.n_nodes = n_nodes;
+  q.imgs_first = V_first;
+  q.scale_log2 = 1.4426950408889634f / tau; q.inv_tau = 1.f / tau; q.inv_HW = 1.f / float(HW);
+  return q;
+}
+
 inline int blocks(long long n, int bs) { return int((n + bs - 1) / bs); }
 
 }  // namespace
@@ -487,17 +559,24 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
                                 int P_pad, int n_nodes, float tau, int precision, int outputs_zeroed,
-                                const uint8_t* desc, unsigned long long* pooled_packed, double* align_sum, void* stream) {
+                                const uint8_t* desc, unsigned long long* pooled_packed, double* align_sum,
+                                const hcomp_spill* spill, void* stream) {
   hc::HeadParams p{};
   p.pooled_packed = pooled_packed;
   p.align_sum = align_sum;
   p.desc = (align_sum != nullptr) ? desc : nullptr;
+  if (spill != nullptr && spill->n_spill > 0) { p.zs = spill->zs; p.ldz = spill->ldz; }
   if (!outputs_zeroed) {
     HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
     if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
   }
-  return run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
-                         precision, p, S(stream));
+  if (int e = run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
+                              precision, p, S(stream)))
+    return e;
+  if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
+  hc::SpillParams q = spill_base(V, V_first, HW, P, n_nodes, tau);
+  q.pooled_packed = pooled_packed; q.align_sum = align_sum; q.desc = p.desc;
+  return run_spill<false>(spill, q, V, S(stream));
 }
 
 int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
@@ -517,7 +596,7 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                       int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int P_c, int n_nodes, float tau,
                       int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
-                      void* dz_bf16, void* stream) {
+                      void* dz_bf16, const hcomp_spill* spill, void* stream) {
   if (P_c <= 0 || P_c % 8 != 0 || P_c > P_pad) return fail(HCOMP_E_ARG, "P_c=%d must be a positive multiple of 8, <= P_pad", P_c);
   const long long n = (long long)V * P;
   hc::HeadParams p{};
@@ -537,8 +616,12 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                                                                reinterpret_cast<int2*>(scat_ws));
   HC_LAUNCH_CHECK("make_scat");
   if (sb) HC_JOIN(sb, S(stream));
-  return run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
-                        precision, p, S(stream));
+  if (int e = run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
+                             precision, p, S(stream)))
+    return e;
+  hc::SpillParams q = spill_base(V, V_first, HW, P, n_nodes, tau);
+  q.scat = p.scat; q.coef_align = p.coef_align; q.dz = p.dz; q.P_c = P_c;
+  return run_spill<true>(spill, q, V, S(stream));
 }
 
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,

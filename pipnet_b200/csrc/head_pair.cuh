@@ -71,7 +71,11 @@ constexpr int TILE_N = 128;          // prototype columns per tile (TMEM columns
 constexpr int TILE_M = 128;          // locations per tile
 constexpr int KBLK = 64;             // bf16 elements per k-block (one 128-byte swizzle row)
 constexpr int MAX_SEGS = 16;         // node segments per tile (S >= 8)
-constexpr int TILE_INTS = 4 + 3 * MAX_SEGS;   // {S, nseg, umma_n, 0, node[16], len[16], poff[16]}
+// tile record: {S, nseg, umma_n, dz_col, spill_n, spill_col0, spill_dst, 0, node[16], len[16], poff[16]}
+//   spill_*: `spill_n` columns of the tile starting at column `spill_col0` belong to SPILL nodes (layout.py): their raw
+//   logits are written to columns [spill_dst, +spill_n) of the scratch matrix and finished by csrc/spill_nodes.cuh
+constexpr int TILE_HDR = 8;
+constexpr int TILE_INTS = TILE_HDR + 3 * MAX_SEGS;
 constexpr int PAIR_STAGE_BYTES = 3 * TILE_M * KBLK * 2;   // A1 + A2 + W = 48 KB
 constexpr int PAIR_MAX_STAGES = 5;
 constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both views' bf16 dZ tiles staged for TMA stores (64 KB)
@@ -110,6 +114,8 @@ struct HeadParams {
   float inv_HW;             // 1 / HW: row -> (image, location) without an integer division per item
   const int32_t* tiles;
   // forward
+  float* zs;                           // [M, ldz] raw logits of the spill columns (fp32); may be null when no tile spills
+  int ldz;
   unsigned long long* pooled_packed;   // [V,P]  (float bits << 32) | (0xFFFFFFFF - flat location)
   double* align_sum;                   // [n_nodes] sum over masked rows of -log(ip + 1e-12); may be null
   const uint8_t* desc;                 // [imgs_first, n_nodes] 1 if image's leaf is below node; null -> no align
@@ -597,6 +603,12 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       const int mt = mg * CL + crank;
       const int32_t* tile = p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS;
       const int nseg = __ldg(tile + 1);
+      [[maybe_unused]] int spill_n = 0, spill_c0 = 0, spill_dst = 0;
+      if constexpr (!BWD) {
+        spill_n = __ldg(tile + 4);
+        spill_c0 = __ldg(tile + 5);
+        spill_dst = __ldg(tile + 6);
+      }
 
       const int row_a = mt * TILE_M + quad * 32 + lane;
       const bool valid_a = row_a < p.halfM;
@@ -626,9 +638,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         const int j = PARTS * js + part;
         if (j < NSEG_MAX && j < nseg) {
           my_cnt = js + 1;
-          seg_node[js] = __ldg(tile + 4 + j);
-          seg_len[js] = __ldg(tile + 4 + MAX_SEGS + j);
-          seg_poff[js] = __ldg(tile + 4 + 2 * MAX_SEGS + j);
+          seg_node[js] = __ldg(tile + TILE_HDR + j);
+          seg_len[js] = __ldg(tile + TILE_HDR + MAX_SEGS + j);
+          seg_poff[js] = __ldg(tile + TILE_HDR + 2 * MAX_SEGS + j);
         }
       }
       if (valid_a && valid_b && v_a < imgs_first) {
@@ -681,6 +693,21 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       };
       if constexpr (BWD) {
         if (my_cnt == 0) wait_staging();     // warps without a segment still take part in the barrier
+      } else {
+        // spill columns: raw logits of both views -> scratch matrix, four columns (16 bytes) per step; the groups of a
+        // tile are dealt round-robin to the warps of the lane quadrant.  Before any TMEM release of this warp.
+        if (spill_n > 0) {
+          float* z1 = p.zs + (size_t)row_a * p.ldz + spill_dst;
+          float* z2 = p.zs + (size_t)(p.halfM + row_a) * p.ldz + spill_dst;
+          for (int g4 = part; 4 * g4 < spill_n; g4 += PARTS) {
+            uint32_t q1[4], q2[4];
+            tmem_ld4(t0 + spill_c0 + 4 * g4, q1);
+            tmem_ld4(t0 + TILE_N + spill_c0 + 4 * g4, q2);
+            tmem_ld_wait();
+            if (valid_a) *reinterpret_cast<uint4*>(z1 + 4 * g4) = make_uint4(q1[0], q1[1], q1[2], q1[3]);
+            if (valid_b) *reinterpret_cast<uint4*>(z2 + 4 * g4) = make_uint4(q2[0], q2[1], q2[2], q2[3]);
+          }
+        }
       }
       auto release_stage = [&]() {     // accumulators of this warp are in registers: hand the TMEM stage back
         tc_fence_before();

@@ -321,6 +321,22 @@ class DeviceLayout:
                              self.path_col.data_ptr(), self.anc.data_ptr(), self.col_nleaves.data_ptr())
         self.tref = C.byref(self.tables)
         self.n_tiles = int(L.tiles.shape[0])
+        # spill nodes (layout.py): host records for the C ABI; the scratch matrices are per call
+        self.spill_host = torch.from_numpy(np.ascontiguousarray(L.spill)).to(torch.int32)
+        self.n_spill = int(L.spill.shape[0])
+        self.n_wide = int((L.spill[:, 5] == 0).sum()) if self.n_spill else 0
+        self.P_s = int(L.P_s)
+
+    def spill_buffers(self, M, device, zs=None, stats=None):
+        """(ctypes hcomp_spill or None, zs, stats): the raw-logit scratch matrix of the spill nodes [M, P_s] and the
+        row statistics of the wide ones [n_wide, M, 2]; allocated by the forward, handed back for the backward"""
+        if self.n_spill == 0:
+            return None, None, None
+        if zs is None:
+            zs = torch.empty(M, self.P_s, device=device, dtype=torch.float32)
+            stats = torch.empty(max(self.n_wide, 1), M, 2, device=device, dtype=torch.float32)
+        sp = _cabi.Spill(self.n_spill, self.P_s, self.spill_host.data_ptr(), zs.data_ptr(), stats.data_ptr())
+        return sp, zs, stats
 
     # convenient aliases
     @property
@@ -409,16 +425,20 @@ class LabelTables:
 
 # --------------------------------------------------------------------------- raw kernels (no autograd)
 def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, labels: Optional[LabelTables], thresh=0.0,
-                          precision=PREC_BF16):
+                          precision=PREC_BF16, spill_out: Optional[list] = None):
+    """spill_out: a list that receives (zs, stats) of the spill nodes (needed again by `head_backward_raw`)"""
     Cc = x_rows.shape[1]
     dev = x_rows.device
+    sp, zs, stats = dl.spill_buffers(V * HW, dev)
+    if spill_out is not None:
+        spill_out[:] = [zs, stats]
     # the packed max table and the align accumulators are merged into with atomics: cleared here (outputs_zeroed = 1)
     packed = torch.zeros(V * dl.P, device=dev, dtype=torch.int64)
     align_sum = torch.zeros(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
     tok = PROFILE.start('k1_proj_softmax_pool_fwd')
     call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
          HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), 1, ptr(labels.desc) if labels is not None else None,
-         ptr(packed), ptr(align_sum), _stream())
+         ptr(packed), ptr(align_sum), C.byref(sp) if sp is not None else None, _stream())
     PROFILE.stop(tok)
     pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)
     argmax = torch.empty(V, dl.P, device=dev, dtype=torch.int32)
@@ -431,10 +451,17 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
 
 
 def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
-                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None, dz_out=None):
+                      pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None, dz_out=None,
+                      spill=None):
+    """spill: (zs, stats) the forward produced for the layout's spill nodes (required when it has any)"""
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
+    sp = None
+    if dl.n_spill:
+        if spill is None or spill[0] is None:
+            raise _cabi.HcompError('this layout has spill nodes: pass the (zs, stats) buffers of the forward')
+        sp, _zs, _st = dl.spill_buffers(M, dev, spill[0], spill[1])
     # compact column axis (layout.row_map_c); `dz_out` lets tests supply a guarded buffer
     dz = dz_out if dz_out is not None else torch.empty(M, dl.P_c, device=dev, dtype=torch.bfloat16)
     assert dz.shape == (M, dl.P_c) and dz.dtype == torch.bfloat16 and dz.is_contiguous()
@@ -445,7 +472,8 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
     call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
          dl.P, dl.P_pad, dl.P_c, dl.N, float(tau), int(precision), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
          ptr(labels.desc) if use_align else None, ptr(labels.n_desc) if use_align else None,
-         ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), _stream())
+         ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), C.byref(sp) if sp is not None else None,
+         _stream())
     PROFILE.stop(tok)
     dx = dw = None
     pending = None
@@ -504,7 +532,9 @@ class HeadProjPool(torch.autograd.Function):
         else:
             x_rows = feature_rows(features.detach())
         wp, wpc = pack_weights(w_flat.detach().contiguous(), dl, precision)
-        pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision)
+        spill = []
+        pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision, spill)
+        ctx.spill = spill                      # raw logits / row statistics of the spill nodes (None, None without any)
         ctx.dl, ctx.geom, ctx.labels, ctx.thresh, ctx.precision = dl, (V, V_first, H, W, Cc, tau), labels, thresh, precision
         ctx.w_group = getattr(w_flat, '_hc_group', None)
         ctx.set_materialize_grads(False)      # unused outputs (argmax, align without the loss) get None, not zero fills
@@ -528,7 +558,7 @@ class HeadProjPool(torch.autograd.Function):
             g_align = g_align.contiguous().float()
         dx, dw, _ = head_backward_raw(x_rows, wp, wpc, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
                                       pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw,
-                                      precision=ctx.precision, w_group=ctx.w_group)
+                                      precision=ctx.precision, w_group=ctx.w_group, spill=ctx.spill)
         d_feat = None
         if need_dx:
             dtype, _cl = ctx.feat_meta

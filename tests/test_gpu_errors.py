@@ -45,7 +45,7 @@ def test_bad_arguments_return_error_codes(bad):
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     with pytest.raises(HcompError) as ei:
         call('hcomp_proj_softmax_pool_fwd', ptr(xr), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, kw['V'],
-             kw['V_first'], kw['HW'], kw['C'], dl.P, kw['P_pad'], dl.N, float(kw['tau']), 0, 1, None, ptr(packed), None, stream)
+             kw['V_first'], kw['HW'], kw['C'], dl.P, kw['P_pad'], dl.N, float(kw['tau']), 0, 1, None, ptr(packed), None, None, stream)
     assert 'failed (-1)' in str(ei.value) and len(_cabi.lib().hcomp_last_error()) > 0
     torch.cuda.synchronize()                                  # the context is still healthy
     pooled, argmax, _ = ops.proj_softmax_pool_raw(xr, wp, dl, V, pb.V_first, HW, 1.0, None)
@@ -62,12 +62,12 @@ def test_unknown_precision_and_segment_class():
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     with pytest.raises(HcompError):
         call('hcomp_proj_softmax_pool_fwd', ptr(xr), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, pb.V_first,
-             HW, pb.C, dl.P, dl.P_pad, dl.N, 1.0, 7, 1, None, ptr(packed), None, stream)
+             HW, pb.C, dl.P, dl.P_pad, dl.N, 1.0, 7, 1, None, ptr(packed), None, None, stream)
     tiles = dl.tiles_host.clone()
     tiles[0, 0] = 24                                          # not an instantiated segment class
     with pytest.raises(HcompError):
         call('hcomp_proj_softmax_pool_fwd', ptr(xr), ptr(wp), ptr(tiles), ptr(dl.tiles_dev), dl.n_tiles, V, pb.V_first,
-             HW, pb.C, dl.P, dl.P_pad, dl.N, 1.0, 0, 1, None, ptr(packed), None, stream)
+             HW, pb.C, dl.P, dl.P_pad, dl.N, 1.0, 0, 1, None, ptr(packed), None, None, stream)
 
 
 @pytest.mark.parametrize("labels", ["all_same", "single_pair"])

@@ -26,6 +26,11 @@ FWD_CASES = [
     ("cub27", 768, 26, 2, dict(num_features=20)),        # real ConvNeXt-26 geometry, image straddles tiles
     ("cub27", 128, 7, 3, dict(per_child=20)),            # recipe B: P_n = 20 / 40 / 60 -> classes 20, 40 and 64
     ("synth12:3", 64, 6, 4, dict(per_child=28)),         # P_n = 56: masked tail inside the 64 class
+    # spill nodes (layout.py): wide nodes (P_n > 64) on dedicated tiles, finished by the row kernels
+    ("cub27", 64, 6, 3, dict(per_child=30)),             # 3-child node: 90 prototypes, beside fused 30 / 60 nodes
+    ("cub27", 96, 7, 2, dict(per_child=40)),             # every node wide (80 / 120): no fused tile at all
+    ("cub08", 64, 6, 3, dict(per_desc=20)),              # num_protos_per_descendant: P_n = 20 x leaves below (up to 160)
+    ("cub27", 768, 26, 1, dict(per_child=20)),           # recipe B at ConvNeXt-26 geometry: the 60-prototype node rides
 ]
 
 
@@ -95,6 +100,9 @@ BWD_CASES = [
     ("cub27", 768, 26, 1, dict(num_features=20)),
     ("cub27", 128, 7, 3, dict(per_child=20)),
     ("synth12:3", 64, 6, 4, dict(per_child=28)),
+    ("cub27", 64, 6, 3, dict(per_child=30)),             # wide node (90 prototypes) beside fused ones
+    ("cub27", 96, 7, 2, dict(per_child=40)),             # all nodes wide
+    ("cub08", 64, 6, 3, dict(per_desc=20)),              # P_n up to 160
 ]
 
 
@@ -211,13 +219,14 @@ def test_dz_store_writes_exactly_its_buffer(case):
     xr = ops.feature_rows(pb.features('cuda'))
     wp, wpc = ops.pack_weights(pb.w_flat('cuda'), dl)
     labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
-    pooled, argmax, _ = ops.proj_softmax_pool_raw(xr, wp, dl, V, pb.V_first, HW, 1.0, labels)
+    sp = []
+    pooled, argmax, _ = ops.proj_softmax_pool_raw(xr, wp, dl, V, pb.V_first, HW, 1.0, labels, spill_out=sp)
     g = torch.Generator(device='cuda').manual_seed(1)
     gp = torch.randn(V, dl.P, device='cuda', generator=g)
     ga = torch.full((dl.N,), 0.3, device='cuda')
     guard = 256
     big = torch.full((M + guard, dl.P_c), float('nan'), device='cuda', dtype=torch.bfloat16)
-    ops.head_backward_raw(xr, wp, wpc, dl, V, pb.V_first, HW, 1.0, argmax, gp, labels, ga, dz_out=big[:M])
+    ops.head_backward_raw(xr, wp, wpc, dl, V, pb.V_first, HW, 1.0, argmax, gp, labels, ga, dz_out=big[:M], spill=sp)
     torch.cuda.synchronize()
     inside, outside = big[:M].float(), big[M:].float()
     assert not torch.isnan(inside).any(), f"{int(torch.isnan(inside).sum())} dZ elements were never written"

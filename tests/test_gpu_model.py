@@ -19,7 +19,8 @@ from pipnet_b200.fixtures import IdentityBackbone, make_args, build_net
 PHASES = [("pretrain", True, False), ("train", False, False), ("finetune", False, True)]
 CASES = [("cub08", 64, 6, 4, dict(num_features=20)), ("cub27", 96, 6, 6, dict(num_protos_per_child=10, num_features=0)),
          ("cub18", 128, 7, 5, dict(num_features=12)),
-         ("cub27", 64, 6, 5, dict(num_protos_per_child=20, num_features=0))]     # recipe B: P_n up to 60
+         ("cub27", 64, 6, 5, dict(num_protos_per_child=20, num_features=0)),     # recipe B: P_n up to 60
+         ("cub27", 128, 6, 4, dict(num_protos_per_child=30, num_features=0))]    # a 90-prototype (wide, spill) node
 
 
 # --softmax values the reference parses (pipnet/pipnet.py:130-136): "y|1" (shipped scripts), "y|2", and a bare "y" = 0.2
@@ -127,10 +128,8 @@ def test_unsupported_variants_raise():
     pp.base_architecture_to_features['identity'] = lambda pretrained=False: IdentityBackbone(64)
     with pytest.raises(Exception):
         pp.get_network(8, make_args(unitconv2d='y'), root=root)
-    root90 = make_tree("cub27", per_child=30)      # the 3-child node gets 90 prototypes > 64
     with pytest.raises(Exception):
-        feats, add_on, pool, cl, k = pp.get_network(27, make_args(num_protos_per_child=30, num_features=0), root=root90)
-        pp.PIPNet(27, k, feats, make_args(num_protos_per_child=30, num_features=0), add_on, pool, cl, 25, root90)
+        pp.get_network(8, make_args(add_on_bias=True), root=root)
 
 
 @pytest.mark.parametrize("mode", ["leave_out", "mask", "both"])

@@ -44,39 +44,79 @@ def test_tree_fixture_shapes():
     assert max(n.num_children() for n in get_tree("cub27").nodes_with_children()) == 3
 
 
+def _check_layout(L, nodes):
+    """invariants of the padded / compact / spill axes that the kernels and run_pair rely on"""
+    H = lay.TILE_INTS - 3 * lay.MAX_SEGS          # header words of a tile record
+    assert L.P == sum(n.num_protos for n in nodes)
+    assert L.P_pad == 128 * L.tiles.shape[0]
+    used = L.row_map[L.row_map >= 0]
+    assert sorted(used.tolist()) == list(range(L.P))          # every prototype exactly once on the padded axis
+    classes = [int(t[0]) for t in L.tiles]
+    assert classes == sorted(classes)                          # one launch per class
+    spill_nodes = {int(r[0]): r for r in L.spill}
+    n_spill_cols = 0
+    # spill block of the compact axis first: one 8-column-rounded block per spill node
+    col = 0
+    for r in L.spill:
+        ni, pn, po, zoff, dzc, cls, dzw = (int(x) for x in r[:7])
+        assert pn == nodes[ni].num_protos and po == int(L.proto_off[ni]) and dzc == col and dzc % 8 == 0
+        assert dzw >= (pn + 7) // 8 * 8 and dzw % 8 == 0
+        assert (cls == 0) == (pn > 64) and (cls == 0 or cls == lay.seg_class(pn))
+        assert L.row_map_c[col:col + pn].tolist() == list(range(po, po + pn)) and (L.row_map_c[col + pn:col + dzw] == -1).all()
+        assert 0 <= zoff and zoff + pn <= L.P_s and (cls == 0 or zoff % 4 == 0)
+        col += dzw
+    fused = [t for t, rec in enumerate(L.tiles) if int(rec[1]) > 0]
+    for t, rec in enumerate(L.tiles):
+        S, nseg, umma_n, dz_col, sp_n, sp_c0, sp_dst = (int(x) for x in rec[:7])
+        assert S in lay.SEG_CLASSES and 0 <= nseg <= 128 // S and umma_n % 16 == 0 and umma_n <= 128
+        assert sp_n % 4 == 0 and nseg * S <= umma_n and (sp_n == 0 or (sp_c0 % 4 == 0 and sp_c0 >= nseg * S and sp_c0 + sp_n <= umma_n))
+        assert nseg > 0 or sp_n > 0
+        for j in range(nseg):
+            ni, ln, po = int(rec[H + j]), int(rec[H + 16 + j]), int(rec[H + 32 + j])
+            assert ni not in spill_nodes and lay.seg_class(nodes[ni].num_protos) == S
+            assert ln == nodes[ni].num_protos <= S and po == int(L.proto_off[ni])
+            assert L.row_map[t * 128 + j * S: t * 128 + j * S + ln].tolist() == list(range(po, po + ln))
+        if sp_n:
+            # the spill columns of the tile carry exactly the prototypes whose logits land in Zs[sp_dst, +sp_n)
+            assert 0 <= sp_dst and sp_dst + sp_n <= L.P_s
+            n_spill_cols += sp_n
+            for c in range(sp_n):
+                proto = int(L.row_map[t * 128 + sp_c0 + c])
+                owner = [r for r in L.spill if int(r[3]) <= sp_dst + c < int(r[3]) + int(r[1])]
+                assert (proto == int(owner[0][2]) + sp_dst + c - int(owner[0][3])) if owner else proto == -1
+        if nseg > 0:
+            width = (nseg * S + 7) // 8 * 8
+            assert dz_col == col and dz_col % 8 == 0
+            assert L.row_map_c[col:col + nseg * S].tolist() == L.row_map[t * 128: t * 128 + nseg * S].tolist()
+            assert (L.row_map_c[col + nseg * S:col + width] == -1).all()
+            same = [i for i in fused if int(L.tiles[i][0]) == S]
+            if t != same[-1]:
+                assert nseg == 128 // S      # within a class only the LAST fused tile may be partial
+            col += width
+        else:
+            assert t > (fused[-1] if fused else -1)      # dedicated spill tiles come last
+    assert n_spill_cols >= sum(int(r[1]) for r in L.spill)
+    assert L.P_c % 8 == 0 and col <= L.P_c < col + 64 and (L.row_map_c[col:] == -1).all()
+    if fused:
+        last_w = L.P_c - int(L.tiles[fused[-1]][3])
+        assert 0 < last_w <= 128
+        if L.P_c % 64:
+            assert L.P_c == col and (col - int(L.tiles[fused[-1]][3])) + (-col) % 64 > 128
+    else:
+        assert L.P_c % 64 == 0
+    assert sorted(L.row_map_c[L.row_map_c >= 0].tolist()) == list(range(L.P))
+    assert L.P_s % 4 == 0
+
+
 @pytest.mark.parametrize("tree,kw", [("cub27", dict(num_features=20)), ("cub08", dict(per_child=20)),
-                                     ("cub18", dict(num_features=12)), ("synth190", dict(num_features=20))])
+                                     ("cub18", dict(num_features=12)), ("synth190", dict(num_features=20)),
+                                     ("cub27", dict(per_child=40)), ("cub08", dict(per_desc=20)), ("cub27", dict(per_child=20))])
 def test_layout_tables(tree, kw):
     root = make_tree(tree, **kw)
     L = lay.build_layout(root)
     nodes = root.nodes_with_children()
     assert L.P == sum(n.num_protos for n in nodes) and L.K == sum(n.num_children() for n in nodes)
-    assert L.P_pad == 128 * L.tiles.shape[0]
-    # every flat prototype appears exactly once on the padded axis, at segment j*S + i of its tile
-    used = L.row_map[L.row_map >= 0]
-    assert sorted(used.tolist()) == list(range(L.P))
-    for t, rec in enumerate(L.tiles):
-        S, nseg, umma_n = int(rec[0]), int(rec[1]), int(rec[2])
-        assert S in lay.SEG_CLASSES and 0 < nseg <= 128 // S and umma_n % 16 == 0 and nseg * S <= umma_n <= 128
-        for j in range(nseg):
-            ni, ln, po = int(rec[4 + j]), int(rec[4 + 16 + j]), int(rec[4 + 32 + j])
-            assert ln == nodes[ni].num_protos <= S and po == L.proto_off[ni]
-            assert L.row_map[t * 128 + j * S: t * 128 + j * S + ln].tolist() == list(range(po, po + ln))
-    assert (np.diff(L.tiles[:, 0]) >= 0).all()                # tiles sorted by class: one launch per class
-    # compact dZ axis: tile t owns [dz_col, dz_col + round8(nseg*S)); same prototypes in the same order, padding -1
-    assert L.P_c % 8 == 0 and L.P <= L.P_c <= L.P_pad + 63
-    col = 0
-    for t, rec in enumerate(L.tiles):
-        S, nseg, dz_col = int(rec[0]), int(rec[1]), int(rec[3])
-        width = (nseg * S + 7) // 8 * 8
-        assert dz_col == col and dz_col % 8 == 0
-        assert L.row_map_c[col:col + width].tolist() == L.row_map[t * 128: t * 128 + width].tolist()
-        assert (L.row_map[t * 128 + width: (t + 1) * 128] == -1).all()
-        col += width
-    assert col <= L.P_c < col + 64 and (L.row_map_c[col:] == -1).all()      # pitch padding owned by the last tile
-    assert L.P_c % 64 == 0 or (L.P_c == col and L.P_c - int(L.tiles[-1][3]) + (-col) % 64 > 128)
-    usedc = L.row_map_c[L.row_map_c >= 0]
-    assert sorted(usedc.tolist()) == list(range(L.P))
+    _check_layout(L, nodes)
     # anc / path tables agree with the tree
     for li, leaf in enumerate(L.leaf_names):
         for ni, n in enumerate(nodes):
@@ -86,13 +126,24 @@ def test_layout_tables(tree, kw):
         assert len(cols) == int((L.anc[li] >= 0).sum())
 
 
-def test_layout_rejects_wide_nodes():
-    root = make_tree("cub27", per_child=20)                     # 3-child node -> 60 prototypes -> the 64 class
-    L = lay.build_layout(root)
-    assert int(L.P_n.max()) == 60 and set(int(t[0]) for t in L.tiles) == {40, 64}
-    root = make_tree("cub27", per_child=30)                     # 90 prototypes: wider than any instantiated class
-    with pytest.raises(Exception):
-        lay.build_layout(root)
+def test_layout_wide_nodes_and_riders():
+    """P_n > 64 (util/node.py:45-55 with many children or 20+ prototypes per child) -> spill nodes on dedicated tiles;
+    a nearly empty last tile -> its nodes ride in the pad columns of the other tiles"""
+    L = lay.build_layout(make_tree("cub27", num_features=20))      # 25 nodes x 20: 4 full tiles + ONE node -> rider
+    assert L.tiles.shape[0] == 4 and L.spill.shape[0] == 1 and int(L.spill[0][1]) == 20 and int(L.spill[0][5]) == 20
+    assert [int(t[4]) for t in L.tiles] == [8, 8, 4, 0] and L.P_s == 20 and L.P_c == 512
+    L = lay.build_layout(make_tree("cub27", per_child=30))         # 3-child node: 90 prototypes -> wide
+    wide = [r for r in L.spill if int(r[5]) == 0]
+    assert int(L.P_n.max()) == 90 and len(wide) == int((L.P_n > 64).sum()) >= 1
+    L = lay.build_layout(make_tree("cub08", per_desc=20))          # flat-style counts: root gets 20 x leaves
+    assert int(L.P_n.max()) == 160 and any(int(t[1]) == 0 for t in L.tiles)
+    old = lay.RIDERS
+    try:
+        lay.RIDERS = False
+        L0 = lay.build_layout(make_tree("cub27", num_features=20))
+        assert L0.tiles.shape[0] == 5 and L0.spill.shape[0] == 0 and L0.P_s == 0
+    finally:
+        lay.RIDERS = old
 
 
 def _gloo_worker(rank, world, port, q):
@@ -138,36 +189,9 @@ def test_layout_invariants_on_random_trees(seed):
     leaves = int(rng.integers(3, 60))
     root = build_tree(synthetic_edges(leaves, seed), Node)
     nodes = root.nodes_with_children()
-    choices = [1, 5, 8, 9, 16, 17, 20, 21, 32, 33, 40, 41, 60, 64] if seed % 2 else [20, 40, 60]
+    choices = ([1, 5, 8, 9, 16, 17, 20, 21, 32, 33, 40, 41, 60, 64] if seed % 2 else [20, 40, 60]) + ([65, 80, 130, 300] if seed % 3 == 0 else [])
     for n in nodes:
         n.num_protos = int(rng.choice(choices))
         n.num_protos_per_child = {}
     L = lay.build_layout(root)
-    assert L.P == sum(n.num_protos for n in nodes)
-    # padded axis: every prototype exactly once, inside a segment of its class
-    used = L.row_map[L.row_map >= 0]
-    assert sorted(used.tolist()) == list(range(L.P))
-    classes = [int(t[0]) for t in L.tiles]
-    assert classes == sorted(classes)
-    col = 0
-    for t, rec in enumerate(L.tiles):
-        S, nseg, umma_n, dz_col = (int(x) for x in rec[:4])
-        assert S in lay.SEG_CLASSES and 1 <= nseg <= 128 // S and umma_n % 16 == 0 and nseg * S <= umma_n <= 128
-        assert dz_col == col and dz_col % 8 == 0
-        width = (nseg * S + 7) // 8 * 8
-        for j in range(nseg):
-            ni, ln, po = int(rec[4 + j]), int(rec[4 + 16 + j]), int(rec[4 + 32 + j])
-            assert lay.seg_class(nodes[ni].num_protos) == S and ln == nodes[ni].num_protos and po == int(L.proto_off[ni])
-        # within a class only the LAST tile may be partial (the store maps assume full tiles are contiguous)
-        same = [i for i, c in enumerate(classes) if c == S]
-        if t != same[-1]:
-            assert nseg == 128 // S
-        assert L.row_map_c[col:col + width].tolist() == L.row_map[t * 128: t * 128 + width].tolist()
-        col += width
-    # compact axis: multiple of 8, padded to 64 when the last tile can absorb it, padding = -1
-    assert L.P_c % 8 == 0 and col <= L.P_c and (L.row_map_c[col:] == -1).all()
-    last_w = L.P_c - int(L.tiles[-1][3])
-    assert 0 < last_w <= 128
-    if L.P_c % 64:
-        assert L.P_c == col and (col - int(L.tiles[-1][3])) + (-col) % 64 > 128
-    assert sorted(L.row_map_c[L.row_map_c >= 0].tolist()) == list(range(L.P))
+    _check_layout(L, nodes)

@@ -27,9 +27,24 @@ def one(path, workload):
     lab = ops.LabelTables(pb.ys.to(dev), dl, B)
     gp = torch.randn(V, dl.P, device=dev, generator=torch.Generator(device=dev).manual_seed(5))
     ga = torch.full((dl.N,), 0.2, device=dev)
-    pooled, argmax, align = ops.proj_softmax_pool_raw(xs[0], wp, dl, V, B, HW, 1.0, lab)
+    skip_k5 = bool(os.environ.get('HC_AB_SKIP_K5'))      # ablation builds whose backward kernel is not runnable
+    sp0 = []
+    pooled, argmax, align = ops.proj_softmax_pool_raw(xs[0], wp, dl, V, B, HW, 1.0, lab, spill_out=sp0)
+    if skip_k5:
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for it in range(3):
+            ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab)
+        ops.PROFILE.enabled = True
+        ops.PROFILE.reset()
+        for it in range(20):
+            ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab)
+        torch.cuda.synchronize()
+        k1 = ops.PROFILE.totals_ms()['k1_proj_softmax_pool_fwd'][0] / 20 * 1e3
+        print(f'{os.path.basename(path):14s} {workload:7s} K1 {k1:7.1f} us   (K1 only)', flush=True)
+        return
     _, _, dz = ops.head_backward_raw(xs[0], wp, wpc, dl, V, B, HW, 1.0, argmax, gp, lab, ga, pooled=pooled, need_dx=False,
-                                     need_dw=False)
+                                     need_dw=False, spill=sp0)
     torch.cuda.synchronize()
     h = hashlib.sha1()
     for t in (pooled, argmax, align, dz):
@@ -40,8 +55,10 @@ def one(path, workload):
         if it == 3:
             torch.cuda.synchronize()
             ops.PROFILE.reset()
-        p_, a_, _ = ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab)
-        ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, a_, gp, lab, ga, pooled=p_, need_dx=False, need_dw=False)
+        sp_ = []
+        p_, a_, _ = ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab, spill_out=sp_)
+        ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, a_, gp, lab, ga, pooled=p_, need_dx=False, need_dw=False,
+                              spill=sp_)
     torch.cuda.synchronize()
     tot = ops.PROFILE.totals_ms()
     k1 = tot['k1_proj_softmax_pool_fwd'][0] / n * 1e3
@@ -77,7 +94,8 @@ def one(path, workload):
         report('K1')
         stamps('K1', 148)
         for it in range(6):
-            ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, argmax, gp, lab, ga, pooled=pooled, need_dx=False, need_dw=False)
+            ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, argmax, gp, lab, ga, pooled=pooled, need_dx=False,
+                                  need_dw=False, spill=sp0)
         report('K5')
         stamps('K5', 148)
 
