@@ -83,6 +83,11 @@ long long hcomp_launch_count(void);
 /* K1 / K5 and the dX / dW GEMMs run as CTA pairs (tcgen05 cta_group::2, M = 256 MMAs) by default; 0 selects the
  * 1-CTA kernels (same results; kept for A/B measurements and tests).  Returns the previous setting. */
 int hcomp_set_cta_pair(int on);
+/* Riders (narrow spill nodes, see the glossary above) are finished in the tail of the fused K1 / K5 launch of their
+ * segment class by default; 0 sends them through the stand-alone row kernels instead (same results; A/B measurements
+ * and tests).  Returns the previous setting.  The forward tail uses one grid barrier per device: two fused forward
+ * launches that both carry riders must not run CONCURRENTLY on different streams of one device. */
+int hcomp_set_rider_fold(int on);
 /* Data-parallel training: the dW all-reduce (NCCL, side stream) is meant to overlap the dX GEMM, but a persistent GEMM
  * that owns every SM leaves the collective's CTAs nowhere to run.  n > 0 makes hcomp_head_bwd_dx launch on (SMs - n)
  * SMs.  Returns the previous setting (default 0). */

@@ -65,7 +65,7 @@ SIGNATURES = {
     'hcomp_allreduce_mean_symm': [_p, _p, _p, _p, _i, _i, _ll, _i, _i, _p],
 }
 EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats',
-           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_reserved_sms', 'hcomp_init'] + list(SIGNATURES)
+           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_rider_fold', 'hcomp_set_reserved_sms', 'hcomp_init'] + list(SIGNATURES)
 
 _lib = None
 
@@ -89,6 +89,8 @@ def lib():
     L.hcomp_desc_losses_ws_bytes.argtypes = [_T, C.c_int]
     L.hcomp_set_cta_pair.restype = C.c_int
     L.hcomp_set_cta_pair.argtypes = [C.c_int]
+    L.hcomp_set_rider_fold.restype = C.c_int
+    L.hcomp_set_rider_fold.argtypes = [C.c_int]
     L.hcomp_set_reserved_sms.restype = C.c_int
     L.hcomp_set_reserved_sms.argtypes = [C.c_int]
     L.hcomp_init.restype = C.c_int

@@ -24,6 +24,7 @@ namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
 bool g_no_pair = false;               // hcomp_set_cta_pair(0): 1-CTA GEMM tiles only (A/B measurements, tests)
+bool g_no_rider_fold = false;        // hcomp_set_rider_fold(0): riders always go through the stand-alone row kernels (A/B, tests)
 int g_reserved_sms = 0;               // hcomp_set_reserved_sms(n): SMs the dX GEMM leaves free for a concurrent collective
 
 int fail(int code, const char* fmt, ...) {
@@ -224,7 +225,8 @@ int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, con
 template <bool BWD>
 int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int32_t* tiles_dev, int n_tiles, int V,
              int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau, int precision, hc::HeadParams base,
-             cudaStream_t st) {
+             const hcomp_spill* spill, bool* riders_folded, cudaStream_t st) {
+  *riders_folded = false;
   if (precision != HCOMP_PREC_BF16 && precision != HCOMP_PREC_FP32X3) return fail(HCOMP_E_ARG, "unknown precision %d", precision);
   const int split = (precision == HCOMP_PREC_FP32X3) ? 6 : 1;   // x / wp hold 3 stacked bf16 split planes
   DevInfo di;
@@ -261,6 +263,22 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   int last_fused_global = -1;             // the last tile with segments owns the pitch padding of the compact dZ axis
   for (int i = 0; i < n_tiles; ++i)
     if (tiles_host[(size_t)i * hc::TILE_INTS + 1] > 0) last_fused_global = i;
+  // Riders (narrow spill nodes) are finished in the tail of the LAST fused launch when they all belong to its segment
+  // class (layout.py takes them out of the last tile of the last class, so they normally do) -- otherwise by the
+  // stand-alone row kernels (run_spill).
+  hc::HeadParams riders{};
+  if (spill != nullptr && spill->n_spill > 0 && spill->recs_host != nullptr && last_fused_global >= 0 && !g_no_rider_fold) {
+    const int last_class = tiles_host[(size_t)last_fused_global * hc::TILE_INTS];
+    bool ok = true;
+    for (int i = 0; i < spill->n_spill && ok; ++i) {
+      const int32_t* r = spill->recs_host + (size_t)i * 8;
+      if (r[5] == 0) continue;                 // wide node
+      if (r[5] != last_class || riders.n_riders >= hc::MAX_RIDERS || r[1] <= 0 || r[1] > r[5]) { ok = false; break; }
+      int* d = riders.rider[riders.n_riders++];
+      d[0] = r[0]; d[1] = r[1]; d[2] = r[2]; d[3] = r[3]; d[4] = r[4]; d[5] = r[6];
+    }
+    if (!ok) riders.n_riders = 0;
+  }
   int t = 0;
   while (t < n_tiles) {
     const int seg = tiles_host[(size_t)t * hc::TILE_INTS];
@@ -321,6 +339,19 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
       }
       if (p.n_full_tiles == 0) { td[0] = td[2]; td[1] = td[3]; }
       if (!has_partial) { td[2] = td[0]; td[3] = td[1]; }
+    }
+    p.n_riders = 0;
+    if (riders.n_riders > 0 && last_fused_global >= t && last_fused_global < e) {
+      for (int i = 0; i < riders.n_riders; ++i) {
+        const int* r = riders.rider[i];
+        if (r[3] < 0 || r[3] + r[1] > p.ldz || r[0] < 0 || r[0] >= n_nodes || r[2] < 0 || r[2] + r[1] > P || p.zs == nullptr)
+          return fail(HCOMP_E_ARG, "malformed rider record %d", i);
+        if (BWD && (r[4] < 0 || r[4] % 8 != 0 || r[5] < r[1] || r[5] % 2 != 0 || r[4] + r[5] > p.P_c))
+          return fail(HCOMP_E_ARG, "rider record %d: dZ columns [%d, +%d) outside P_c=%d", i, r[4], r[5], p.P_c);
+      }
+      p.n_riders = riders.n_riders;
+      memcpy(p.rider, riders.rider, sizeof(p.rider));
+      *riders_folded = true;
     }
     // CTA pairs (cta_group::2) whenever there are at least two pair tiles along M
     const bool pair = !g_no_pair && p.num_m_tiles >= 2;
@@ -412,7 +443,7 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
 // Row kernels of the spill nodes (csrc/spill_nodes.cuh): forward = softmax / max-pool / align from the raw logits K1 wrote
 // to zs; backward = their dZ columns (no GEMM recompute).
 template <bool BWD>
-int run_spill(const hcomp_spill* sp, const hc::SpillParams& base, int V, cudaStream_t st) {
+int run_spill(const hcomp_spill* sp, const hc::SpillParams& base, int V, bool riders_folded, cudaStream_t st) {
   if (sp == nullptr || sp->n_spill <= 0) return 0;
   if (sp->recs_host == nullptr || sp->zs == nullptr || sp->ldz <= 0 || sp->ldz % 4 != 0)
     return fail(HCOMP_E_ARG, "spill nodes: records / scratch matrix missing (ldz=%d)", sp->ldz);
@@ -442,6 +473,7 @@ int run_spill(const hcomp_spill* sp, const hc::SpillParams& base, int V, cudaStr
       }
       continue;
     }
+    if (riders_folded) continue;          // finished in the tail of the fused kernel
     if (p.P_n > cls) return fail(HCOMP_E_ARG, "spill record %d: %d prototypes in class %d", i, p.P_n, cls);
 #define HC_SPILL_CASE(SEG)                                                                    \
     case SEG:                                                                                 \
@@ -476,6 +508,11 @@ int hcomp_abi_version(void) { return HCOMP_ABI_VERSION; }
 int hcomp_set_cta_pair(int on) {
   const int prev = g_no_pair ? 0 : 1;
   g_no_pair = (on == 0);
+  return prev;
+}
+int hcomp_set_rider_fold(int on) {
+  const int prev = g_no_rider_fold ? 0 : 1;
+  g_no_rider_fold = (on == 0);
   return prev;
 }
 int hcomp_set_reserved_sms(int n) {
@@ -570,13 +607,14 @@ int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const i
     HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
     if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
   }
+  bool folded = false;
   if (int e = run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
-                              precision, p, S(stream)))
+                              precision, p, spill, &folded, S(stream)))
     return e;
   if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
   hc::SpillParams q = spill_base(V, V_first, HW, P, n_nodes, tau);
   q.pooled_packed = pooled_packed; q.align_sum = align_sum; q.desc = p.desc;
-  return run_spill<false>(spill, q, V, S(stream));
+  return run_spill<false>(spill, q, V, folded, S(stream));
 }
 
 int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
@@ -616,12 +654,14 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                                                                reinterpret_cast<int2*>(scat_ws));
   HC_LAUNCH_CHECK("make_scat");
   if (sb) HC_JOIN(sb, S(stream));
+  if (spill != nullptr && spill->n_spill > 0) { p.zs = spill->zs; p.ldz = spill->ldz; }
+  bool folded = false;
   if (int e = run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
-                             precision, p, S(stream)))
+                             precision, p, spill, &folded, S(stream)))
     return e;
   hc::SpillParams q = spill_base(V, V_first, HW, P, n_nodes, tau);
   q.scat = p.scat; q.coef_align = p.coef_align; q.dz = p.dz; q.P_c = P_c;
-  return run_spill<true>(spill, q, V, S(stream));
+  return run_spill<true>(spill, q, V, folded, S(stream));
 }
 
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,
@@ -960,6 +1000,22 @@ int hcomp_debug_pair_counters(unsigned long long* out16) {
 int hcomp_debug_pair_stamps(unsigned long long* out640) {
   HC_CUDA(cudaDeviceSynchronize());
   HC_CUDA(cudaMemcpyFromSymbol(out640, hc::g_pair_stamps, sizeof(unsigned long long) * 640));
+  return 0;
+}
+/* per-item event trace of four CTAs of the LAST pair-kernel launch: out[4*16*8] ns (cleared after the read) */
+int hcomp_debug_pair_trace(unsigned long long* out512) {
+  HC_CUDA(cudaDeviceSynchronize());
+  HC_CUDA(cudaMemcpyFromSymbol(out512, hc::g_pair_trace, sizeof(unsigned long long) * 512));
+  static unsigned long long z[512];
+  HC_CUDA(cudaMemcpyToSymbol(hc::g_pair_trace, z, sizeof(z)));
+  return 0;
+}
+/* all epilogue warps of CTA 0 of the LAST pair-kernel launch: out[12*16*8] ns (cleared after the read) */
+int hcomp_debug_pair_wtrace(unsigned long long* out1536) {
+  HC_CUDA(cudaDeviceSynchronize());
+  HC_CUDA(cudaMemcpyFromSymbol(out1536, hc::g_pair_wtrace, sizeof(unsigned long long) * 1536));
+  static unsigned long long z[1536];
+  HC_CUDA(cudaMemcpyToSymbol(hc::g_pair_wtrace, z, sizeof(z)));
   return 0;
 }
 #endif

@@ -41,6 +41,23 @@
 #ifndef HC_FWD_STAGES
 #define HC_FWD_STAGES 5
 #endif
+//   HC_UPFRONT    1: forward epilogue warps read all their segments out of TMEM before any arithmetic (PairCfg::UPFRONT)
+#ifndef HC_UPFRONT
+#define HC_UPFRONT 0
+#endif
+//   HC_REPART     1: forward kernel of the narrow classes (12 epilogue warps): setmaxnreg moves registers from the service
+//                    warpgroup (56) to the epilogue warpgroups (152) -- room for the joint two-view pooling pass
+//   HC_POOL_PAIR  1: one pooling pass for both views of a segment (40 REDUX, 40 ballots, one table exchange)
+#ifndef HC_REPART
+#define HC_REPART 1
+#endif
+#ifndef HC_POOL_PAIR
+#define HC_POOL_PAIR 1
+#endif
+//   HC_POOL_GENERAL_ATOMIC 1: warps with an image boundary / invalid rows pool with per-row atomics (pool_rows_atomic)
+#ifndef HC_POOL_GENERAL_ATOMIC
+#define HC_POOL_GENERAL_ATOMIC 0
+#endif
 //   HC_POLL_WAIT  1: the producer / MMA threads poll their barriers (test_wait) instead of suspending (try_wait)
 #ifndef HC_POLL_WAIT
 #define HC_POLL_WAIT 0
@@ -60,11 +77,23 @@ __device__ unsigned long long g_pair_dbg[16];
 // per-CTA wall-clock stamps (globaltimer ns): [b][0] kernel entry, [1] setup done (TMEM allocated, cluster synced),
 // [2] epilogue warp 4 leaves its item loop, [3] CTA exit
 __device__ unsigned long long g_pair_stamps[160][4];
+// per-item event trace (globaltimer ns) of four CTAs (blockIdx 0, 1, 72, 147 -> slots 0..3), up to 16 items each:
+// [0] MMA: before wait(tmem_empty) [1] after it [2] first operand stage landed [3] last k-block issued + committed
+// [4] epilogue warp 4: before wait(tmem_full) [5] after it [6] TMEM stage released [7] item done
+__device__ unsigned long long g_pair_trace[4][16][8];
+// all epilogue warps of CTA 0: [logical warp - 4][item][0 = accumulators seen, 1 = stage released, 2 = item done]
+__device__ unsigned long long g_pair_wtrace[12][16][8];   // [3..6]: first segment: TMEM loaded / softmax done / view 1 pooled / view 2 pooled
+#define HC_WTRACE(w, n, ev) do { if (blockIdx.x == 0 && lane == 0 && (w) < 12 && (n) < 16) g_pair_wtrace[w][n][ev] = global_timer_ns(); } while (0)
+#define HC_TRACE_SLOT() (blockIdx.x == 0 ? 0 : blockIdx.x == 1 ? 1 : blockIdx.x == 72 ? 2 : blockIdx.x == 147 ? 3 : -1)
+#define HC_TRACE(slot, n, ev) do { if ((slot) >= 0 && (n) < 16) g_pair_trace[slot][n][ev] = global_timer_ns(); } while (0)
 #define HC_T(var) const long long var = clock64()
 #define HC_ACC(acc, a, b) acc += (b) - (a)
 #else
 #define HC_T(var)
 #define HC_ACC(acc, a, b)
+#define HC_TRACE_SLOT() (-1)
+#define HC_TRACE(slot, n, ev)
+#define HC_WTRACE(w, n, ev)
 #endif
 
 constexpr int TILE_N = 128;          // prototype columns per tile (TMEM columns per accumulator)
@@ -89,7 +118,7 @@ constexpr int PAIR_DZ_STAGE_BYTES = 2 * TILE_M * TILE_N * 2;   // backward: both
 template <bool BWD, bool CG2> struct PairMem {
   static constexpr int STAGE_BYTES = CG2 ? (2 * TILE_M * KBLK * 2 + (TILE_N / 2) * KBLK * 2) : PAIR_STAGE_BYTES;   // 40 / 48 KB
   static constexpr int STAGES = BWD ? (CG2 ? 4 : 3) : (CG2 ? HC_FWD_STAGES : 4);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + ((BWD || HC_POOL_V2) ? 256 : 4096);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + (BWD ? PAIR_DZ_STAGE_BYTES : 0) + 1024 + 256 + ((BWD || HC_POOL_V2) ? 256 : 8192);
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 };
 template <int S> struct PairCfg {
@@ -99,6 +128,15 @@ template <int S> struct PairCfg {
   static constexpr int THREADS = 128 + 32 * EPI_WARPS;
   static constexpr int NSEG_MAX = 128 / S;
   static constexpr int SLOTS = (NSEG_MAX + PARTS - 1) / PARTS;
+  // Forward kernel, narrow classes: an epilogue warp pulls ALL its segments of both views out of TMEM as soon as the
+  // accumulators are complete (SLOTS * 2 * S registers) and hands the stage back before any arithmetic.  Measured with
+  // per-item event traces (profiles/r2_k1_analysis.md): with the release after the last segment's load the slowest of
+  // the 24 epilogue warps of a CTA pair (the sub-partition arbiter starves low warp ids) released ~2/3 into the item's
+  // epilogue, the MMAs of item i+2 waited for it and the epilogue then waited for those MMAs -- the two-stage
+  // accumulator ring degenerated into lock-step (6.1 us per item instead of 4.5).  Needs the register re-partitioning
+  // below (setmaxnreg: service warpgroup 56, epilogue warpgroups 152 registers per thread).
+  static constexpr bool UPFRONT = HC_UPFRONT && (S <= 20) && (SLOTS * 2 * S <= 96);
+  static constexpr int EPI_REGS = 152, SVC_REGS = 56;
 };
 
 struct HeadParams {
@@ -124,6 +162,9 @@ struct HeadParams {
   const float* coef_align;             // [imgs_first, n_nodes] upstream * 0.5 / (n_desc * HW) (0 if masked); may be null
   __nv_bfloat16* dz;                   // [M, P_c]: COMPACT column axis (tile t starts at column tiles[t][3], used columns only)
   int P_c;                             // columns of dz
+  // riders finished in the tail of this launch (class == the launch's class; 0 = none): see the rider tail of the kernel
+  int n_riders;
+  int rider[8][6];                     // {node, P_n, poff, zoff, dz_col, dz_width}
   int n_full_tiles;                    // tiles of this launch that hold the class's full segment count (the rest: <= 1 partial tile)
   int w_full, w_partial;               // compact widths (multiples of 8) of a full tile / of the partial last tile
 };
@@ -135,7 +176,7 @@ template <bool BWD> struct PairSmemT {
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   uint32_t pad_[3];
-  uint4 pool_x[(BWD || HC_POOL_V2) ? 1 : 240];   // forward, pooling v1: per epilogue warp 2 * XQ column maxima and first-lane ballots
+  uint4 pool_x[(BWD || HC_POOL_V2) ? 1 : 480];   // forward, pooling v1: per epilogue warp 4 * XQ uint4: column maxima and first-lane ballots (two views, or two row groups of one view)
 };
 
 template <int S, bool MASK>
@@ -160,47 +201,79 @@ __device__ __forceinline__ void softmax_row(uint32_t* raw, int len, float scale_
     s[i + 1] = ex2(t1);
     add2(l4[i & 3], l4[(i & 3) + 1], l4[i & 3], l4[(i & 3) + 1], s[i], s[i + 1]);
   }
-  const float inv = __frcp_rn((l4[0] + l4[1]) + (l4[2] + l4[3]));
+  // rcp.approx (<= 1 ulp): branch-free, so the two views' softmax rows of a segment stay in ONE basic block and the
+  // scheduler can interleave their MUFU streams (rcp.rn carries a slow-path branch)
+  const float inv = rcp_approx((l4[0] + l4[1]) + (l4[2] + l4[3]));
 #pragma unroll
   for (int i = 0; i < S; i += 2) mul2(s[i], s[i + 1], s[i], s[i + 1], inv, inv);
 }
 
-// Max over the warp's rows (per column) with first-row tie break, merged into the packed
-// [V,P] table with one 64-bit atomicMax per (row group, column).
+// General case of the max-pool: the warp's 32 rows hold invalid rows (end of the view half) and / or rows of TWO images
+// (676 locations = 5.28 tiles: every fifth item has an image boundary in one of its four lane quadrants).  Same
+// structure as pool_segment_fast -- per column REDUX.MAX over the rows of the first image and over the rows of the
+// second one, ONE ballot for both groups (every row compares with the maximum of its own group), the per-column results
+// published through the warp's shared-memory table -- so a boundary warp costs ~1.3x a plain one.  (The first version
+// looped over the two groups with chains of predicated selects: 2.2x, and since the slowest of the 24 epilogue warps of
+// a CTA pair gates the accumulator hand-back, every boundary item stalled its whole cluster; per-warp traces in
+// profiles/r2_k1_analysis.md.)
 template <int S>
-__device__ __forceinline__ void pool_segment(const float* s, bool valid, int v_row, int v_first, bool has_boundary,
-                                             int loc_first, int lane_b, int len, int lane,
+__device__ __forceinline__ void pool_segment(const float* s, bool valid, bool first_img, bool has_boundary, int loc_first,
+                                             int lane_b, int len, int lane, uint4* xch /* [3][XQ] */,
                                              unsigned long long* packed_v0 /* &packed[(view img 0 of warp)*P + poff] */,
                                              int P) {
-#pragma unroll 1
-  for (int g = 0; g < 2; ++g) {
-    if (g == 1 && !has_boundary) break;
-    const bool in_g = valid && ((g == 0) ? (v_row == v_first) : (v_row != v_first));
-    if (__ballot_sync(0xffffffffu, in_g) == 0u) continue;
-    uint32_t m0 = 0, b0 = 0, m1 = 0, b1 = 0;
-    uint32_t mx[S];
+  constexpr int XQ = PairCfg<S>::XQ;
+  const bool in_a = valid && first_img, in_b = valid && !first_img;
+  const uint32_t xs = smem_u32(xch);
+  constexpr int CH = (S % 16 == 0) ? 16 : (S % 20 == 0 ? 20 : (S % 8 == 0 ? 8 : 4));     // columns per round: bounds the live registers
 #pragma unroll
-    for (int i = 0; i < S; ++i)     // S independent REDUX back to back (softmax >= 0: uint order == float order)
-      mx[i] = redux_max_u32(in_g ? __float_as_uint(s[i]) : 0u);
+  for (int c0 = 0; c0 < S; c0 += CH) {
+    uint32_t mxa[CH], mxb[CH], bal[CH];
 #pragma unroll
-    for (int i = 0; i < S; ++i) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, in_g && __float_as_uint(s[i]) == mx[i]);
-      if ((i & 31) == lane) {
-        if (i < 32) { m0 = mx[i]; b0 = bal; } else { m1 = mx[i]; b1 = bal; }
+    // softmax >= 0: uint order == float order, 0 is neutral.  Straight-line on purpose: a warp-uniform `if` around the
+    // second reduction made the compiler wrap EVERY REDUX in its own convergence check + read-back, which serialised
+    // the ~40-cycle REDUX latencies (2 us per segment)
+    for (int i = 0; i < CH; ++i) mxa[i] = redux_max_u32(in_a ? __float_as_uint(s[c0 + i]) : 0u);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) mxb[i] = redux_max_u32(in_b ? __float_as_uint(s[c0 + i]) : 0u);
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      bal[i] = __ballot_sync(0xffffffffu, valid && __float_as_uint(s[c0 + i]) == (first_img ? mxa[i] : mxb[i]));
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < CH / 4; ++i) {
+        const int q = c0 / 4 + i;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * q), "r"(mxa[4 * i]), "r"(mxa[4 * i + 1]),
+                     "r"(mxa[4 * i + 2]), "r"(mxa[4 * i + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * (XQ + q)), "r"(bal[4 * i]),
+                     "r"(bal[4 * i + 1]), "r"(bal[4 * i + 2]), "r"(bal[4 * i + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * (2 * XQ + q)), "r"(mxb[4 * i]),
+                     "r"(mxb[4 * i + 1]), "r"(mxb[4 * i + 2]), "r"(mxb[4 * i + 3]) : "memory");
       }
     }
-    unsigned long long* dst = packed_v0 + (size_t)g * P;
-    if (lane < len) {
-      const int fl = __ffs(b0) - 1;
-      const uint32_t loc = (g == 0) ? (loc_first + fl) : (fl - lane_b);
-      atomicMax(dst + lane, ((unsigned long long)m0 << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
-    }
-    if (S > 32 && lane + 32 < len) {
-      const int fl = __ffs(b1) - 1;
-      const uint32_t loc = (g == 0) ? (loc_first + fl) : (fl - lane_b);
-      atomicMax(dst + 32 + lane, ((unsigned long long)m1 << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
+  }
+  __syncwarp();
+  // rows of the first image: lanes [0, min(lane_b, 32)); of the second: lanes [lane_b, 32) (only with a boundary)
+  const uint32_t mask_a = (has_boundary && lane_b < 32) ? ((1u << lane_b) - 1u) : 0xffffffffu;
+#pragma unroll
+  for (int h = 0; h < (S + 31) / 32; ++h) {
+    const int c = h * 32 + lane;
+    if (c < len) {
+      uint32_t xma, xbc, xmb;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xma) : "r"(xs + 4 * c) : "memory");
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xbc) : "r"(xs + 16 * XQ + 4 * c) : "memory");
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xmb) : "r"(xs + 32 * XQ + 4 * c) : "memory");
+      const uint32_t ba = xbc & mask_a, bb = xbc & ~mask_a;
+      if (ba) {
+        const uint32_t loc = loc_first + (__ffs(ba) - 1);
+        atomicMax(packed_v0 + c, ((unsigned long long)xma << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
+      }
+      if (bb) {
+        const uint32_t loc = (__ffs(bb) - 1) - lane_b;
+        atomicMax(packed_v0 + P + c, ((unsigned long long)xmb << 32) | (unsigned long long)(0xFFFFFFFFu - loc));
+      }
     }
   }
+  __syncwarp();      // table is rewritten by the next call
 }
 
 // Fast path of pool_segment for the common case: all 32 rows of the warp are valid and belong to ONE image.
@@ -241,6 +314,79 @@ __device__ __forceinline__ void pool_segment_fast(const float* s, int loc_first,
   __syncwarp();      // table is rewritten by the next call
 }
 
+
+// General case, version 3: every valid row merges its own (value, location) key into the packed table of ITS image --
+// S predicated 64-bit RED.MAX per view, no warp reduction, no table exchange.  32 atomics per column instead of one,
+// but only the few warps with an image boundary or invalid rows take this path (4.7 % of the 32-row chunks), the REDs
+// are fire-and-forget, and the key order (larger value, then smaller location) keeps the first-occurrence rule.  The
+// reduction-based version above costs ~3x the fast path and, because the slowest of a CTA pair's 24 epilogue warps
+// gates the accumulator hand-back, set the pace of every item with a boundary in it (profiles/r2_k1_analysis.md).
+template <int S>
+__device__ __forceinline__ void pool_rows_atomic(const float* s, bool valid, int len, uint32_t lo_key, unsigned long long* own_dst) {
+  if (valid) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+      if (i < len) {
+        asm volatile("{ .reg .b64 v; mov.b64 v, {%1, %2}; red.global.max.u64 [%0], v; }"
+                     ::"l"(own_dst + i), "r"(lo_key), "r"(__float_as_uint(s[i])) : "memory");
+      }
+    }
+  }
+}
+
+// Both views of a segment in ONE pass (all 32 rows valid, one image): 2 x S REDUX back to back, 2 x S ballots, one
+// table exchange and one pair of __syncwarp for both -- the per-view version paid the REDUX / ballot / shared-memory
+// round-trip latencies twice per segment with nothing independent to fill them (the epilogue runs at ~0.35 IPC per
+// sub-partition with no pipe above 30 %: it is latency-bound, profiles/r2_k1_analysis.md).
+template <int S>
+__device__ __forceinline__ void pool_pair_fast(const float* s1, const float* s2, int loc_first, int len, int lane,
+                                               uint4* xch /* [4][XQ] */, unsigned long long* dst1, unsigned long long* dst2) {
+  constexpr int XQ = PairCfg<S>::XQ;
+  const uint32_t xs = smem_u32(xch);
+  constexpr int CH = (S % 16 == 0) ? 16 : (S % 20 == 0 ? 20 : (S % 8 == 0 ? 8 : 4));     // columns per round
+#pragma unroll
+  for (int c0 = 0; c0 < S; c0 += CH) {
+    uint32_t m1[CH], m2[CH], b1[CH], b2[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) m1[i] = redux_max_u32(__float_as_uint(s1[c0 + i]));
+#pragma unroll
+    for (int i = 0; i < CH; ++i) m2[i] = redux_max_u32(__float_as_uint(s2[c0 + i]));
+#pragma unroll
+    for (int i = 0; i < CH; ++i) b1[i] = __ballot_sync(0xffffffffu, __float_as_uint(s1[c0 + i]) == m1[i]);
+#pragma unroll
+    for (int i = 0; i < CH; ++i) b2[i] = __ballot_sync(0xffffffffu, __float_as_uint(s2[c0 + i]) == m2[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < CH / 4; ++i) {
+        const int q = c0 / 4 + i;
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * q), "r"(m1[4 * i]), "r"(m1[4 * i + 1]),
+                     "r"(m1[4 * i + 2]), "r"(m1[4 * i + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * (XQ + q)), "r"(b1[4 * i]),
+                     "r"(b1[4 * i + 1]), "r"(b1[4 * i + 2]), "r"(b1[4 * i + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * (2 * XQ + q)), "r"(m2[4 * i]),
+                     "r"(m2[4 * i + 1]), "r"(m2[4 * i + 2]), "r"(m2[4 * i + 3]) : "memory");
+        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(xs + 16 * (3 * XQ + q)), "r"(b2[4 * i]),
+                     "r"(b2[4 * i + 1]), "r"(b2[4 * i + 2]), "r"(b2[4 * i + 3]) : "memory");
+      }
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < (S + 31) / 32; ++h) {
+    const int c = h * 32 + lane;
+    if (c < len) {
+      uint32_t xm1, xb1, xm2, xb2;
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xm1) : "r"(xs + 4 * c) : "memory");
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xb1) : "r"(xs + 16 * XQ + 4 * c) : "memory");
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xm2) : "r"(xs + 32 * XQ + 4 * c) : "memory");
+      asm volatile("ld.shared.b32 %0, [%1];" : "=r"(xb2) : "r"(xs + 48 * XQ + 4 * c) : "memory");
+      const uint32_t l1 = loc_first + (__ffs(xb1) - 1), l2 = loc_first + (__ffs(xb2) - 1);
+      atomicMax(dst1 + c, ((unsigned long long)xm1 << 32) | (unsigned long long)(0xFFFFFFFFu - l1));
+      atomicMax(dst2 + c, ((unsigned long long)xm2 << 32) | (unsigned long long)(0xFFFFFFFFu - l2));
+    }
+  }
+  __syncwarp();      // table is rewritten by the next call
+}
 
 // ---- pooling v2.  Per column: one REDUX.MAX over the warp's rows, then every row that HOLDS the maximum merges
 // (value, location) into the packed table itself with a predicated 64-bit RED.MAX -- normally exactly one lane; on
@@ -352,6 +498,166 @@ __device__ __forceinline__ void add_scatter(float* g, const ScatEntries<S>& se, 
   }
 }
 
+// ================================================================================================ rider / spill rows
+// Row code of the SPILL nodes (layout.py): nodes whose raw logits the GEMM epilogue only writes to the scratch matrix
+// Zs[M, ldz].  The narrow ones ("riders") are finished either in the tail of the fused kernels below or by the
+// stand-alone kernels of csrc/spill_nodes.cuh; the wide ones (P_n > 64) always by spill_nodes.cuh.
+struct SpillParams {
+  const float* zs;          // [M, ldz]
+  int ldz;
+  int M, halfM, rowsB, HW, P, n_nodes, imgs_first;
+  float scale_log2, inv_tau, inv_HW;
+  // node record
+  int node, P_n, poff, zoff, dz_col, dz_width;
+  // forward
+  unsigned long long* pooled_packed;
+  double* align_sum;
+  const uint8_t* desc;
+  // backward
+  const int2* scat;
+  const float* coef_align;
+  __nv_bfloat16* dz;
+  int P_c;
+  float* stats;             // wide nodes: [M, 2] {row max, 1 / row sum}; forward writes, pooling + backward read
+};
+
+__device__ __forceinline__ void row_to_img(int row, int HW, float inv_HW, int& v, int& loc) {
+  v = __float2int_rz(__int2float_rz(row) * inv_HW);
+  loc = row - v * HW;
+  while (loc < 0) { --v; loc += HW; }
+  while (loc >= HW) { ++v; loc -= HW; }
+}
+
+// ------------------------------------------------------------------------------------------------ narrow, forward
+// one warp = 32 consecutive locations of view 1 and the same locations of view 2 (row_a = the lane's location, the
+// chunk's first row is < halfM); xch = the warp's pooling table (4 * XQ uint4 of shared memory)
+template <int S>
+__device__ __forceinline__ void spill_narrow_fwd_rows(const SpillParams& p, int row_a, int lane, uint4* xch) {
+  const bool valid_a = row_a < p.halfM, valid_b = row_a < p.rowsB;
+  int v_a, loc;
+  row_to_img(row_a, p.HW, p.inv_HW, v_a, loc);
+  const int v_first = __shfl_sync(0xffffffffu, v_a, 0);
+  const int loc_first = __shfl_sync(0xffffffffu, loc, 0);
+  const bool has_boundary = __ballot_sync(0xffffffffu, v_a != v_first) != 0u;
+  const int lane_b = p.HW - loc_first;
+  const int nv_a = __popc(__ballot_sync(0xffffffffu, valid_a));
+  const int nv_b = __popc(__ballot_sync(0xffffffffu, valid_b));
+  uint32_t ra[S], rb[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) ra[i] = rb[i] = 0u;
+  const int n4 = (p.P_n + 3) >> 2;
+  if (valid_a) {
+    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)row_a * p.ldz + p.zoff);
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i)
+      if (i < n4) { const float4 t = __ldg(z + i); ra[4*i] = __float_as_uint(t.x); ra[4*i+1] = __float_as_uint(t.y); ra[4*i+2] = __float_as_uint(t.z); ra[4*i+3] = __float_as_uint(t.w); }
+  }
+  if (valid_b) {
+    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)(p.halfM + row_a) * p.ldz + p.zoff);
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i)
+      if (i < n4) { const float4 t = __ldg(z + i); rb[4*i] = __float_as_uint(t.x); rb[4*i+1] = __float_as_uint(t.y); rb[4*i+2] = __float_as_uint(t.z); rb[4*i+3] = __float_as_uint(t.w); }
+  }
+  float s1[S], s2[S];
+  softmax_row<S, true>(ra, p.P_n, p.scale_log2, s1);
+  softmax_row<S, true>(rb, p.P_n, p.scale_log2, s2);
+  float ip = 0.f;
+  {
+    float ip4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < S; i += 2)
+      fma2(ip4[i & 3], ip4[(i & 3) + 1], s1[i], s1[i + 1], s2[i], s2[i + 1], ip4[i & 3], ip4[(i & 3) + 1]);
+    ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
+  }
+  if (p.desc != nullptr && p.align_sum != nullptr) {
+    float a = 0.f;
+    if (valid_a && valid_b && v_a < p.imgs_first && p.desc[(size_t)v_a * p.n_nodes + p.node]) a = -__logf(ip + 1e-12f);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0 && a != 0.f) atomicAdd(p.align_sum + p.node, (double)a);
+  }
+  unsigned long long* t1 = p.pooled_packed + (size_t)v_first * p.P + p.poff;
+  unsigned long long* t2 = t1 + (size_t)p.imgs_first * p.P;
+  if (nv_a == 32 && !has_boundary) pool_segment_fast<S>(s1, loc_first, p.P_n, lane, xch, t1);
+  else if (nv_a > 0) pool_segment<S>(s1, valid_a, v_a == v_first, has_boundary, loc_first, lane_b, p.P_n, lane, xch, t1, p.P);
+  if (nv_b == 32 && !has_boundary) pool_segment_fast<S>(s2, loc_first, p.P_n, lane, xch, t2);
+  else if (nv_b > 0) pool_segment<S>(s2, valid_b, v_a == v_first, has_boundary, loc_first, lane_b, p.P_n, lane, xch, t2, p.P);
+}
+
+// ------------------------------------------------------------------------------------------------ narrow, backward
+template <int S>
+__device__ __forceinline__ void narrow_dz_row(const SpillParams& p, const float* s, const float* s_other, float ca, int v_img,
+                                              int loc, int row) {
+  float g[S];
+  float dot = 0.f;
+  const int2* sc = p.scat + (size_t)v_img * p.P + p.poff;
+#pragma unroll
+  for (int i = 0; i < S; ++i) {
+    g[i] = -ca * s_other[i];
+    if (i < p.P_n) {
+      const int2 e = __ldg(sc + i);          // {argmax location of (image, prototype), pooled gradient}
+      if (e.x == loc) g[i] += __int_as_float(e.y);
+    }
+    dot = fmaf(g[i], s[i], dot);
+  }
+  __nv_bfloat16* out = p.dz + (size_t)row * p.P_c + p.dz_col;
+  // masked columns (k >= P_n) have s[k] = 0, so their dZ is an exact zero; columns past S (the 8-column rounding of the
+  // node's dZ block, or the pitch padding it owns) are zero-filled explicitly
+#pragma unroll
+  for (int k = 0; k < S; k += 2)
+    if (k < p.dz_width)
+      *reinterpret_cast<uint32_t*>(out + k) = pack_bf16x2(s[k] * (g[k] - dot) * p.inv_tau, s[k + 1] * (g[k + 1] - dot) * p.inv_tau);
+  for (int k = S; k < p.dz_width; k += 2) *reinterpret_cast<uint32_t*>(out + k) = 0u;
+}
+
+// one thread = one location of view 1 and the same location of view 2
+template <int S>
+__device__ __forceinline__ void spill_narrow_bwd_row(const SpillParams& p, int row_a) {
+  if (row_a >= p.halfM) return;
+  const bool valid_b = row_a < p.rowsB;
+  int v_a, loc;
+  row_to_img(row_a, p.HW, p.inv_HW, v_a, loc);
+  uint32_t ra[S], rb[S];
+#pragma unroll
+  for (int i = 0; i < S; ++i) ra[i] = rb[i] = 0u;
+  const int n4 = (p.P_n + 3) >> 2;
+  {
+    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)row_a * p.ldz + p.zoff);
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i)
+      if (i < n4) { const float4 t = __ldg(z + i); ra[4*i] = __float_as_uint(t.x); ra[4*i+1] = __float_as_uint(t.y); ra[4*i+2] = __float_as_uint(t.z); ra[4*i+3] = __float_as_uint(t.w); }
+  }
+  if (valid_b) {
+    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)(p.halfM + row_a) * p.ldz + p.zoff);
+#pragma unroll
+    for (int i = 0; i < S / 4; ++i)
+      if (i < n4) { const float4 t = __ldg(z + i); rb[4*i] = __float_as_uint(t.x); rb[4*i+1] = __float_as_uint(t.y); rb[4*i+2] = __float_as_uint(t.z); rb[4*i+3] = __float_as_uint(t.w); }
+  }
+  float s1[S], s2[S];
+  softmax_row<S, true>(ra, p.P_n, p.scale_log2, s1);
+  softmax_row<S, true>(rb, p.P_n, p.scale_log2, s2);
+  float ip = 0.f;
+  {
+    float ip4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < S; i += 2)
+      fma2(ip4[i & 3], ip4[(i & 3) + 1], s1[i], s1[i + 1], s2[i], s2[i + 1], ip4[i & 3], ip4[(i & 3) + 1]);
+    ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
+  }
+  float ca = 0.f;
+  if (valid_b && v_a < p.imgs_first && p.coef_align != nullptr) ca = p.coef_align[(size_t)v_a * p.n_nodes + p.node] * __frcp_rn(ip + 1e-12f);
+  narrow_dz_row<S>(p, s1, s2, ca, v_a, loc, row_a);
+  if (valid_b) narrow_dz_row<S>(p, s2, s1, ca, v_a + p.imgs_first, loc, p.halfM + row_a);
+}
+
+
+struct RiderRec { int node, P_n, poff, zoff, dz_col, dz_width; };
+constexpr int MAX_RIDERS = 8;
+// grid barrier of the forward kernel's rider tail: {arrivals, generation}.  One launch at a time per device may use it
+// (launches on one stream are ordered; concurrent launches of the fused forward on DIFFERENT streams must not both
+// carry folded riders -- documented in include/hcomp_head.h)
+__device__ unsigned int g_rider_barrier[2];
+
 template <int S, bool BWD, bool CG2>
 __global__ void __launch_bounds__(PairCfg<S>::THREADS, 1)
 head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
@@ -373,7 +679,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* dzstage = smem + PAIR_STAGES * STAGE_BYTES;          // backward only: view 1 boxes, then view 2 boxes
   using PairSmem = PairSmemT<BWD>;
-  static_assert(sizeof(PairSmem) <= ((BWD || HC_POOL_V2) ? 256 : 4096), "barrier block");
+  static_assert(sizeof(PairSmem) <= ((BWD || HC_POOL_V2) ? 256 : 8192), "barrier block");
   PairSmem* sb = reinterpret_cast<PairSmem*>(dzstage + (BWD ? PAIR_DZ_STAGE_BYTES : 0));
 
   // logical warp: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = idle, 4.. = epilogue.  HC_ROLES_TOP maps the
@@ -421,7 +727,13 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
   if (threadIdx.x == 0 && blockIdx.x < 160) g_pair_stamps[blockIdx.x][1] = global_timer_ns();
 #endif
 
-  if (warp == 0 || warp == 2 || warp == 3) {
+  // register re-partitioning (forward, HC_ROLES_TOP layout: physical warps 0..EPI_WARPS-1 = epilogue warpgroups, the
+  // last four = the service warpgroup)
+  constexpr bool REPART = !BWD && HC_REPART && HC_ROLES_TOP && EPI_WARPS == 12;
+
+  if (warp < 4) {
+  if constexpr (REPART) setmaxnreg_dec<PairCfg<S>::SVC_REGS>();
+  if (warp != 1) {
     // ------------------------------------------------------------ TMA producers
     // THREE single-thread producers, one per operand box of a k-block (warp 0: view-1 feature tile, warp 2: view-2
     // feature tile, warp 3: prototype tile): measured with per-role cycle counters (profiles/r2_k1_analysis.md), one
@@ -492,7 +804,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
 #endif
     }
-  } else if (warp == 1 && leader) {
+  } else if (leader) {
     // ------------------------------------------------------------ MMA issuer (CG2: the even CTA issues for the pair)
     // The whole warp walks the (warp-uniform) loop so that addresses and descriptors stay in uniform registers;
     // only the issue block is single-lane (elect.sync elects the same lane every time, which matters because
@@ -511,6 +823,8 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
     const int dr = num_workers % n_groups;
     const int32_t* tile_rec = p.tiles + (size_t)p.tile_begin * TILE_INTS + 2;
     int umma_n_next = worker < total_items ? __ldg(tile_rec + (size_t)nt * TILE_INTS) : 16;
+    [[maybe_unused]] const int trace_slot = lane == 0 ? HC_TRACE_SLOT() : -1;
+    [[maybe_unused]] int trace_n = 0;
     for (int item = worker; item < total_items; item += num_workers) {
       const int umma_n = umma_n_next;
       nt += dr;
@@ -518,7 +832,9 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       if (item + num_workers < total_items) umma_n_next = __ldg(tile_rec + (size_t)nt * TILE_INTS);
       const uint32_t idesc = make_idesc(CL * TILE_M, umma_n, false, false);
       HC_T(tm0);
+      HC_TRACE(trace_slot, trace_n, 0);
       HC_SVC_WAIT(&sb->tmem_empty[acc], acc_phase ^ 1);
+      HC_TRACE(trace_slot, trace_n, 1);
       HC_T(tm1);
       HC_ACC(dbg_te, tm0, tm1);
       tc_fence_after();
@@ -537,6 +853,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
         HC_T(tf0);
         HC_SVC_WAIT(&sb->full[stage], phase);
         HC_T(tf1);
+        if (kb == 0) HC_TRACE(trace_slot, trace_n, 2);
         tc_fence_after();
         if (elect_one()) {
           const uint32_t a0 = ((smem_base + stage * STAGE_BYTES) >> 4) | LOF;   // 16-byte units
@@ -570,6 +887,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #endif
         if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
       }
+      HC_TRACE(trace_slot, trace_n, 3);
+#ifdef HC_EXP_TIMING
+      ++trace_n;
+#endif
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
@@ -579,8 +900,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       atomicAdd(&g_pair_dbg[5], (unsigned long long)dbg_mi); atomicAdd(&g_pair_dbg[6], (unsigned long long)dbg_mn);
     }
 #endif
-  } else if (warp >= 4) {
+  }
+  } else {
     // ------------------------------------------------------------ epilogue
+    if constexpr (REPART) setmaxnreg_inc<PairCfg<S>::EPI_REGS>();
     const int quad = warp & 3;
     const int part = (warp - 4) >> 2;
     const int imgs_first = p.imgs_first;
@@ -593,9 +916,12 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #endif
     int mg_i = worker / n_groups, nt_i = worker - mg_i * n_groups;      // advanced without divisions (item += num_workers)
     const int dq = num_workers / n_groups, dr = num_workers - dq * n_groups;
+    [[maybe_unused]] const int trace_slot = (warp == 4 && lane == 0) ? HC_TRACE_SLOT() : -1;
+    [[maybe_unused]] int trace_n = -1;
     for (int item = worker; item < total_items; item += num_workers) {
 #ifdef HC_EXP_TIMING
       ++dbg_en;
+      ++trace_n;
 #endif
       const int mg = mg_i, nt = nt_i;
       mg_i += dq; nt_i += dr;
@@ -671,12 +997,15 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
       }
 
       HC_T(te0);
+      HC_TRACE(trace_slot, trace_n, 4);
 #if defined(HC_POLL_EPI)      // timing experiment only: epilogue warps poll instead of suspending
       mbar_wait_poll(&sb->tmem_full[acc], acc_phase);
 #else
       mbar_wait(&sb->tmem_full[acc], acc_phase);
 #endif
       HC_T(te1);
+      HC_TRACE(trace_slot, trace_n, 5);
+      HC_WTRACE(warp - 4, trace_n, 0);
       HC_ACC(dbg_ew, te0, te1);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * (2 * TILE_N);
@@ -716,8 +1045,25 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           if constexpr (CG2) mbar_arrive_cluster(&sb->tmem_empty[acc], 0);    // the leader's MMA warp waits for both CTAs
           else mbar_arrive(&sb->tmem_empty[acc]);
         }
+        HC_TRACE(trace_slot, trace_n, 6);
+        HC_WTRACE(warp - 4, trace_n, 1);
       };
-      if (my_cnt == 0) release_stage();     // nothing to read from this stage
+      constexpr bool UPFRONT = !BWD && PairCfg<S>::UPFRONT;
+      [[maybe_unused]] uint32_t ra_all[UPFRONT ? SLOTS : 1][S], rb_all[UPFRONT ? SLOTS : 1][S];
+      if constexpr (UPFRONT) {
+        // all segments of this warp -> registers, then the stage goes straight back to the MMA issuer
+#pragma unroll
+        for (int js = 0; js < SLOTS; ++js) {
+          if (js < my_cnt) {
+            tmem_ld_cols<S>(t0 + (PARTS * js + part) * S, ra_all[js]);
+            tmem_ld_cols<S>(t0 + TILE_N + (PARTS * js + part) * S, rb_all[js]);
+          }
+        }
+        tmem_ld_wait();
+        release_stage();
+      } else {
+        if (my_cnt == 0) release_stage();     // nothing to read from this stage
+      }
 
 #pragma unroll
       for (int js = 0; js < SLOTS; ++js) {
@@ -726,12 +1072,17 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const int node = seg_node[js];
           const int len = seg_len[js];
           const int poff = seg_poff[js];
-          uint32_t ra[S], rb[S];
-          tmem_ld_cols<S>(t0 + j * S, ra);
-          tmem_ld_cols<S>(t0 + TILE_N + j * S, rb);
-          tmem_ld_wait();
-          // last segment of this warp is in registers: release now, the arithmetic below overlaps the next MMAs
-          if (js == my_cnt - 1) release_stage();
+          uint32_t ra_one[UPFRONT ? 1 : S], rb_one[UPFRONT ? 1 : S];
+          uint32_t* ra = UPFRONT ? ra_all[js] : ra_one;
+          uint32_t* rb = UPFRONT ? rb_all[js] : rb_one;
+          if constexpr (!UPFRONT) {
+            tmem_ld_cols<S>(t0 + j * S, ra);
+            tmem_ld_cols<S>(t0 + TILE_N + j * S, rb);
+            tmem_ld_wait();
+            // last segment of this warp is in registers: release now, the arithmetic below overlaps the next MMAs
+            if (js == my_cnt - 1) release_stage();
+          }
+          if (js == 0) HC_WTRACE(warp - 4, trace_n, 3);
 #ifdef HC_EXP_NO_EPI       // timing experiment only: main loop without the epilogue arithmetic
           continue;
 #endif
@@ -756,6 +1107,7 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           const float ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
 
           if constexpr (!BWD) {
+            if (js == 0) HC_WTRACE(warp - 4, trace_n, 4);
             if (seg_aux[js] != 0.f) align_acc[js] = -__logf(ip + 1e-12f);
 #ifdef HC_EXP_NO_POOL      // timing experiment only: no column reduction (the softmax stays alive through ip / the align term)
             align_acc[js] += ip * 1e-30f;
@@ -780,18 +1132,32 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
               }
             }
 #else
-            uint4* xch = &sb->pool_x[(warp - 4) * 2 * PairCfg<S>::XQ];
-            static_assert(PairCfg<S>::EPI_WARPS * 2 * PairCfg<S>::XQ <= 240, "pooling table");
+            uint4* xch = &sb->pool_x[(warp - 4) * 4 * PairCfg<S>::XQ];
+            static_assert(PairCfg<S>::EPI_WARPS * 4 * PairCfg<S>::XQ <= 480, "pooling table");
+            if (HC_POOL_PAIR && nv_a == 32 && nv_b == 32 && !has_boundary) {
+              unsigned long long* t1 = p.pooled_packed + (size_t)v_first * p.P + poff;
+              pool_pair_fast<S>(s1, s2, loc_first, len, lane, xch, t1, t1 + (size_t)imgs_first * p.P);
+            } else {
+#if HC_POOL_GENERAL_ATOMIC
+            unsigned long long* own = p.pooled_packed + (size_t)v_a * p.P + poff;
+            pool_rows_atomic<S>(s1, valid_a, len, lo_key, own);
+            if (js == 0) HC_WTRACE(warp - 4, trace_n, 5);
+            pool_rows_atomic<S>(s2, valid_b, len, lo_key, own + (size_t)imgs_first * p.P);
+#else
             if (nv_a == 32 && !has_boundary)
               pool_segment_fast<S>(s1, loc_first, len, lane, xch, p.pooled_packed + (size_t)v_first * p.P + poff);
             else if (nv_a > 0)
-              pool_segment<S>(s1, valid_a, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
+              pool_segment<S>(s1, valid_a, v_a == v_first, has_boundary, loc_first, lane_b, len, lane, xch,
                               p.pooled_packed + (size_t)v_first * p.P + poff, p.P);
+            if (js == 0) HC_WTRACE(warp - 4, trace_n, 5);
             if (nv_b == 32 && !has_boundary)
               pool_segment_fast<S>(s2, loc_first, len, lane, xch, p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff);
             else if (nv_b > 0)
-              pool_segment<S>(s2, valid_b, v_a, v_first, has_boundary, loc_first, lane_b, len, lane,
+              pool_segment<S>(s2, valid_b, v_a == v_first, has_boundary, loc_first, lane_b, len, lane, xch,
                               p.pooled_packed + (size_t)(v_first + imgs_first) * p.P + poff, p.P);
+#endif
+            }
+            if (js == 0) HC_WTRACE(warp - 4, trace_n, 6);
 #endif
           } else {
             const float ca = seg_aux[js] * __frcp_rn(ip + 1e-12f);
@@ -840,10 +1206,10 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
 #pragma unroll
           for (int js = 0; js < SLOTS; ++js) {
             if (js < my_cnt) {
-              float v = align_acc[js];
-#pragma unroll
-              for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-              if (lane == 0 && v != 0.f) atomicAdd(p.align_sum + seg_node[js], (double)v);
+              // warp sum in fixed point (2^-20 units: terms are -log(ip + 1e-12) in [0, 27.7], 32 of them stay below
+              // 2^31): ONE integer REDUX instead of five shuffle + add rounds, and the sum does not depend on lane order
+              const int vs = redux_add_s32(__float2int_rn(align_acc[js] * 1048576.f));
+              if (lane == 0 && vs != 0) atomicAdd(p.align_sum + seg_node[js], (double)vs * (1.0 / 1048576.0));
             }
           }
         }
@@ -879,8 +1245,72 @@ head_pair_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_consta
           tma_store_commit();
         }
       }
+      HC_TRACE(trace_slot, trace_n, 7);
+      HC_WTRACE(warp - 4, trace_n, 2);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
+    }
+    // ------------------------------------------------------------ rider tail
+    // Riders (layout.py): narrow nodes of a nearly empty last tile whose columns ride in the pad columns of other tiles.
+    // Their rows are finished HERE, by the epilogue warps, instead of by a separate launch (+7 us forward, +16 us
+    // backward when measured as stand-alone kernels: a launch gap plus a latency-bound kernel at ~9 warps per SM).
+    if (p.n_riders > 0) {
+      SpillParams q;
+      q.zs = p.zs; q.ldz = p.ldz;
+      q.M = p.M; q.halfM = p.halfM; q.rowsB = p.rowsB; q.HW = p.HW; q.P = p.P; q.n_nodes = p.n_nodes; q.imgs_first = imgs_first;
+      q.scale_log2 = p.scale_log2; q.inv_tau = p.inv_tau; q.inv_HW = p.inv_HW;
+      q.pooled_packed = p.pooled_packed; q.align_sum = p.align_sum; q.desc = p.desc;
+      q.scat = p.scat; q.coef_align = p.coef_align; q.dz = p.dz; q.P_c = p.P_c; q.stats = nullptr;
+      const int n_chunks = (p.halfM + 31) >> 5;
+      if constexpr (!BWD) {
+        // forward: the riders' logits come from every CTA's items -> grid barrier (all CTAs are co-resident: one per
+        // SM, grid <= number of SMs).  Sense-reversing: the last arriver resets the count and bumps the generation.
+        __threadfence();
+        named_bar_sync(2, 32 * EPI_WARPS);
+        if (warp == 4 && lane == 0) {
+          const unsigned int gen = ld_acquire_gpu_u32(&g_rider_barrier[1]);
+          if (atomicAdd(&g_rider_barrier[0], 1u) == gridDim.x - 1) {
+            g_rider_barrier[0] = 0u;
+            __threadfence();
+            st_release_gpu_u32(&g_rider_barrier[1], gen + 1u);
+          } else {
+            uint64_t t_start = 0;
+            uint32_t spins = 0;
+            while (ld_acquire_gpu_u32(&g_rider_barrier[1]) == gen) {
+              __nanosleep(100);
+              if ((++spins & 1023u) == 0u) {
+                const uint64_t now = global_timer_ns();
+                if (t_start == 0) t_start = now;
+                else if (now - t_start > 2000000000ull) { printf("hcomp: rider grid barrier timed out (block %d)\n", blockIdx.x); __trap(); }
+              }
+            }
+          }
+          __threadfence();
+        }
+        named_bar_sync(2, 32 * EPI_WARPS);
+        uint4* xch = &sb->pool_x[(warp - 4) * 4 * PairCfg<S>::XQ];
+        const int gw = blockIdx.x * EPI_WARPS + (warp - 4), nw = gridDim.x * EPI_WARPS;
+        for (int r = 0; r < p.n_riders; ++r) {
+          q.node = p.rider[r][0]; q.P_n = p.rider[r][1]; q.poff = p.rider[r][2]; q.zoff = p.rider[r][3];
+          q.dz_col = p.rider[r][4]; q.dz_width = p.rider[r][5];
+          for (int ch = gw; ch < n_chunks; ch += nw) spill_narrow_fwd_rows<S>(q, ch * 32 + lane, lane, xch);
+        }
+      } else {
+        // backward: the riders' dZ needs only the forward's scratch matrix and the scatter / align tables, not this
+        // launch's GEMM.  When the items do not divide evenly, the clusters with one item fewer take all rider rows
+        // (they would idle for one item otherwise); else every cluster takes its share.
+        const int rem = total_items % num_workers;
+        const int first = rem;                                   // workers [rem, num_workers) are the short ones
+        const int n_part = (num_workers - first) * CL;
+        if (worker >= first) {
+          const int gw = ((worker - first) * CL + crank) * EPI_WARPS + (warp - 4), nw = n_part * EPI_WARPS;
+          for (int r = 0; r < p.n_riders; ++r) {
+            q.node = p.rider[r][0]; q.P_n = p.rider[r][1]; q.poff = p.rider[r][2]; q.zoff = p.rider[r][3];
+            q.dz_col = p.rider[r][4]; q.dz_width = p.rider[r][5];
+            for (int ch = gw; ch < n_chunks; ch += nw) spill_narrow_bwd_row<S>(q, ch * 32 + lane);
+          }
+        }
+      }
     }
     if constexpr (BWD) {
       if (warp == 4 && lane == 0) tma_store_wait_all();

@@ -15,156 +15,19 @@
 
 namespace hc {
 
-struct SpillParams {
-  const float* zs;          // [M, ldz]
-  int ldz;
-  int M, halfM, rowsB, HW, P, n_nodes, imgs_first;
-  float scale_log2, inv_tau, inv_HW;
-  // node record
-  int node, P_n, poff, zoff, dz_col, dz_width;
-  // forward
-  unsigned long long* pooled_packed;
-  double* align_sum;
-  const uint8_t* desc;
-  // backward
-  const int2* scat;
-  const float* coef_align;
-  __nv_bfloat16* dz;
-  int P_c;
-  float* stats;             // wide nodes: [M, 2] {row max, 1 / row sum}; forward writes, pooling + backward read
-};
-
-__device__ __forceinline__ void row_to_img(int row, int HW, float inv_HW, int& v, int& loc) {
-  v = __float2int_rz(__int2float_rz(row) * inv_HW);
-  loc = row - v * HW;
-  while (loc < 0) { --v; loc += HW; }
-  while (loc >= HW) { ++v; loc -= HW; }
-}
-
-// ------------------------------------------------------------------------------------------------ narrow, forward
-// grid: ceil(halfM / 32) warps (8 warps per block); lane = one location of view 1 and the same location of view 2
+// ------------------------------------------------------------------------------------------------ narrow nodes
+// stand-alone launches of the rider row functions (head_pair.cuh) for the riders the fused kernels do not finish in
+// their own tail (csrc/cabi.cu: run_pair folds the riders of the last segment class)
 template <int S>
 __global__ void __launch_bounds__(256) spill_narrow_fwd_kernel(const SpillParams p) {
-  __shared__ uint4 xch_all[8][2 * PairCfg<S>::XQ];
+  __shared__ uint4 xch_all[8][4 * PairCfg<S>::XQ];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row_a = (blockIdx.x * 8 + warp) * 32 + lane;
   if ((blockIdx.x * 8 + warp) * 32 >= p.halfM) return;                 // warp-uniform
-  const bool valid_a = row_a < p.halfM, valid_b = row_a < p.rowsB;
-  int v_a, loc;
-  row_to_img(row_a, p.HW, p.inv_HW, v_a, loc);
-  const int v_first = __shfl_sync(0xffffffffu, v_a, 0);
-  const int loc_first = __shfl_sync(0xffffffffu, loc, 0);
-  const bool has_boundary = __ballot_sync(0xffffffffu, v_a != v_first) != 0u;
-  const int lane_b = p.HW - loc_first;
-  const int nv_a = __popc(__ballot_sync(0xffffffffu, valid_a));
-  const int nv_b = __popc(__ballot_sync(0xffffffffu, valid_b));
-  uint32_t ra[S], rb[S];
-#pragma unroll
-  for (int i = 0; i < S; ++i) ra[i] = rb[i] = 0u;
-  const int n4 = (p.P_n + 3) >> 2;
-  if (valid_a) {
-    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)row_a * p.ldz + p.zoff);
-#pragma unroll
-    for (int i = 0; i < S / 4; ++i)
-      if (i < n4) { const float4 t = __ldg(z + i); ra[4*i] = __float_as_uint(t.x); ra[4*i+1] = __float_as_uint(t.y); ra[4*i+2] = __float_as_uint(t.z); ra[4*i+3] = __float_as_uint(t.w); }
-  }
-  if (valid_b) {
-    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)(p.halfM + row_a) * p.ldz + p.zoff);
-#pragma unroll
-    for (int i = 0; i < S / 4; ++i)
-      if (i < n4) { const float4 t = __ldg(z + i); rb[4*i] = __float_as_uint(t.x); rb[4*i+1] = __float_as_uint(t.y); rb[4*i+2] = __float_as_uint(t.z); rb[4*i+3] = __float_as_uint(t.w); }
-  }
-  float s1[S], s2[S];
-  softmax_row<S, true>(ra, p.P_n, p.scale_log2, s1);
-  softmax_row<S, true>(rb, p.P_n, p.scale_log2, s2);
-  float ip = 0.f;
-  {
-    float ip4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < S; i += 2)
-      fma2(ip4[i & 3], ip4[(i & 3) + 1], s1[i], s1[i + 1], s2[i], s2[i + 1], ip4[i & 3], ip4[(i & 3) + 1]);
-    ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
-  }
-  if (p.desc != nullptr && p.align_sum != nullptr) {
-    float a = 0.f;
-    if (valid_a && valid_b && v_a < p.imgs_first && p.desc[(size_t)v_a * p.n_nodes + p.node]) a = -__logf(ip + 1e-12f);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-    if (lane == 0 && a != 0.f) atomicAdd(p.align_sum + p.node, (double)a);
-  }
-  uint4* xch = xch_all[warp];
-  unsigned long long* t1 = p.pooled_packed + (size_t)v_first * p.P + p.poff;
-  unsigned long long* t2 = t1 + (size_t)p.imgs_first * p.P;
-  if (nv_a == 32 && !has_boundary) pool_segment_fast<S>(s1, loc_first, p.P_n, lane, xch, t1);
-  else if (nv_a > 0) pool_segment<S>(s1, valid_a, v_a, v_first, has_boundary, loc_first, lane_b, p.P_n, lane, t1, p.P);
-  if (nv_b == 32 && !has_boundary) pool_segment_fast<S>(s2, loc_first, p.P_n, lane, xch, t2);
-  else if (nv_b > 0) pool_segment<S>(s2, valid_b, v_a, v_first, has_boundary, loc_first, lane_b, p.P_n, lane, t2, p.P);
+  spill_narrow_fwd_rows<S>(p, (blockIdx.x * 8 + warp) * 32 + lane, lane, xch_all[warp]);
 }
-
-// ------------------------------------------------------------------------------------------------ narrow, backward
-template <int S>
-__device__ __forceinline__ void narrow_dz_row(const SpillParams& p, const float* s, const float* s_other, float ca, int v_img,
-                                              int loc, int row) {
-  float g[S];
-  float dot = 0.f;
-  const int2* sc = p.scat + (size_t)v_img * p.P + p.poff;
-#pragma unroll
-  for (int i = 0; i < S; ++i) {
-    g[i] = -ca * s_other[i];
-    if (i < p.P_n) {
-      const int2 e = __ldg(sc + i);          // {argmax location of (image, prototype), pooled gradient}
-      if (e.x == loc) g[i] += __int_as_float(e.y);
-    }
-    dot = fmaf(g[i], s[i], dot);
-  }
-  __nv_bfloat16* out = p.dz + (size_t)row * p.P_c + p.dz_col;
-  // masked columns (k >= P_n) have s[k] = 0, so their dZ is an exact zero; columns past S (the 8-column rounding of the
-  // node's dZ block, or the pitch padding it owns) are zero-filled explicitly
-#pragma unroll
-  for (int k = 0; k < S; k += 2)
-    if (k < p.dz_width)
-      *reinterpret_cast<uint32_t*>(out + k) = pack_bf16x2(s[k] * (g[k] - dot) * p.inv_tau, s[k + 1] * (g[k + 1] - dot) * p.inv_tau);
-  for (int k = S; k < p.dz_width; k += 2) *reinterpret_cast<uint32_t*>(out + k) = 0u;
-}
-
 template <int S>
 __global__ void __launch_bounds__(256) spill_narrow_bwd_kernel(const SpillParams p) {
-  const int row_a = blockIdx.x * 256 + threadIdx.x;
-  if (row_a >= p.halfM) return;
-  const bool valid_b = row_a < p.rowsB;
-  int v_a, loc;
-  row_to_img(row_a, p.HW, p.inv_HW, v_a, loc);
-  uint32_t ra[S], rb[S];
-#pragma unroll
-  for (int i = 0; i < S; ++i) ra[i] = rb[i] = 0u;
-  const int n4 = (p.P_n + 3) >> 2;
-  {
-    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)row_a * p.ldz + p.zoff);
-#pragma unroll
-    for (int i = 0; i < S / 4; ++i)
-      if (i < n4) { const float4 t = __ldg(z + i); ra[4*i] = __float_as_uint(t.x); ra[4*i+1] = __float_as_uint(t.y); ra[4*i+2] = __float_as_uint(t.z); ra[4*i+3] = __float_as_uint(t.w); }
-  }
-  if (valid_b) {
-    const float4* z = reinterpret_cast<const float4*>(p.zs + (size_t)(p.halfM + row_a) * p.ldz + p.zoff);
-#pragma unroll
-    for (int i = 0; i < S / 4; ++i)
-      if (i < n4) { const float4 t = __ldg(z + i); rb[4*i] = __float_as_uint(t.x); rb[4*i+1] = __float_as_uint(t.y); rb[4*i+2] = __float_as_uint(t.z); rb[4*i+3] = __float_as_uint(t.w); }
-  }
-  float s1[S], s2[S];
-  softmax_row<S, true>(ra, p.P_n, p.scale_log2, s1);
-  softmax_row<S, true>(rb, p.P_n, p.scale_log2, s2);
-  float ip = 0.f;
-  {
-    float ip4[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-    for (int i = 0; i < S; i += 2)
-      fma2(ip4[i & 3], ip4[(i & 3) + 1], s1[i], s1[i + 1], s2[i], s2[i + 1], ip4[i & 3], ip4[(i & 3) + 1]);
-    ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
-  }
-  float ca = 0.f;
-  if (valid_b && v_a < p.imgs_first && p.coef_align != nullptr) ca = p.coef_align[(size_t)v_a * p.n_nodes + p.node] * __frcp_rn(ip + 1e-12f);
-  narrow_dz_row<S>(p, s1, s2, ca, v_a, loc, row_a);
-  if (valid_b) narrow_dz_row<S>(p, s2, s1, ca, v_a + p.imgs_first, loc, p.halfM + row_a);
+  spill_narrow_bwd_row<S>(p, blockIdx.x * 256 + threadIdx.x);
 }
 
 // ------------------------------------------------------------------------------------------------ wide nodes

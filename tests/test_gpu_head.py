@@ -281,3 +281,38 @@ def test_all_segment_classes_in_one_model(seed):
     gw_ref = torch.cat([w[n].grad for n in L.node_names])
     assert rel_err(feats.grad, x.grad) <= 2e-2, f'dX rel err {rel_err(feats.grad, x.grad)}'
     assert rel_err(w_flat.grad, gw_ref) <= 2e-2, f'dW rel err {rel_err(w_flat.grad, gw_ref)}'
+
+
+@pytest.mark.parametrize("geom", [(64, 6, 3), (768, 26, 2)], ids=["C64-H6", "C768-H26"])
+def test_rider_tail_matches_standalone_row_kernels(geom, cta_pair_mode):
+    """cub27 with 20 prototypes per node: 4 full tiles + ONE node whose columns ride in the pad columns of the other
+    tiles (layout.py).  The fused kernels finish that node in their own tail (grid barrier in the forward); the
+    stand-alone row kernels (hcomp_set_rider_fold(0)) must give the same pooled table, argmax, align sums and dZ."""
+    from pipnet_b200 import ops, _cabi
+    Cc, H, B = geom
+    pb = Problem("cub27", Cc, H, B, seed=11, num_features=20)
+    assert pb.layout.spill.shape[0] == 1 and int(pb.layout.spill[0][5]) == 20
+    dl = ops.DeviceLayout(pb.layout, 'cuda')
+    V, HW = pb.V, H * H
+    xr = ops.feature_rows(pb.features('cuda'))
+    wp, wpc = ops.pack_weights(pb.w_flat('cuda'), dl)
+    labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
+    g = torch.Generator(device='cuda').manual_seed(3)
+    gp = torch.randn(V, dl.P, device='cuda', generator=g)
+    ga = torch.full((dl.N,), 0.3, device='cuda')
+    out = []
+    for fold in (1, 0):
+        prev = _cabi.lib().hcomp_set_rider_fold(fold)
+        try:
+            for _ in range(2):                    # twice: the forward tail's grid barrier must be reusable
+                sp = []
+                pooled, argmax, align = ops.proj_softmax_pool_raw(xr, wp, dl, V, pb.V_first, HW, 0.7, labels, spill_out=sp)
+                _, _, dz = ops.head_backward_raw(xr, wp, wpc, dl, V, pb.V_first, HW, 0.7, argmax, gp, labels, ga, pooled=pooled,
+                                                 need_dx=False, need_dw=False, spill=sp)
+            torch.cuda.synchronize()
+            out.append((pooled.clone(), argmax.clone(), align.clone(), dz.clone()))
+        finally:
+            _cabi.lib().hcomp_set_rider_fold(prev)
+    assert torch.equal(out[0][0], out[1][0]) and torch.equal(out[0][1], out[1][1])
+    assert torch.allclose(out[0][2], out[1][2], rtol=1e-6, atol=0)          # double atomics: order of the partial sums
+    assert torch.equal(out[0][3], out[1][3])

@@ -16,6 +16,8 @@ def one(path, workload):
         _cabi.LIB_PATH = os.path.abspath(path)
     from pipnet_b200 import ops
     from oracle.problems import Problem
+    if os.environ.get('HC_AB_NOFOLD'):
+        _cabi.lib().hcomp_set_rider_fold(0)
     tree, nf, batch = {'cub27': ('cub27', 20, 64), 'cub190': ('synth190', 20, 32)}[workload]
     dev = torch.device('cuda:0')
     pb = Problem(tree, 768, 26, batch, seed=1, num_features=nf)
@@ -88,16 +90,61 @@ def one(path, workload):
                   f'| epilogue loop end {a[:,2].min():.1f}..{a[:,2].max():.1f} (median {np.median(a[:,2]):.1f}) | exit {a[:,3].min():.1f}..{a[:,3].max():.1f}',
                   flush=True)
 
+        def trace(tag):
+            if not hasattr(L, 'hcomp_debug_pair_trace'):
+                return
+            tb = (C.c_ulonglong * 512)()
+            L.hcomp_debug_pair_trace(tb)
+            import numpy as np
+            a = np.array(list(tb), dtype=np.int64).reshape(4, 16, 8)
+            names = ['mma:wait_te', 'mma:te_ok', 'mma:k0_full', 'mma:issued', 'epi:wait_tf', 'epi:tf_ok', 'epi:release', 'epi:done']
+            for slot, cta in enumerate((0, 1, 72, 147)):
+                t = a[slot]
+                nz = t[t > 0]
+                if nz.size == 0:
+                    continue
+                t0 = nz.min()
+                print(f'   {tag} trace CTA {cta} (us since its first event; ' + ' '.join(names) + ')')
+                for i in range(16):
+                    if (t[i] > 0).any():
+                        print('      item %2d: ' % i + ' '.join('%7.2f' % ((x - t0) / 1e3) if x > 0 else '      -' for x in t[i]))
+
+        def wtrace(tag):
+            if not hasattr(L, 'hcomp_debug_pair_wtrace'):
+                return
+            tb = (C.c_ulonglong * 1536)()
+            L.hcomp_debug_pair_wtrace(tb)
+            import numpy as np
+            a8 = np.array(list(tb), dtype=np.int64).reshape(12, 16, 8)
+            a = a8[:, :, :3]
+            nz = a[a > 0]
+            if nz.size == 0:
+                return
+            t0 = nz.min()
+            print(f'   {tag} CTA 0, all epilogue warps (us): rows = items, per warp [accumulators seen / released / done]; warp w: quadrant w%4, part w//4')
+            for i in range(16):
+                if (a[:, i] > 0).any():
+                    print('      item %2d: ' % i + ' | '.join('%5.1f %5.1f %5.1f' % tuple((x - t0) / 1e3 for x in a[w, i]) for w in range(12)))
+            print(f'   {tag} CTA 0, first segment of warps 2 and 3 (us after the accumulators were seen): loaded / softmax / pooled view 1 / pooled view 2')
+            for i in range(16):
+                if (a8[2, i] > 0).any():
+                    print('      item %2d: ' % i + ' | '.join(' '.join('%5.2f' % ((a8[w, i, e] - a8[w, i, 0]) / 1e3) for e in (3, 4, 5, 6)) for w in (2, 3)))
+
         L.hcomp_debug_pair_counters(buf)
+        trace('warm')
+        wtrace('warm')
         for it in range(6):
             ops.proj_softmax_pool_raw(xs[it % 2], wp, dl, V, B, HW, 1.0, lab)
         report('K1')
         stamps('K1', 148)
+        trace('K1')
+        wtrace('K1')
         for it in range(6):
             ops.head_backward_raw(xs[it % 2], wp, wpc, dl, V, B, HW, 1.0, argmax, gp, lab, ga, pooled=pooled, need_dx=False,
                                   need_dw=False, spill=sp0)
         report('K5')
         stamps('K5', 148)
+        trace('K5')
 
 
 if __name__ == '__main__':
