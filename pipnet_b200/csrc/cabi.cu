@@ -134,23 +134,23 @@ int make_tmap(CUtensorMap* m, const void* base, unsigned long long inner, unsign
   return 0;
 }
 
-// 3D bf16 store map over the compact dZ matrix: {w columns of a tile, n_tiles tiles at `w`-column pitch, rows}; boxes
-// are [64 cols x 1 tile x box_rows rows], 128B-swizzled in shared memory like the 2D maps.
-int make_tmap_dz(CUtensorMap* m, const void* base, unsigned w, unsigned n_tiles, unsigned long long rows,
-                 unsigned long long pitch_elems, unsigned box_rows) {
+// 4D bf16 store map over the compact dZ matrix [n_imgs * HW, pitch]: {w columns of a tile, n_tiles tiles at `w`-column
+// pitch, location, image}; boxes of [64 cols x 1 tile x 32 locations x 1 image].
+int make_tmap_dz4(CUtensorMap* m, const void* base, unsigned w, unsigned n_tiles, unsigned long long HW,
+                  unsigned long long n_imgs, unsigned long long pitch_elems) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(HCOMP_E_ARG, "dZ tile base not 16-byte aligned");
-  if ((pitch_elems * 2) % 16 != 0 || (w * 2) % 16 != 0 || w == 0 || n_tiles == 0 || rows == 0)
-    return fail(HCOMP_E_ARG, "bad compact dZ geometry (w %u, tiles %u, rows %llu, pitch %llu)", w, n_tiles, rows, pitch_elems);
-  cuuint64_t gdim[3] = {w, n_tiles, rows};
-  cuuint64_t gstr[2] = {(cuuint64_t)w * 2, pitch_elems * 2};
-  cuuint32_t box[3] = {64, 1, box_rows};
-  cuuint32_t estr[3] = {1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+  if ((pitch_elems * 2) % 16 != 0 || (w * 2) % 16 != 0 || w == 0 || n_tiles == 0 || HW == 0 || n_imgs == 0)
+    return fail(HCOMP_E_ARG, "bad compact dZ geometry (w %u, tiles %u, HW %llu, images %llu, pitch %llu)", w, n_tiles, HW, n_imgs, pitch_elems);
+  cuuint64_t gdim[4] = {w, n_tiles, HW, n_imgs};
+  cuuint64_t gstr[3] = {(cuuint64_t)w * 2, pitch_elems * 2, HW * pitch_elems * 2};
+  cuuint32_t box[4] = {64, 1, 32, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled (dZ) failed with %d (w %u tiles %u rows %llu)", int(r), w, n_tiles, rows);
+  if (r != CUDA_SUCCESS) return fail(HCOMP_E_CUDA, "cuTensorMapEncodeTiled (dZ) failed with %d (w %u tiles %u HW %llu)", int(r), w, n_tiles, HW);
   return 0;
 }
 
@@ -193,8 +193,8 @@ int launch_persistent(Kern kern, const char* name, int cluster, int workers, int
 }
 
 template <int SEG, bool BWD, bool CG2>
-int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap* td /* [4]: dz1, dz2, dz1 partial, dz2 partial */,
-                const hc::HeadParams& p, int sms, cudaStream_t st) {
+int launch_pair(const hc::FeatureMaps& tx, const CUtensorMap& tw,
+                const CUtensorMap* td /* [2]: dZ full tiles, partial tile */, const hc::HeadParams& p, int sms, cudaStream_t st) {
   auto kern = hc::head_pair_kernel<SEG, BWD, CG2>;
   constexpr int SMEM = hc::PairMem<BWD, CG2>::SMEM_BYTES;
   static std::atomic<unsigned long long> attr_done{0};
@@ -204,11 +204,11 @@ int launch_pair(const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap*
   const int slots = sms / CL;
   const int workers = items < slots ? items : slots;
   return launch_persistent(kern, BWD ? "head_pair_kernel<bwd>" : "head_pair_kernel<fwd>", CL, workers,
-                           hc::PairCfg<SEG>::THREADS, SMEM, st, tx, tw, td[0], td[1], td[2], td[3], p);
+                           hc::PairCfg<SEG>::THREADS, SMEM, st, tx, tw, td[0], td[1], p);
 }
 
 template <bool BWD, bool CG2>
-int launch_pair_class(int seg, const CUtensorMap& tx, const CUtensorMap& tw, const CUtensorMap* td,
+int launch_pair_class(int seg, const hc::FeatureMaps& tx, const CUtensorMap& tw, const CUtensorMap* td,
                       const hc::HeadParams& p, int sms, cudaStream_t st) {
   switch (seg) {
     case 8: return launch_pair<8, BWD, CG2>(tx, tw, td, p, sms, st);
@@ -232,7 +232,7 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   DevInfo di;
   if (int e = dev_info(&di)) return e;
   if (V <= 0 || V_first <= 0 || V_first > V || V - V_first > V_first) return fail(HCOMP_E_ARG, "bad view split V=%d V_first=%d", V, V_first);
-  if (HW < 32) return fail(HCOMP_E_ARG, "HW=%d < 32 locations per image is not supported", HW);
+  if (HW <= 0) return fail(HCOMP_E_ARG, "HW=%d", HW);
   if (C % 8 != 0 || C <= 0) return fail(HCOMP_E_ARG, "C=%d must be a positive multiple of 8", C);
   if (P_pad != n_tiles * hc::TILE_N) return fail(HCOMP_E_ARG, "P_pad=%d != 128*n_tiles", P_pad);
   if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
@@ -240,20 +240,31 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   if (M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
   const int planes = split > 1 ? 3 : 1;
   if (planes * M > 0x7fffffffLL - 2 * hc::TILE_M) return fail(HCOMP_E_ARG, "too many rows");
-  CUtensorMap tx, tw, tw_half;          // tw_half: 64-row boxes for the CTA-pair variant (each CTA keeps half a tile)
-  if (int e = make_tmap(&tx, x, C, planes * M, C, hc::KBLK, hc::TILE_M)) return e;
+  hc::FeatureMaps tx;
+  CUtensorMap tw, tw_half;              // tw_half: 64-row boxes for the CTA-pair variant (each CTA keeps half a tile)
+  const int cpi = cdiv(HW, 32), rem = HW - 32 * (cpi - 1);
+  for (int r = 0; r < 4; ++r) {
+    if (int e = make_tmap(&tx.full[r], x, C, planes * M, C, hc::KBLK, 32u * (r + 1))) return e;
+    if (int e = make_tmap(&tx.tail[r], x, C, planes * M, C, hc::KBLK, 32u * r + rem)) return e;
+  }
   if (int e = make_tmap(&tw, wp, C, (unsigned long long)planes * P_pad, C, hc::KBLK, hc::TILE_N)) return e;
   if (int e = make_tmap(&tw_half, wp, C, (unsigned long long)planes * P_pad, C, hc::KBLK, hc::TILE_N / 2)) return e;
   hc::HeadParams p = base;
   p.M = int(M);
   p.halfM = V_first * HW;
   p.rowsB = int(M) - p.halfM;
-  CUtensorMap td[4];                    // backward: dZ leaves through TMA stores (per class: full tiles / partial tile x view half)
+  CUtensorMap td[2];                    // backward: dZ leaves through TMA stores (per class: full tiles / partial tile)
   memset(td, 0, sizeof(td));
   p.HW = HW; p.C = C; p.P = P; p.P_pad = P_pad;
   p.split_terms = split;
   p.num_k_blocks = cdiv(C, hc::KBLK) * split;
-  p.num_m_tiles = cdiv(p.halfM, hc::TILE_M);
+  p.cpi = cdiv(HW, 32);
+  p.inv_cpi = 1.f / float(p.cpi);
+  p.rem = rem;
+  p.num_chunks = V_first * p.cpi;
+  p.num_m_tiles = cdiv(p.num_chunks, 4);
+  p.imgs_second = V - V_first;
+  p.imgs_total = V;
   p.n_nodes = n_nodes;
   p.imgs_first = V_first;
   p.scale_log2 = 1.4426950408889634f / tau;
@@ -324,21 +335,14 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
           return fail(HCOMP_E_ARG, "tile %d: compact dZ column %d, expected %d", i, tiles_host[(size_t)i * hc::TILE_INTS + 3], want);
       }
       if (c_full + p.n_full_tiles * p.w_full + p.w_partial > p.P_c) return fail(HCOMP_E_ARG, "compact dZ columns exceed P_c=%d", p.P_c);
-      __nv_bfloat16* h1 = p.dz;
-      __nv_bfloat16* h2 = p.dz + (size_t)p.halfM * p.P_c;
-      const unsigned long long rows2 = p.rowsB > 0 ? p.rowsB : p.halfM;      // no second half: keep valid (unused) maps
-      if (p.rowsB <= 0) h2 = h1;
-      if (p.n_full_tiles > 0) {
-        if (int er = make_tmap_dz(&td[0], h1 + c_full, p.w_full, p.n_full_tiles, p.halfM, p.P_c, hc::TILE_M)) return er;
-        if (int er = make_tmap_dz(&td[1], h2 + c_full, p.w_full, p.n_full_tiles, rows2, p.P_c, hc::TILE_M)) return er;
-      }
+      if (p.n_full_tiles > 0)
+        if (int er = make_tmap_dz4(&td[0], p.dz + c_full, p.w_full, p.n_full_tiles, HW, V, p.P_c)) return er;
       if (has_partial) {
         const int c_part = c_full + p.n_full_tiles * p.w_full;
-        if (int er = make_tmap_dz(&td[2], h1 + c_part, p.w_partial, 1, p.halfM, p.P_c, hc::TILE_M)) return er;
-        if (int er = make_tmap_dz(&td[3], h2 + c_part, p.w_partial, 1, rows2, p.P_c, hc::TILE_M)) return er;
+        if (int er = make_tmap_dz4(&td[1], p.dz + c_part, p.w_partial, 1, HW, V, p.P_c)) return er;
       }
-      if (p.n_full_tiles == 0) { td[0] = td[2]; td[1] = td[3]; }
-      if (!has_partial) { td[2] = td[0]; td[3] = td[1]; }
+      if (p.n_full_tiles == 0) td[0] = td[1];
+      if (!has_partial) td[1] = td[0];
     }
     p.n_riders = 0;
     if (riders.n_riders > 0 && last_fused_global >= t && last_fused_global < e) {
@@ -346,7 +350,7 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
         const int* r = riders.rider[i];
         if (r[3] < 0 || r[3] + r[1] > p.ldz || r[0] < 0 || r[0] >= n_nodes || r[2] < 0 || r[2] + r[1] > P || p.zs == nullptr)
           return fail(HCOMP_E_ARG, "malformed rider record %d", i);
-        if (BWD && (r[4] < 0 || r[4] % 8 != 0 || r[5] < r[1] || r[5] % 2 != 0 || r[4] + r[5] > p.P_c))
+        if (BWD && (r[4] < 0 || r[4] % 8 != 0 || r[5] < r[1] || r[5] % 8 != 0 || r[4] + r[5] > p.P_c))
           return fail(HCOMP_E_ARG, "rider record %d: dZ columns [%d, +%d) outside P_c=%d", i, r[4], r[5], p.P_c);
       }
       p.n_riders = riders.n_riders;
@@ -456,7 +460,7 @@ int run_spill(const hcomp_spill* sp, const hc::SpillParams& base, int V, bool ri
     const int cls = r[5];
     if (p.P_n <= 0 || p.zoff < 0 || p.zoff + p.P_n > p.ldz || p.node < 0 || p.node >= p.n_nodes || p.poff < 0 || p.poff + p.P_n > p.P)
       return fail(HCOMP_E_ARG, "malformed spill record %d", i);
-    if (BWD && (p.dz_col < 0 || p.dz_col % 8 != 0 || p.dz_width < p.P_n || p.dz_width % 2 != 0 || p.dz_col + p.dz_width > p.P_c))
+    if (BWD && (p.dz_col < 0 || p.dz_col % 8 != 0 || p.dz_width < p.P_n || p.dz_width % 8 != 0 || p.dz_col + p.dz_width > p.P_c))
       return fail(HCOMP_E_ARG, "spill record %d: dZ columns [%d, +%d) outside P_c=%d", i, p.dz_col, p.dz_width, p.P_c);
     if (cls == 0) {                       // wide node
       if (sp->stats == nullptr) return fail(HCOMP_E_ARG, "spill nodes: statistics workspace missing");

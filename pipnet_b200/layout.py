@@ -25,6 +25,8 @@ TILE_INTS = 8 + 3 * MAX_SEGS      # {S, nseg, umma_n, dz_col, spill_n, spill_col
 SEG_CLASSES = (8, 16, 20, 32, 40, 64)        # instantiated epilogues (pipnet_b200/csrc/cabi.cu)
 SPILL_INTS = 8                     # spill-node record {node, P_n, poff, zoff, dz_col, S class (0 = wide), dz_width, 0}
 RIDERS = True                      # move the nodes of a sparsely used last tile into spare pad columns (see build_layout)
+MAX_RIDERS = 2
+MAX_TILES_WITH_RIDERS = 8
 
 
 def seg_class(p_n: int) -> int:
@@ -158,7 +160,11 @@ def build_layout(root) -> HeadLayout:
         others = tile_nodes[:-1]
         spare = sum(((TILE_COLS - len(ch) * s_) // 4) * 4 for s_, ch in others)
         need = sum(((int(P_n[i]) + 3) // 4) * 4 for i in chunk_last)
-        if len(chunk_last) * s_last <= TILE_COLS // 2 and need <= spare:
+        # worth it only when the saved tile is a large share of the launch (a pass over the feature matrix per tile) and the
+        # riders are few: each rider costs one extra row pass in the kernel tails (measured: cub27, 5 -> 4 tiles, K1 -7 %;
+        # cub190 with 3 riders out of 32 tiles was slower than keeping the tile)
+        if (len(chunk_last) * s_last <= TILE_COLS // 2 and need <= spare and len(chunk_last) <= MAX_RIDERS
+                and len(tile_nodes) <= MAX_TILES_WITH_RIDERS):
             rider_ids = list(chunk_last)
             tile_nodes = others
     # Zs columns: riders first (their pieces are handed to the pad slots in order), then the wide nodes

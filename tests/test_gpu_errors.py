@@ -40,7 +40,7 @@ def test_bad_arguments_return_error_codes(bad):
     wp, _ = ops.pack_weights(pb.w_flat('cuda'), dl)
     packed = torch.zeros(V * dl.P, device='cuda', dtype=torch.int64)
     kw = dict(V=V, V_first=pb.V_first, HW=HW, C=Cc, P_pad=dl.P_pad, tau=1.0)
-    kw.update({'hw': dict(HW=16), 'c': dict(C=Cc + 4), 'vfirst': dict(V_first=V + 1), 'tau': dict(tau=0.0),
+    kw.update({'hw': dict(HW=0), 'c': dict(C=Cc + 4), 'vfirst': dict(V_first=V + 1), 'tau': dict(tau=0.0),
                'ppad': dict(P_pad=dl.P_pad + 128)}[bad])
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     with pytest.raises(HcompError) as ei:
