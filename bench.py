@@ -38,6 +38,11 @@ WORKLOADS = {
     'cub190': dict(tree='synth190', num_features=20, batch=32, C=768, H=26),
     # recipe B of SURVEY.md 8(d): 20 prototypes per CHILD (P_n = 20 / 40 / 60, P = 1020)
     'cub27b': dict(tree='cub27', num_features=0, per_child=20, batch=64, C=768, H=26),
+    # BASELINE.json config 4: ResNet-50 features (C = 2048, 28 x 28, NCHW-contiguous as torchvision emits them),
+    # 30 prototypes per node on a 38-leaf tree, batch 128
+    'fish38': dict(tree='synth38', num_features=30, batch=128, C=2048, H=28, nchw=True),
+    # BASELINE.json config 5: large-tree INFERENCE sweep (single view, batch 1024/GPU; 1486-leaf synthetic tree: SURVEY 8d)
+    'inat': dict(tree='synth1486', num_features=20, batch=1024, C=768, H=26, mode='inference'),
 }
 METRIC = 'train images/sec (prototype head fwd+bwd)'
 UNIT = 'images/s'
@@ -190,6 +195,220 @@ def oracle_cpu_throughput(wl, batch, steps, warmup, budget_s=25.0):
                                      f'{wl["H"]}x{wl["H"]}x{wl["C"]}), fp32 oracle port, fwd+losses+bwd')
 
 
+def quick_train_record(a, name, dev, rank, world, steps=20):
+    """Reduced measurement of another training workload inside the same process: graph-captured step, device timing, max
+    over ranks; at N > 1 also the step with the gradient exchange disabled (difference = exposed collective time)."""
+    import torch.distributed as dist
+    from pipnet_b200 import ops
+    from pipnet_b200 import train as tr
+    from pipnet_b200.fixtures import build_net, make_args
+    from pipnet_b200.graphs import GraphedHeadStep
+    wl = WORKLOADS[name]
+    B, C, H = wl['batch'], wl['C'], wl['H']
+    V = 2 * B
+    args = make_args(num_features=wl['num_features'], num_protos_per_child=wl.get('per_child', 0))
+    net, root = build_net(wl['tree'], C, args, seed=1)
+    net = net.to(dev)
+    net.train()
+    L = net.layout
+    g = torch.Generator().manual_seed(4321 + rank)
+    feats, labels = [], []
+    for i in range(2):
+        x = torch.randn(V, H, H, C, generator=g, dtype=torch.float32).to(torch.bfloat16)
+        feats.append(x.to(dev).permute(0, 3, 1, 2))
+        y = torch.randint(0, L.L, (B,), generator=torch.Generator().manual_seed(17 + i + 100 * rank))
+        labels.append(torch.cat([y, y]).to(dev))
+    w = tr._phase_weights(False, 1, 10, args)
+
+    def loss_fn(x, ys):
+        lab = tr.make_labels(net, ys)
+        features, pf, pooled, out = net(x, labels=lab)
+        res = tr.calculate_loss(1, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                root=root, kernel_orth=True, tanh_desc=False, align=False, uni=False, align_pf=True,
+                                tanh=True, args=args, device=dev, labels=lab, **w)
+        return res[0]
+
+    def timed(graphs):
+        for i in range(3):
+            graphs[i % 2].replay()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            graphs[i % 2].replay()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / steps
+
+    params = list(net.parameters())
+    graphs = [GraphedHeadStep(loss_fn, params, feats[i], labels[i]) for i in range(2)]
+    ms = timed(graphs)
+    rec = {'value': world * B / (ms * 1e-3), 'unit': UNIT, 'ms_per_step': ms, 'steps': steps,
+           'config': f'{name}: tree {wl["tree"]} ({L.N} nodes, P={L.P}), batch {B}/GPU, fwd+bwd, one CUDA graph replay per step',
+           'grad_bucket_bytes': int(sum(p.numel() for p in params if p.requires_grad) * 4)}
+    if world > 1:
+        del graphs
+        saved, ops.GRAD_ALLREDUCE_GROUP = ops.GRAD_ALLREDUCE_GROUP, None
+        try:
+            local = [GraphedHeadStep(loss_fn, params, feats[i], labels[i]) for i in range(2)]
+            ms_local = timed(local)
+        finally:
+            ops.GRAD_ALLREDUCE_GROUP = saved
+        rec['ms_per_step_without_exchange'] = ms_local
+        rec['allreduce_exposed_us'] = (ms - ms_local) * 1e3
+    return rec
+
+
+def run_inference(a):
+    """BASELINE.json config 5: inference sweep -- single view, prototype head forward (projection + softmax + max-pool,
+    inference threshold) + node classifiers + joint leaf prediction; no collective (independent images per rank)."""
+    import torch.distributed as dist
+    from pipnet_b200 import _cabi, ops
+    from pipnet_b200.fixtures import build_net, make_args
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the prototype head has no CPU path')
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        dist.init_process_group('nccl', device_id=dev)
+    wl = WORKLOADS[a.workload]
+    B, C, H = wl['batch'], wl['C'], wl['H']
+    V, HW = B, H * H
+    args = make_args(num_features=wl['num_features'], num_protos_per_child=wl.get('per_child', 0))
+    net, root = build_net(wl['tree'], C, args, seed=1)
+    net = net.to(dev)
+    net.eval()
+    L = net.layout
+    g = torch.Generator().manual_seed(99 + rank)
+    feats = []
+    for i in range(2):
+        x = torch.randn(V, H, H, C, generator=g, dtype=torch.float32).to(torch.bfloat16)
+        feats.append(x.to(dev).permute(0, 3, 1, 2))
+
+    def fwd(x):
+        with torch.no_grad():
+            _f, _pf, pooled, out = net(x, inference=True)
+            _root_out, joint = net.get_joint_distribution(out, device=dev)
+            return joint.argmax(dim=1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(3):
+        fwd(feats[i % 2])
+    barrier()
+    launches0 = _cabi.lib().hcomp_launch_count()
+    fwd(feats[0])
+    torch.cuda.synchronize()
+    launches_per_step = _cabi.lib().hcomp_launch_count() - launches0
+    static_x = [f.clone() for f in feats]
+    graphs, outs = [], []
+    try:
+        for i in range(2):
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr):
+                outs.append(fwd(static_x[i]))
+            graphs.append(gr)
+    except Exception as ex:
+        sys.stderr.write(f'graph capture unavailable, timing the eager forward: {ex!r}\n')
+        graphs = None
+
+    def run_step(i):
+        if graphs is not None:
+            graphs[i % 2].replay()
+            return outs[i % 2]
+        return fwd(feats[i % 2])
+
+    for i in range(max(a.warmup, 3)):
+        run_step(i)
+    # K1 alone, CUDA events around the C-ABI call in a saturated loop
+    ops.PROFILE.reset()
+    ops.PROFILE.enabled = True
+    for i in range(5):
+        fwd(feats[i % 2])
+    torch.cuda.synchronize()
+    ops.PROFILE.enabled = False
+    prof = ops.PROFILE.totals_ms()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(a.steps):
+        run_step(i)
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t) / a.steps
+    value = world * B / (ms_per_step * 1e-3)
+    # end to end: features from pinned host memory, predictions back to the host
+    host_x = [f.permute(0, 2, 3, 1).contiguous().cpu().pin_memory() for f in feats]
+    host_pred = torch.empty(V, dtype=torch.int64).pin_memory()
+    e2e_steps = max(3, min(a.steps, 10))
+    barrier()
+    e0.record()
+    for i in range(e2e_steps):
+        j = i % 2
+        (static_x[j] if graphs is not None else feats[j]).permute(0, 2, 3, 1).copy_(host_x[j], non_blocking=True)
+        host_pred.copy_(run_step(i), non_blocking=True)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t) / e2e_steps
+    if rank == 0:
+        peaks = load_peaks()
+        k1_ms, k1_n = prof.get('k1_proj_softmax_pool_fwd', (0.0, 0))
+        k1_avg = k1_ms / max(k1_n, 1)
+        flops = 2.0 * V * HW * C * L.P
+        achieved = flops / (k1_avg * 1e-3) / 1e12 if k1_avg > 0 else 0.0
+        long_region = ms_per_step * a.steps > 1000.0
+        peak = peaks['bf16_sustained'] if long_region else peaks['bf16_burst']
+        line = {'metric': 'inference images/sec (prototype head forward + joint leaf prediction)', 'value': value, 'unit': UNIT,
+                'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3), 'ms_per_step': ms_per_step, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16', 'data': 'synthetic',
+                'config': {'workload': f'{a.workload}: tree {wl["tree"]} ({L.N} nodes, P={L.P}), batch {B}/GPU, single view of '
+                                       f'{H}x{H}x{C} bf16 features, inference forward + node classifiers + joint leaf argmax',
+                           'global_batch': world * B, 'parallelism': f'dp{world} (independent images, no collective)',
+                           'launch': 'one CUDA graph replay per step' if graphs is not None else 'eager',
+                           'l2_policy': f'two alternating input batches of {feats[0].numel() * 2 / 1e6:.0f} MB each (> 126 MB L2)'},
+                'clocks': clocks,
+                'e2e': {'value': world * B / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_x[0].numel() * 2),
+                        'd2h_bytes_per_step': int(V * 8), 'steps': e2e_steps, 'ms_per_step': e2e_ms},
+                'gpu_launches': int(launches_per_step * a.steps),
+                'roofline': {'bound': 'tensor', 'kernel': 'head_pair_kernel<fwd, single view> (projection+softmax+maxpool)',
+                             'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak if peak else None,
+                             'peak_kind': ('sustained' if long_region else 'burst') + ', ' + peaks['source'],
+                             'avg_launch_ms': k1_avg, 'algorithmic_flops_per_launch': flops, 'traffic': None,
+                             'kernels': {k: {'ms_per_step': v[0] / 5, 'calls': v[1]} for k, v in prof.items()}},
+                'cpu_baseline': None}
+        print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    if world > 1:
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_reference(a):
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
@@ -244,8 +463,11 @@ def run_ours(a):
     g = torch.Generator().manual_seed(1234 + rank)
     feats, labels_h = [], []
     for i in range(2):
-        x = torch.randn(V, H, H, C, generator=g, dtype=torch.float32).to(torch.bfloat16)
-        feats.append(x.to(dev).permute(0, 3, 1, 2))           # [V,C,H,W] view with NHWC strides
+        if wl.get('nchw'):      # ResNet contract: NCHW-contiguous (the head's transpose kernel is part of every step)
+            feats.append(torch.randn(V, C, H, H, generator=g, dtype=torch.float32).to(torch.bfloat16).to(dev))
+        else:
+            x = torch.randn(V, H, H, C, generator=g, dtype=torch.float32).to(torch.bfloat16)
+            feats.append(x.to(dev).permute(0, 3, 1, 2))           # [V,C,H,W] view with NHWC strides
         y = torch.randint(0, L.L, (B,), generator=torch.Generator().manual_seed(7 + i + 100 * rank))
         labels_h.append(torch.cat([y, y]))
     labels_d = [y.to(dev) for y in labels_h]
@@ -286,6 +508,35 @@ def run_ours(a):
     barrier()
     eager_ms = e0.elapsed_time(e1) / eager_steps
     launches_per_step = (_cabi.lib().hcomp_launch_count() - launches0) / eager_steps
+
+    # ---------------- the reference-facing API path: what `train_pipnet` runs per step when shapes are static -- the head step
+    # (forward, losses, head backward) as ONE graph replay behind a differentiable op on the backbone's feature map
+    # (pipnet_b200.train.GraphedHeadTrainStep; includes the copy of the feature map into the graph's static input)
+    api_ms = None
+    try:
+        loss_kwargs = dict(epoch=1, net_normalization_multiplier=net._multiplier, pretrain=False, finetune=False, criterion=None,
+                           EPS=1e-8, root=root, kernel_orth=True, tanh_desc=use_td, align=False, uni=False, align_pf=True,
+                           tanh=True, args=args, device=dev, **w)
+        gh = tr.GraphedHeadTrainStep(net, feats[0].detach().requires_grad_(True), labels_d[0], loss_kwargs)
+
+        def api_step(i):
+            for p in net.parameters():
+                p.grad = None
+            x = feats[i % 2].detach().requires_grad_(True)
+            gh(x, labels_d[i % 2]).backward()
+
+        for i in range(3):
+            api_step(i)
+        barrier()
+        e0.record()
+        for i in range(eager_steps):
+            api_step(i)
+        e1.record()
+        barrier()
+        api_ms = e0.elapsed_time(e1) / eager_steps
+        del gh
+    except Exception as ex:
+        sys.stderr.write(f'API-path graph step unavailable: {ex!r}\n')
 
     # ---------------- per-kernel durations: CUDA events around the C-ABI calls of the four large kernels in a
     # GPU-saturated loop (host enqueues run ahead of the device, so a bracket holds the kernel and nothing else;
@@ -353,6 +604,15 @@ def run_ours(a):
         run_step(i)
     barrier()
 
+    if a.sustained > 0:              # size the timed region from a short probe
+        barrier()
+        e0.record()
+        for i in range(10):
+            run_step(i)
+        e1.record()
+        barrier()
+        a.steps = max(a.steps, int(a.sustained * 1e3 / (e0.elapsed_time(e1) / 10)) + 1)
+
     # ---------------- device-resident timing
     sampler = ClockSampler(local)
     sampler.start()
@@ -392,9 +652,10 @@ def run_ours(a):
                     f.write(f'{e.time_range.start - t0:10.1f} {e.time_range.end - e.time_range.start:8.1f}  {e.name[:90]}\n')
 
     # ---------------- end-to-end from pinned host buffers
-    host_x = [f.permute(0, 2, 3, 1).contiguous().cpu().pin_memory() for f in feats]
+    nchw = bool(wl.get('nchw'))
+    host_x = [(f.contiguous() if nchw else f.permute(0, 2, 3, 1).contiguous()).cpu().pin_memory() for f in feats]
     host_y = [y.pin_memory() for y in labels_h]
-    dev_x = torch.empty(V, H, H, C, device=dev, dtype=torch.bfloat16)
+    dev_x = torch.empty((V, C, H, H) if nchw else (V, H, H, C), device=dev, dtype=torch.bfloat16)
     dev_y = torch.empty(V, device=dev, dtype=torch.int64)
     host_loss = torch.empty((), dtype=torch.float32).pin_memory()
     e2e_steps = max(3, min(a.steps, 20))
@@ -412,7 +673,7 @@ def run_ours(a):
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(done[j])                  # the previous step that read this buffer has finished
             if graphs is not None:
-                graphs[j].static_x.detach().permute(0, 2, 3, 1).copy_(host_x[j], non_blocking=True)
+                (graphs[j].static_x.detach() if nchw else graphs[j].static_x.detach().permute(0, 2, 3, 1)).copy_(host_x[j], non_blocking=True)
                 graphs[j].static_y.copy_(host_y[j], non_blocking=True)
             else:
                 dev_xs[j].copy_(host_x[j], non_blocking=True)
@@ -427,7 +688,7 @@ def run_ours(a):
         if graphs is not None:
             loss, _ = graphs[j].replay()
         else:
-            loss, _ = step(dev_xs[j].permute(0, 3, 1, 2), dev_ys[j])
+            loss, _ = step(dev_xs[j] if nchw else dev_xs[j].permute(0, 3, 1, 2), dev_ys[j])
         host_loss.copy_(loss.detach(), non_blocking=True)
         done[j].record(main_stream)
 
@@ -455,6 +716,37 @@ def run_ours(a):
     e2e = {'value': world * B / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': int(host_x[0].numel() * 2 + V * 8),
            'd2h_bytes_per_step': 4, 'steps': e2e_steps, 'ms_per_step': e2e_ms,
            'pipeline': 'H2D of step i+1 on a copy stream overlaps the compute of step i (two device input buffers)'}
+
+    # ---------------- N > 1: are the exchanged head gradients the mean of the per-rank gradients?  (one un-timed step)
+    dp_check = None
+    if world > 1:
+        def flat_grads():
+            return torch.cat([p.grad.detach().reshape(-1).float() for p in net.parameters() if p.grad is not None])
+        step(feats[0], labels_d[0])
+        torch.cuda.synchronize()
+        got = flat_grads().clone()
+        saved_group, ops.GRAD_ALLREDUCE_GROUP = ops.GRAD_ALLREDUCE_GROUP, None
+        step(feats[0], labels_d[0])
+        ops.GRAD_ALLREDUCE_GROUP = saved_group
+        torch.cuda.synchronize()
+        want = flat_grads().clone()
+        dist.all_reduce(want, op=dist.ReduceOp.SUM)
+        want /= world
+        err = (got - want).abs().max() / want.abs().max().clamp_min(1e-30)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        # dW is a split-K fp32 atomic accumulation (order varies run to run) on top of bf16 dZ: 1e-3 of the largest entry
+        dp_check = {'max_rel_err': float(err), 'ok': bool(float(err) <= 1e-3), 'n_values': int(got.numel()),
+                    'what': 'head gradients after the in-backward exchange vs the all-reduced mean of the per-rank gradients '
+                            '(same inputs, exchange disabled), max |diff| / max |mean|, max over ranks',
+                    'exchange': 'symmetric-memory multimem all-reduce' if getattr(ops, 'GRAD_EXCHANGE', '') == 'symm' else 'nccl'}
+
+    # ---------------- every line also carries BASELINE.json config 3 (cub190, 32 images per GPU) as a sub-record
+    sub = {}
+    if a.workload == 'cub27' and not a.no_subrecords:
+        try:
+            sub['cub190'] = quick_train_record(a, 'cub190', dev, rank, world, steps=max(5, min(a.steps, 20)))
+        except Exception as ex:
+            sub['cub190'] = {'error': repr(ex)}
 
     # ---------------- optional: the same step behind a real backbone on synthetic 224x224 images (N = 1 only)
     image_level = None
@@ -501,10 +793,17 @@ def run_ours(a):
                            'global_batch': world * B, 'parallelism': f'dp{world}',
                            'launch': ('one CUDA graph replay per step' if graphs is not None else 'eager'),
                            'eager_ms_per_step': eager_ms,
+                           'api_path': 'train_pipnet replays the head step as one CUDA graph between backbone forward and backward '
+                                       '(GraphedHeadTrainStep, eager fallback on shape / phase change)',
+                           'api_ms_per_step': api_ms,
                            'l2_policy': f'two alternating input batches of {feats[0].numel() * 2 / 1e6:.0f} MB each (> 126 MB L2)'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': cpu}
         if image_level is not None:
             line['image_level'] = image_level
+        if dp_check is not None:
+            line['dp_check'] = dp_check
+        if sub:
+            line['workloads'] = sub
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:
@@ -523,6 +822,10 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cub27', choices=sorted(WORKLOADS))
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-subrecords', action='store_true', help='skip the cub190 sub-record of the default line')
+    ap.add_argument('--sustained', type=float, default=0.0,
+                    help='run the timed region for at least this many seconds (overrides --steps): clocks under sustained load, '
+                         'roofline against the sustained peak')
     ap.add_argument('--with-backbone', action='store_true',
                     help='also report images/s of ConvNeXt-tiny-26 (torchvision, random init, bf16 autocast) + head on 224x224 images')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'])
@@ -531,6 +834,8 @@ def main():
     a = ap.parse_args()
     if a.impl == 'reference':
         run_reference(a)
+    elif WORKLOADS[a.workload].get('mode') == 'inference':
+        run_inference(a)
     else:
         run_ours(a)
 

@@ -72,10 +72,23 @@ __global__ void __launch_bounds__(256) allreduce_mean_kernel(const AllreducePara
   const long long lo = per * p.rank, hi = (lo + per < n4) ? lo + per : n4;
   ar_barrier(p, channel);                       // every rank's producers (dW GEMM, ...) are done: stream order + this
   if (p.mc != nullptr) {
-    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {
-      float4 v = mm_ld_reduce_add(p.mc + 4 * i);          // sum over ranks, computed by the switch
-      v.x *= p.scale; v.y *= p.scale; v.z *= p.scale; v.w *= p.scale;
-      mm_st(p.mc + 4 * i, v);                             // lands in every rank's bucket
+    // UNROLL in-switch reductions in flight per thread before the first store: one multimem.ld_reduce is a ~2-3 us round
+    // trip through the switch, so a load -> store chain per element left the links idle (cub190's 11.7 MB bucket took
+    // 264 us = 44 GB/s on 8 CTAs at 2 GPUs)
+    constexpr int UNROLL = 8;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * UNROLL) {
+      float4 v[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u)
+        if (i0 + u * stride < hi) v[u] = mm_ld_reduce_add(p.mc + 4 * (i0 + u * stride));       // sum over ranks, computed by the switch
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        if (i0 + u * stride < hi) {
+          v[u].x *= p.scale; v[u].y *= p.scale; v[u].z *= p.scale; v[u].w *= p.scale;
+          mm_st(p.mc + 4 * (i0 + u * stride), v[u]);                                           // lands in every rank's bucket
+        }
+      }
     }
   } else {
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += (long long)gridDim.x * blockDim.x) {

@@ -89,7 +89,8 @@ ASYNC_GRAD_ALLREDUCE = True
 # the few SMs the dX GEMM is told to leave free.  'nccl': one NCCL all-reduce (the fallback when symmetric memory or the
 # group's peer mapping is not available, e.g. ranks on different nodes).  Env HC_GRAD_EXCHANGE=nccl forces the fallback.
 GRAD_EXCHANGE = os.environ.get('HC_GRAD_EXCHANGE', 'symm')
-SYMM_CTAS = int(os.environ.get('HC_SYMM_CTAS', '8'))          # CTAs of the all-reduce kernel = SMs reserved from the dX GEMM
+SYMM_CTAS = int(os.environ.get('HC_SYMM_CTAS', '8'))          # minimum CTAs of the all-reduce kernel = SMs reserved from the dX GEMM
+SYMM_CTAS_MAX = 32                                            # large buckets (cub190: 11.7 MB) get one CTA per 128 KB of this rank's shard
 
 
 class _SymmBuffers:
@@ -115,7 +116,10 @@ class _SymmBuffers:
         self.turn = 0
         h = self.hdls[0]
         pad_words = int(h.signal_pad_size) // 4
-        if SYMM_CTAS * self.world > pad_words:
+        self.ctas = max(SYMM_CTAS, min(SYMM_CTAS_MAX, (numel * 4 // self.world) // (128 * 1024)))
+        while self.ctas > 1 and self.ctas * self.world > pad_words:
+            self.ctas //= 2
+        if self.ctas * self.world > pad_words:
             raise RuntimeError('signal pad too small for the all-reduce channels')
         self.multicast = all(int(getattr(x, 'multicast_ptr', 0) or 0) != 0 for x in self.hdls)
 
@@ -223,7 +227,7 @@ def _bucket_allreduce():
             mc = int(h.multicast_ptr) if sb.multicast else 0
             call('hcomp_allreduce_mean_symm', ptr(sb.bufs[b.symm_turn]), C.c_void_p(mc) if mc else None,
                  C.c_void_p(int(h.buffer_ptrs_dev)), C.c_void_p(int(h.signal_pad_ptrs_dev)), sb.rank, sb.world,
-                 C.c_longlong(sb.padded), 0, SYMM_CTAS, C.c_void_p(side.cuda_stream))
+                 C.c_longlong(sb.padded), 0, sb.ctas, C.c_void_p(side.cuda_stream))
         else:
             dist.all_reduce(b.flat, op=dist.ReduceOp.AVG, group=GRAD_ALLREDUCE_GROUP)
     b.flat.record_stream(side)
@@ -233,7 +237,7 @@ def _bucket_allreduce():
 def collective_sms() -> int:
     """SMs the dX GEMM leaves free while the gradient exchange is in flight"""
     if _bucket is not None and _bucket.symm is not None:
-        return max(COLLECTIVE_SMS, SYMM_CTAS)
+        return max(COLLECTIVE_SMS, _bucket.symm.ctas)
     return COLLECTIVE_SMS
 
 

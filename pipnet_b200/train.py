@@ -259,6 +259,127 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
     return out_res
 
 
+
+# --------------------------------------------------------------------------- graphed head step (behind train_pipnet)
+class _HeadReplay(torch.autograd.Function):
+    """autograd node of a replayed head step: forward = the captured loss, backward = the captured d loss / d features
+    (the head parameters' gradients are delivered to `.grad` directly, they never travel through autograd)"""
+
+    @staticmethod
+    def forward(ctx, features, anchor, gh):
+        ctx.gh = gh
+        return gh.loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        gh = ctx.gh
+        for p, gp in zip(gh.params, gh.param_grads):
+            if gp is None:
+                continue
+            if p.grad is None:
+                p.grad = gp                     # static storage, overwritten by the next replay (after optimizer.step)
+            else:
+                p.grad.add_(gp)
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        gx = gh.grad_x
+        if not gh.unit_grad:
+            gx = gx * g
+        return (gx.to(gh.feat_dtype) if gx.dtype != gh.feat_dtype else gx), None, None
+
+
+class GraphedHeadTrainStep:
+    """Head forward + losses + head backward of ONE training step captured into a CUDA graph and exposed as a
+    differentiable op on the backbone's feature map: `loss = step(features, ys); loss.backward()` runs the backbone's
+    backward from the captured feature gradient and leaves the head parameters' gradients in `.grad`.
+    Static shapes only; `train_pipnet` keys its cache on everything that changes the captured work and falls back to the
+    eager path otherwise (`pipnet/train.py:229-264` is the loop this replaces: ~30 launches + autograd bookkeeping per
+    step, 1.4 ms of host time for 0.3 ms of kernels)."""
+
+    def __init__(self, net, features, ys, loss_kwargs, warmup=3, unit_grad=True):
+        m = _unwrap(net)
+        self.m, self.unit_grad = m, unit_grad
+        backbone_ids = {id(p) for p in m._net.parameters()}
+        self.params = [p for p in m.parameters() if id(p) not in backbone_ids and p.requires_grad]
+        self.static_x = features.detach().clone().requires_grad_(True)
+        self.static_y = ys.detach().clone()
+        self.feat_dtype = features.dtype
+        self.node_acc = {}
+        # keeps the node in the autograd graph when the backbone is frozen (features without grad): the head parameters'
+        # gradients are delivered by its backward either way
+        self.anchor = torch.zeros((), device=features.device, requires_grad=True)
+
+        def run():
+            labels = make_labels(net, self.static_y)
+            saved = m._net
+            try:
+                m._net = torch.nn.Identity()          # the backbone already ran: the head's input IS the feature map
+                f, pf, pooled, out = m(self.static_x, labels=labels)
+            finally:
+                m._net = saved
+            res = calculate_loss(loss_kwargs['epoch'], net, {}, f, pf, pooled, out, self.static_y, labels=labels,
+                                 node_accuracy=self.node_acc, train_iter=None, print=False,
+                                 **{k: v for k, v in loss_kwargs.items() if k != 'epoch'})
+            return res, out, labels
+
+        def zero():
+            for p in self.params:
+                p.grad = None
+            self.static_x.grad = None
+
+        saved_grads = [p.grad for p in self.params]
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                zero()
+                self.node_acc.clear()
+                run()[0][0].backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        zero()
+        self.node_acc.clear()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.res, self.out, self.labels = run()
+            self.res[0].backward()
+        self.loss = self.res[0].detach()
+        self.grad_x = self.static_x.grad
+        self.param_grads = [p.grad for p in self.params]
+        for p, g in zip(self.params, saved_grads):      # capture must not leave gradients behind
+            p.grad = g
+
+    def __call__(self, features, ys):
+        self.static_x.detach().copy_(features, non_blocking=True)
+        self.static_y.copy_(ys, non_blocking=True)
+        self.graph.replay()
+        return _HeadReplay.apply(features, self.anchor, self)
+
+
+_GRAPH_CACHE = {}
+
+
+def _graphed_head(net, features, ys, loss_kwargs, flags_key):
+    """cached `GraphedHeadTrainStep` for this (net, shapes, phase, loss switches, trainable set) or None -> eager"""
+    m = _unwrap(net)
+    if os.environ.get('HC_HEAD_GRAPH', '1') == '0' or not features.is_cuda or net is not m:     # DDP-wrapped: eager
+        return None
+    head_state = tuple(bool(p.requires_grad) for p in m.parameters())
+    key = (id(m), tuple(features.shape), features.dtype, tuple(features.stride()), tuple(ys.shape), flags_key, head_state,
+           id(ops.GRAD_ALLREDUCE_GROUP), bool(features.requires_grad))
+    gh = _GRAPH_CACHE.get(key)
+    if gh is None:
+        if len(_GRAPH_CACHE) >= 4:
+            _GRAPH_CACHE.clear()
+        try:
+            gh = GraphedHeadTrainStep(net, features, ys, loss_kwargs)
+        except Exception as ex:                      # capture is an optimisation of the launch path, not of the math
+            import warnings
+            warnings.warn(f'head step not captured ({ex!r}); running it eagerly')
+            gh = False
+        _GRAPH_CACHE[key] = gh
+    return gh or None
+
 # --------------------------------------------------------------------------- epoch drivers
 def _class_to_idx(loader):
     ds = loader.dataset
@@ -344,22 +465,54 @@ def _run_epoch(net, loader, optimizer_net, optimizer_classifier, scheduler_net, 
                 xs, ys = batch
                 xs, ys = xs.to(device, non_blocking=True), ys.to(device, non_blocking=True)
                 xs, ys = torch.cat([xs, xs]), torch.cat([ys, ys])                       # pipnet/train.py:652-653
-            labels = make_labels(net, ys)
-            if train:
-                features, proto_features, pooled, out = net(xs, labels=labels)
+            loss_kwargs = dict(epoch=epoch, net_normalization_multiplier=m._multiplier, pretrain=pretrain, finetune=finetune,
+                               criterion=criterion, EPS=1e-8, root=m.root, label2name=None, OOD_loss_required=False,
+                               kernel_orth=kw.get('kernel_orth', False), tanh_desc=kw.get('tanh_desc', False),
+                               align=kw.get('align', True), uni=kw.get('uni', True), align_pf=kw.get('align_pf', False),
+                               tanh=kw.get('tanh', False), minmaximize=kw.get('minmaximize', False),
+                               cluster_desc=kw.get('cluster_desc', False), sep_desc=kw.get('sep_desc', False),
+                               subspace_sep=kw.get('subspace_sep', False), byol=kw.get('byol', False), train=train, args=args,
+                               device=device, **w)
+            gh = None
+            if train and net is m and xs.is_cuda and os.environ.get('HC_HEAD_GRAPH', '1') != '0':
+                # static shapes: the whole head step (forward, losses, head backward) is ONE CUDA-graph replay between the
+                # backbone's forward and backward; anything that changes the captured work is part of the cache key
+                feats_bb = m._net(xs)
+                flags_key = (bool(pretrain), bool(finetune), epoch if 'y' in getattr(args, 'mask_prune_overspecific', 'n') else 0,
+                             tuple(sorted((k, repr(v)) for k, v in loss_kwargs.items()
+                                          if k not in ('epoch', 'net_normalization_multiplier', 'root', 'args', 'criterion', 'device'))),
+                             repr(sorted(vars(args).items())) if args is not None else '')
+                gh = _graphed_head(net, feats_bb, ys, loss_kwargs, flags_key)
+                if gh is None:                       # eager head on the features already computed
+                    labels = make_labels(net, ys)
+                    saved_bb = m._net
+                    try:
+                        m._net = torch.nn.Identity()
+                        features, proto_features, pooled, out = m(feats_bb, labels=labels)
+                    finally:
+                        m._net = saved_bb
+            if gh is not None:
+                loss = gh(feats_bb, ys)
+                res, out, labels = gh.res, gh.out, gh.labels
+                dacc = gh.node_acc.get('__device__')
+                if dacc is not None:
+                    acc_ep = node_accuracy.setdefault('__device__', {'n_examples': torch.zeros_like(dacc['n_examples']),
+                                                                     'n_correct': torch.zeros_like(dacc['n_correct'])})
+                    acc_ep['n_examples'] += dacc['n_examples']
+                    acc_ep['n_correct'] += dacc['n_correct']
+                it.lazy_postfix = (gh.loss, res[8], res[9], res[10], res[13], 'graph')
             else:
-                features, proto_features, pooled, out = net(xs, apply_overspecificity_mask=kw.get('apply_overspecificity_mask', False),
-                                                            labels=labels)
-            res = calculate_loss(epoch, net, {}, features, proto_features, pooled, out, ys,
-                                 net_normalization_multiplier=m._multiplier, pretrain=pretrain, finetune=finetune,
-                                 criterion=criterion, train_iter=it, print=True, EPS=1e-8, root=m.root, label2name=None,
-                                 node_accuracy=node_accuracy, OOD_loss_required=False, kernel_orth=kw.get('kernel_orth', False),
-                                 tanh_desc=kw.get('tanh_desc', False), align=kw.get('align', True), uni=kw.get('uni', True),
-                                 align_pf=kw.get('align_pf', False), tanh=kw.get('tanh', False),
-                                 minmaximize=kw.get('minmaximize', False), cluster_desc=kw.get('cluster_desc', False),
-                                 sep_desc=kw.get('sep_desc', False), subspace_sep=kw.get('subspace_sep', False),
-                                 byol=kw.get('byol', False), train=train, args=args, device=device, labels=labels, **w)
-            loss, class_d, _, tanh_d, _, _, orth_d = res[:7]
+                if not (train and net is m and xs.is_cuda and os.environ.get('HC_HEAD_GRAPH', '1') != '0'):
+                    labels = make_labels(net, ys)
+                    if train:
+                        features, proto_features, pooled, out = net(xs, labels=labels)
+                    else:
+                        features, proto_features, pooled, out = net(xs, apply_overspecificity_mask=kw.get('apply_overspecificity_mask', False),
+                                                                    labels=labels)
+                res = calculate_loss(additional_network_outputs={}, features=features, proto_features=proto_features,
+                                     pooled=pooled, out=out, ys=ys, net=net, train_iter=it, print=True,
+                                     node_accuracy=node_accuracy, labels=labels, **loss_kwargs)
+                loss = res[0]
             if train:
                 loss.backward()
                 if not pretrain:

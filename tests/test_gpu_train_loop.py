@@ -130,3 +130,43 @@ def test_shipped_script_flags_through_epoch_drivers():
                              kernel_orth=True, tanh_desc=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
                              leave_out_classes=[leaf_children[0]], apply_overspecificity_mask=True)
     assert 0.0 <= info['fine_accuracy'] <= 1.0
+
+
+@pytest.mark.parametrize("phase", ["pretrain", "train", "finetune"])
+def test_graphed_head_step_matches_eager_epoch(phase, monkeypatch):
+    """`train_pipnet` replays the head step (forward, losses, head backward) as ONE CUDA graph between the backbone's
+    forward and backward when shapes are static (pipnet_b200.train.GraphedHeadTrainStep).  Two epochs through the graph
+    path must leave the same parameters, losses and accuracies as the eager path (HC_HEAD_GRAPH=0)."""
+    from pipnet_b200 import train as tr
+    pretrain, finetune = phase == "pretrain", phase == "finetune"
+    results = []
+    for graph in ("1", "0"):
+        monkeypatch.setenv("HC_HEAD_GRAPH", graph)
+        tr._GRAPH_CACHE.clear()
+        args = make_args()
+        net, root = build_net("cub18", 64, args, seed=5)
+        names = net.layout.node_names
+        for n in names:
+            getattr(net, '_' + n + '_add_on').weight.requires_grad = not finetune
+            getattr(net, '_' + n + '_classification').weight.requires_grad = not pretrain
+        opt_net = torch.optim.SGD([{'params': [getattr(net, '_' + n + '_add_on').weight], 'lr': 1e-2} for n in names])
+        opt_cls = torch.optim.SGD([getattr(net, '_' + n + '_classification').weight for n in names], lr=1e-2)
+        sch_net = torch.optim.lr_scheduler.CosineAnnealingLR(opt_net, T_max=40)
+        sch_cls = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt_cls, T_0=5)
+        infos = []
+        for epoch in (1, 2):
+            info, _ = tr.train_pipnet(net, _loader(net, True), opt_net, opt_cls, sch_net, sch_cls, None, epoch, 3, 'cuda',
+                                      pretrain=pretrain, finetune=finetune, kernel_orth=True, align=False, uni=False,
+                                      align_pf=True, tanh=True, args=args)
+            infos.append(info)
+        used_graph = any(v for v in tr._GRAPH_CACHE.values())
+        assert used_graph == (graph == "1")
+        params = torch.cat([p.detach().flatten().float() for p in net.parameters()])
+        results.append((infos, params))
+    (ig, pg), (ie, pe) = results
+    # dW is a split-K fp32 atomic accumulation: identical up to summation order
+    assert float((pg - pe).abs().max()) <= 1e-5 * float(pe.abs().max())
+    for a, b in zip(ig, ie):
+        assert abs(a['loss'] - b['loss']) <= 1e-5 * max(1.0, abs(b['loss']))
+        assert a['fine_accuracy'] == b['fine_accuracy']
+        assert a['node_accuracy'] == b['node_accuracy']
