@@ -696,113 +696,137 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       const int kb_per_term = p.num_k_blocks / p.split_terms;
       const int plane_rows = box < 2 ? p.M : p.P_pad;     // fp32-accurate mode: operand planes are stacked along the rows
       const int32_t* tile_rec = p.tiles + (size_t)p.tile_begin * TILE_INTS + 2;     // word 2 = the MMA's N of a tile
-      int umma_n = (CG2 && box == 2 && worker < total_items) ? __ldg(tile_rec + (size_t)nt * TILE_INTS) : 0;
-      const bool wide_img = p.cpi >= 4;                 // an image spans at least one tile: a tile has <= 2 runs
-      for (int item = worker; item < total_items; item += num_workers) {
-        // Feature tile (boxes 0 / 1) = four 32-location chunks that never straddle an image (chunk c -> image c / cpi,
-        // locations 32 * (c % cpi) ...): consecutive chunks of one image are ONE box of 32 * len rows, or of
-        // 32 * (len - 1) + rem rows when the run ends the image (the rows past HW are not fetched).  With
-        // 676 = 21 * 32 + 4 locations a tile is one box, two at an image boundary; tiny maps (6 x 6) up to four.
-        // The producer is ONE thread: everything here is a handful of instructions on purpose -- a few hundred
-        // instructions of per-item arithmetic drained the five-stage ring at every item boundary.
-        int row1 = 0, row2 = 0, k0 = 0;
-        uint32_t off2 = 0, tx_bytes = 0;
-        bool two = false;
-        const CUtensorMap* map1 = &tmap_w;
-        const CUtensorMap* map2 = &tmap_w;
-        if (box < 2) {
-          const int c0 = (mg * CL + crank) * 4;
-          int img0 = __float2int_rz(__int2float_rz(c0) * p.inv_cpi);     // c0 / cpi: float estimate + exact fix-up
-          k0 = c0 - img0 * p.cpi;
-          if (k0 < 0) { --img0; k0 += p.cpi; }
-          if (k0 >= p.cpi) { ++img0; k0 -= p.cpi; }
-          if (box == 1) img0 += p.imgs_first;
-          row1 = img0 * p.HW + 32 * k0;
-          if (wide_img) {
-            const bool wrap = k0 + 4 >= p.cpi;                 // the tile holds the last chunk of image img0
-            const int len1 = wrap ? p.cpi - k0 : 4;
-            map1 = wrap ? &tmap_x.tail[len1 - 1] : &tmap_x.full[3];
-            two = len1 < 4;
-            map2 = &tmap_x.full[3 - len1 >= 0 ? 3 - len1 : 0];   // 4 - len1 chunks from location 0 of the next image
-            row2 = row1 - 32 * k0 + p.HW;
-            off2 = uint32_t(len1) * (32 * KBLK * 2);
-            int rows = TILE_M - (wrap ? 32 - p.rem : 0);
-            if constexpr (CG2) {                             // the leader also expects the peer's boxes (4 chunks after / before mine)
-              int kp = k0 + (crank == 0 ? 4 : -4);
-              if (kp >= p.cpi) kp -= p.cpi;
-              if (kp < 0) kp += p.cpi;
-              rows += TILE_M - (kp + 4 >= p.cpi ? 32 - p.rem : 0);
-            }
-            tx_bytes = uint32_t(rows) * (KBLK * 2);
-          } else {
-            auto tile_rows = [&](int kk) {
-              int rows = 0;
-              for (int j = 0; j < 4; ++j) { rows += kk == p.cpi - 1 ? p.rem : 32; if (++kk == p.cpi) kk = 0; }
-              return rows;
-            };
-            int rows = tile_rows(k0);
-            if constexpr (CG2) {
-              int kp = k0 + (crank == 0 ? 4 : -4);
-              while (kp >= p.cpi) kp -= p.cpi;
-              while (kp < 0) kp += p.cpi;
-              rows += tile_rows(kp);
-            }
-            tx_bytes = uint32_t(rows) * (KBLK * 2);
-          }
-        } else {
-          row1 = (p.tile_begin + nt) * TILE_N + (CG2 ? crank * (umma_n >> 1) : 0);   // CG2: my half of the tile's N
-          tx_bytes = CG2 ? 2 * BOX_W : BOX_W;
+      // One k-block of one operand box: wait for the stage, announce the bytes, post the box(es).  CG2: completion bytes
+      // are credited to the leader's barrier (tmap_w has a 64-row box there).
+      auto post_begin = [&](uint32_t tx_bytes) -> uint8_t* {
+        HC_SVC_WAIT(&sb->empty[stage], phase ^ 1);
+        if constexpr (!CG2) mbar_arrive_expect_tx(&sb->full[stage], tx_bytes);
+        else if (leader) mbar_arrive_expect_tx(&sb->full[stage], tx_bytes);     // my box(es) + the peer CTA's
+        else mbar_arrive_cluster(&sb->full[stage], 0);
+        return smem + stage * STAGE_BYTES + box_off;
+      };
+      auto post_box = [&](uint8_t* dst, const CUtensorMap* map, int col, int row) {
+        if constexpr (!CG2) tma_load_2d(dst, map, &sb->full[stage], col, row);
+        else tma_load_2d_2cta(dst, map, &sb->full[stage], col, row);
+      };
+      // (k chunk, row offset of the operand plane) of the next k-block without a division.  fp32-accurate mode: the k loop
+      // runs over six cross products of the 3-way bf16 splits, smallest terms first -- the tensor core's fp32
+      // accumulation truncates, so only the last (hi*hi) pass should run at full accumulator magnitude
+      int kc = 0, term = 0, ro = 0;
+      auto k_reset = [&]() { kc = 0; term = 0; ro = p.split_terms > 1 ? (box < 2 ? 2 * plane_rows : 0) : 0; };
+      auto k_next = [&]() {
+        if (++kc == kb_per_term) {
+          kc = 0;
+          ++term;
+          if (p.split_terms > 1)
+            ro = (box < 2 ? ((0x001102 >> (4 * term)) & 3)              // lo, hi, mid, mid, hi, hi
+                          : ((0x010120 >> (4 * term)) & 3)) * plane_rows;     // hi, lo, mid, hi, mid, hi
         }
-        mg += dq; nt += dr;
-        if (nt >= n_groups) { nt -= n_groups; ++mg; }
-        if (CG2 && box == 2 && item + num_workers < total_items)        // next item's record: in flight during this k loop
-          umma_n = __ldg(tile_rec + (size_t)nt * TILE_INTS);
-        int kc = 0, term = 0;
-        int ro = p.split_terms > 1 ? (box < 2 ? 2 * plane_rows : 0) : 0;       // term 0: feature plane lo (2), prototype plane hi (0)
-        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-          HC_T(tp0);
-          HC_SVC_WAIT(&sb->empty[stage], phase ^ 1);
-          HC_T(tp1);
-          uint8_t* dst = smem + stage * STAGE_BYTES + box_off;
-          if constexpr (!CG2) mbar_arrive_expect_tx(&sb->full[stage], tx_bytes);
-          else if (leader) mbar_arrive_expect_tx(&sb->full[stage], tx_bytes);     // my box(es) + the peer CTA's
-          else mbar_arrive_cluster(&sb->full[stage], 0);
-          // CG2: completion bytes are credited to the leader's barrier (tmap_w has a 64-row box there)
-          if (box == 2 || wide_img) {
-            if constexpr (!CG2) tma_load_2d(dst, map1, &sb->full[stage], kc * KBLK, ro + row1);
-            else tma_load_2d_2cta(dst, map1, &sb->full[stage], kc * KBLK, ro + row1);
-            if (two) {
-              if constexpr (!CG2) tma_load_2d(dst + off2, map2, &sb->full[stage], kc * KBLK, ro + row2);
-              else tma_load_2d_2cta(dst + off2, map2, &sb->full[stage], kc * KBLK, ro + row2);
-            }
-          } else {
-            // tiny maps (fewer than 4 chunks per image): up to four runs, worked out on the fly
-            int j = 0, frow = ro + row1, k = k0;
+        if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
+      };
+      // Feature tile (boxes 0 / 1) = four 32-location chunks that never straddle an image (chunk c -> image c / cpi,
+      // locations 32 * (c % cpi) ...): consecutive chunks of one image are ONE box of 32 * len rows, or of
+      // 32 * (len - 1) + rem rows when the run ends the image (the rows past HW are not fetched).
+      // The producer is ONE thread and its per-item code sits between two items' loads: measured, ~260 instructions
+      // (float division fix-ups, the tiny-map path, spills under the 56-register cap) were a 1 - 1.5 us bubble in the
+      // operand ring at EVERY item (profiles/r2_k1_analysis.md).  Hence three separate loops, each with the bare minimum.
+      if (box == 2) {
+        // ---- prototype tile
+        int umma_n = (CG2 && worker < total_items) ? __ldg(tile_rec + (size_t)nt * TILE_INTS) : 0;
+        for (int item = worker; item < total_items; item += num_workers) {
+          const int row = (p.tile_begin + nt) * TILE_N + (CG2 ? crank * (umma_n >> 1) : 0);   // CG2: my half of the tile's N
+          nt += dr;
+          if (nt >= n_groups) nt -= n_groups;
+          if (CG2 && item + num_workers < total_items)        // next item's record: in flight during this k loop
+            umma_n = __ldg(tile_rec + (size_t)nt * TILE_INTS);
+          k_reset();
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            uint8_t* dst = post_begin(CG2 ? 2 * BOX_W : BOX_W);
+            post_box(dst, &tmap_w, kc * KBLK, ro + row);
+            k_next();
+          }
+        }
+      } else if (p.cpi >= 4) {
+        // ---- feature tile, an image spans at least one tile: one box, or two at an image boundary.  (image, chunk)
+        // of the tile's first chunk advance by constants from item to item (item += num_workers moves the m group by
+        // dq, or dq + 1 when the prototype tile index wraps)
+        const int step_c = 4 * CL * dq;                         // chunks per regular item step
+        const int d_img = step_c / p.cpi, d_k = step_c - d_img * p.cpi;
+        const int e_img = (4 * CL) / p.cpi, e_k = 4 * CL - e_img * p.cpi;       // the extra m group of a wrap
+        const int c_first = (mg * CL + crank) * 4;
+        int img0 = c_first / p.cpi, k0 = c_first - img0 * p.cpi;
+        if (box == 1) img0 += p.imgs_first;
+        const int short_rows = 32 - p.rem;                      // rows a tile does NOT fetch when it holds the end of an image
+        for (int item = worker; item < total_items; item += num_workers) {
+          const bool wrap = k0 + 4 >= p.cpi;                    // the tile holds the last chunk of image img0
+          const int len1 = wrap ? p.cpi - k0 : 4;
+          const CUtensorMap* map1 = wrap ? &tmap_x.tail[len1 - 1] : &tmap_x.full[3];
+          const bool two = len1 < 4;
+          const CUtensorMap* map2 = &tmap_x.full[two ? 3 - len1 : 0];     // 4 - len1 chunks from location 0 of the next image
+          const int row1 = img0 * p.HW + 32 * k0, row2 = (img0 + 1) * p.HW;
+          const uint32_t off2 = uint32_t(len1) * (32 * KBLK * 2);
+          int rows = TILE_M - (wrap ? short_rows : 0);
+          if constexpr (CG2) {                                  // the leader also expects the peer's boxes (4 chunks after / before mine)
+            int kp = k0 + (crank == 0 ? 4 : -4);
+            if (kp >= p.cpi) kp -= p.cpi;
+            if (kp < 0) kp += p.cpi;
+            rows += TILE_M - (kp + 4 >= p.cpi ? short_rows : 0);
+          }
+          const uint32_t tx_bytes = uint32_t(rows) * (KBLK * 2);
+          // next item's first chunk
+          img0 += d_img; k0 += d_k;
+          nt += dr;
+          if (nt >= n_groups) { nt -= n_groups; img0 += e_img; k0 += e_k; }
+          while (k0 >= p.cpi) { k0 -= p.cpi; ++img0; }
+          k_reset();
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            HC_T(tp0);
+            uint8_t* dst = post_begin(tx_bytes);
+            HC_T(tp1);
+            post_box(dst, map1, kc * KBLK, ro + row1);
+            if (two) post_box(dst + off2, map2, kc * KBLK, ro + row2);
+            HC_T(tp2);
+#ifdef HC_EXP_TIMING
+            if (box == 0) { dbg_i += tp2 - tp1; dbg_w += tp1 - tp0; ++dbg_n; }
+#endif
+            k_next();
+          }
+        }
+      } else {
+        // ---- feature tile, tiny maps (fewer than 4 chunks per image): up to four runs, worked out on the fly
+        auto tile_rows = [&](int kk) {
+          int rows = 0;
+          for (int j = 0; j < 4; ++j) { rows += kk == p.cpi - 1 ? p.rem : 32; if (++kk == p.cpi) kk = 0; }
+          return rows;
+        };
+        for (int item = worker; item < total_items; item += num_workers) {
+          const int c0 = (mg * CL + crank) * 4;
+          int img0 = c0 / p.cpi;
+          const int k0 = c0 - img0 * p.cpi;
+          if (box == 1) img0 += p.imgs_first;
+          int rows = tile_rows(k0);
+          if constexpr (CG2) {
+            int kp = k0 + (crank == 0 ? 4 : -4);
+            while (kp >= p.cpi) kp -= p.cpi;
+            while (kp < 0) kp += p.cpi;
+            rows += tile_rows(kp);
+          }
+          const uint32_t tx_bytes = uint32_t(rows) * (KBLK * 2);
+          mg += dq; nt += dr;
+          if (nt >= n_groups) { nt -= n_groups; ++mg; }
+          k_reset();
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            uint8_t* dst = post_begin(tx_bytes);
+            int j = 0, frow = ro + img0 * p.HW + 32 * k0, k = k0;
             while (j < 4) {
               const int len = min(4 - j, p.cpi - k);
               const bool ends = k + len == p.cpi;
-              const CUtensorMap* xm = ends ? &tmap_x.tail[len - 1] : &tmap_x.full[len - 1];
-              if constexpr (!CG2) tma_load_2d(dst + j * (32 * KBLK * 2), xm, &sb->full[stage], kc * KBLK, frow);
-              else tma_load_2d_2cta(dst + j * (32 * KBLK * 2), xm, &sb->full[stage], kc * KBLK, frow);
+              post_box(dst + j * (32 * KBLK * 2), ends ? &tmap_x.tail[len - 1] : &tmap_x.full[len - 1], kc * KBLK, frow);
               frow += ends ? 32 * (len - 1) + p.rem : 32 * len;
               j += len; k = ends ? 0 : k + len;
             }
+            k_next();
           }
-          HC_T(tp2);
-#ifdef HC_EXP_TIMING
-          if (box == 0) { HC_ACC(dbg_w, tp0, tp1); HC_ACC(dbg_i, tp1, tp2); ++dbg_n; }
-#endif
-          // next k-block: (k chunk, row offset of the operand plane) without a division.  fp32-accurate mode: the k loop
-          // runs over six cross products of the 3-way bf16 splits, smallest terms first -- the tensor core's fp32
-          // accumulation truncates, so only the last (hi*hi) pass should run at full accumulator magnitude
-          if (++kc == kb_per_term) {
-            kc = 0;
-            ++term;
-            if (p.split_terms > 1)
-              ro = (box < 2 ? ((0x001102 >> (4 * term)) & 3)              // lo, hi, mid, mid, hi, hi
-                            : ((0x010120 >> (4 * term)) & 3)) * plane_rows;     // hi, lo, mid, hi, mid, hi
-          }
-          if (++stage == PAIR_STAGES) { stage = 0; phase ^= 1; }
         }
       }
 #ifdef HC_EXP_TIMING
@@ -1217,6 +1241,9 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
     }
+#ifdef HC_EXP_TIMING
+    if (warp == 4 && lane == 0 && blockIdx.x < 160) g_pair_stamps[blockIdx.x][2] = global_timer_ns();      // item loop done
+#endif
     // ------------------------------------------------------------ rider tail
     // Riders (layout.py): narrow nodes of a nearly empty last tile whose columns ride in the pad columns of other tiles.
     // Their rows are finished HERE, by the epilogue warps, instead of by a separate launch (+7 us forward, +16 us
@@ -1255,12 +1282,59 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
           __threadfence();
         }
         named_bar_sync(2, 32 * EPI_WARPS);
+        // image-aligned 32-location chunks dealt round-robin to all epilogue warps of the grid: the same straight-line
+        // code as a TMEM segment of the item loop (one image per warp, joint two-view pooling), operands from L2
         uint4* xch = &sb->pool_x[(warp - 4) * 4 * PairCfg<S>::XQ];
         const int gw = blockIdx.x * EPI_WARPS + (warp - 4), nw = gridDim.x * EPI_WARPS;
-        for (int r = 0; r < p.n_riders; ++r) {
-          q.node = p.rider[r][0]; q.P_n = p.rider[r][1]; q.poff = p.rider[r][2]; q.zoff = p.rider[r][3];
-          q.dz_col = p.rider[r][4]; q.dz_width = p.rider[r][5];
-          for (int ch = gw; ch < n_chunks; ch += nw) spill_narrow_fwd_rows<S>(q, ch * 32 + lane, lane, xch);
+        for (int ch = gw; ch < p.num_chunks; ch += nw) {
+          const int img = ch / p.cpi, loc_first = 32 * (ch - img * p.cpi);
+          const int loc = loc_first + lane;
+          const bool valid_a = loc < p.HW, valid_b = valid_a && img < p.imgs_second;
+          const int nv_a = __popc(__ballot_sync(0xffffffffu, valid_a));
+          const size_t row_a = (size_t)img * p.HW + loc;
+          for (int r = 0; r < p.n_riders; ++r) {
+            const int node = p.rider[r][0], len = p.rider[r][1], poff = p.rider[r][2], zoff = p.rider[r][3];
+            uint32_t ra[S], rb[S];
+#pragma unroll
+            for (int i = 0; i < S; ++i) ra[i] = rb[i] = 0u;
+            const int n4 = (len + 3) >> 2;
+            if (valid_a) {
+              const float4* z = reinterpret_cast<const float4*>(p.zs + row_a * p.ldz + zoff);
+#pragma unroll
+              for (int i = 0; i < S / 4; ++i)
+                if (i < n4) { const float4 t = __ldcg(z + i); ra[4*i] = __float_as_uint(t.x); ra[4*i+1] = __float_as_uint(t.y); ra[4*i+2] = __float_as_uint(t.z); ra[4*i+3] = __float_as_uint(t.w); }
+            }
+            if (valid_b) {
+              const float4* z = reinterpret_cast<const float4*>(p.zs + ((size_t)p.halfM + row_a) * p.ldz + zoff);
+#pragma unroll
+              for (int i = 0; i < S / 4; ++i)
+                if (i < n4) { const float4 t = __ldcg(z + i); rb[4*i] = __float_as_uint(t.x); rb[4*i+1] = __float_as_uint(t.y); rb[4*i+2] = __float_as_uint(t.z); rb[4*i+3] = __float_as_uint(t.w); }
+            }
+            float s1[S], s2[S];
+            softmax_row<S, true>(ra, len, p.scale_log2, s1);
+            softmax_row<S, true>(rb, len, p.scale_log2, s2);
+            float ip4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < S; i += 2)
+              fma2(ip4[i & 3], ip4[(i & 3) + 1], s1[i], s1[i + 1], s2[i], s2[i + 1], ip4[i & 3], ip4[(i & 3) + 1]);
+            const float ip = (ip4[0] + ip4[1]) + (ip4[2] + ip4[3]);
+            if (p.desc != nullptr && p.align_sum != nullptr) {
+              float a = 0.f;
+              if (valid_b && p.desc[(size_t)img * p.n_nodes + node]) a = -__logf(ip + 1e-12f);
+              const int vs = redux_add_s32(__float2int_rn(a * 1048576.f));
+              if (lane == 0 && vs != 0) atomicAdd(p.align_sum + node, (double)vs * (1.0 / 1048576.0));
+            }
+            unsigned long long* t1 = p.pooled_packed + (size_t)img * p.P + poff;
+            if (nv_a < 32) {
+#pragma unroll
+              for (int i = 0; i < S; ++i) {
+                s1[i] = valid_a ? s1[i] : 0.f;
+                s2[i] = valid_a ? s2[i] : 0.f;
+              }
+            }
+            if (img < p.imgs_second) pool_pair_fast<S>(s1, s2, loc_first, len, lane, xch, t1, t1 + (size_t)imgs_first * p.P);
+            else pool_segment_fast<S>(s1, loc_first, len, lane, xch, t1);
+          }
         }
       } else {
         // backward: the riders' dZ needs only the forward's scratch matrix and the scatter / align tables, not this
@@ -1285,7 +1359,6 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
 #ifdef HC_EXP_TIMING
     if (warp == 4 && lane == 0) {
       const long long te_end = clock64();
-      if (blockIdx.x < 160) g_pair_stamps[blockIdx.x][2] = global_timer_ns();
       if (blockIdx.x == 0) {      // SM clock during the kernel: cycles / ns of one CTA's epilogue loop
         atomicAdd(&g_pair_dbg[10], (unsigned long long)(te_end - te_begin));
         atomicAdd(&g_pair_dbg[11], (unsigned long long)(global_timer_ns() - tns_begin));
