@@ -807,11 +807,17 @@ def run_ours(a):
         print(json.dumps(line), flush=True)
     sys.stdout.flush()
     if world > 1:
-        # graph-captured NCCL work makes process-group teardown unreliable: synchronise, then leave without it
+        # normal teardown (the step's graphs hold the head's own exchange kernel, or NCCL work on the fallback path, so they
+        # go first); a watchdog ends the process if the process-group destructor still hangs behind captured NCCL work
+        graphs = None
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()
-        os._exit(0)
+        watchdog = threading.Timer(20.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
+        dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def main():

@@ -114,6 +114,12 @@ int hcomp_split3_f32(const float* src, void* dst_bf16_3planes, long long n, void
 int hcomp_pack_weights_split3(const float* w_flat, const int32_t* row_map, int P_pad, int C, void* wp3_bf16, void* stream);
 /* NCHW-contiguous features (ResNet) -> bf16 rows [V*HW, C]. */
 int hcomp_nchw_to_rows_bf16(const void* src, int src_is_bf16, int V, int C, int HW, void* dst_bf16, void* stream);
+/* Backbone hand-off: out rows [V*HW, C] (bf16, channels-last) = gamma[c] * keep[v] * y[row, c] + res[row, c],
+ * the tail of the last ConvNeXt block (torchvision CNBlock.forward: layer_scale * block(input), stochastic depth, += input;
+ * features/convnext_features.py:18-25, util/args.py:503 `features.7.2`) written straight into the feature matrix the
+ * projection kernel reads.  y / res: channels-last rows, fp32 or bf16; keep: per-image stochastic-depth factor or NULL. */
+int hcomp_scale_residual_rows_bf16(const void* y, int y_is_bf16, const void* res, int res_is_bf16, const float* gamma,
+                                   const float* keep, int V, int C, int HW, void* out_bf16, void* stream);
 /* tgt[V,N], desc[V_first,N], n_desc[N] from labels (pipnet/train.py:934-937). ys is int64[V]. */
 int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc,
                        int32_t* n_desc, void* stream);

@@ -43,6 +43,7 @@ SIGNATURES = {
     'hcomp_pack_weights': [_p, _p, _i, _i, _p, _p],
     'hcomp_cast_f32_to_bf16': [_p, _p, _ll, _p],
     'hcomp_nchw_to_rows_bf16': [_p, _i, _i, _i, _i, _p, _p],
+    'hcomp_scale_residual_rows_bf16': [_p, _i, _p, _i, _p, _p, _i, _i, _i, _p, _p],
     'hcomp_label_tables': [_p, _T, _i, _i, _p, _p, _p, _p],
     'hcomp_split3_f32': [_p, _p, _ll, _p],
     'hcomp_pack_weights_split3': [_p, _p, _i, _i, _p, _p],

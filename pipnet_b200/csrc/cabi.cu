@@ -588,6 +588,27 @@ int hcomp_nchw_to_rows_bf16(const void* src, int src_is_bf16, int V, int C, int 
   return 0;
 }
 
+int hcomp_scale_residual_rows_bf16(const void* y, int y_is_bf16, const void* res, int res_is_bf16, const float* gamma,
+                                   const float* keep, int V, int C, int HW, void* out_bf16, void* stream) {
+  if (V <= 0 || HW <= 0 || C <= 0 || C % 8 != 0) return fail(HCOMP_E_ARG, "scale_residual: V=%d HW=%d C=%d (C must be a multiple of 8)", V, HW, C);
+  if (((reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(res) | reinterpret_cast<uintptr_t>(out_bf16) |
+        reinterpret_cast<uintptr_t>(gamma)) & 15) != 0)
+    return fail(HCOMP_E_ARG, "scale_residual: operands must be 16-byte aligned");
+  const long long n8 = (long long)V * HW * C / 8;
+  int grid = blocks(n8, 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(out_bf16);
+#define HC_SR(TY, TR) hc::scale_residual_rows_kernel<TY, TR><<<grid, 256, 0, S(stream)>>>( \
+      reinterpret_cast<const TY*>(y), reinterpret_cast<const TR*>(res), gamma, keep, n8, C / 8, HW, out)
+  if (y_is_bf16 && res_is_bf16) HC_SR(__nv_bfloat16, __nv_bfloat16);
+  else if (y_is_bf16) HC_SR(__nv_bfloat16, float);
+  else if (res_is_bf16) HC_SR(float, __nv_bfloat16);
+  else HC_SR(float, float);
+#undef HC_SR
+  HC_LAUNCH_CHECK("scale_residual_rows");
+  return 0;
+}
+
 int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc,
                        int32_t* n_desc, void* stream) {
   HC_CUDA(cudaMemsetAsync(n_desc, 0, sizeof(int32_t) * t->n_nodes, S(stream)));

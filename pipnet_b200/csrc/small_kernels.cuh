@@ -104,6 +104,52 @@ __global__ void nchw_to_rows_bf16_kernel(const T* __restrict__ src, __nv_bfloat1
   }
 }
 
+// ---------------------------------------------------------------- backbone hand-off
+// X rows (bf16, channels-last) = layer_scale[c] * keep[v] * y[row, c] + residual[row, c]: the tail of the LAST ConvNeXt
+// block (torchvision CNBlock.forward: layer_scale * block(input), stochastic depth, += input; the reference uses the
+// stock model, features/convnext_features.py:18-25, util/args.py:503 names features.7.2).  One pass writes the feature
+// matrix K1's TMA reads -- no separate scale / add / cast / layout kernels between the backbone and the head.
+// y, residual: channels-last rows [M, C], fp32 or bf16; 8 channels (16 output bytes) per thread.
+template <typename TY, typename TR>
+__global__ void __launch_bounds__(256) scale_residual_rows_kernel(const TY* __restrict__ y, const TR* __restrict__ res,
+                                                                  const float* __restrict__ gamma, const float* __restrict__ keep,
+                                                                  long long n8, int C8, int HW, __nv_bfloat16* __restrict__ out) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / C8;
+    const int c = int(i - row * C8) * 8;
+    const float k = keep != nullptr ? keep[row / HW] : 1.f;
+    float yv[8], rv[8];
+    if constexpr (sizeof(TY) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(y) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(y) + 2 * i + 1);
+      yv[0] = a.x; yv[1] = a.y; yv[2] = a.z; yv[3] = a.w; yv[4] = b.x; yv[5] = b.y; yv[6] = b.z; yv[7] = b.w;
+    } else {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(y) + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); yv[2 * j] = f.x; yv[2 * j + 1] = f.y; }
+    }
+    if constexpr (sizeof(TR) == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(res) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(res) + 2 * i + 1);
+      rv[0] = a.x; rv[1] = a.y; rv[2] = a.z; rv[3] = a.w; rv[4] = b.x; rv[5] = b.y; rv[6] = b.z; rv[7] = b.w;
+    } else {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(res) + i);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { const float2 f = __bfloat1622float2(h[j]); rv[2 * j] = f.x; rv[2 * j + 1] = f.y; }
+    }
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+    const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    uint4 o;
+    uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaf(g[2 * j] * k, yv[2 * j], rv[2 * j]), fmaf(g[2 * j + 1] * k, yv[2 * j + 1], rv[2 * j + 1]));
+      ow[j] = *reinterpret_cast<const uint32_t*>(&h2);
+    }
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
 // ---------------------------------------------------------------- pool unpack
 // packed = (float bits << 32) | (0xFFFFFFFF - location)  ->  pooled, argmax (+ inference threshold,
 // pipnet/pipnet.py:168-169: pooled < 0.1 -> 0).

@@ -384,6 +384,49 @@ def feature_rows(features: torch.Tensor):
 PREC_BF16, PREC_FP32X3 = 0, 1
 
 
+class ScaleResidualRows(torch.autograd.Function):
+    """Tail of the last ConvNeXt block fused into the producer of the head's feature matrix:
+    features = layer_scale * keep * y + residual written ONCE, as bf16 channels-last rows -- exactly what the projection
+    kernel's TMA reads (torchvision `CNBlock.forward`; the reference uses the stock model, features/convnext_features.py:18-25).
+    y: the block's NHWC-in-memory output [V,C,H,W]; residual: the block's input; gamma: layer_scale [C,1,1];
+    keep: per-image stochastic-depth factor [V] or None.  Returns [V,C,H,W] bf16 with channels-last strides."""
+
+    @staticmethod
+    def forward(ctx, y, residual, gamma, keep):
+        _require_cuda(y, 'block output')
+        V, Cc, H, W = y.shape
+        yr = y if y.is_contiguous(memory_format=torch.channels_last) else y.contiguous(memory_format=torch.channels_last)
+        rr = residual if residual.is_contiguous(memory_format=torch.channels_last) else residual.contiguous(memory_format=torch.channels_last)
+        if yr.dtype not in (torch.float32, torch.bfloat16) or rr.dtype not in (torch.float32, torch.bfloat16):
+            raise _cabi.HcompError(f'unsupported backbone dtypes {yr.dtype} / {rr.dtype}')
+        g = gamma.detach().reshape(-1).float().contiguous()
+        k = keep.detach().float().contiguous() if keep is not None else None
+        out = torch.empty(V, H, W, Cc, device=y.device, dtype=torch.bfloat16)
+        call('hcomp_scale_residual_rows_bf16', ptr(yr), int(yr.dtype == torch.bfloat16), ptr(rr), int(rr.dtype == torch.bfloat16),
+             ptr(g), ptr(k), V, Cc, H * W, ptr(out), _stream())
+        ctx.save_for_backward(y, gamma, keep)
+        ctx.res_dtype = residual.dtype
+        return out.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, grad):
+        y, gamma, keep = ctx.saved_tensors
+        g32 = grad.float()
+        kk = keep.view(-1, 1, 1, 1).float() if keep is not None else None
+        gy = gres = ggamma = None
+        if ctx.needs_input_grad[0]:
+            t = g32 * gamma.float().view(1, -1, 1, 1)
+            gy = (t * kk if kk is not None else t).to(y.dtype)
+        if ctx.needs_input_grad[1]:
+            gres = grad.to(ctx.res_dtype)
+        if ctx.needs_input_grad[2]:
+            t = g32 * y.float()
+            if kk is not None:
+                t = t * kk
+            ggamma = t.sum(dim=(0, 2, 3)).view_as(gamma).to(gamma.dtype)
+        return gy, gres, ggamma, None
+
+
 def pack_weights(w_flat: torch.Tensor, dl: DeviceLayout, precision=PREC_BF16):
     """fp32 flat kernels [P,C] -> (wp, wpc): wp = tile-padded bf16 [P_pad,C] for the fused projection kernels (3 stacked
     split planes in fp32-accurate mode), wpc = bf16 [P_c,C] on the compact dZ axis for the dX GEMM."""

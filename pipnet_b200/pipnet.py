@@ -20,6 +20,7 @@ Unsupported research variants raise `Exception` like the reference does for inva
 from __future__ import annotations
 
 import argparse
+import os
 from collections import OrderedDict
 from typing import Dict, List, Optional
 
@@ -428,7 +429,40 @@ def _convnext_tiny(threshold, pretrained=False):
     model.classifier = nn.Identity()
     if threshold is not None:
         _relax_strides(model, threshold)
+    if os.environ.get('HC_FUSE_BACKBONE_TAIL', '1') != '0':
+        fuse_convnext_tail(model)
     return model
+
+
+def fuse_convnext_tail(model) -> bool:
+    """Backbone hand-off: make the LAST ConvNeXt block (`features.7.2`, the one `util/args.py:503` names) emit
+    the head's feature matrix itself -- its `layer_scale * block(x)`, stochastic depth and residual add run as ONE kernel
+    that writes bf16 channels-last rows (`ops.ScaleResidualRows`), so nothing (no scale / add / cast / layout pass) sits
+    between the backbone and the projection kernel.  Same parameters, same state_dict; CPU tensors keep the stock path."""
+    try:
+        from torchvision.models.convnext import CNBlock
+    except Exception:
+        return False
+    blocks = [m for m in model.modules() if isinstance(m, CNBlock)]
+    if not blocks:
+        return False
+    last = blocks[-1]
+
+    def forward(input):
+        y = last.block(input)
+        if not y.is_cuda:
+            return last.stochastic_depth(last.layer_scale * y) + input
+        keep = None
+        p_drop = float(getattr(last.stochastic_depth, 'p', 0.0))
+        if last.training and p_drop > 0.0:                      # torchvision.ops.stochastic_depth, mode "row"
+            survival = 1.0 - p_drop
+            keep = torch.empty(y.shape[0], device=y.device, dtype=torch.float32).bernoulli_(survival)
+            if survival > 0.0:
+                keep.div_(survival)
+        return ops.ScaleResidualRows.apply(y, input, last.layer_scale, keep)
+
+    last.forward = forward
+    return True
 
 
 def convnext_tiny_26_features(pretrained=False, **kw): return _convnext_tiny(100, pretrained)

@@ -170,3 +170,51 @@ def test_graphed_head_step_matches_eager_epoch(phase, monkeypatch):
         assert abs(a['loss'] - b['loss']) <= 1e-5 * max(1.0, abs(b['loss']))
         assert a['fine_accuracy'] == b['fine_accuracy']
         assert a['node_accuracy'] == b['node_accuracy']
+
+
+@pytest.mark.parametrize("autocast", [False, True], ids=["fp32", "bf16-autocast"])
+def test_fused_convnext_tail_matches_stock_block(autocast):
+    """SURVEY 8f-4, second half: the last ConvNeXt block (`features.7.2`) writes the head's bf16 channels-last feature
+    matrix itself (`layer_scale * block(x)` + stochastic depth + residual in one kernel, ops.ScaleResidualRows).  Output and
+    gradients must match the stock torchvision block, and the head must consume the result without any cast / layout call."""
+    from torchvision.models.convnext import CNBlock
+    from pipnet_b200 import ops, pipnet as pp, _cabi
+    torch.manual_seed(0)
+    stock = CNBlock(768, 1e-6, 0.0).cuda()
+    with torch.no_grad():
+        stock.layer_scale.copy_(torch.rand_like(stock.layer_scale) + 0.5)
+    import copy
+    fused = copy.deepcopy(stock)
+    holder = torch.nn.Sequential(fused)
+    assert pp.fuse_convnext_tail(holder)
+    x = torch.randn(4, 768, 13, 13, device='cuda').contiguous(memory_format=torch.channels_last)
+    g = torch.randn(4, 768, 13, 13, device='cuda')
+    outs = []
+    for blk in (stock, fused):
+        xi = x.clone().requires_grad_(True)
+        with torch.autocast('cuda', dtype=torch.bfloat16, enabled=autocast):
+            y = blk(xi)
+        (y.float() * g).sum().backward()
+        outs.append((y.detach().float(), xi.grad.float(), blk.layer_scale.grad.float(),
+                     blk.block[0].weight.grad.float()))
+    (y0, gx0, gg0, gw0), (y1, gx1, gg1, gw1) = outs
+    assert fused(x).dtype == torch.bfloat16 and fused(x).is_contiguous(memory_format=torch.channels_last)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    assert rel(y1, y0) <= 2e-2 and rel(gx1, gx0) <= 2e-2 and rel(gg1, gg0) <= 2e-2 and rel(gw1, gw0) <= 2e-2
+    # stochastic depth in training mode: dropped images are the plain residual
+    drop = copy.deepcopy(stock)
+    drop.stochastic_depth.p = 1.0
+    hd = torch.nn.Sequential(drop)
+    pp.fuse_convnext_tail(hd)
+    drop.train()
+    assert rel(drop(x).float(), x) <= 1e-2
+    # the head reads the fused output in place: no cast / transpose call between backbone and projection kernel
+    names = []
+    real_call = ops.call
+    try:
+        ops.call = lambda name, *a: (names.append(name), real_call(name, *a))[1]
+        rows = ops.feature_rows(fused(x))
+    finally:
+        ops.call = real_call
+    assert rows.dtype == torch.bfloat16 and rows.shape == (4 * 169, 768)
+    assert 'hcomp_cast_f32_to_bf16' not in names and 'hcomp_nchw_to_rows_bf16' not in names
