@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define HCOMP_ABI_VERSION 5
+#define HCOMP_ABI_VERSION 6
 #define HCOMP_TILE_INTS 56
 #define HCOMP_TILE_COLS 128
 #define HCOMP_MAX_SEGS 16
@@ -192,6 +192,44 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
                           const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V, int V_first, int C,
                           int flags, const float* weights_host, float eps, float multiplier, const float* ws,
                           const uint8_t* rel, float* gvec, float* g_pooled, float* g_out, float* g_w, void* stream);
+
+/* ---- fused chains (ABI v6): the same arithmetic as the entry points above in four multi-role launches ------------- */
+/* The small per-step work between the four large kernels is launch-latency bound (27 launches, 36 us of a 0.31 ms
+ * cub27 step); these calls do it in ONE launch each.  Results equal the separate calls (same arithmetic per element;
+ * block-level sums may associate differently).
+ *
+ * hcomp_head_prologue: everything K1 needs --
+ *   rows > 0      : hcomp_pack_weights(w_flat, row_map, rows, C, wp_bf16)
+ *   packed != NULL: clears pooled_packed[n_packed] and align_sum[n_align] (then call K1 with outputs_zeroed = 1)
+ *   ys != NULL    : hcomp_label_tables(ys, t, V, V_first, tgt, desc, n_desc), n_desc needs no clearing. */
+int hcomp_head_prologue(const float* w_flat, const int32_t* row_map, int rows, int C, void* wp_bf16,
+                        unsigned long long* packed, long long n_packed, double* align_sum, int n_align, const long long* ys,
+                        const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc, void* stream);
+/* hcomp_unpack_pool + hcomp_align_finalize (align / align_sum / n_desc may be NULL) + hcomp_classifier_fwd (out / wc may
+ * be NULL; the inference threshold applies to the classifier's input like pipnet/pipnet.py:168-170). */
+int hcomp_pool_classify_fwd(const unsigned long long* packed, const double* align_sum, const int32_t* n_desc, const float* wc,
+                            const float* bias, const hcomp_tables* t, int V, int HW, float thresh, float* pooled,
+                            int32_t* argmax, float* align, float* out, void* stream);
+/* Workspace of the chained losses: hcomp_head_losses_ws_floats(t) + V * N floats (row log-sum-exp of the class term). */
+long long hcomp_head_chain_ws_floats(const hcomp_tables* t, int V);
+/* The weights-only part of the orth term (Gram matrices, ||E||^2, relevance mask) into ws / rel; may run on ANY stream
+ * before hcomp_head_chain_fwd (e.g. beside K1) -- then pass HCOMP_LOSS_ORTH_READY there. */
+#define HCOMP_LOSS_ORTH_READY 16
+int hcomp_orth_gram(const float* w_flat, const float* wc, const hcomp_tables* t, int C, float* ws, uint8_t* rel, void* stream);
+/* hcomp_head_losses_fwd in one launch (plus two for the orth term unless HCOMP_LOSS_ORTH_READY).  counter: one DEVICE
+ * uint32 that is zero on entry and left zero (last-block-done combine); one call at a time per counter. */
+int hcomp_head_chain_fwd(const float* pooled, const float* out, const float* align, const float* w_flat, const float* wc,
+                         const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V, int V_first, int C,
+                         int flags, const float* weights_host, float eps, float multiplier, float* total, float* stats,
+                         int32_t* n_correct, float* ws, uint8_t* rel, unsigned int* counter, void* stream);
+/* Backward of hcomp_head_chain_fwd CHAINED THROUGH THE CLASSIFIER (out = classifier(pooled, wc, bias)): one launch gives
+ * g_pooled [V,P] (tanh term + class term through relu(Wc)), g_wc [n_welems], g_bias [K], g_align [N]; the orth term's
+ * g_w [P,C] runs beside it.  d loss / d out is never materialised.  Any output may be NULL. */
+int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float* out, const float* w_flat, const float* wc,
+                         const int8_t* tgt, const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V,
+                         int V_first, int C, int flags, const float* weights_host, float eps, float multiplier,
+                         const float* ws, const uint8_t* rel, float* g_pooled, float* g_wc, float* g_bias, float* g_align,
+                         float* g_w, void* stream);
 
 /* ---- descendant-structured loss terms switched on by the shipped scripts ------------------------ */
 /* (run_pipnet_20protos_multi_runs_seed42.sh: --tanh_desc "y|0.05" --minimize_contrasting_set 'y'

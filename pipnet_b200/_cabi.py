@@ -11,7 +11,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libhcomp_head.so')
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 
 class HcompError(RuntimeError):
@@ -57,6 +57,11 @@ SIGNATURES = {
     'hcomp_classifier_bwd': [_p, _p, _p, _T, _i, _p, _i, _p, _p, _p],
     'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p],
     'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_prologue': [_p, _p, _i, _i, _p, _p, _ll, _p, _i, _p, _T, _i, _i, _p, _p, _p, _p],
+    'hcomp_pool_classify_fwd': [_p, _p, _p, _p, _p, _T, _i, _i, _f, _p, _p, _p, _p, _p],
+    'hcomp_orth_gram': [_p, _p, _T, _i, _p, _p, _p],
+    'hcomp_head_chain_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_chain_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_desc_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_desc_losses_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p, _p],
@@ -66,7 +71,7 @@ SIGNATURES = {
     'hcomp_allreduce_mean_symm': [_p, _p, _p, _p, _i, _i, _ll, _i, _i, _p],
 }
 EXPORTS = ['hcomp_abi_version', 'hcomp_last_error', 'hcomp_num_sms', 'hcomp_launch_count', 'hcomp_head_losses_ws_floats',
-           'hcomp_desc_losses_ws_bytes', 'hcomp_set_cta_pair', 'hcomp_set_rider_fold', 'hcomp_set_reserved_sms', 'hcomp_init'] + list(SIGNATURES)
+           'hcomp_desc_losses_ws_bytes', 'hcomp_head_chain_ws_floats', 'hcomp_set_cta_pair', 'hcomp_set_rider_fold', 'hcomp_set_reserved_sms', 'hcomp_init'] + list(SIGNATURES)
 
 _lib = None
 
@@ -86,6 +91,8 @@ def lib():
     L.hcomp_launch_count.restype = C.c_longlong
     L.hcomp_head_losses_ws_floats.restype = C.c_longlong
     L.hcomp_head_losses_ws_floats.argtypes = [_T]
+    L.hcomp_head_chain_ws_floats.restype = C.c_longlong
+    L.hcomp_head_chain_ws_floats.argtypes = [_T, C.c_int]
     L.hcomp_desc_losses_ws_bytes.restype = C.c_longlong
     L.hcomp_desc_losses_ws_bytes.argtypes = [_T, C.c_int]
     L.hcomp_set_cta_pair.restype = C.c_int

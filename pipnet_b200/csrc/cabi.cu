@@ -666,19 +666,15 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
   p.scat = reinterpret_cast<const int2*>(scat_ws);
   p.dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
   p.P_c = P_c;
-  SideBranch* sb = nullptr;
-  if (g_align != nullptr && desc != nullptr && n_desc != nullptr) {       // beside make_scat
-    if (int e = side_branch(&sb, 0)) return e;
-    HC_FORK(sb, S(stream));
-    hc::align_coef_kernel<<<blocks((long long)V_first * n_nodes, 256), 256, 0, sb->stream>>>(desc, n_desc, g_align, V_first,
-                                                                                            n_nodes, HW, coef_ws);
-    HC_LAUNCH_CHECK("align_coef");
-    p.coef_align = coef_ws;
+  {                                     // scatter table + align coefficients: one launch
+    const bool use_align = g_align != nullptr && desc != nullptr && n_desc != nullptr;
+    const int nb_scat = blocks(n, 256), nb_coef = use_align ? blocks((long long)V_first * n_nodes, 256) : 0;
+    hc::bwd_prep_kernel<<<nb_scat + nb_coef, 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
+                                                                  reinterpret_cast<int2*>(scat_ws), nb_scat, desc, n_desc,
+                                                                  g_align, V_first, n_nodes, HW, coef_ws);
+    HC_LAUNCH_CHECK("bwd_prep");
+    if (use_align) p.coef_align = coef_ws;
   }
-  hc::make_scat_kernel<<<blocks(n, 256), 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
-                                                               reinterpret_cast<int2*>(scat_ws));
-  HC_LAUNCH_CHECK("make_scat");
-  if (sb) HC_JOIN(sb, S(stream));
   if (spill != nullptr && spill->n_spill > 0) { p.zs = spill->zs; p.ldz = spill->ldz; }
   bool folded = false;
   if (int e = run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
@@ -851,6 +847,132 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
   }
   if (sb_bwd) HC_JOIN(sb_bwd, S(stream));
   if (sb_tb) HC_JOIN(sb_tb, S(stream));
+  return 0;
+}
+
+// ---------------------------------------------------------------- fused chains (ABI v6)
+int hcomp_head_prologue(const float* w_flat, const int32_t* row_map, int rows, int C, void* wp_bf16,
+                        unsigned long long* packed, long long n_packed, double* align_sum, int n_align, const long long* ys,
+                        const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc, void* stream) {
+  hc::PrologueParams q{};
+  if (rows > 0) {
+    if (C % 8 != 0) return fail(HCOMP_E_ARG, "prologue: C=%d must be a multiple of 8", C);
+    q.w = w_flat; q.row_map = row_map; q.rows = rows; q.C = C; q.wp = reinterpret_cast<__nv_bfloat16*>(wp_bf16);
+    q.nb_pack = blocks((long long)rows * (C >> 3), 256);
+  }
+  if (packed != nullptr || align_sum != nullptr) {
+    q.packed = packed; q.n_packed = packed ? n_packed : 0; q.align_sum = align_sum; q.n_align = n_align;
+    q.nb_zero = blocks((q.n_packed + 1) / 2, 256);
+    if (q.nb_zero == 0) q.nb_zero = 1;
+  }
+  if (ys != nullptr) {
+    q.ys = ys; q.anc = t->anc; q.V = V; q.V_first = V_first; q.N = t->n_nodes; q.L = t->n_leaves;
+    q.tgt = tgt; q.desc = desc; q.n_desc = n_desc;
+    q.nb_tgt = blocks((long long)V * t->n_nodes, 256);
+    q.nb_cnt = blocks(t->n_nodes, 8);
+  }
+  const int grid = q.nb_pack + q.nb_zero + q.nb_tgt + q.nb_cnt;
+  if (grid == 0) return 0;
+  hc::head_prologue_kernel<<<grid, 256, 0, S(stream)>>>(q);
+  HC_LAUNCH_CHECK("head_prologue");
+  return 0;
+}
+
+int hcomp_pool_classify_fwd(const unsigned long long* packed, const double* align_sum, const int32_t* n_desc, const float* wc,
+                            const float* bias, const hcomp_tables* t, int V, int HW, float thresh, float* pooled,
+                            int32_t* argmax, float* align, float* out, void* stream) {
+  hc::PoolClassifyParams q{};
+  q.packed = packed; q.align_sum = align_sum; q.n_desc = n_desc; q.wc = wc; q.bias = bias;
+  q.col_node = t->col_node; q.proto_off = t->proto_off; q.cls_off = t->cls_off; q.wc_off = t->wc_off;
+  q.V = V; q.P = t->n_protos; q.K = t->n_cols; q.N = t->n_nodes; q.HW = HW; q.thresh = thresh;
+  q.pooled = pooled; q.argmax = argmax; q.align = align; q.out = out;
+  q.nb_unpack = blocks((long long)V * t->n_protos, 256);
+  q.nb_cls = (out != nullptr && wc != nullptr) ? blocks((long long)V * t->n_cols, 256) : 0;
+  const int nb_align = (align != nullptr && align_sum != nullptr && n_desc != nullptr) ? blocks(t->n_nodes, 256) : 0;
+  hc::pool_classify_fwd_kernel<<<q.nb_unpack + q.nb_cls + nb_align, 256, 0, S(stream)>>>(q);
+  HC_LAUNCH_CHECK("pool_classify_fwd");
+  return 0;
+}
+
+long long hcomp_head_chain_ws_floats(const hcomp_tables* t, int V) {
+  return hcomp_head_losses_ws_floats(t) + (long long)V * t->n_nodes;
+}
+
+int hcomp_orth_gram(const float* w_flat, const float* wc, const hcomp_tables* t, int C, float* ws, uint8_t* rel, void* stream) {
+  const LossWs w = loss_ws(ws, t);
+  if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
+  const long long warps = (long long)t->n_nodes * t->p_max * t->p_max;
+  hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
+                                                                      t->n_nodes, C, t->p_max, w.E, rel);
+  HC_LAUNCH_CHECK("orth_gram");
+  hc::orth_sumsq_kernel<<<blocks((long long)t->n_nodes * 32, 128), 128, 0, S(stream)>>>(w.E, t->proto_off, t->n_nodes,
+                                                                                       t->p_max, w.orth_sq);
+  HC_LAUNCH_CHECK("orth_sumsq");
+  return 0;
+}
+
+int hcomp_head_chain_fwd(const float* pooled, const float* out, const float* align, const float* w_flat, const float* wc,
+                         const int8_t* tgt, const int32_t* n_desc, const hcomp_tables* t, int V, int V_first, int C,
+                         int flags, const float* weights_host, float eps, float multiplier, float* total, float* stats,
+                         int32_t* n_correct, float* ws, uint8_t* rel, unsigned int* counter, void* stream) {
+  const LossWs w = loss_ws(ws, t);
+  const bool do_tanh = flags & HCOMP_LOSS_TANH, do_orth = flags & HCOMP_LOSS_ORTH, do_cls = flags & HCOMP_LOSS_CLASS;
+  if ((flags & HCOMP_LOSS_SPARSITY) && !(multiplier > 0.f)) return fail(HCOMP_E_ARG, "class loss: log1p(out**m) needs m > 0 (got %g)", multiplier);
+  if (do_orth && !(flags & HCOMP_LOSS_ORTH_READY))
+    if (int e = hcomp_orth_gram(w_flat, wc, t, C, ws, rel, stream)) return e;
+  hc::ChainFwdParams q{};
+  q.pooled = pooled; q.out = out; q.align = align; q.orth_sq = do_orth ? w.orth_sq : nullptr;
+  q.tgt = tgt; q.n_desc = n_desc; q.child_w = t->child_w; q.proto_off = t->proto_off; q.cls_off = t->cls_off;
+  q.V = V; q.V_first = V_first; q.N = t->n_nodes; q.P = t->n_protos; q.K = t->n_cols;
+  q.eps = eps; q.mult = (flags & HCOMP_LOSS_SPARSITY) ? multiplier : 0.f; q.do_tanh = do_tanh; q.do_cls = do_cls;
+  for (int i = 0; i < 4; ++i) q.lw.w[i] = weights_host[i];
+  q.tanh_part = w.tanh_part; q.colsum = w.colsum; q.cls = w.cls; q.lse = ws + hcomp_head_losses_ws_floats(t);
+  q.n_correct = n_correct; q.stats = stats; q.total = total; q.counter = counter;
+  hc::head_chain_fwd_kernel<<<dim3(t->n_nodes, 3), 256, 0, S(stream)>>>(q);
+  HC_LAUNCH_CHECK("head_chain_fwd");
+  return 0;
+}
+
+int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float* out, const float* w_flat, const float* wc,
+                         const int8_t* tgt, const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V,
+                         int V_first, int C, int flags, const float* weights_host, float eps, float multiplier,
+                         const float* ws, const uint8_t* rel, float* g_pooled, float* g_wc, float* g_bias, float* g_align,
+                         float* g_w, void* stream) {
+  const LossWs w = loss_ws(const_cast<float*>(ws), t);
+  const int N = t->n_nodes;
+  if ((flags & HCOMP_LOSS_SPARSITY) && !(multiplier > 0.f)) return fail(HCOMP_E_ARG, "class loss: log1p(out**m) needs m > 0 (got %g)", multiplier);
+  SideBranch* sb = nullptr;
+  if (g_w) {
+    if (flags & HCOMP_LOSS_ORTH) {      // weights-only term: beside the chain kernel
+      if (int e = side_branch(&sb)) return e;
+      HC_FORK(sb, S(stream));
+      hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
+          w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
+      HC_LAUNCH_CHECK("orth_bwd");
+    } else {
+      HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
+    }
+  }
+  hc::ChainBwdParams q{};
+  q.g_total = g_total; q.pooled = pooled; q.out = out; q.wc = wc; q.colsum = w.colsum;
+  q.lse = ws + hcomp_head_losses_ws_floats(t); q.tgt = tgt; q.n_desc = n_desc; q.child_w = t->child_w;
+  q.proto_node = t->proto_node; q.proto_off = t->proto_off; q.cls_off = t->cls_off; q.wc_off = t->wc_off;
+  q.col_node = t->col_node; q.welem_col = t->welem_col; q.welem_proto = t->welem_proto;
+  q.V = V; q.V_first = V_first; q.N = N; q.P = t->n_protos; q.K = t->n_cols; q.n_w = t->n_welems;
+  q.eps = eps; q.mult = (flags & HCOMP_LOSS_SPARSITY) ? multiplier : 0.f;
+  q.do_tanh = (flags & HCOMP_LOSS_TANH) ? 1 : 0; q.do_cls = (flags & HCOMP_LOSS_CLASS) ? 1 : 0;
+  for (int i = 0; i < 4; ++i) q.lw.w[i] = weights_host[i];
+  q.g_pooled = g_pooled; q.g_wc = g_wc; q.g_bias = g_bias; q.g_align = g_align;
+  q.nb_pooled = g_pooled ? blocks((long long)V * t->n_protos, 256) : 0;
+  q.nb_wc = g_wc ? blocks(t->n_welems, 8) : 0;
+  q.nb_bias = g_bias ? blocks(t->n_cols, 256) : 0;
+  const int nb_align = g_align ? blocks(N, 256) : 0;
+  const int grid = q.nb_pooled + q.nb_wc + q.nb_bias + nb_align;
+  if (grid > 0) {
+    hc::head_chain_bwd_kernel<<<grid, 256, 0, S(stream)>>>(q);
+    HC_LAUNCH_CHECK("head_chain_bwd");
+  }
+  if (sb) HC_JOIN(sb, S(stream));
   return 0;
 }
 

@@ -518,6 +518,363 @@ __global__ void make_scat_kernel(const int32_t* __restrict__ argmax, const float
   scat[i] = make_int2(argmax[i], __float_as_int(g));
 }
 
+// ================================================================ fused chains (ABI v6)
+// The per-step small work between the four large kernels used to be ~27 launches on the critical path (36 us of an
+// 0.31 ms cub27 step, almost all of it launch latency).  The same arithmetic in FOUR multi-role launches: a block's role
+// is a range of blockIdx.x, roles never communicate inside a launch (except the last-block-done combine of the losses).
+
+// ---- head prologue: everything K1 needs, one launch ---------------------------------------------------------------
+//   role A  pack the prototype kernels into their bf16 GEMM layouts (pack_weights_kernel's job)
+//   role B  clear the packed max table and the align accumulators K1 merges into with atomics
+//   role C  label tables (label_tables_kernel's job, without the n_desc memset: one warp per node counts)
+struct PrologueParams {
+  const float* w; const int32_t* row_map; int rows, C; __nv_bfloat16* wp;        // A (rows == 0: skipped)
+  unsigned long long* packed; long long n_packed; double* align_sum; int n_align;   // B
+  const long long* ys; const int8_t* anc; int V, V_first, N, L;                     // C (ys == nullptr: skipped)
+  int8_t* tgt; uint8_t* desc; int32_t* n_desc;
+  int nb_pack, nb_zero, nb_tgt, nb_cnt;
+};
+__global__ void __launch_bounds__(256) head_prologue_kernel(const PrologueParams q) {
+  int b = blockIdx.x;
+  if (b < q.nb_pack) {
+    const int c8 = q.C >> 3;
+    const long long idx = (long long)b * 256 + threadIdx.x;
+    if (idx >= (long long)q.rows * c8) return;
+    const int r = int(idx / c8), c = int(idx - (long long)r * c8) * 8;
+    const int src = q.row_map[r];
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (src >= 0) {
+      const float4 a = *reinterpret_cast<const float4*>(q.w + (size_t)src * q.C + c);
+      const float4 e = *reinterpret_cast<const float4*>(q.w + (size_t)src * q.C + c + 4);
+      o.x = pack_bf16x2(a.x, a.y); o.y = pack_bf16x2(a.z, a.w);
+      o.z = pack_bf16x2(e.x, e.y); o.w = pack_bf16x2(e.z, e.w);
+    }
+    *reinterpret_cast<uint4*>(q.wp + (size_t)r * q.C + c) = o;
+    return;
+  }
+  b -= q.nb_pack;
+  if (b < q.nb_zero) {                                  // 2 table entries (16 bytes) per thread; n_packed is even or the tail is scalar
+    const long long i = ((long long)b * 256 + threadIdx.x) * 2;
+    if (i + 1 < q.n_packed) *reinterpret_cast<uint4*>(q.packed + i) = make_uint4(0, 0, 0, 0);
+    else if (i < q.n_packed) q.packed[i] = 0ull;
+    if (b == 0 && q.align_sum != nullptr)
+      for (int n = threadIdx.x; n < q.n_align; n += 256) q.align_sum[n] = 0.0;
+    return;
+  }
+  b -= q.nb_zero;
+  if (b < q.nb_tgt) {
+    const int idx = b * 256 + threadIdx.x;
+    if (idx >= q.V * q.N) return;
+    const int v = idx / q.N, n = idx - v * q.N;
+    const long long y = q.ys[v];
+    const int8_t t = (y >= 0 && y < q.L) ? q.anc[(size_t)y * q.N + n] : int8_t(-1);
+    q.tgt[idx] = t;
+    if (v < q.V_first) q.desc[idx] = (t >= 0);
+    return;
+  }
+  b -= q.nb_tgt;
+  {                                                     // n_desc[n]: one warp per node, lanes over the rows
+    const int n = b * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (n >= q.N) return;
+    int cnt = 0;
+    for (int v = lane; v < q.V; v += 32) {
+      const long long y = q.ys[v];
+      cnt += (y >= 0 && y < q.L && q.anc[(size_t)y * q.N + n] >= 0) ? 1 : 0;
+    }
+    cnt = __reduce_add_sync(0xffffffffu, cnt);
+    if (lane == 0) q.n_desc[n] = cnt;
+  }
+}
+
+// ---- forward finish: pool unpack + align finalize + classifier, one launch ----------------------------------------
+// (unpack_pool_kernel + align_finalize_kernel + classifier_fwd_kernel; the classifier reads the packed table itself, so
+// the three roles are independent)
+struct PoolClassifyParams {
+  const unsigned long long* packed; const double* align_sum; const int32_t* n_desc;
+  const float* wc; const float* bias;
+  const int32_t *col_node, *proto_off, *cls_off, *wc_off;
+  int V, P, K, N, HW; float thresh;
+  float* pooled; int32_t* argmax; float* align; float* out;
+  int nb_unpack, nb_cls;
+};
+__global__ void __launch_bounds__(256) pool_classify_fwd_kernel(const PoolClassifyParams q) {
+  int b = blockIdx.x;
+  if (b < q.nb_unpack) {
+    const long long i = (long long)b * 256 + threadIdx.x;
+    if (i >= (long long)q.V * q.P) return;
+    const unsigned long long k = q.packed[i];
+    float v = __uint_as_float((uint32_t)(k >> 32));
+    if (v < q.thresh) v = 0.f;
+    q.pooled[i] = v;
+    q.argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+    return;
+  }
+  b -= q.nb_unpack;
+  if (b < q.nb_cls) {
+    const int idx = b * 256 + threadIdx.x;
+    if (idx >= q.V * q.K) return;
+    const int v = idx / q.K, k = idx - v * q.K;
+    const int n = q.col_node[k];
+    const int p0 = q.proto_off[n], pn = q.proto_off[n + 1] - p0;
+    const float* w = q.wc + q.wc_off[n] + (size_t)(k - q.cls_off[n]) * pn;
+    const unsigned long long* x = q.packed + (size_t)v * q.P + p0;
+    float acc = 0.f;
+    for (int p = 0; p < pn; ++p) {
+      float xv = __uint_as_float((uint32_t)(x[p] >> 32));
+      if (xv < q.thresh) xv = 0.f;
+      acc = fmaf(fmaxf(w[p], 0.f), xv, acc);
+    }
+    q.out[idx] = acc + (q.bias ? q.bias[k] : 0.f);
+    return;
+  }
+  b -= q.nb_cls;
+  const int n = b * 256 + threadIdx.x;
+  if (n >= q.N) return;
+  const int nd = q.n_desc[n] / 2;
+  q.align[n] = nd > 0 ? float(q.align_sum[n] / (double(nd) * double(q.HW))) : 0.f;
+}
+
+// ---- all per-node loss terms + their combination, one launch ------------------------------------------------------
+// grid (N, 3): y = 0 / 1 the tanh term of a view half, y = 2 the class term (+ accuracy counters, + the row log-sum-exp
+// kept for the backward); the LAST block to finish (device counter, left at zero) combines the terms.
+struct ChainFwdParams {
+  const float* pooled; const float* out; const float* align; const float* orth_sq;   // align / orth_sq may be NULL
+  const int8_t* tgt; const int32_t* n_desc; const float* child_w;
+  const int32_t *proto_off, *cls_off;
+  int V, V_first, N, P, K; float eps, mult; int do_tanh, do_cls;
+  LossWeights lw;
+  float *tanh_part, *colsum, *cls, *lse; int32_t* n_correct;
+  float* stats; float* total; unsigned int* counter;
+};
+__global__ void __launch_bounds__(256) head_chain_fwd_kernel(const ChainFwdParams q) {
+  __shared__ float sh[8][64];
+  __shared__ float red[32];
+  __shared__ int last;
+  const int n = blockIdx.x, role = blockIdx.y;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (role < 2) {
+    if (q.do_tanh) {                                   // same arithmetic as tanh_loss_fwd_kernel
+      const int h = role;
+      const int p0 = q.proto_off[n], pn = q.proto_off[n + 1] - p0;
+      const int vb = h ? q.V_first : 0, ve = h ? q.V : q.V_first;
+      float acc = 0.f;
+      for (int pc = 0; pc < pn; pc += 64) {
+        float t0 = 0.f, t1 = 0.f;
+        const int pa = pc + lane, pb = pc + 32 + lane;
+        for (int v = vb + warp; v < ve; v += 8) {
+          if (q.tgt[(size_t)v * q.N + n] >= 0) {
+            const float* row = q.pooled + (size_t)v * q.P + p0;
+            if (pa < pn) t0 += row[pa];
+            if (pb < pn) t1 += row[pb];
+          }
+        }
+        sh[warp][lane] = t0;
+        sh[warp][32 + lane] = t1;
+        __syncthreads();
+        if (threadIdx.x < 64 && pc + threadIdx.x < pn) {
+          float t = 0.f;
+#pragma unroll
+          for (int w = 0; w < 8; ++w) t += sh[w][threadIdx.x];
+          q.colsum[(size_t)h * q.P + p0 + pc + threadIdx.x] = t;
+          acc += logf(tanhf(t) + q.eps);
+        }
+        __syncthreads();
+      }
+      acc = block_sum(acc, red);
+      if (threadIdx.x == 0) q.tanh_part[h * q.N + n] = q.n_desc[n] > 0 ? -0.5f * acc / float(pn) : 0.f;
+    }
+  } else {                                             // class term: class_loss_fwd_kernel + lse
+    const int k0 = q.cls_off[n], kn = q.cls_off[n + 1] - k0;
+    float acc = 0.f, corr = 0.f;
+    for (int v = threadIdx.x; v < q.V; v += 256) {
+      const int t = q.tgt[(size_t)v * q.N + n];
+      if (t < 0) continue;
+      const float* o = q.out + (size_t)v * q.K + k0;
+      float mx = -INFINITY, best = -INFINITY;
+      int arg = 0;
+      for (int c = 0; c < kn; ++c) {
+        const float x = sparsity_x(o[c], q.mult);
+        mx = fmaxf(mx, x);
+        if (o[c] > best) { best = o[c]; arg = c; }
+      }
+      float se = 0.f, xt = 0.f;
+      for (int c = 0; c < kn; ++c) {
+        const float x = sparsity_x(o[c], q.mult);
+        se += expf(x - mx);
+        if (c == t) xt = x;
+      }
+      const float l = logf(se) + mx;
+      q.lse[(size_t)v * q.N + n] = l;
+      acc += q.child_w[k0 + t] * (l - xt);
+      corr += (arg == t) ? 1.f : 0.f;
+    }
+    acc = block_sum(acc, red);
+    corr = block_sum(corr, red);
+    if (threadIdx.x == 0) {
+      const int nd = q.n_desc[n];
+      q.cls[n] = nd > 0 ? acc / float(nd) : 0.f;
+      q.n_correct[n] = int(corr + 0.5f);
+    }
+  }
+  // ---- last block done: combine (loss_combine_kernel's arithmetic)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = (atomicAdd(q.counter, 1u) == gridDim.x * gridDim.y - 1u);
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float acc = 0.f;
+  for (int m = threadIdx.x; m < q.N; m += 256) {
+    const bool on = q.n_desc[m] > 0;
+    const float a = (q.align && on) ? __ldcg(q.align + m) : 0.f;
+    const float t = (q.do_tanh && on) ? __ldcg(q.tanh_part + m) + __ldcg(q.tanh_part + q.N + m) : 0.f;
+    const float o = (q.orth_sq && on) ? sqrtf(__ldcg(q.orth_sq + m)) : 0.f;
+    const float c = (q.do_cls && on) ? __ldcg(q.cls + m) : 0.f;
+    q.stats[m] = a; q.stats[q.N + m] = t; q.stats[2 * q.N + m] = o; q.stats[3 * q.N + m] = c;
+    acc += q.lw.w[0] * a + q.lw.w[1] * t + q.lw.w[2] * o + q.lw.w[3] * c;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) { *q.total = acc; *q.counter = 0u; }
+}
+
+// ---- backward of the tanh + class terms chained through the classifier, one launch --------------------------------
+//   role A  g_pooled[v,p] = tanh term + sum_c g_out[v,c] * relu(Wc[c,p])          (tanh_loss_bwd + class_loss_bwd +
+//   role B  g_Wc[c,p]     = [Wc > 0] * sum_v g_out[v,c] * pooled[v,p]              classifier_bwd_* + the autograd add)
+//   role C  g_bias[k]     = sum_v g_out[v,k]
+//   role D  g_align[n]    = g_total * w_align
+// with g_out[v,c] = g_total * w_class / n_desc * w[t] * (softmax(x)[c] - [c == t]) * dx/dout rebuilt on the fly from the
+// logits and the row log-sum-exp of the forward (never stored).
+struct ChainBwdParams {
+  const float* g_total; const float* pooled; const float* out; const float* wc; const float* colsum; const float* lse;
+  const int8_t* tgt; const int32_t* n_desc; const float* child_w;
+  const int32_t *proto_node, *proto_off, *cls_off, *wc_off, *col_node, *welem_col, *welem_proto;
+  int V, V_first, N, P, K, n_w; float eps, mult; int do_tanh, do_cls;
+  LossWeights lw;
+  float *g_pooled, *g_wc, *g_bias, *g_align;            // any may be NULL
+  int nb_pooled, nb_wc, nb_bias;
+};
+__device__ __forceinline__ float chain_gout(const ChainBwdParams& q, int v, int n, int t, int k0, int c, float coef) {
+  const float o = q.out[(size_t)v * q.K + k0 + c];
+  const float sm = expf(sparsity_x(o, q.mult) - q.lse[(size_t)v * q.N + n]);
+  return coef * (sm - (c == t ? 1.f : 0.f)) * sparsity_dx(o, q.mult);
+}
+__global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParams q) {
+  int b = blockIdx.x;
+  const float gT = q.g_total[0];
+  if (b < q.nb_pooled) {
+    const long long idx = (long long)b * 256 + threadIdx.x;
+    if (idx >= (long long)q.V * q.P) return;
+    const int v = int(idx / q.P), p = int(idx - (long long)v * q.P);
+    const int n = q.proto_node[p];
+    const int t = q.tgt[(size_t)v * q.N + n];
+    float g = 0.f;
+    if (t >= 0) {
+      const int p0 = q.proto_off[n], pn = q.proto_off[n + 1] - p0;
+      if (q.do_tanh) {
+        const float th = tanhf(q.colsum[(size_t)(v >= q.V_first) * q.P + p]);
+        g = gT * q.lw.w[1] * (-0.5f / float(pn)) * (1.f - th * th) / (th + q.eps);
+      }
+      if (q.do_cls) {
+        const int k0 = q.cls_off[n], kn = q.cls_off[n + 1] - k0;
+        const float coef = gT * q.lw.w[3] / float(q.n_desc[n]) * q.child_w[k0 + t];
+        const float* w = q.wc + q.wc_off[n] + (p - p0);
+        float acc = 0.f;
+        for (int c = 0; c < kn; ++c) acc = fmaf(chain_gout(q, v, n, t, k0, c, coef), fmaxf(w[(size_t)c * pn], 0.f), acc);
+        g += acc;
+      }
+    }
+    q.g_pooled[idx] = g;
+    return;
+  }
+  b -= q.nb_pooled;
+  if (b < q.nb_wc) {                                    // one warp per classifier weight element
+    const int wid = b * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (wid >= q.n_w) return;
+    float acc = 0.f;
+    if (q.do_cls && q.wc[wid] > 0.f) {
+      const int k = q.welem_col[wid], p = q.welem_proto[wid];
+      const int n = q.col_node[k];
+      const int k0 = q.cls_off[n];
+      const int nd = q.n_desc[n];
+      const float base = nd > 0 ? gT * q.lw.w[3] / float(nd) : 0.f;
+      for (int v = lane; v < q.V; v += 32) {
+        const int t = q.tgt[(size_t)v * q.N + n];
+        if (t < 0) continue;
+        acc = fmaf(chain_gout(q, v, n, t, k0, k - k0, base * q.child_w[k0 + t]), q.pooled[(size_t)v * q.P + p], acc);
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) q.g_wc[wid] = acc;
+    return;
+  }
+  b -= q.nb_wc;
+  if (b < q.nb_bias) {
+    const int k = b * 256 + threadIdx.x;
+    if (k >= q.K) return;
+    float acc = 0.f;
+    if (q.do_cls) {
+      const int n = q.col_node[k];
+      const int k0 = q.cls_off[n];
+      const int nd = q.n_desc[n];
+      const float base = nd > 0 ? gT * q.lw.w[3] / float(nd) : 0.f;
+      for (int v = 0; v < q.V; ++v) {
+        const int t = q.tgt[(size_t)v * q.N + n];
+        if (t >= 0) acc += chain_gout(q, v, n, t, k0, k - k0, base * q.child_w[k0 + t]);
+      }
+    }
+    q.g_bias[k] = acc;
+    return;
+  }
+  b -= q.nb_bias;
+  const int n = b * 256 + threadIdx.x;
+  if (n < q.N && q.g_align != nullptr) q.g_align[n] = gT * q.lw.w[0];
+}
+
+// orth_bwd_kernel with the upstream gradient taken as g_total * weight (no loss_grads launch in front of it)
+__global__ void orth_bwd_scaled_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_node,
+                                       const int32_t* __restrict__ proto_off, int C, int P_max, const float* __restrict__ loss,
+                                       const float* __restrict__ E, const uint8_t* __restrict__ rel,
+                                       const float* __restrict__ g_total, float weight, float* __restrict__ g_w) {
+  const int row = blockIdx.x;
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int n = proto_node[row];
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const float L = loss[n], g = g_total[0] * weight;
+  float acc = 0.f;
+  if (rel[row] && L > 0.f && g != 0.f) {
+    const float* Er = E + ((size_t)n * P_max + (row - p0)) * P_max;
+    const float* wn = w + (size_t)p0 * C + c;
+#pragma unroll 4
+    for (int j = 0; j < pn; ++j) acc = fmaf(Er[j], wn[(size_t)j * C], acc);
+    acc *= g * 2.f / L;
+  }
+  g_w[(size_t)row * C + c] = acc;
+}
+
+// ---- backward prep: scatter table + align coefficients, one launch (make_scat_kernel + align_coef_kernel) ---------
+__global__ void __launch_bounds__(256) bwd_prep_kernel(const int32_t* __restrict__ argmax, const float* __restrict__ g_pooled,
+                                                       const float* __restrict__ pooled, float thresh, long long n,
+                                                       int2* __restrict__ scat, int nb_scat, const uint8_t* __restrict__ desc,
+                                                       const int32_t* __restrict__ n_desc, const float* __restrict__ g_align,
+                                                       int B, int N, int HW, float* __restrict__ coef) {
+  int b = blockIdx.x;
+  if (b < nb_scat) {
+    const long long i = (long long)b * 256 + threadIdx.x;
+    if (i >= n) return;
+    float g = g_pooled[i];
+    if (pooled != nullptr && pooled[i] < thresh) g = 0.f;
+    scat[i] = make_int2(argmax[i], __float_as_int(g));
+    return;
+  }
+  b -= nb_scat;
+  const int idx = b * 256 + threadIdx.x;
+  if (idx >= B * N) return;
+  const int m = idx % N;
+  const int nd = n_desc[m] / 2;
+  coef[idx] = (desc[idx] && nd > 0) ? g_align[m] * 0.5f / (float(nd) * float(HW)) : 0.f;
+}
+
 // ---------------------------------------------------------------- joint leaf distribution (util/node.py:383-385, pipnet/pipnet.py:173-185)
 // probs[v,k] = softmax_c(log1p(out^2)/tau) within each node; leaf[v,l] = product of probs along the path.
 // override[k] >= 0 forces the probability of child column k for every sample (leave-out classes: 1 on the left-out leaf

@@ -330,6 +330,8 @@ class DeviceLayout:
         self.n_spill = int(L.spill.shape[0])
         self.n_wide = int((L.spill[:, 5] == 0).sum()) if self.n_spill else 0
         self.P_s = int(L.P_s)
+        # last-block-done counter of the chained loss kernel (zero between calls; one call at a time per layout)
+        self.counter = torch.zeros(4, device=d, dtype=torch.int32)
 
     def spill_buffers(self, M, device, zs=None, stats=None):
         """(ctypes hcomp_spill or None, zs, stats): the raw-logit scratch matrix of the spill nodes [M, P_s] and the
@@ -456,18 +458,58 @@ def feature_rows_split3(features: torch.Tensor) -> torch.Tensor:
 
 class LabelTables:
     """Per-batch tables derived from the labels (pipnet/train.py:934-937): tgt[V,N] child label or -1,
-    desc[V_first,N], n_desc[N]."""
+    desc[V_first,N], n_desc[N].  The tables are filled lazily: the fused head forward computes them inside its prologue
+    launch (`head_prologue`); any other first reader triggers the stand-alone kernel."""
 
     def __init__(self, ys: torch.Tensor, dl: DeviceLayout, V_first: int):
         _require_cuda(ys, 'labels')
         ys = ys.to(torch.int64).contiguous()
         V = ys.numel()
         self.V, self.V_first = V, V_first
+        self.dl = dl
         self.ys = ys                      # leaf index per row (the descendant-structured loss terms group rows by leaf)
-        self.tgt = torch.empty(V, dl.N, device=ys.device, dtype=torch.int8)
-        self.desc = torch.empty(V_first, dl.N, device=ys.device, dtype=torch.uint8)
-        self.n_desc = torch.empty(dl.N, device=ys.device, dtype=torch.int32)
-        call('hcomp_label_tables', ptr(ys), dl.tref, V, V_first, ptr(self.tgt), ptr(self.desc), ptr(self.n_desc), _stream())
+        self._tgt = torch.empty(V, dl.N, device=ys.device, dtype=torch.int8)
+        self._desc = torch.empty(V_first, dl.N, device=ys.device, dtype=torch.uint8)
+        self._n_desc = torch.empty(dl.N, device=ys.device, dtype=torch.int32)
+        self.pending = True
+
+    def ensure(self):
+        if self.pending:
+            self.pending = False
+            call('hcomp_label_tables', ptr(self.ys), self.dl.tref, self.V, self.V_first, ptr(self._tgt), ptr(self._desc),
+                 ptr(self._n_desc), _stream())
+        return self
+
+    @property
+    def tgt(self): return self.ensure()._tgt
+    @property
+    def desc(self): return self.ensure()._desc
+    @property
+    def n_desc(self): return self.ensure()._n_desc
+
+
+def head_prologue(w_flat: Optional[torch.Tensor], dl: DeviceLayout, V: int, labels: Optional["LabelTables"], dev):
+    """ONE launch for everything the fused projection kernel needs (hcomp_head_prologue): bf16 weight layouts (wp, wpc),
+    the cleared packed max table / align accumulators, and -- when `labels` are still pending -- the label tables."""
+    wp = wpc = both = None
+    rows = Cc = 0
+    if w_flat is not None:
+        _require_cuda(w_flat, 'prototype kernels')
+        Cc = w_flat.shape[1]
+        rows = dl.P_pad + dl.P_c
+        both = torch.empty(rows, Cc, device=dev, dtype=torch.bfloat16)
+        wp, wpc = both[:dl.P_pad], both[dl.P_pad:]
+    packed = torch.empty(V * dl.P, device=dev, dtype=torch.int64)
+    align_sum = torch.empty(dl.N, device=dev, dtype=torch.float64) if labels is not None else None
+    lab = labels if (labels is not None and labels.pending) else None
+    if lab is not None:
+        lab.pending = False
+    call('hcomp_head_prologue', ptr(w_flat), ptr(dl.row_map_all), rows, Cc, ptr(both), ptr(packed),
+         C.c_longlong(packed.numel()), ptr(align_sum), dl.N, ptr(lab.ys) if lab is not None else None, dl.tref,
+         lab.V if lab is not None else 0, lab.V_first if lab is not None else 0,
+         ptr(lab._tgt) if lab is not None else None, ptr(lab._desc) if lab is not None else None,
+         ptr(lab._n_desc) if lab is not None else None, _stream())
+    return wp, wpc, packed, align_sum
 
 
 # --------------------------------------------------------------------------- raw kernels (no autograd)
@@ -495,6 +537,29 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
         align = torch.empty(dl.N, device=dev, dtype=torch.float32)
         call('hcomp_align_finalize', ptr(align_sum), ptr(labels.n_desc), dl.N, HW, ptr(align), _stream())
     return pooled, argmax, align
+
+
+def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, labels: Optional[LabelTables], packed, align_sum,
+                           thresh=0.0, precision=PREC_BF16, spill_out: Optional[list] = None, wc=None, bias=None):
+    """K1 + ONE finishing launch (hcomp_pool_classify_fwd: unpack, align finalize, classifier).  `packed` / `align_sum`
+    come cleared from `head_prologue`.  Returns pooled, argmax, align (None without labels), out (None without wc)."""
+    Cc = x_rows.shape[1]
+    dev = x_rows.device
+    sp, zs, stats = dl.spill_buffers(V * HW, dev)
+    if spill_out is not None:
+        spill_out[:] = [zs, stats]
+    tok = PROFILE.start('k1_proj_softmax_pool_fwd')
+    call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
+         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), 1, ptr(labels.desc) if labels is not None else None,
+         ptr(packed), ptr(align_sum), C.byref(sp) if sp is not None else None, _stream())
+    PROFILE.stop(tok)
+    pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)
+    argmax = torch.empty(V, dl.P, device=dev, dtype=torch.int32)
+    align = torch.empty(dl.N, device=dev, dtype=torch.float32) if labels is not None else None
+    out = torch.empty(V, dl.K, device=dev, dtype=torch.float32) if wc is not None else None
+    call('hcomp_pool_classify_fwd', ptr(packed), ptr(align_sum), ptr(labels.n_desc) if labels is not None else None, ptr(wc),
+         ptr(bias), dl.tref, V, HW, float(thresh), ptr(pooled), ptr(argmax), ptr(align), ptr(out), _stream())
+    return pooled, argmax, align, out
 
 
 def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
@@ -567,39 +632,77 @@ def gemm_bf16(a, b, M, N, K, a_mn, b_mn, out_mode=1, splits=1):
 
 # --------------------------------------------------------------------------- autograd
 class HeadProjPool(torch.autograd.Function):
-    """features, flat prototype kernels -> pooled [V,P], per-node align loss [N] (zeros without labels).
-    Saves only the bf16 operands + argmax: the V x P x H x W map is recomputed tile by tile in backward."""
+    """features, flat prototype kernels -> pooled [V,P], per-node align loss [N] (zeros without labels), argmax and --
+    when the classifier weights are passed -- the child logits out [V,K] (pipnet/pipnet.py:1035-1036), finished by the
+    same launch that unpacks the pooled table.
+    Saves only the bf16 operands + argmax: the V x P x H x W map is recomputed tile by tile in backward.
+    Three launches forward (prologue, K1, finish); backward: prep, K5, dW, dX (+ the classifier's own backward kernels
+    only when a gradient arrives at `out` -- the chained losses, `HeadLosses(..., chain=True)`, never send one)."""
 
     @staticmethod
-    def forward(ctx, features, w_flat, dl: DeviceLayout, V_first, tau, labels, thresh, precision=PREC_BF16):
+    def forward(ctx, features, w_flat, dl: DeviceLayout, V_first, tau, labels, thresh, precision=PREC_BF16, wc_flat=None,
+                bias=None):
         V, Cc, H, W = features.shape
         HW = H * W
+        dev = features.device
+        wf = w_flat.detach().contiguous()
         if precision == PREC_FP32X3:
             x_rows = feature_rows_split3(features.detach())
+            wp, wpc = pack_weights(wf, dl, precision)
+            _wp, _wpc, packed, align_sum = head_prologue(None, dl, V, labels, dev)
         else:
             x_rows = feature_rows(features.detach())
-        wp, wpc = pack_weights(w_flat.detach().contiguous(), dl, precision)
+            wp, wpc, packed, align_sum = head_prologue(wf, dl, V, labels, dev)
+        wc = wc_flat.detach().contiguous() if wc_flat is not None else None
+        bs = bias.detach().contiguous() if bias is not None else None
         spill = []
-        pooled, argmax, align = proj_softmax_pool_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, thresh, precision, spill)
+        pooled, argmax, align, out = proj_pool_classify_raw(x_rows, wp, dl, V, V_first, HW, tau, labels, packed, align_sum,
+                                                            thresh, precision, spill, wc, bs)
         ctx.spill = spill                      # raw logits / row statistics of the spill nodes (None, None without any)
         ctx.dl, ctx.geom, ctx.labels, ctx.thresh, ctx.precision = dl, (V, V_first, H, W, Cc, tau), labels, thresh, precision
         ctx.w_group = getattr(w_flat, '_hc_group', None)
+        ctx.cls_groups = (getattr(wc_flat, '_hc_group', None) if wc_flat is not None else None,
+                          getattr(bias, '_hc_group', None) if bias is not None else None)
+        ctx.has_cls = (wc_flat is not None, bias is not None)
         ctx.set_materialize_grads(False)      # unused outputs (argmax, align without the loss) get None, not zero fills
         ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
-        ctx.save_for_backward(x_rows, wp, wpc, argmax, pooled)
+        ctx.save_for_backward(x_rows, wp, wpc, argmax, pooled, wc)
         ctx.mark_non_differentiable(argmax)
         if align is None:
-            align = torch.zeros(dl.N, device=features.device, dtype=torch.float32)
-        return pooled, align, argmax
+            align = torch.zeros(dl.N, device=dev, dtype=torch.float32)
+        return pooled, align, argmax, out
 
     @staticmethod
-    def backward(ctx, g_pooled, g_align, _g_argmax):
-        x_rows, wp, wpc, argmax, pooled = ctx.saved_tensors
+    def backward(ctx, g_pooled, g_align, _g_argmax, g_out=None):
+        x_rows, wp, wpc, argmax, pooled, wc = ctx.saved_tensors
         V, V_first, H, W, Cc, tau = ctx.geom
         dl = ctx.dl
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        dev = x_rows.device
+        g_wc = g_bias = None
+        if g_out is not None and ctx.has_cls[0]:
+            # somebody differentiated through `out` directly (not the chained losses): the classifier's own backward
+            need_wc, need_bias = ctx.needs_input_grad[8], ctx.has_cls[1] and ctx.needs_input_grad[9]
+            wc_grp, bias_grp = ctx.cls_groups
+            b_wc, b_bias = need_wc and _bucket_mode(wc_grp), need_bias and _bucket_mode(bias_grp)
+            if need_wc:
+                g_wc = _bucket_segment(wc_grp, dev) if b_wc else torch.empty_like(wc)
+            if need_bias:
+                g_bias = _bucket_segment(bias_grp, dev) if b_bias else torch.empty(dl.K, device=dev, dtype=torch.float32)
+            accumulate = g_pooled is not None
+            g_pooled = g_pooled.contiguous().float().clone() if accumulate else torch.empty(V, dl.P, device=dev, dtype=torch.float32)
+            call('hcomp_classifier_bwd', ptr(g_out.contiguous().float()), ptr(pooled), ptr(wc), dl.tref, V, ptr(g_pooled),
+                 int(accumulate), ptr(g_wc), ptr(g_bias), _stream())
+            if b_wc:
+                g_wc = None
+            if b_bias:
+                g_bias = None
+            if GRAD_ALLREDUCE_GROUP is not None:
+                for g in (g_wc, g_bias):
+                    if g is not None:
+                        torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g))
         if g_pooled is None:
-            g_pooled = torch.zeros(V, dl.P, device=x_rows.device, dtype=torch.float32)
+            g_pooled = torch.zeros(V, dl.P, device=dev, dtype=torch.float32)
         g_pooled = g_pooled.contiguous().float()
         if g_align is not None:
             g_align = g_align.contiguous().float()
@@ -612,7 +715,7 @@ class HeadProjPool(torch.autograd.Function):
             d_feat = dx.view(V, H, W, Cc).permute(0, 3, 1, 2)     # channels-last view of the row buffer
             if dtype != torch.bfloat16:
                 d_feat = d_feat.to(dtype)
-        return d_feat, dw, None, None, None, None, None, None
+        return d_feat, dw, None, None, None, None, None, None, g_wc, g_bias
 
 
 class NonNegClassifier(torch.autograd.Function):
@@ -663,16 +766,68 @@ class NonNegClassifier(torch.autograd.Function):
 LOSS_TANH, LOSS_ORTH, LOSS_CLASS, LOSS_SPARSITY = 1, 2, 4, 8
 
 
+LOSS_ORTH_READY = 16
+_orth_stream = None
+_orth_slot = None          # (key, ws, rel, event) of the latest `orth_prefetch`
+
+
+def _chain_ws(dl: DeviceLayout, V: int, dev):
+    n = int(_cabi.lib().hcomp_head_chain_ws_floats(dl.tref, V))
+    return torch.empty(n, device=dev, dtype=torch.float32), torch.empty(dl.P, device=dev, dtype=torch.uint8)
+
+
+def _orth_key(w_flat, wc_flat, dl, V):
+    return (w_flat.data_ptr(), w_flat._version, wc_flat.data_ptr(), wc_flat._version, id(dl), int(V))
+
+
+def orth_prefetch(w_flat: torch.Tensor, wc_flat: torch.Tensor, dl: DeviceLayout, V: int):
+    """Start the weights-only part of the kernel-orthogonality term (Gram matrices, ||E||^2, relevance mask;
+    pipnet/train.py:1136-1151) on a side stream NOW, so that it runs beside the projection kernel instead of on the
+    critical path between the forward and the backward.  `HeadLosses` picks the result up (and always re-joins the side
+    stream); the model calls this at the start of the head forward when the previous step's loss used the term."""
+    global _orth_stream, _orth_slot
+    if w_flat.shape[1] <= dl.layout.p_max:
+        return
+    wf, wc = w_flat.detach().contiguous(), wc_flat.detach().contiguous()
+    if _orth_stream is None:
+        _orth_stream = torch.cuda.Stream()
+    ws, rel = _chain_ws(dl, V, wf.device)
+    side = _orth_stream
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        call('hcomp_orth_gram', ptr(wf), ptr(wc), dl.tref, wf.shape[1], ptr(ws), ptr(rel), C.c_void_p(side.cuda_stream))
+        ev = torch.cuda.Event()
+        ev.record(side)
+    ws.record_stream(side)
+    rel.record_stream(side)
+    _orth_slot = (_orth_key(w_flat, wc_flat, dl, V), ws, rel, ev)
+
+
+def _orth_take(key):
+    """join the prefetch branch (always) and return its (ws, rel) when it matches `key`"""
+    global _orth_slot
+    slot, _orth_slot = _orth_slot, None
+    if slot is None:
+        return None
+    torch.cuda.current_stream().wait_event(slot[3])
+    return (slot[1], slot[2]) if slot[0] == key else None
+
+
 class HeadLosses(torch.autograd.Function):
     """All per-node loss terms of the shipped recipe in one forward / one backward call:
     total = sum_n (w_align*align[n] + w_tanh*tanh[n] + w_orth*orth[n] + w_class*class[n]) (weights include the 1/N
     of `pipnet/train.py:1071,1084,1149,1165`).  Returns (total, stats[4,N], n_correct[N]); only `total` is
     differentiable.  The relevance mask of the orth term comes from the classifier weights, which get no
-    gradient from it (boolean indexing in the reference, `pipnet/train.py:1140`)."""
+    gradient from it (boolean indexing in the reference, `pipnet/train.py:1140`).
+
+    chain=True (what `calculate_loss` uses when `out` is the model's own classifier output of `pooled`): the forward is ONE
+    launch, and the backward -- ONE launch beside the orth term's -- goes straight THROUGH the classifier: it returns the
+    gradients of `pooled` (tanh term + class term through relu(Wc)), `wc_flat` and `bias`, and nothing for `out` (so the
+    classifier's own autograd node has nothing to do).  chain=False: `out` is an independent input with its own gradient."""
 
     @staticmethod
     def forward(ctx, pooled, out, align, w_flat, wc_flat, labels: LabelTables, dl: DeviceLayout, flags, weights, eps,
-                multiplier=2.0):
+                multiplier=2.0, bias=None, chain=False):
         # multiplier: exponent of the class term's log1p(out ** m) (net._multiplier, pipnet/train.py:1158)
         pooled, out = pooled.contiguous(), out.contiguous()
         V = pooled.shape[0]
@@ -683,53 +838,92 @@ class HeadLosses(torch.autograd.Function):
         total = torch.empty((), device=dev, dtype=torch.float32)
         stats = torch.empty(4, dl.N, device=dev, dtype=torch.float32)
         n_correct = torch.empty(dl.N, device=dev, dtype=torch.int32)
-        ws = torch.empty(int(_cabi.lib().hcomp_head_losses_ws_floats(dl.tref)), device=dev, dtype=torch.float32)
-        rel = torch.empty(dl.P, device=dev, dtype=torch.uint8)
         wf = w_flat.detach().contiguous() if use_orth else None
         wc = wc_flat.detach().contiguous() if wc_flat is not None else None
         al = align.detach().contiguous() if align is not None else None
-        call('hcomp_head_losses_fwd', ptr(pooled), ptr(out), ptr(al), ptr(wf), ptr(wc), ptr(labels.tgt), ptr(labels.n_desc),
-             dl.tref, V, labels.V_first, Cc, int(flags), wts, float(eps), float(multiplier), ptr(total), ptr(stats),
-             ptr(n_correct), ptr(ws), ptr(rel), _stream())
+        ready = _orth_take(_orth_key(w_flat, wc_flat, dl, V) if (use_orth and chain and wc_flat is not None) else None)
+        if chain:
+            fl = int(flags)
+            if ready is not None:
+                ws, rel = ready
+                fl |= LOSS_ORTH_READY
+            else:
+                ws, rel = _chain_ws(dl, V, dev)
+            call('hcomp_head_chain_fwd', ptr(pooled), ptr(out), ptr(al), ptr(wf), ptr(wc), ptr(labels.tgt), ptr(labels.n_desc),
+                 dl.tref, V, labels.V_first, Cc, fl, wts, float(eps), float(multiplier), ptr(total), ptr(stats),
+                 ptr(n_correct), ptr(ws), ptr(rel), ptr(dl.counter), _stream())
+        else:
+            ws = torch.empty(int(_cabi.lib().hcomp_head_losses_ws_floats(dl.tref)), device=dev, dtype=torch.float32)
+            rel = torch.empty(dl.P, device=dev, dtype=torch.uint8)
+            call('hcomp_head_losses_fwd', ptr(pooled), ptr(out), ptr(al), ptr(wf), ptr(wc), ptr(labels.tgt), ptr(labels.n_desc),
+                 dl.tref, V, labels.V_first, Cc, int(flags), wts, float(eps), float(multiplier), ptr(total), ptr(stats),
+                 ptr(n_correct), ptr(ws), ptr(rel), _stream())
         ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc, float(multiplier))
         ctx.has = (align is not None, w_flat is not None and use_orth)
+        ctx.chain = bool(chain)
         ctx.w_group = getattr(w_flat, '_hc_group', None) if w_flat is not None else None
+        ctx.cls_groups = (getattr(wc_flat, '_hc_group', None) if wc_flat is not None else None,
+                          getattr(bias, '_hc_group', None) if bias is not None else None)
+        ctx.has_bias = bias is not None
         ctx.set_materialize_grads(False)      # stats / n_correct are not differentiable: no zero-filled grads for them
-        ctx.save_for_backward(out, wf if use_orth else None, stats, ws, rel)
+        ctx.save_for_backward(out, wf if use_orth else None, stats, ws, rel, pooled if chain else None, wc if chain else None)
         ctx.mark_non_differentiable(stats, n_correct)
         return total, stats, n_correct
 
     @staticmethod
     def backward(ctx, g_total, _gs, _gc):
         if g_total is None:
-            return (None,) * 11
-        out, wf, stats, ws, rel = ctx.saved_tensors
+            return (None,) * 13
+        out, wf, stats, ws, rel, pooled, wc = ctx.saved_tensors
         dl, labels = ctx.dl, ctx.labels
         flags, weights, eps, V, Cc, multiplier = ctx.cfg
         dev = out.device
         wts = (C.c_float * 4)(*weights)
         g_total = g_total.contiguous().float()
-        gvec = torch.empty(4, dl.N, device=dev, dtype=torch.float32)
         need_pooled, need_out, need_align, need_w = (ctx.needs_input_grad[0], ctx.needs_input_grad[1],
                                                      ctx.needs_input_grad[2] and ctx.has[0],
                                                      ctx.needs_input_grad[3] and ctx.has[1])
         g_pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32) if need_pooled else None
-        g_out = torch.empty(V, dl.K, device=dev, dtype=torch.float32) if need_out else None
         bucketed = need_w and _bucket_mode(ctx.w_group)
         g_w = None
         if need_w:      # bucket mode: the orth gradient (identical on every rank) lands where K7 will accumulate dW
             g_w = (_bucket_segment(ctx.w_group, dev).view(dl.P, Cc) if bucketed
                    else torch.empty(dl.P, Cc, device=dev, dtype=torch.float32))
-        call('hcomp_head_losses_bwd', ptr(g_total), ptr(out), ptr(wf), ptr(labels.tgt), ptr(labels.n_desc), ptr(stats), dl.tref,
-             V, labels.V_first, Cc, flags, wts, eps, multiplier, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out),
-             ptr(g_w), _stream())
+        g_out = g_wc = g_bias = g_align = None
+        if ctx.chain:
+            need_wc, need_bias = ctx.needs_input_grad[4], ctx.has_bias and ctx.needs_input_grad[11]
+            wc_grp, bias_grp = ctx.cls_groups
+            b_wc, b_bias = need_wc and _bucket_mode(wc_grp), need_bias and _bucket_mode(bias_grp)
+            if need_wc:
+                g_wc = _bucket_segment(wc_grp, dev) if b_wc else torch.empty_like(wc)
+            if need_bias:
+                g_bias = _bucket_segment(bias_grp, dev) if b_bias else torch.empty(dl.K, device=dev, dtype=torch.float32)
+            g_align = torch.empty(dl.N, device=dev, dtype=torch.float32) if need_align else None
+            call('hcomp_head_chain_bwd', ptr(g_total), ptr(pooled), ptr(out), ptr(wf), ptr(wc), ptr(labels.tgt),
+                 ptr(labels.n_desc), ptr(stats), dl.tref, V, labels.V_first, Cc, flags, wts, eps, multiplier, ptr(ws), ptr(rel),
+                 ptr(g_pooled), ptr(g_wc), ptr(g_bias), ptr(g_align), ptr(g_w), _stream())
+            if b_wc:
+                g_wc = None                     # reduced with the bucket, delivered at the end of the backward pass
+            if b_bias:
+                g_bias = None
+            if GRAD_ALLREDUCE_GROUP is not None:        # autograd path: one flat mean all-reduce for all nodes' classifiers
+                for g in (g_wc, g_bias):
+                    if g is not None:
+                        torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g))
+        else:
+            gvec = torch.empty(4, dl.N, device=dev, dtype=torch.float32)
+            g_out = torch.empty(V, dl.K, device=dev, dtype=torch.float32) if need_out else None
+            call('hcomp_head_losses_bwd', ptr(g_total), ptr(out), ptr(wf), ptr(labels.tgt), ptr(labels.n_desc), ptr(stats), dl.tref,
+                 V, labels.V_first, Cc, flags, wts, eps, multiplier, ptr(ws), ptr(rel), ptr(gvec), ptr(g_pooled), ptr(g_out),
+                 ptr(g_w), _stream())
+            g_align = gvec[0] if need_align else None
         if bucketed:
             g_w = None
         elif g_w is not None and GRAD_ALLREDUCE_GROUP is not None:
             # the orth term is skipped for nodes without a descendant in the LOCAL batch (pipnet/train.py:941-942), so
             # its gradient differs across ranks like any other and needs the mean too
             torch.cuda.current_stream().wait_stream(_allreduce_grad_sync_(g_w))
-        return g_pooled, g_out, (gvec[0] if need_align else None), g_w, None, None, None, None, None, None, None
+        return g_pooled, g_out, g_align, g_w, g_wc, None, None, None, None, None, None, g_bias, None
 
 DESC_TANH_DESC, DESC_CONTRAST, DESC_MASK_PRUNE, DESC_GEOMETRIC, DESC_SG_SCORE = 1, 2, 4, 8, 16
 

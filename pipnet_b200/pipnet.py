@@ -263,6 +263,7 @@ class PIPNet(nn.Module):
         for g in family:
             g.family = family
         self._dl: Optional[ops.DeviceLayout] = None
+        self._orth_hint = False     # the last calculate_loss used the kernel-orthogonality term (ops.orth_prefetch)
         # 'bf16': bf16 GEMM operands (default, the benchmarked path); 'fp32': fp32-accurate projection (3-way bf16 split
         # operands, six cross terms through the same tcgen05 kernel) for the <= 1e-5 contract on fp32 inputs
         self.head_precision = getattr(args, 'head_precision', 'bf16')
@@ -314,9 +315,10 @@ class PIPNet(nn.Module):
 
     # ------------------------------------------------------------------ forward
     def head(self, features: Tensor, *, inference=False, labels: Optional[ops.LabelTables] = None,
-             V_first: Optional[int] = None):
+             V_first: Optional[int] = None, classify: bool = False):
         """The fused head on backbone features.  Returns flat tensors:
-        pooled [V,P], out [V,K], align [N] (zeros unless `labels` given), argmax [V,P] int32."""
+        pooled [V,P], align [N] (zeros unless `labels` given), argmax [V,P] int32, dl -- and with `classify=True` also
+        out [V,K] (the per-node NonNegLinear, finished by the same launch that unpacks the pooled table)."""
         V = features.shape[0]
         dl = self.device_layout(features.device)
         if V_first is None:
@@ -324,8 +326,18 @@ class PIPNet(nn.Module):
         x = features.detach() if getattr(self.args, 'sg_before_protos', 'n') == 'y' else features
         w_flat = self.flat_prototype_kernels()
         prec = ops.PREC_FP32X3 if self.head_precision == 'fp32' else ops.PREC_BF16
-        pooled, align, argmax = ops.HeadProjPool.apply(x, w_flat, dl, V_first, self.softmax_tau, labels,
-                                                       0.1 if inference else 0.0, prec)
+        wc = bias = None
+        if classify:
+            wc = self.flat_classifier_weights()
+            bias = self._bias_group.gather() if self._bias_group is not None else None
+            if (labels is not None and self._orth_hint and torch.is_grad_enabled() and w_flat.requires_grad
+                    and features.is_cuda):
+                # the last loss used the kernel-orthogonality term: start its weights-only part beside the projection
+                ops.orth_prefetch(w_flat, wc, dl, V)
+        pooled, align, argmax, out = ops.HeadProjPool.apply(x, w_flat, dl, V_first, self.softmax_tau, labels,
+                                                            0.1 if inference else 0.0, prec, wc, bias)
+        if classify:
+            return pooled, align, argmax, dl, out
         return pooled, align, argmax, dl
 
     def classify(self, pooled_flat: Tensor, dl: ops.DeviceLayout) -> Tensor:
@@ -337,16 +349,21 @@ class PIPNet(nn.Module):
             if grp is not None:
                 grp.invalidate()
         features = self._net(xs)
-        pooled_flat, align, argmax, dl = self.head(features, inference=inference, labels=labels)
         if apply_overspecificity_mask:
+            pooled_flat, align, argmax, dl = self.head(features, inference=inference, labels=labels)
             # Gumbel hard sample on proto_presence (pipnet/pipnet.py:164-166), one draw for the whole flat axis
             pres = self.flat_presence_logits()
             mask = F.gumbel_softmax(pres, tau=0.5, hard=True, dim=-1)[:, 1].unsqueeze(0)
             pooled_flat = mask * pooled_flat
-        out_flat = self.classify(pooled_flat, dl)
+            out_flat = self.classify(pooled_flat, dl)
+        else:
+            pooled_flat, align, argmax, dl, out_flat = self.head(features, inference=inference, labels=labels, classify=True)
         L = self.layout
         pooled = NodeDict(pooled_flat, L.node_names, L.proto_off)
         out = NodeDict(out_flat, L.node_names, L.cls_off)
+        # `out` is this model's classifier applied to exactly `pooled.flat`: lets calculate_loss chain the class term's
+        # backward through the classifier in one launch (ops.HeadLosses, chain=True)
+        out.chained_from = pooled_flat
         pooled.align = align                                    # per-node align_pf loss (zeros without labels)
         pooled.align_valid = labels is not None
         proto_features = LazyProtoFeatures(self, features, self.softmax_tau, NodeDict(argmax, L.node_names, L.proto_off))

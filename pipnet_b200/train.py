@@ -217,8 +217,13 @@ def calculate_loss(epoch, net, additional_network_outputs, features, proto_featu
     if not (args is not None and getattr(args, 'pipnet_sparsity', 'y') == 'n'):
         flags |= ops.LOSS_SPARSITY
     mult = _multiplier_value(net_normalization_multiplier) if (use_cls and (flags & ops.LOSS_SPARSITY)) else 2.0
+    m._orth_hint = bool(use_orth)             # the next head forward starts the term's weights-only part beside K1
+    # `out` is the model's classifier applied to `pooled.flat` (PIPNet.forward says so): the class term's backward goes
+    # straight through the classifier inside the fused loss backward, d loss / d out is never materialised
+    chain = getattr(out, 'chained_from', None) is pooled.flat
+    bias = m._bias_group.gather() if (chain and m._bias_group is not None) else None
     loss, stats, n_correct = ops.HeadLosses.apply(pooled.flat, out.flat, align_vec, m.flat_prototype_kernels() if use_orth else None,
-                                                  m.flat_classifier_weights(), labels, dl, flags, wts, EPS, mult)
+                                                  m.flat_classifier_weights(), labels, dl, flags, wts, EPS, mult, bias, chain)
     if (not finetune) and (not pretrain) and tanh_desc:                             # pipnet/train.py:1089-1133
         dflags |= ops.DESC_TANH_DESC
         dw[0] = float(args.tanh_desc.split('|')[1]) / N

@@ -1,0 +1,143 @@
+"""Fused chains (ABI v6): the multi-role launches -- head prologue, forward finish, chained losses forward / backward,
+orth prefetch -- against the separate entry points they replace, on the same inputs.  Element-wise roles must be
+bit-identical; block sums may associate differently (1e-6 relative)."""
+import ctypes as C
+
+import pytest
+import torch
+
+from pipnet_b200.fixtures import make_args, build_net
+
+pytestmark = pytest.mark.gpu
+
+
+def _close(a, b, tol=2e-6):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max()) <= tol * max(1e-6, float(b.abs().max()))
+
+
+def _problem(tree="cub27", C_=64, H=6, B=6, bias=False, **over):
+    from pipnet_b200 import train as tr
+    over.setdefault('num_features', 20)
+    args = make_args(bias=bias, **over)
+    net, root = build_net(tree, C_, args)
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2 * B, C_, H, H, generator=g)
+    ys = torch.randint(0, net.layout.L, (B,), generator=g)
+    ys = torch.cat([ys, ys]).cuda()
+    xs = x.cuda().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    return net, root, args, xs, ys, tr
+
+
+def test_prologue_matches_separate_calls():
+    from pipnet_b200 import ops
+    net, root, args, xs, ys, tr = _problem()
+    dl = net.device_layout('cuda')
+    w = net.flat_prototype_kernels().detach().contiguous()
+    V = xs.shape[0]
+    lab_a = ops.LabelTables(ys, dl, V // 2)
+    wp, wpc, packed, align_sum = ops.head_prologue(w, dl, V, lab_a, xs.device)
+    assert not lab_a.pending
+    lab_b = ops.LabelTables(ys, dl, V // 2).ensure()
+    wp0, wpc0 = ops.pack_weights(w, dl)
+    torch.cuda.synchronize()
+    assert torch.equal(wp.view(torch.int16), wp0.view(torch.int16)) and torch.equal(wpc.view(torch.int16), wpc0.view(torch.int16))
+    assert int(packed.abs().max()) == 0 and float(align_sum.abs().max()) == 0.0
+    assert torch.equal(lab_a._tgt, lab_b._tgt) and torch.equal(lab_a._desc, lab_b._desc) and torch.equal(lab_a._n_desc, lab_b._n_desc)
+    # odd table length (scalar tail of the 16-byte clears) and labels already computed
+    dirty = torch.full((V * dl.P + 1,), -1, device='cuda', dtype=torch.int64)
+    ops.call('hcomp_head_prologue', None, None, 0, 0, None, ops.ptr(dirty), C.c_longlong(V * dl.P - 1), None, 0, None, dl.tref,
+             0, 0, None, None, None, ops._stream())
+    torch.cuda.synchronize()
+    assert int(dirty[:V * dl.P - 1].abs().max()) == 0 and int(dirty[V * dl.P - 1]) == -1
+
+
+@pytest.mark.parametrize("bias", [False, True], ids=["nobias", "bias"])
+@pytest.mark.parametrize("inference", [False, True], ids=["train", "inference"])
+def test_forward_finish_matches_separate_calls(bias, inference):
+    from pipnet_b200 import ops
+    net, root, args, xs, ys, tr = _problem(bias=bias)
+    if bias:
+        with torch.no_grad():
+            for p in net._bias_group.params:
+                p.uniform_(-0.5, 0.5)
+    labels = tr.make_labels(net, ys)
+    with torch.no_grad():
+        _, _, pooled, out = net(xs, inference=inference, labels=labels)           # fused finish
+        dl = net.device_layout('cuda')
+        p0, al0, am0, _ = net.head(xs, inference=inference, labels=labels)         # same head, separate classifier kernel
+        out0 = net.classify(p0, dl)
+    torch.cuda.synchronize()
+    assert torch.equal(pooled.flat, p0) and torch.equal(pooled.align, al0)
+    assert torch.equal(out.flat, out0)
+
+
+@pytest.mark.parametrize("bias", [False, True], ids=["nobias", "bias"])
+@pytest.mark.parametrize("phase", [("pretrain", True, False), ("train", False, False), ("finetune", False, True)],
+                         ids=lambda p: p[0])
+def test_chained_losses_match_unchained(phase, bias):
+    """calculate_loss with the chained backward (one launch through the classifier) against the same loss with `out`
+    as an independent autograd input (separate loss kernels + the classifier's own backward + autograd's adds)"""
+    from pipnet_b200 import ops
+    _, pretrain, finetune = phase
+    net, root, args, xs, ys, tr = _problem(bias=bias, tree="cub18", C_=128, H=7, B=5, num_features=12)
+    if bias:
+        with torch.no_grad():
+            for p in net._bias_group.params:
+                p.uniform_(-0.5, 0.5)
+    w = tr._phase_weights(pretrain, 3, 10, args)
+    names = net.layout.node_names
+    results = []
+    for chained in (True, False):
+        net.zero_grad(set_to_none=True)
+        x = xs.clone().requires_grad_(True)
+        labels = tr.make_labels(net, ys)
+        features, pf, pooled, out = net(x, labels=labels)
+        if not chained:
+            out.chained_from = None
+        res = tr.calculate_loss(3, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                pretrain=pretrain, finetune=finetune, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                                device='cuda', labels=labels, **w)
+        res[0].backward()
+        torch.cuda.synchronize()
+        grads = {'x': x.grad.float() if x.grad is not None else None}
+        for pname, prm in net.named_parameters():
+            if not pname.startswith('_net.'):
+                grads[pname] = prm.grad.clone() if prm.grad is not None else None
+        results.append((float(res[0]), res.stats.clone(), grads))
+    (la, sa, ga), (lb, sb, gb) = results
+    assert abs(la - lb) <= 2e-6 * max(1.0, abs(lb))
+    assert _close(sa, sb)
+    assert set(ga) == set(gb)
+    for k in ga:
+        assert (ga[k] is None) == (gb[k] is None), k
+        if ga[k] is not None:
+            tol = 2e-2 if (k == 'x' or k.endswith('_add_on.weight')) else 1e-5      # bf16 dZ between the two runs' g_pooled
+            assert _close(ga[k], gb[k], tol), (k, float((ga[k] - gb[k]).abs().max()), float(gb[k].abs().max()))
+
+
+def test_orth_prefetch_gives_the_same_loss():
+    """the model starts the orth term's weights-only part beside K1 once a loss has used the term; same numbers"""
+    from pipnet_b200 import ops
+    net, root, args, xs, ys, tr = _problem()
+    w = tr._phase_weights(False, 3, 10, args)
+    vals = []
+    for it in range(3):
+        net.zero_grad(set_to_none=True)
+        labels = tr.make_labels(net, ys)
+        features, pf, pooled, out = net(xs.clone().requires_grad_(True), labels=labels)
+        if it > 0:
+            assert ops._orth_slot is not None, 'prefetch was not issued'
+        res = tr.calculate_loss(3, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                                device='cuda', labels=labels, **w)
+        assert ops._orth_slot is None, 'prefetch branch was not re-joined'
+        res[0].backward()
+        gw = torch.cat([getattr(net, '_' + n + '_add_on').weight.grad.flatten() for n in net.layout.node_names])
+        vals.append((float(res[0]), res.stats[2].clone(), gw.clone()))
+    assert net._orth_hint
+    for v in vals[1:]:
+        assert abs(v[0] - vals[0][0]) <= 1e-6 * max(1.0, abs(vals[0][0])) and torch.equal(v[1], vals[0][1])
+        assert _close(v[2], vals[0][2], 1e-4)          # dW: split-K red.add order varies run to run

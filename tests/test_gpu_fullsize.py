@@ -38,8 +38,8 @@ def _setup(name, seed=0):
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_pool_argmax_consistent_with_materialised_map(name):
     ops, L, dl, x, w, labels, (V, C, H) = _setup(name)
-    pooled, align, argmax = ops.HeadProjPool.apply(x, w, dl, V // 2, 1.0, labels, 0.0)
-    pooled2, align2, argmax2 = ops.HeadProjPool.apply(x, w, dl, V // 2, 1.0, labels, 0.0)
+    pooled, align, argmax, _out = ops.HeadProjPool.apply(x, w, dl, V // 2, 1.0, labels, 0.0)
+    pooled2, align2, argmax2, _out = ops.HeadProjPool.apply(x, w, dl, V // 2, 1.0, labels, 0.0)
     torch.cuda.synchronize()
     assert torch.equal(pooled, pooled2) and torch.equal(argmax, argmax2)          # deterministic values / locations
     assert float(pooled.min()) > 0 and float(pooled.max()) <= 1.0 + 1e-6
@@ -58,7 +58,7 @@ def test_identical_views_align_closed_form():
     """view 2 == view 1 => S1 == S2 and align_n = -mean_{b,hw} log(sum_p S^2 + 1e-12) over the node's images."""
     ops, L, dl, x, w, labels, (V, C, H) = _setup("cub27-b64", seed=3)
     x = torch.cat([x[: V // 2], x[: V // 2]]).contiguous(memory_format=torch.channels_last)
-    pooled, align, argmax = ops.HeadProjPool.apply(x, w, dl, V // 2, 1.0, labels, 0.0)
+    pooled, align, argmax, _out = ops.HeadProjPool.apply(x, w, dl, V // 2, 1.0, labels, 0.0)
     torch.cuda.synchronize()
     assert torch.equal(pooled[: V // 2], pooled[V // 2:]) and torch.equal(argmax[: V // 2], argmax[V // 2:])
     for ni in (0, 7, L.N - 1):
@@ -83,7 +83,7 @@ def test_backward_linearity_and_spot_checks(name):
     def grads(G, a):
         xr = x.detach().clone().requires_grad_(True)
         wr = w.detach().clone().requires_grad_(True)
-        pooled, align, argmax = ops.HeadProjPool.apply(xr, wr, dl, V // 2, 1.0, labels, 0.0)
+        pooled, align, argmax, _out = ops.HeadProjPool.apply(xr, wr, dl, V // 2, 1.0, labels, 0.0)
         ((pooled * G).sum() + a * align.sum()).backward()
         return xr.grad.float(), wr.grad, argmax, pooled.detach()
 

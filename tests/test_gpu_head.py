@@ -122,7 +122,7 @@ def test_backward_dx_dw(case, tau):
     feats = pb.features('cuda').requires_grad_(True)
     w_flat = pb.w_flat('cuda').requires_grad_(True)
     labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
-    pooled, align, _ = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, tau, labels, 0.0)
+    pooled, align, _, _out = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, tau, labels, 0.0)
     loss = (pooled.double() * G.cuda()).sum() + (align.double() * a.cuda()).sum()
     loss.backward()
     torch.cuda.synchronize()
@@ -159,7 +159,7 @@ def test_fp32_accurate_mode_on_fp32_inputs(case):
     masks, _ = ho.node_targets(pb.root, pb.ys, pb.label2name)
     errs = {}
     for name, prec in (("fp32", ops.PREC_FP32X3), ("bf16", ops.PREC_BF16)):
-        pooled, align, argmax = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0, prec)
+        pooled, align, argmax, _out = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0, prec)
         torch.cuda.synchronize()
         errs[name] = rel_err(pooled, pr)
         a_err = 0.0
@@ -186,7 +186,7 @@ def test_fp32_accurate_mode_backward_runs():
     w_flat = pb.w_flat('cuda').requires_grad_(True)
     g = torch.Generator().manual_seed(1)
     G = torch.randn(pb.V, pb.layout.P, generator=g, dtype=torch.float64)
-    pooled, align, _ = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0, ops.PREC_FP32X3)
+    pooled, align, _, _out = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0, ops.PREC_FP32X3)
     ((pooled.double() * G.cuda()).sum() + align.double().sum()).backward()
     torch.cuda.synchronize()
     x = pb.x.clone().requires_grad_(True)
@@ -260,7 +260,7 @@ def test_all_segment_classes_in_one_model(seed):
     feats = pb.features('cuda').requires_grad_(True)
     w_flat = pb.w_flat('cuda').requires_grad_(True)
     labels = ops.LabelTables(pb.ys.cuda(), dl, pb.V_first)
-    pooled, align, argmax = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0)
+    pooled, align, argmax, _out = ops.HeadProjPool.apply(feats, w_flat, dl, pb.V_first, 1.0, labels, 0.0)
     loss = (pooled.double() * G.cuda()).sum() + (align.double() * a.cuda()).sum()
     loss.backward()
     torch.cuda.synchronize()
