@@ -638,13 +638,13 @@ def run_ours(a):
         import contextlib
         barrier()
         ctxm = profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) if rank == 0 else contextlib.nullcontext()
-        with ctxm as prof:
+        with ctxm as tprof:
             for i in range(2):                 # every rank replays: the step contains collectives
                 run_step(i)
             torch.cuda.synchronize()
         barrier()
         if rank == 0:
-            evs = sorted([e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
+            evs = sorted([e for e in tprof.events() if e.device_type == torch.autograd.DeviceType.CUDA], key=lambda e: e.time_range.start)
             t0 = evs[0].time_range.start if evs else 0
             os.makedirs(os.path.join(ROOT, 'gpurun_out'), exist_ok=True)
             with open(os.path.join(ROOT, 'gpurun_out', 'trace_rank0.txt'), 'w') as f:

@@ -144,7 +144,8 @@ int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, 
 /* ---- K5-K7: backward -------------------------------------------------------------------------- */
 /* dZ = S * (G - sum_p G*S) / tau with G = align gradient + g_pooled scattered at argmax; recomputes the
  * logits tile (same GEMM as K1).  scat_ws: int2[V*P], coef_ws: float[V_first*N] workspaces.
- * g_align (per node upstream gradient), desc may be NULL.
+ * g_align (per node upstream gradient), desc may be NULL.  argmax == NULL: scat_ws / coef_ws already hold the tables
+ * (hcomp_head_chain_bwd wrote them); g_pooled / pooled are then unused.
  * dz: bf16 [V*HW, P_c] on the COMPACT column axis: tile t owns columns [tiles[t][3], + used width), used width =
  * segments * S rounded up to 8; within a segment class the full tiles are contiguous (layout.py builds the table,
  * row_map_c[P_c] maps a compact column to its flat prototype or -1).  Every column of dz is written. */
@@ -224,12 +225,17 @@ int hcomp_head_chain_fwd(const float* pooled, const float* out, const float* ali
                          int32_t* n_correct, float* ws, uint8_t* rel, unsigned int* counter, void* stream);
 /* Backward of hcomp_head_chain_fwd CHAINED THROUGH THE CLASSIFIER (out = classifier(pooled, wc, bias)): one launch gives
  * g_pooled [V,P] (tanh term + class term through relu(Wc)), g_wc [n_welems], g_bias [K], g_align [N]; the orth term's
- * g_w [P,C] runs beside it.  d loss / d out is never materialised.  Any output may be NULL. */
+ * g_w [P,C] runs beside it.  d loss / d out is never materialised.  Any output may be NULL.
+ * scat_out / coef_out (optional; with argmax [V,P], thresh and desc, HW of the forward): the same launch also writes the
+ * scatter table int2[V*P] and the align coefficients float[V_first*N] that hcomp_head_bwd_dz builds from g_pooled /
+ * g_align; pass them to hcomp_head_bwd_dz as scat_ws / coef_ws with argmax = NULL ("tables are ready") -- valid only when
+ * exactly this g_pooled and g_align reach the head backward (no other gradient was added in between). */
 int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float* out, const float* w_flat, const float* wc,
                          const int8_t* tgt, const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V,
                          int V_first, int C, int flags, const float* weights_host, float eps, float multiplier,
                          const float* ws, const uint8_t* rel, float* g_pooled, float* g_wc, float* g_bias, float* g_align,
-                         float* g_w, void* stream);
+                         float* g_w, const int32_t* argmax, float thresh, const uint8_t* desc, int HW, void* scat_out,
+                         float* coef_out, void* stream);
 
 /* ---- descendant-structured loss terms switched on by the shipped scripts ------------------------ */
 /* (run_pipnet_20protos_multi_runs_seed42.sh: --tanh_desc "y|0.05" --minimize_contrasting_set 'y'

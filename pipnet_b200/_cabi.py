@@ -61,7 +61,8 @@ SIGNATURES = {
     'hcomp_pool_classify_fwd': [_p, _p, _p, _p, _p, _T, _i, _i, _f, _p, _p, _p, _p, _p],
     'hcomp_orth_gram': [_p, _p, _T, _i, _p, _p, _p],
     'hcomp_head_chain_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
-    'hcomp_head_chain_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p, _p],
+    'hcomp_head_chain_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p,
+                             _p, _f, _p, _i, _p, _p, _p],
     'hcomp_desc_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_desc_losses_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p, _p],

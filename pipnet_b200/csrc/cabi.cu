@@ -666,7 +666,9 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
   p.scat = reinterpret_cast<const int2*>(scat_ws);
   p.dz = reinterpret_cast<__nv_bfloat16*>(dz_bf16);
   p.P_c = P_c;
-  {                                     // scatter table + align coefficients: one launch
+  if (argmax == nullptr) {              // scat_ws / coef_ws were filled by hcomp_head_chain_bwd
+    if (g_align != nullptr && desc != nullptr && n_desc != nullptr) p.coef_align = coef_ws;
+  } else {                              // scatter table + align coefficients: one launch
     const bool use_align = g_align != nullptr && desc != nullptr && n_desc != nullptr;
     const int nb_scat = blocks(n, 256), nb_coef = use_align ? blocks((long long)V_first * n_nodes, 256) : 0;
     hc::bwd_prep_kernel<<<nb_scat + nb_coef, 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
@@ -905,9 +907,6 @@ int hcomp_orth_gram(const float* w_flat, const float* wc, const hcomp_tables* t,
   hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
                                                                       t->n_nodes, C, t->p_max, w.E, rel);
   HC_LAUNCH_CHECK("orth_gram");
-  hc::orth_sumsq_kernel<<<blocks((long long)t->n_nodes * 32, 128), 128, 0, S(stream)>>>(w.E, t->proto_off, t->n_nodes,
-                                                                                       t->p_max, w.orth_sq);
-  HC_LAUNCH_CHECK("orth_sumsq");
   return 0;
 }
 
@@ -922,13 +921,14 @@ int hcomp_head_chain_fwd(const float* pooled, const float* out, const float* ali
     if (int e = hcomp_orth_gram(w_flat, wc, t, C, ws, rel, stream)) return e;
   hc::ChainFwdParams q{};
   q.pooled = pooled; q.out = out; q.align = align; q.orth_sq = do_orth ? w.orth_sq : nullptr;
+  q.E = w.E; q.P_max = t->p_max;
   q.tgt = tgt; q.n_desc = n_desc; q.child_w = t->child_w; q.proto_off = t->proto_off; q.cls_off = t->cls_off;
   q.V = V; q.V_first = V_first; q.N = t->n_nodes; q.P = t->n_protos; q.K = t->n_cols;
   q.eps = eps; q.mult = (flags & HCOMP_LOSS_SPARSITY) ? multiplier : 0.f; q.do_tanh = do_tanh; q.do_cls = do_cls;
   for (int i = 0; i < 4; ++i) q.lw.w[i] = weights_host[i];
   q.tanh_part = w.tanh_part; q.colsum = w.colsum; q.cls = w.cls; q.lse = ws + hcomp_head_losses_ws_floats(t);
   q.n_correct = n_correct; q.stats = stats; q.total = total; q.counter = counter;
-  hc::head_chain_fwd_kernel<<<dim3(t->n_nodes, 3), 256, 0, S(stream)>>>(q);
+  hc::head_chain_fwd_kernel<<<dim3(t->n_nodes, do_orth ? 4 : 3), 256, 0, S(stream)>>>(q);
   HC_LAUNCH_CHECK("head_chain_fwd");
   return 0;
 }
@@ -937,21 +937,20 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
                          const int8_t* tgt, const int32_t* n_desc, const float* stats, const hcomp_tables* t, int V,
                          int V_first, int C, int flags, const float* weights_host, float eps, float multiplier,
                          const float* ws, const uint8_t* rel, float* g_pooled, float* g_wc, float* g_bias, float* g_align,
-                         float* g_w, void* stream) {
+                         float* g_w, const int32_t* argmax, float thresh, const uint8_t* desc, int HW, void* scat_out,
+                         float* coef_out, void* stream) {
   const LossWs w = loss_ws(const_cast<float*>(ws), t);
   const int N = t->n_nodes;
   if ((flags & HCOMP_LOSS_SPARSITY) && !(multiplier > 0.f)) return fail(HCOMP_E_ARG, "class loss: log1p(out**m) needs m > 0 (got %g)", multiplier);
+  // the orth term's g_w (weights only) runs beside the chain kernel: fork BEFORE the chain launch (so the branch does not
+  // depend on it), launch the chain kernel FIRST (the branch's P x C/256 blocks would otherwise queue in front of it)
   SideBranch* sb = nullptr;
-  if (g_w) {
-    if (flags & HCOMP_LOSS_ORTH) {      // weights-only term: beside the chain kernel
-      if (int e = side_branch(&sb)) return e;
-      HC_FORK(sb, S(stream));
-      hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
-          w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
-      HC_LAUNCH_CHECK("orth_bwd");
-    } else {
-      HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
-    }
+  const bool orth_branch = g_w != nullptr && (flags & HCOMP_LOSS_ORTH);
+  if (orth_branch) {
+    if (int e = side_branch(&sb)) return e;
+    HC_FORK(sb, S(stream));
+  } else if (g_w != nullptr) {
+    HC_CUDA(cudaMemsetAsync(g_w, 0, sizeof(float) * (size_t)t->n_protos * C, S(stream)));
   }
   hc::ChainBwdParams q{};
   q.g_total = g_total; q.pooled = pooled; q.out = out; q.wc = wc; q.colsum = w.colsum;
@@ -966,11 +965,26 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
   q.nb_pooled = g_pooled ? blocks((long long)V * t->n_protos, 256) : 0;
   q.nb_wc = g_wc ? blocks(t->n_welems, 8) : 0;
   q.nb_bias = g_bias ? blocks(t->n_cols, 256) : 0;
-  const int nb_align = g_align ? blocks(N, 256) : 0;
-  const int grid = q.nb_pooled + q.nb_wc + q.nb_bias + nb_align;
+  q.nb_align = g_align ? blocks(N, 256) : 0;
+  int nb_coef = 0;
+  if (scat_out != nullptr) {
+    if (g_pooled == nullptr || argmax == nullptr) return fail(HCOMP_E_ARG, "chain_bwd: scat_out needs g_pooled and argmax");
+    q.scat = reinterpret_cast<int2*>(scat_out); q.argmax = argmax; q.thresh = thresh;
+  }
+  if (coef_out != nullptr) {
+    if (desc == nullptr) return fail(HCOMP_E_ARG, "chain_bwd: coef_out needs desc");
+    q.coef = coef_out; q.desc = desc; q.HW = HW;
+    nb_coef = blocks((long long)V_first * N, 256);
+  }
+  const int grid = q.nb_pooled + q.nb_wc + q.nb_bias + q.nb_align + nb_coef;
   if (grid > 0) {
     hc::head_chain_bwd_kernel<<<grid, 256, 0, S(stream)>>>(q);
     HC_LAUNCH_CHECK("head_chain_bwd");
+  }
+  if (orth_branch) {
+    hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
+        w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
+    HC_LAUNCH_CHECK("orth_bwd");
   }
   if (sb) HC_JOIN(sb, S(stream));
   return 0;

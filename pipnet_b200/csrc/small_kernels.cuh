@@ -635,10 +635,12 @@ __global__ void __launch_bounds__(256) pool_classify_fwd_kernel(const PoolClassi
 }
 
 // ---- all per-node loss terms + their combination, one launch ------------------------------------------------------
-// grid (N, 3): y = 0 / 1 the tanh term of a view half, y = 2 the class term (+ accuracy counters, + the row log-sum-exp
-// kept for the backward); the LAST block to finish (device counter, left at zero) combines the terms.
+// grid (N, 3 or 4): y = 0 / 1 the tanh term of a view half, y = 2 the class term (+ accuracy counters, + the row
+// log-sum-exp kept for the backward), y = 3 ||E_n||^2 of the orth term (orth_sumsq_kernel's job; E from hcomp_orth_gram);
+// the LAST block to finish (device counter, left at zero) combines the terms.
 struct ChainFwdParams {
-  const float* pooled; const float* out; const float* align; const float* orth_sq;   // align / orth_sq may be NULL
+  const float* pooled; const float* out; const float* align; float* orth_sq;   // align / orth_sq may be NULL
+  const float* E; int P_max;                                                    // Gram slab [N, P_max, P_max] (orth on)
   const int8_t* tgt; const int32_t* n_desc; const float* child_w;
   const int32_t *proto_off, *cls_off;
   int V, V_first, N, P, K; float eps, mult; int do_tanh, do_cls;
@@ -683,6 +685,16 @@ __global__ void __launch_bounds__(256) head_chain_fwd_kernel(const ChainFwdParam
       acc = block_sum(acc, red);
       if (threadIdx.x == 0) q.tanh_part[h * q.N + n] = q.n_desc[n] > 0 ? -0.5f * acc / float(pn) : 0.f;
     }
+  } else if (role == 3) {                              // ||E_n||_F^2, fixed order (deterministic)
+    const int pn = q.proto_off[n + 1] - q.proto_off[n];
+    const float* En = q.E + (size_t)n * q.P_max * q.P_max;
+    float acc = 0.f;
+    for (int ij = threadIdx.x; ij < pn * pn; ij += 256) {
+      const float e = En[(ij / pn) * q.P_max + (ij % pn)];
+      acc = fmaf(e, e, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) q.orth_sq[n] = acc;
   } else {                                             // class term: class_loss_fwd_kernel + lse
     const int k0 = q.cls_off[n], kn = q.cls_off[n + 1] - k0;
     float acc = 0.f, corr = 0.f;
@@ -751,7 +763,10 @@ struct ChainBwdParams {
   int V, V_first, N, P, K, n_w; float eps, mult; int do_tanh, do_cls;
   LossWeights lw;
   float *g_pooled, *g_wc, *g_bias, *g_align;            // any may be NULL
-  int nb_pooled, nb_wc, nb_bias;
+  int nb_pooled, nb_wc, nb_bias, nb_align;
+  // optional: K5's scatter table / align coefficients straight from here (bwd_prep_kernel's job), valid when this
+  // g_pooled / g_align reach the head backward unchanged (the host checks)
+  const int32_t* argmax; float thresh; int2* scat; const uint8_t* desc; int HW; float* coef;
 };
 __device__ __forceinline__ float chain_gout(const ChainBwdParams& q, int v, int n, int t, int k0, int c, float coef) {
   const float o = q.out[(size_t)v * q.K + k0 + c];
@@ -784,6 +799,10 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
       }
     }
     q.g_pooled[idx] = g;
+    if (q.scat != nullptr) {
+      const float gs = (q.thresh > 0.f && q.pooled[idx] < q.thresh) ? 0.f : g;    // inference threshold kills the gradient too
+      q.scat[idx] = make_int2(q.argmax[idx], __float_as_int(gs));
+    }
     return;
   }
   b -= q.nb_pooled;
@@ -826,8 +845,17 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
     return;
   }
   b -= q.nb_bias;
-  const int n = b * 256 + threadIdx.x;
-  if (n < q.N && q.g_align != nullptr) q.g_align[n] = gT * q.lw.w[0];
+  if (b < q.nb_align) {
+    const int n = b * 256 + threadIdx.x;
+    if (n < q.N) q.g_align[n] = gT * q.lw.w[0];
+    return;
+  }
+  b -= q.nb_align;
+  const int idx = b * 256 + threadIdx.x;                // align coefficients [V_first, N] (align_coef_kernel)
+  if (idx >= q.V_first * q.N) return;
+  const int m = idx % q.N;
+  const int nd = q.n_desc[m] / 2;
+  q.coef[idx] = (q.desc[idx] && nd > 0) ? gT * q.lw.w[0] * 0.5f / (float(nd) * float(q.HW)) : 0.f;
 }
 
 // orth_bwd_kernel with the upstream gradient taken as g_total * weight (no loss_grads launch in front of it)

@@ -28,19 +28,24 @@ class GraphedHeadStep:
         self.static_y = ys_example.detach().clone()
         self.loss: Optional[torch.Tensor] = None
         self.grad_x: Optional[torch.Tensor] = None
+        from . import ops
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                self._zero()
-                fn(self.static_x, self.static_y).backward()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self._zero()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = fn(self.static_x, self.static_y)
-            self.loss.backward()
+        # the captured step owns its gradient storage: head-parameter gradients go through the flat bucket
+        # (ops.local_grad_bucket: no per-producer zero fills, no autograd add of the orth gradient and dW)
+        one = self._one = torch.ones((), device=x_example.device)      # root gradient: static, instead of a ones_like fill per step
+        with ops.local_grad_bucket():
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    self._zero()
+                    fn(self.static_x, self.static_y).backward(gradient=one)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self._zero()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.loss = fn(self.static_x, self.static_y)
+                self.loss.backward(gradient=one)
         self.grad_x = self.static_x.grad
 
     def _zero(self):

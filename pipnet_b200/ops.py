@@ -181,28 +181,61 @@ class _GradBucket:
                         p_.grad = p_.grad.clone()
             buf.zero_()
             self.flat = buf[:off]
+        elif GRAD_ALLREDUCE_GROUP is None:
+            # local bucket (nothing is exchanged): no up-front clear -- a segment is cleared on first touch unless its first
+            # producer overwrites every element (orth term, classifier, presence logits), so the usual step has no fill
+            self.flat = torch.empty(off, device=device, dtype=torch.float32)
+            self.lazy_zero = True
         else:
             self.flat = torch.zeros(off, device=device, dtype=torch.float32)
         self.produced = []
         self.reduced = False
 
-    def segment(self, grp):
+    lazy_zero = False
+
+    def segment(self, grp, overwrite=False):
         o = self.offsets[id(grp)]
+        seg = self.flat[o:o + self.sizes[id(grp)]]
         if grp not in self.produced:
             self.produced.append(grp)
-        return self.flat[o:o + self.sizes[id(grp)]]
+            if self.lazy_zero and not overwrite:
+                seg.zero_()
+        return seg
 
 
 _bucket: Optional[_GradBucket] = None
 
 
+# Single-process steps can use the bucket too (no exchange): every producer of a head-parameter gradient (orth term, dW
+# GEMM, classifier) writes into its segment of one buffer and `param.grad` becomes a view of it -- no zero fill per
+# producer, no autograd add of the orth gradient and dW (3 us of a 0.3 ms step).  Off by default: gradients must travel
+# through autograd for DistributedDataParallel's hooks and for torch.autograd.grad(); the captured training step
+# (train.GraphedHeadTrainStep, which owns the delivery of param.grad anyway) switches it on around its capture.
+LOCAL_GRAD_BUCKET = False
+
+
+class local_grad_bucket:
+    """context manager: head-parameter gradients of backward passes run inside go through the flat bucket"""
+
+    def __enter__(self):
+        global LOCAL_GRAD_BUCKET
+        self.prev, LOCAL_GRAD_BUCKET = LOCAL_GRAD_BUCKET, True
+        return self
+
+    def __exit__(self, *exc):
+        global LOCAL_GRAD_BUCKET
+        LOCAL_GRAD_BUCKET = self.prev
+        return False
+
+
 def _bucket_mode(grp) -> bool:
-    return (GRAD_ALLREDUCE_GROUP is not None and ASYNC_GRAD_ALLREDUCE and grp is not None
+    return (((GRAD_ALLREDUCE_GROUP is not None and ASYNC_GRAD_ALLREDUCE) or LOCAL_GRAD_BUCKET) and grp is not None
             and getattr(grp, 'family', None) is not None)
 
 
-def _bucket_segment(grp, device) -> torch.Tensor:
-    """This step's gradient segment of parameter group `grp` (zero-initialised; producers write or accumulate)."""
+def _bucket_segment(grp, device, overwrite=False) -> torch.Tensor:
+    """This step's gradient segment of parameter group `grp` (zero-initialised; producers write or accumulate).
+    overwrite=True: the caller writes EVERY element of the segment (lets the local bucket skip the clear)."""
     global _bucket
     if _bucket is not None and _bucket.reduced:
         # a second head forward contributed to the same loss and its backward runs after the exchange was issued: the
@@ -213,12 +246,14 @@ def _bucket_segment(grp, device) -> torch.Tensor:
     if _bucket is None:
         _bucket = _GradBucket(grp.family, device)
         torch.autograd.Variable._execution_engine.queue_callback(_bucket_finalize)
-    return _bucket.segment(grp)
+    return _bucket.segment(grp, overwrite)
 
 
 def _bucket_allreduce():
     import torch.distributed as dist
     b = _bucket
+    if GRAD_ALLREDUCE_GROUP is None:            # local bucket: nothing to exchange (and later producers may still write)
+        return
     side = _side()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
@@ -250,7 +285,8 @@ def _bucket_finalize():
     try:
         if not b.reduced:                       # the dW GEMM did not run in this pass (frozen prototypes): reduce now
             _bucket_allreduce()
-        torch.cuda.current_stream().wait_stream(_side())
+        if GRAD_ALLREDUCE_GROUP is not None:    # (local bucket: nothing ran on the side stream; waiting on it would also
+            torch.cuda.current_stream().wait_stream(_side())     # pull a non-captured stream into a graph capture)
         for grp in b.produced:
             seg = b.segment(grp)
             for p_, (off, numel, shape) in zip(grp.params, grp.meta):
@@ -553,6 +589,10 @@ def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, la
          HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), 1, ptr(labels.desc) if labels is not None else None,
          ptr(packed), ptr(align_sum), C.byref(sp) if sp is not None else None, _stream())
     PROFILE.stop(tok)
+    global ORTH_REQUEST
+    if ORTH_REQUEST is not None:           # fork the orth term's Gram kernel HERE: it runs beside the finishing launch below
+        req, ORTH_REQUEST = ORTH_REQUEST, None      # (forked before K1 its blocks delay K1's persistent CTAs by ~5 us)
+        orth_prefetch(*req)
     pooled = torch.empty(V, dl.P, device=dev, dtype=torch.float32)
     argmax = torch.empty(V, dl.P, device=dev, dtype=torch.int32)
     align = torch.empty(dl.N, device=dev, dtype=torch.float32) if labels is not None else None
@@ -564,8 +604,9 @@ def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, la
 
 def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
                       pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None, dz_out=None,
-                      spill=None):
-    """spill: (zs, stats) the forward produced for the layout's spill nodes (required when it has any)"""
+                      spill=None, tables=None):
+    """spill: (zs, stats) the forward produced for the layout's spill nodes (required when it has any);
+    tables: (scat, coef) already built from exactly these g_pooled / g_align by hcomp_head_chain_bwd (`_PrepSlot`)"""
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
@@ -577,8 +618,12 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
     # compact column axis (layout.row_map_c); `dz_out` lets tests supply a guarded buffer
     dz = dz_out if dz_out is not None else torch.empty(M, dl.P_c, device=dev, dtype=torch.bfloat16)
     assert dz.shape == (M, dl.P_c) and dz.dtype == torch.bfloat16 and dz.is_contiguous()
-    scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
-    coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
+    if tables is not None:
+        scat, coef = tables
+        argmax = None                       # "tables are ready"
+    else:
+        scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
+        coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
     use_align = labels is not None and g_align is not None
     tok = PROFILE.start('k5_bwd_dz')
     call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
@@ -631,6 +676,29 @@ def gemm_bf16(a, b, M, N, K, a_mn, b_mn, out_mode=1, splits=1):
 
 
 # --------------------------------------------------------------------------- autograd
+class _PrepSlot:
+    """Hand-off between the chained loss backward and the head backward of ONE step: the loss backward can write K5's
+    scatter table / align coefficients in its own launch (it produces g_pooled and g_align anyway); the head backward uses
+    them iff the gradients it receives are exactly those tensors, unmodified (pointer + version), else builds its own."""
+
+    def __init__(self, argmax, thresh, labels, V_first, HW):
+        self.argmax, self.thresh, self.labels, self.V_first, self.HW = argmax, float(thresh), labels, V_first, HW
+        self.ready = None            # (g_pooled ptr, version, g_align ptr or 0, version, scat, coef)
+
+    @staticmethod
+    def _key(t):
+        return (0, 0) if t is None else (t.data_ptr(), t._version)
+
+    def publish(self, g_pooled, g_align, scat, coef):
+        self.ready = (self._key(g_pooled), self._key(g_align), scat, coef)
+
+    def take(self, g_pooled, g_align):
+        r, self.ready = self.ready, None
+        if r is not None and r[0] == self._key(g_pooled) and r[1] == self._key(g_align):
+            return r[2], r[3]
+        return None
+
+
 class HeadProjPool(torch.autograd.Function):
     """features, flat prototype kernels -> pooled [V,P], per-node align loss [N] (zeros without labels), argmax and --
     when the classifier weights are passed -- the child logits out [V,K] (pipnet/pipnet.py:1035-1036), finished by the
@@ -668,6 +736,7 @@ class HeadProjPool(torch.autograd.Function):
         ctx.feat_meta = (features.dtype, features.is_contiguous(memory_format=torch.channels_last))
         ctx.save_for_backward(x_rows, wp, wpc, argmax, pooled, wc)
         ctx.mark_non_differentiable(argmax)
+        ctx.prep = pooled._hc_prep = _PrepSlot(argmax, thresh, labels, V_first, HW)
         if align is None:
             align = torch.zeros(dl.N, device=dev, dtype=torch.float32)
         return pooled, align, argmax, out
@@ -685,14 +754,23 @@ class HeadProjPool(torch.autograd.Function):
             need_wc, need_bias = ctx.needs_input_grad[8], ctx.has_cls[1] and ctx.needs_input_grad[9]
             wc_grp, bias_grp = ctx.cls_groups
             b_wc, b_bias = need_wc and _bucket_mode(wc_grp), need_bias and _bucket_mode(bias_grp)
+            # bucket mode: the chained losses of the same backward pass may already have written these segments (both the
+            # loss and another consumer of `out` in one graph): then this contribution is added, not written over
+            add_wc = b_wc and _bucket is not None and wc_grp in _bucket.produced
+            add_bias = b_bias and _bucket is not None and bias_grp in _bucket.produced
             if need_wc:
-                g_wc = _bucket_segment(wc_grp, dev) if b_wc else torch.empty_like(wc)
+                g_wc = _bucket_segment(wc_grp, dev, True) if (b_wc and not add_wc) else torch.empty_like(wc)
             if need_bias:
-                g_bias = _bucket_segment(bias_grp, dev) if b_bias else torch.empty(dl.K, device=dev, dtype=torch.float32)
+                g_bias = (_bucket_segment(bias_grp, dev, True) if (b_bias and not add_bias)
+                          else torch.empty(dl.K, device=dev, dtype=torch.float32))
             accumulate = g_pooled is not None
             g_pooled = g_pooled.contiguous().float().clone() if accumulate else torch.empty(V, dl.P, device=dev, dtype=torch.float32)
             call('hcomp_classifier_bwd', ptr(g_out.contiguous().float()), ptr(pooled), ptr(wc), dl.tref, V, ptr(g_pooled),
                  int(accumulate), ptr(g_wc), ptr(g_bias), _stream())
+            if add_wc:
+                _bucket_segment(wc_grp, dev).add_(g_wc)
+            if add_bias:
+                _bucket_segment(bias_grp, dev).add_(g_bias)
             if b_wc:
                 g_wc = None
             if b_bias:
@@ -708,7 +786,8 @@ class HeadProjPool(torch.autograd.Function):
             g_align = g_align.contiguous().float()
         dx, dw, _ = head_backward_raw(x_rows, wp, wpc, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
                                       pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw,
-                                      precision=ctx.precision, w_group=ctx.w_group, spill=ctx.spill)
+                                      precision=ctx.precision, w_group=ctx.w_group, spill=ctx.spill,
+                                      tables=ctx.prep.take(g_pooled, g_align))
         d_feat = None
         if need_dx:
             dtype, _cl = ctx.feat_meta
@@ -746,9 +825,9 @@ class NonNegClassifier(torch.autograd.Function):
         b_wc, b_bias = need_wc and _bucket_mode(wc_grp), need_bias and _bucket_mode(bias_grp)
         g_wc = g_bias = None
         if need_wc:
-            g_wc = _bucket_segment(wc_grp, pooled.device) if b_wc else torch.empty_like(wc_flat)
+            g_wc = _bucket_segment(wc_grp, pooled.device, True) if b_wc else torch.empty_like(wc_flat)
         if need_bias:
-            g_bias = (_bucket_segment(bias_grp, pooled.device) if b_bias
+            g_bias = (_bucket_segment(bias_grp, pooled.device, True) if b_bias
                       else torch.empty(dl.K, device=pooled.device, dtype=torch.float32))
         call('hcomp_classifier_bwd', ptr(g_out), ptr(pooled), ptr(wc_flat), dl.tref, V, ptr(g_pooled), 0, ptr(g_wc),
              ptr(g_bias), _stream())
@@ -767,6 +846,7 @@ LOSS_TANH, LOSS_ORTH, LOSS_CLASS, LOSS_SPARSITY = 1, 2, 4, 8
 
 
 LOSS_ORTH_READY = 16
+ORTH_REQUEST = None       # (w_flat, wc_flat, dl, V): the model asks the next fused head forward to start `orth_prefetch` after K1
 _orth_stream = None
 _orth_slot = None          # (key, ws, rel, event) of the latest `orth_prefetch`
 
@@ -781,10 +861,10 @@ def _orth_key(w_flat, wc_flat, dl, V):
 
 
 def orth_prefetch(w_flat: torch.Tensor, wc_flat: torch.Tensor, dl: DeviceLayout, V: int):
-    """Start the weights-only part of the kernel-orthogonality term (Gram matrices, ||E||^2, relevance mask;
-    pipnet/train.py:1136-1151) on a side stream NOW, so that it runs beside the projection kernel instead of on the
-    critical path between the forward and the backward.  `HeadLosses` picks the result up (and always re-joins the side
-    stream); the model calls this at the start of the head forward when the previous step's loss used the term."""
+    """Start the weights-only part of the kernel-orthogonality term (Gram matrices + relevance mask;
+    pipnet/train.py:1136-1151) on a side stream NOW, off the critical path between the forward and the backward.
+    `HeadLosses` picks the result up (and always re-joins the side stream).  The model requests it (`ORTH_REQUEST`) for
+    the head forward when the previous step's loss used the term; the fused forward issues it right after K1."""
     global _orth_stream, _orth_slot
     if w_flat.shape[1] <= dl.layout.p_max:
         return
@@ -861,6 +941,7 @@ class HeadLosses(torch.autograd.Function):
         ctx.dl, ctx.labels, ctx.cfg = dl, labels, (int(flags), [float(x) for x in weights], float(eps), V, Cc, float(multiplier))
         ctx.has = (align is not None, w_flat is not None and use_orth)
         ctx.chain = bool(chain)
+        ctx.prep = getattr(pooled, '_hc_prep', None) if chain else None
         ctx.w_group = getattr(w_flat, '_hc_group', None) if w_flat is not None else None
         ctx.cls_groups = (getattr(wc_flat, '_hc_group', None) if wc_flat is not None else None,
                           getattr(bias, '_hc_group', None) if bias is not None else None)
@@ -887,7 +968,7 @@ class HeadLosses(torch.autograd.Function):
         bucketed = need_w and _bucket_mode(ctx.w_group)
         g_w = None
         if need_w:      # bucket mode: the orth gradient (identical on every rank) lands where K7 will accumulate dW
-            g_w = (_bucket_segment(ctx.w_group, dev).view(dl.P, Cc) if bucketed
+            g_w = (_bucket_segment(ctx.w_group, dev, True).view(dl.P, Cc) if bucketed
                    else torch.empty(dl.P, Cc, device=dev, dtype=torch.float32))
         g_out = g_wc = g_bias = g_align = None
         if ctx.chain:
@@ -895,13 +976,27 @@ class HeadLosses(torch.autograd.Function):
             wc_grp, bias_grp = ctx.cls_groups
             b_wc, b_bias = need_wc and _bucket_mode(wc_grp), need_bias and _bucket_mode(bias_grp)
             if need_wc:
-                g_wc = _bucket_segment(wc_grp, dev) if b_wc else torch.empty_like(wc)
+                g_wc = _bucket_segment(wc_grp, dev, True) if b_wc else torch.empty_like(wc)
             if need_bias:
-                g_bias = _bucket_segment(bias_grp, dev) if b_bias else torch.empty(dl.K, device=dev, dtype=torch.float32)
+                g_bias = _bucket_segment(bias_grp, dev, True) if b_bias else torch.empty(dl.K, device=dev, dtype=torch.float32)
             g_align = torch.empty(dl.N, device=dev, dtype=torch.float32) if need_align else None
+            # K5's scatter table / align coefficients from the same launch (used by the head backward iff these very
+            # gradients reach it, `_PrepSlot`)
+            slot = ctx.prep if (need_pooled and ctx.prep is not None and ctx.prep.labels is labels
+                                and ctx.prep.argmax.shape == g_pooled.shape) else None
+            scat = coef = None
+            if slot is not None:
+                scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
+                coef = torch.empty(max(1, labels.V_first * dl.N), device=dev, dtype=torch.float32)
+            use_coef = slot is not None and g_align is not None
             call('hcomp_head_chain_bwd', ptr(g_total), ptr(pooled), ptr(out), ptr(wf), ptr(wc), ptr(labels.tgt),
                  ptr(labels.n_desc), ptr(stats), dl.tref, V, labels.V_first, Cc, flags, wts, eps, multiplier, ptr(ws), ptr(rel),
-                 ptr(g_pooled), ptr(g_wc), ptr(g_bias), ptr(g_align), ptr(g_w), _stream())
+                 ptr(g_pooled), ptr(g_wc), ptr(g_bias), ptr(g_align), ptr(g_w),
+                 ptr(slot.argmax) if slot is not None else None, slot.thresh if slot is not None else 0.0,
+                 ptr(labels.desc) if use_coef else None, slot.HW if slot is not None else 0, ptr(scat),
+                 ptr(coef) if use_coef else None, _stream())
+            if slot is not None:
+                slot.publish(g_pooled, g_align, scat, coef)
             if b_wc:
                 g_wc = None                     # reduced with the bucket, delivered at the end of the backward pass
             if b_bias:
@@ -983,7 +1078,7 @@ class DescLosses(torch.autograd.Function):
         bucketed = need_pres and _bucket_mode(ctx.pp_group)
         g_pres = None
         if need_pres:
-            g_pres = (_bucket_segment(ctx.pp_group, dev).view(dl.P, 2) if bucketed
+            g_pres = (_bucket_segment(ctx.pp_group, dev, True).view(dl.P, 2) if bucketed
                       else torch.empty(dl.P, 2, device=dev, dtype=torch.float32))
         call('hcomp_desc_losses_bwd', ptr(g_loss), ptr(pooled), ptr(wc), ptr(pres), ptr(gum), ptr(labels.ys), ptr(labels.tgt),
              ptr(labels.n_desc), dl.tref, V, labels.V_first, flags, wts, eps, boost, tau, ptr(ws), ptr(g_pooled), ptr(g_pres),

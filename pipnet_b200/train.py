@@ -335,19 +335,23 @@ class GraphedHeadTrainStep:
         saved_grads = [p.grad for p in self.params]
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                zero()
-                self.node_acc.clear()
-                run()[0][0].backward()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        zero()
-        self.node_acc.clear()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.res, self.out, self.labels = run()
-            self.res[0].backward()
+        # this object delivers param.grad itself (_HeadReplay.backward), so the head's gradients can go through the flat
+        # bucket: no per-producer zero fills, no autograd add of the orth gradient and dW
+        one = self._one = torch.ones((), device=features.device)         # root gradient: static, instead of a ones_like fill per step
+        with ops.local_grad_bucket():
+            with torch.cuda.stream(side):
+                for _ in range(warmup):
+                    zero()
+                    self.node_acc.clear()
+                    run()[0][0].backward(gradient=one)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            zero()
+            self.node_acc.clear()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.res, self.out, self.labels = run()
+                self.res[0].backward(gradient=one)
         self.loss = self.res[0].detach()
         self.grad_x = self.static_x.grad
         self.param_grads = [p.grad for p in self.params]

@@ -141,3 +141,38 @@ def test_orth_prefetch_gives_the_same_loss():
     for v in vals[1:]:
         assert abs(v[0] - vals[0][0]) <= 1e-6 * max(1.0, abs(vals[0][0])) and torch.equal(v[1], vals[0][1])
         assert _close(v[2], vals[0][2], 1e-4)          # dW: split-K red.add order varies run to run
+
+
+@pytest.mark.parametrize("extra_consumer", [False, True], ids=["sole-consumer", "extra-consumer"])
+def test_prep_tables_hand_off(extra_consumer):
+    """the chained loss backward writes K5's scatter table / align coefficients itself; the head backward takes them iff
+    the very same g_pooled / g_align reach it -- with a second consumer of `pooled` autograd sums two gradients and the
+    head backward must build its own tables from the sum"""
+    from pipnet_b200 import ops
+    net, root, args, xs, ys, tr = _problem()
+    w = tr._phase_weights(False, 3, 10, args)
+    grads, taken = [], []
+    real_call = ops.call
+    for chained in (True, False):
+        net.zero_grad(set_to_none=True)
+        x = xs.clone().requires_grad_(True)
+        labels = tr.make_labels(net, ys)
+        features, pf, pooled, out = net(x, labels=labels)
+        if not chained:
+            out.chained_from = None
+        res = tr.calculate_loss(3, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                pretrain=False, finetune=False, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                                device='cuda', labels=labels, **w)
+        loss = res[0] + (0.01 * pooled.flat.square().sum() if extra_consumer else 0.0)
+        try:
+            ops.call = lambda name, *a: (taken.append((chained, a[15] is None)) if name == 'hcomp_head_bwd_dz' else None,
+                                         real_call(name, *a))[1]
+            loss.backward()
+        finally:
+            ops.call = real_call
+        torch.cuda.synchronize()
+        grads.append((x.grad.float(), torch.cat([getattr(net, '_' + n + '_add_on').weight.grad.flatten()
+                                                  for n in net.layout.node_names])))
+    assert taken == [(True, not extra_consumer), (False, False)], taken
+    assert _close(grads[0][0], grads[1][0], 2e-2) and _close(grads[0][1], grads[1][1], 2e-2)
