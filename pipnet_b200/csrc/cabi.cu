@@ -769,7 +769,7 @@ int hcomp_head_losses_fwd(const float* pooled, const float* out, const float* al
     if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
     if (int e = side_branch(&sb)) return e;
     HC_FORK(sb, S(stream));
-    const long long warps = (long long)t->n_nodes * t->p_max * t->p_max;
+    const long long warps = (long long)t->n_nodes * (t->p_max * (t->p_max + 1) / 2);     // upper triangle
     hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, sb->stream>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
                                                                          t->n_nodes, C, t->p_max, w.E, rel);
     HC_LAUNCH_CHECK("orth_gram");
@@ -903,7 +903,7 @@ long long hcomp_head_chain_ws_floats(const hcomp_tables* t, int V) {
 int hcomp_orth_gram(const float* w_flat, const float* wc, const hcomp_tables* t, int C, float* ws, uint8_t* rel, void* stream) {
   const LossWs w = loss_ws(ws, t);
   if (t->p_max >= C) return fail(HCOMP_E_ARG, "orth loss needs P_n < C (P_max=%d, C=%d)", t->p_max, C);
-  const long long warps = (long long)t->n_nodes * t->p_max * t->p_max;
+  const long long warps = (long long)t->n_nodes * (t->p_max * (t->p_max + 1) / 2);     // upper triangle
   hc::orth_gram_kernel<<<blocks(warps * 32, 256), 256, 0, S(stream)>>>(w_flat, wc, t->proto_off, t->cls_off, t->wc_off,
                                                                       t->n_nodes, C, t->p_max, w.E, rel);
   HC_LAUNCH_CHECK("orth_gram");
@@ -982,8 +982,14 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
     HC_LAUNCH_CHECK("head_chain_bwd");
   }
   if (orth_branch) {
-    hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
-        w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
+    const size_t smem = sizeof(float) * ((size_t)t->p_max * 128 + (size_t)t->p_max * t->p_max + t->p_max);
+    if (t->p_max <= 64 && smem <= 48 * 1024) {        // tile kernel: at most 16 rows per row group, default shared-memory limit
+      hc::orth_bwd_tile_kernel<<<dim3(N, (C + 127) / 128), 512, smem, sb->stream>>>(
+          w_flat, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
+    } else {
+      hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
+          w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
+    }
     HC_LAUNCH_CHECK("orth_bwd");
   }
   if (sb) HC_JOIN(sb, S(stream));

@@ -387,12 +387,14 @@ __global__ void orth_gram_kernel(const float* __restrict__ w, const float* __res
   const long long wid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   const int slots = P_max * P_max;
-  const int n = int(wid / slots);
+  const int tri = P_max * (P_max + 1) / 2;            // E is symmetric: warps only for the upper triangle (j >= i),
+  const int n = int(wid / tri);                       // mirrored below -- half the warps, one wave on cub27
   if (n >= N) return;
-  const int ij = int(wid - (long long)n * slots);
-  const int i = ij / P_max, j = ij - i * P_max;
+  int rem = int(wid - (long long)n * tri), i = 0;
+  while (rem >= P_max - i) { rem -= P_max - i; ++i; }
+  const int j = i + rem;
   const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
-  if (i >= pn || j >= pn || j < i) return;            // E is symmetric: upper triangle computed, mirrored below
+  if (i >= pn || j >= pn) return;
   const int kn = cls_off[n + 1] - cls_off[n];
   const float* wcn = wc + wc_off[n];
   bool ri = false, rj = false;                        // relevant = some classifier weight > 1e-3 (pipnet/train.py:1140)
@@ -401,21 +403,18 @@ __global__ void orth_gram_kernel(const float* __restrict__ w, const float* __res
     rj |= wcn[(size_t)c * pn + j] > 0.001f;
   }
   if (i == j && lane == 0) rel[p0 + i] = ri;
-  float e = 0.f;
-  if (ri && rj) {
-    const float* a = w + (size_t)(p0 + i) * C;
-    const float* b = w + (size_t)(p0 + j) * C;
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    int c = lane;
-    for (; c + 96 < C; c += 128) {
-      d0 = fmaf(a[c], b[c], d0);
-      d1 = fmaf(a[c + 32], b[c + 32], d1);
-      d2 = fmaf(a[c + 64], b[c + 64], d2);
-      d3 = fmaf(a[c + 96], b[c + 96], d3);
-    }
-    for (; c < C; c += 32) d0 = fmaf(a[c], b[c], d0);
-    e = warp_sum((d0 + d1) + (d2 + d3)) - (i == j ? 1.f : 0.f);
+  // the dot product does not wait for the relevance flags (its loads are issued beside theirs; the kernel is load latency)
+  const float* a = w + (size_t)(p0 + i) * C;
+  const float* b = w + (size_t)(p0 + j) * C;
+  float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  int c = lane;
+  for (; c + 224 < C; c += 256) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) d[u] = fmaf(a[c + 32 * u], b[c + 32 * u], d[u]);
   }
+  for (; c < C; c += 32) d[0] = fmaf(a[c], b[c], d[0]);
+  const float dot = warp_sum(((d[0] + d[1]) + (d[2] + d[3])) + ((d[4] + d[5]) + (d[6] + d[7])));
+  const float e = (ri && rj) ? dot - (i == j ? 1.f : 0.f) : 0.f;
   if (lane == 0) {
     float* En = E + (size_t)n * slots;
     En[i * P_max + j] = e;
@@ -663,12 +662,23 @@ __global__ void __launch_bounds__(256) head_chain_fwd_kernel(const ChainFwdParam
       for (int pc = 0; pc < pn; pc += 64) {
         float t0 = 0.f, t1 = 0.f;
         const int pa = pc + lane, pb = pc + 32 + lane;
-        for (int v = vb + warp; v < ve; v += 8) {
-          if (q.tgt[(size_t)v * q.N + n] >= 0) {
-            const float* row = q.pooled + (size_t)v * q.P + p0;
-            if (pa < pn) t0 += row[pa];
-            if (pb < pn) t1 += row[pb];
+        // four rows per trip, every load issued before the first use (the kernel is pure load latency); same summation
+        // order as tanh_loss_fwd_kernel (rows ascending per warp)
+        for (int v = vb + warp; v < ve; v += 32) {
+          int on[4];
+          float x0[4], x1[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int vv = v + 8 * u;
+            const bool ok = vv < ve;
+            on[u] = ok ? int(q.tgt[(size_t)vv * q.N + n]) : -1;
+            const float* row = q.pooled + (size_t)(ok ? vv : v) * q.P + p0;
+            x0[u] = (pa < pn) ? row[pa] : 0.f;
+            x1[u] = (pb < pn) ? row[pb] : 0.f;
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (on[u] >= 0) { t0 += x0[u]; t1 += x1[u]; }
         }
         sh[warp][lane] = t0;
         sh[warp][32 + lane] = t1;
@@ -794,6 +804,7 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
         const float coef = gT * q.lw.w[3] / float(q.n_desc[n]) * q.child_w[k0 + t];
         const float* w = q.wc + q.wc_off[n] + (p - p0);
         float acc = 0.f;
+#pragma unroll 4
         for (int c = 0; c < kn; ++c) acc = fmaf(chain_gout(q, v, n, t, k0, c, coef), fmaxf(w[(size_t)c * pn], 0.f), acc);
         g += acc;
       }
@@ -816,10 +827,12 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
       const int k0 = q.cls_off[n];
       const int nd = q.n_desc[n];
       const float base = nd > 0 ? gT * q.lw.w[3] / float(nd) : 0.f;
-      for (int v = lane; v < q.V; v += 32) {
-        const int t = q.tgt[(size_t)v * q.N + n];
-        if (t < 0) continue;
-        acc = fmaf(chain_gout(q, v, n, t, k0, k - k0, base * q.child_w[k0 + t]), q.pooled[(size_t)v * q.P + p], acc);
+#pragma unroll 4
+      for (int v = lane; v < q.V; v += 32) {            // loads unconditional (rows without a label read a valid dummy
+        const int t = q.tgt[(size_t)v * q.N + n];       // column; their lse is uninitialised, the select drops the result)
+        const float gout = chain_gout(q, v, n, t, k0, k - k0, base * q.child_w[k0 + (t < 0 ? 0 : t)]);
+        const float pl = q.pooled[(size_t)v * q.P + p];
+        acc = t >= 0 ? fmaf(gout, pl, acc) : acc;
       }
     }
     acc = warp_sum(acc);
@@ -878,6 +891,66 @@ __global__ void orth_bwd_scaled_kernel(const float* __restrict__ w, const int32_
     acc *= g * 2.f / L;
   }
   g_w[(size_t)row * C + c] = acc;
+}
+
+// Same result as orth_bwd_scaled_kernel for nodes of at most 64 prototypes, organised for latency: one block per (node,
+// 128-channel chunk) = 128 channels x 4 row groups.  Phase 1 stages E_n (pn x pn), the relevance flags and the node's
+// kernel columns (pn x 128) in shared memory with ONE batch of independent coalesced loads per thread; phase 2: thread
+// (channel, row group) produces rows rg, rg + 4, ... of its channel from shared memory.  The row-per-block kernel above
+// walks pn dependent L2 round trips per thread (8 us for 25 nodes x 20 prototypes).
+__global__ void __launch_bounds__(512) orth_bwd_tile_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off,
+                                                            int C, int P_max, const float* __restrict__ loss,
+                                                            const float* __restrict__ E, const uint8_t* __restrict__ rel,
+                                                            const float* __restrict__ g_total, float weight,
+                                                            float* __restrict__ g_w) {
+  extern __shared__ float osm[];                        // Ws[pn][128], Es[pn][pn], rel_s[pn]
+  const int n = blockIdx.x;
+  const int ch = threadIdx.x & 127, rg = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + ch;
+  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
+  const float L = loss[n], g = g_total[0] * weight;
+  float* Ws = osm;
+  float* Es = osm + pn * 128;
+  float* rel_s = Es + pn * pn;
+  const bool active = L > 0.f && g != 0.f;
+  if (active) {
+    float t[16];                                        // pn <= 64: at most 16 rows per row group
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = rg + 4 * u;
+      t[u] = (j < pn && c < C) ? w[(size_t)(p0 + j) * C + c] : 0.f;
+    }
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, e4 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f;
+    const int nn = pn * pn;                             // <= 4096 = 8 per thread
+    auto ld = [&](int ij) { return ij < nn ? E[((size_t)n * P_max + ij / pn) * P_max + ij % pn] : 0.f; };
+    e0 = ld(threadIdx.x); e1 = ld(threadIdx.x + 512); e2 = ld(threadIdx.x + 1024); e3 = ld(threadIdx.x + 1536);
+    if (nn > 2048) { e4 = ld(threadIdx.x + 2048); e5 = ld(threadIdx.x + 2560); e6 = ld(threadIdx.x + 3072); e7 = ld(threadIdx.x + 3584); }
+    const float r = threadIdx.x < pn ? float(rel[p0 + threadIdx.x]) : 0.f;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) {
+      const int j = rg + 4 * u;
+      if (j < pn) Ws[j * 128 + ch] = t[u];
+    }
+    const float ev[8] = {e0, e1, e2, e3, e4, e5, e6, e7};
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int ij = threadIdx.x + 512 * u;
+      if (ij < nn) Es[ij] = ev[u];
+    }
+    if (threadIdx.x < pn) rel_s[threadIdx.x] = r;
+  }
+  __syncthreads();
+  if (c >= C) return;
+  const float sc = active ? g * 2.f / L : 0.f;
+  for (int i = rg; i < pn; i += 4) {
+    float acc = 0.f;
+    if (active && rel_s[i] != 0.f) {
+#pragma unroll 4
+      for (int j = 0; j < pn; ++j) acc = fmaf(Es[i * pn + j], Ws[j * 128 + ch], acc);
+      acc *= sc;
+    }
+    g_w[(size_t)(p0 + i) * C + c] = acc;
+  }
 }
 
 // ---- backward prep: scatter table + align coefficients, one launch (make_scat_kernel + align_coef_kernel) ---------
