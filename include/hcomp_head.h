@@ -128,7 +128,8 @@ int hcomp_label_tables(const long long* ys, const hcomp_tables* t, int V, int V_
 /* Replaces conv1x1 -> /tau -> softmax(dim=1) -> AdaptiveMaxPool2d for every node
  * (pipnet/pipnet.py:124-159) and the align_pf reduction (pipnet/train.py:1063-1069).
  * x: bf16 [V*HW, C]; views [0,V_first) are paired with views [V_first, V) (train: V_first = V/2).
- * pooled_packed[V,P] and align_sum[N] are cleared by the call unless outputs_zeroed != 0 (the caller already did).
+ * outputs_zeroed: bit 0 = pooled_packed[V,P] and align_sum[N] are already cleared (else the call clears them); bit 1 = leave
+ * the narrow spill nodes ("riders") to hcomp_pool_classify_fwd (no grid barrier / rider tail in the fused kernel).
  * desc/align_sum may be NULL. */
 int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const int32_t* tiles_host,
                                 const int32_t* tiles_dev, int n_tiles, int V, int V_first, int HW, int C, int P,
@@ -207,10 +208,17 @@ int hcomp_head_prologue(const float* w_flat, const int32_t* row_map, int rows, i
                         unsigned long long* packed, long long n_packed, double* align_sum, int n_align, const long long* ys,
                         const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc, void* stream);
 /* hcomp_unpack_pool + hcomp_align_finalize (align / align_sum / n_desc may be NULL) + hcomp_classifier_fwd (out / wc may
- * be NULL; the inference threshold applies to the classifier's input like pipnet/pipnet.py:168-170). */
-int hcomp_pool_classify_fwd(const unsigned long long* packed, const double* align_sum, const int32_t* n_desc, const float* wc,
+ * be NULL; the inference threshold applies to the classifier's input like pipnet/pipnet.py:168-170).
+ * deferred (may be NULL): the layout's spill record when the forward call was told to leave its narrow spill nodes
+ * ("riders") unfinished (outputs_zeroed bit 1 of hcomp_proj_softmax_pool_fwd; only narrow records, at most 4).  One block
+ * per (rider, image pair) then runs the rider's softmax / max-pool / align rows from the raw-logit scratch matrix, unpacks
+ * that pair's pooled entries of the node and applies the node's classifier; the fused forward kernel loses its grid
+ * barrier and rider tail.  Needs V_first, tau, desc (may be NULL without the align term) and `counter`: DEVICE uint32[5],
+ * zero on entry, left zero (word 1 + i: last-block-done of rider i). */
+int hcomp_pool_classify_fwd(const unsigned long long* packed, double* align_sum, const int32_t* n_desc, const float* wc,
                             const float* bias, const hcomp_tables* t, int V, int HW, float thresh, float* pooled,
-                            int32_t* argmax, float* align, float* out, void* stream);
+                            int32_t* argmax, float* align, float* out, const hcomp_spill* deferred, int V_first, float tau,
+                            const uint8_t* desc, unsigned int* counter, void* stream);
 /* Workspace of the chained losses: hcomp_head_losses_ws_floats(t) + V * N floats (row log-sum-exp of the class term). */
 long long hcomp_head_chain_ws_floats(const hcomp_tables* t, int V);
 /* The weights-only part of the orth term (Gram matrices, ||E||^2, relevance mask) into ws / rel; may run on ANY stream

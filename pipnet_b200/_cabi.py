@@ -58,7 +58,7 @@ SIGNATURES = {
     'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p],
     'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_head_prologue': [_p, _p, _i, _i, _p, _p, _ll, _p, _i, _p, _T, _i, _i, _p, _p, _p, _p],
-    'hcomp_pool_classify_fwd': [_p, _p, _p, _p, _p, _T, _i, _i, _f, _p, _p, _p, _p, _p],
+    'hcomp_pool_classify_fwd': [_p, _p, _p, _p, _p, _T, _i, _i, _f, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
     'hcomp_orth_gram': [_p, _p, _T, _i, _p, _p, _p],
     'hcomp_head_chain_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_head_chain_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p,

@@ -225,7 +225,7 @@ int launch_pair_class(int seg, const hc::FeatureMaps& tx, const CUtensorMap& tw,
 template <bool BWD>
 int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int32_t* tiles_dev, int n_tiles, int V,
              int V_first, int HW, int C, int P, int P_pad, int n_nodes, float tau, int precision, hc::HeadParams base,
-             const hcomp_spill* spill, bool* riders_folded, cudaStream_t st) {
+             const hcomp_spill* spill, bool* riders_folded, cudaStream_t st, bool no_fold = false) {
   *riders_folded = false;
   if (precision != HCOMP_PREC_BF16 && precision != HCOMP_PREC_FP32X3) return fail(HCOMP_E_ARG, "unknown precision %d", precision);
   const int split = (precision == HCOMP_PREC_FP32X3) ? 6 : 1;   // x / wp hold 3 stacked bf16 split planes
@@ -278,7 +278,7 @@ int run_pair(const void* x, const void* wp, const int32_t* tiles_host, const int
   // class (layout.py takes them out of the last tile of the last class, so they normally do) -- otherwise by the
   // stand-alone row kernels (run_spill).
   hc::HeadParams riders{};
-  if (spill != nullptr && spill->n_spill > 0 && spill->recs_host != nullptr && last_fused_global >= 0 && !g_no_rider_fold) {
+  if (spill != nullptr && spill->n_spill > 0 && spill->recs_host != nullptr && last_fused_global >= 0 && !g_no_rider_fold && !no_fold) {
     const int last_class = tiles_host[(size_t)last_fused_global * hc::TILE_INTS];
     bool ok = true;
     for (int i = 0; i < spill->n_spill && ok; ++i) {
@@ -628,18 +628,21 @@ int hcomp_proj_softmax_pool_fwd(const void* x_bf16, const void* wp_bf16, const i
   p.align_sum = align_sum;
   p.desc = (align_sum != nullptr) ? desc : nullptr;
   if (spill != nullptr && spill->n_spill > 0) { p.zs = spill->zs; p.ldz = spill->ldz; }
-  if (!outputs_zeroed) {
+  if (!(outputs_zeroed & 1)) {
     HC_CUDA(cudaMemsetAsync(pooled_packed, 0, sizeof(unsigned long long) * (size_t)V * P, S(stream)));
     if (align_sum) HC_CUDA(cudaMemsetAsync(align_sum, 0, sizeof(double) * n_nodes, S(stream)));
   }
+  // bit 1: the narrow spill nodes (riders) are NOT finished here -- neither in the kernel's tail (no grid barrier, the
+  // kernel ends with its item loop) nor by the row kernels: hcomp_pool_classify_fwd does it, given the same `spill`
+  const bool defer = (outputs_zeroed & 2) != 0;
   bool folded = false;
   if (int e = run_pair<false>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
-                              precision, p, spill, &folded, S(stream)))
+                              precision, p, spill, &folded, S(stream), defer))
     return e;
   if (!(tau > 0.f)) return fail(HCOMP_E_ARG, "softmax tau must be > 0");
   hc::SpillParams q = spill_base(V, V_first, HW, P, n_nodes, tau);
   q.pooled_packed = pooled_packed; q.align_sum = align_sum; q.desc = p.desc;
-  return run_spill<false>(spill, q, V, folded, S(stream));
+  return run_spill<false>(spill, q, V, folded || defer, S(stream));
 }
 
 int hcomp_unpack_pool(const unsigned long long* packed, long long n, float thresh, float* pooled, int32_t* argmax,
@@ -880,18 +883,61 @@ int hcomp_head_prologue(const float* w_flat, const int32_t* row_map, int rows, i
   return 0;
 }
 
-int hcomp_pool_classify_fwd(const unsigned long long* packed, const double* align_sum, const int32_t* n_desc, const float* wc,
+int hcomp_pool_classify_fwd(const unsigned long long* packed, double* align_sum, const int32_t* n_desc, const float* wc,
                             const float* bias, const hcomp_tables* t, int V, int HW, float thresh, float* pooled,
-                            int32_t* argmax, float* align, float* out, void* stream) {
+                            int32_t* argmax, float* align, float* out, const hcomp_spill* deferred, int V_first, float tau,
+                            const uint8_t* desc, unsigned int* counter, void* stream) {
   hc::PoolClassifyParams q{};
   q.packed = packed; q.align_sum = align_sum; q.n_desc = n_desc; q.wc = wc; q.bias = bias;
   q.col_node = t->col_node; q.proto_off = t->proto_off; q.cls_off = t->cls_off; q.wc_off = t->wc_off;
   q.V = V; q.P = t->n_protos; q.K = t->n_cols; q.N = t->n_nodes; q.HW = HW; q.thresh = thresh;
-  q.pooled = pooled; q.argmax = argmax; q.align = align; q.out = out;
-  q.nb_unpack = blocks((long long)V * t->n_protos, 256);
-  q.nb_cls = (out != nullptr && wc != nullptr) ? blocks((long long)V * t->n_cols, 256) : 0;
-  const int nb_align = (align != nullptr && align_sum != nullptr && n_desc != nullptr) ? blocks(t->n_nodes, 256) : 0;
-  hc::pool_classify_fwd_kernel<<<q.nb_unpack + q.nb_cls + nb_align, 256, 0, S(stream)>>>(q);
+  q.pooled = pooled; q.argmax = argmax; q.out = (out != nullptr && wc != nullptr) ? out : nullptr;
+  q.align = (align != nullptr && align_sum != nullptr && n_desc != nullptr) ? align : nullptr;
+  int nb_rider = 0;
+  const bool have_riders = deferred != nullptr && deferred->n_spill > 0;
+  const int BS = have_riders ? 512 : 256;               // block size of the two kernel variants
+  q.nb_unpack = blocks((long long)V * t->n_protos, BS);
+  q.nb_cls = q.out ? blocks((long long)V * t->n_cols, BS) : 0;
+  q.nb_align = q.align ? blocks(t->n_nodes, BS) : 0;
+  if (have_riders) {
+    if (deferred->recs_host == nullptr || deferred->zs == nullptr || deferred->ldz <= 0 || deferred->ldz % 4 != 0)
+      return fail(HCOMP_E_ARG, "deferred riders: records / scratch matrix missing (ldz=%d)", deferred->ldz);
+    if (!(tau > 0.f) || V_first <= 0 || V_first > V || counter == nullptr)
+      return fail(HCOMP_E_ARG, "deferred riders: need tau > 0, 0 < V_first <= V and a counter block");
+    const hc::SpillParams base = spill_base(V, V_first, HW, t->n_protos, t->n_nodes, tau);
+    for (int i = 0; i < deferred->n_spill; ++i) {
+      const int32_t* r = deferred->recs_host + (size_t)i * 8;
+      if (r[5] == 0) return fail(HCOMP_E_ARG, "deferred riders: record %d is a wide node (finished by the forward call)", i);
+      if (q.n_riders >= 4) return fail(HCOMP_E_ARG, "deferred riders: at most 4");
+      hc::SpillParams& p = q.rider[q.n_riders];
+      p = base;
+      p.zs = deferred->zs; p.ldz = deferred->ldz;
+      p.node = r[0]; p.P_n = r[1]; p.poff = r[2]; p.zoff = r[3];
+      p.pooled_packed = const_cast<unsigned long long*>(packed);
+      p.align_sum = q.align ? align_sum : nullptr;
+      p.desc = q.align ? desc : nullptr;
+      if (p.P_n <= 0 || p.P_n > 64 || p.zoff < 0 || p.zoff + p.P_n > p.ldz || p.node < 0 || p.node >= p.n_nodes || p.poff < 0 ||
+          p.poff + p.P_n > p.P)
+        return fail(HCOMP_E_ARG, "malformed deferred rider record %d", i);
+      ++q.n_riders;
+    }
+    q.align_sum_rw = align_sum; q.counter = counter;
+    nb_rider = q.n_riders * V_first;
+  }
+  if (nb_rider > 0) {
+    int pmax = 1;
+    for (int i = 0; i < q.n_riders; ++i) pmax = q.rider[i].P_n > pmax ? q.rider[i].P_n : pmax;
+    // rider_finish_block's carve-up: the pair's logits [2][HW][P_n | 1], row statistics [4][HW], slice results, scratch
+    const size_t smem = sizeof(float) * ((size_t)2 * HW * (pmax | 1) + (size_t)4 * HW + 512 + 512 + 128 + 32);
+    constexpr int SMEM_CAP = 200 * 1024;
+    if (smem > SMEM_CAP)
+      return fail(HCOMP_E_ARG, "deferred riders: HW=%d x P_n=%d does not fit the finish kernel's shared memory (clear bit 1)", HW, pmax);
+    static std::atomic<unsigned long long> attr_done{0};
+    if (int e = ensure_dyn_smem(hc::pool_classify_fwd_kernel<true>, SMEM_CAP, attr_done)) return e;
+    hc::pool_classify_fwd_kernel<true><<<q.nb_unpack + q.nb_cls + q.nb_align + nb_rider, 512, smem, S(stream)>>>(q);
+  } else {
+    hc::pool_classify_fwd_kernel<false><<<q.nb_unpack + q.nb_cls + q.nb_align, 256, 0, S(stream)>>>(q);
+  }
   HC_LAUNCH_CHECK("pool_classify_fwd");
   return 0;
 }
@@ -982,14 +1028,10 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
     HC_LAUNCH_CHECK("head_chain_bwd");
   }
   if (orth_branch) {
-    const size_t smem = sizeof(float) * ((size_t)t->p_max * 128 + (size_t)t->p_max * t->p_max + t->p_max);
-    if (t->p_max <= 64 && smem <= 48 * 1024) {        // tile kernel: at most 16 rows per row group, default shared-memory limit
-      hc::orth_bwd_tile_kernel<<<dim3(N, (C + 127) / 128), 512, smem, sb->stream>>>(
-          w_flat, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
-    } else {
-      hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
-          w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
-    }
+    // (a shared-memory tiled variant -- one block per node x channel chunk, E_n and the kernel columns staged once -- was
+    // measured at 10 us against this kernel's 8 us and removed; profiles/r2_k1_analysis.md section 7)
+    hc::orth_bwd_scaled_kernel<<<dim3(t->n_protos, (C + 255) / 256), 256, 0, sb->stream>>>(
+        w_flat, t->proto_node, t->proto_off, C, t->p_max, stats + 2 * N, w.E, rel, g_total, weights_host[2], g_w);
     HC_LAUNCH_CHECK("orth_bwd");
   }
   if (sb) HC_JOIN(sb, S(stream));

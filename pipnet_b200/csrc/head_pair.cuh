@@ -453,9 +453,12 @@ __device__ __forceinline__ void row_to_img(int row, int HW, float inv_HW, int& v
 // ------------------------------------------------------------------------------------------------ narrow, forward
 // one warp = 32 consecutive locations of view 1 and the same locations of view 2 (row_a = the lane's location, the
 // chunk's first row is < halfM); xch = the warp's pooling table (4 * XQ uint4 of shared memory)
+// row_end: rows at or past it are treated as invalid (a caller that owns ONE image passes the image's end, so that the
+// lanes of its last chunk which belong to the next image are left to that image's owner)
 template <int S>
-__device__ __forceinline__ void spill_narrow_fwd_rows(const SpillParams& p, int row_a, int lane, uint4* xch) {
-  const bool valid_a = row_a < p.halfM, valid_b = row_a < p.rowsB;
+__device__ __forceinline__ void spill_narrow_fwd_rows(const SpillParams& p, int row_a, int lane, uint4* xch,
+                                                      int row_end = 0x7fffffff) {
+  const bool valid_a = row_a < p.halfM && row_a < row_end, valid_b = row_a < p.rowsB && row_a < row_end;
   int v_a, loc;
   row_to_img(row_a, p.HW, p.inv_HW, v_a, loc);
   const int v_first = __shfl_sync(0xffffffffu, v_a, 0);

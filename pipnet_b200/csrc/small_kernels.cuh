@@ -5,6 +5,7 @@
 // per-node Python loops (pipnet/pipnet.py:124-170, pipnet/train.py:933-1194).
 #pragma once
 #include "ptx.cuh"
+#include "head_pair.cuh"   // rider row code (spill_narrow_fwd_rows) used by the forward finish kernel
 
 namespace hc {
 
@@ -380,7 +381,7 @@ __global__ void tanh_loss_bwd_kernel(const float* __restrict__ colsum, const int
 // spread over the whole GPU: ONE WARP per entry (n, i, j >= i) of the [N, P_max, P_max] slab, operands read straight from
 // L2 (all prototype kernels are 1.5 MB) with independent coalesced loads; the slab is kept for the backward.
 // A block-per-node version that staged W_n in shared memory spent 10 of its 17 us in the serial copy loop.
-__global__ void orth_gram_kernel(const float* __restrict__ w, const float* __restrict__ wc,
+__global__ void __launch_bounds__(256, 5) orth_gram_kernel(const float* __restrict__ w, const float* __restrict__ wc,
                                  const int32_t* __restrict__ proto_off, const int32_t* __restrict__ cls_off,
                                  const int32_t* __restrict__ wc_off, int N, int C, int P_max, float* __restrict__ E,
                                  uint8_t* __restrict__ rel) {
@@ -594,26 +595,213 @@ struct PoolClassifyParams {
   const int32_t *col_node, *proto_off, *cls_off, *wc_off;
   int V, P, K, N, HW; float thresh;
   float* pooled; int32_t* argmax; float* align; float* out;
-  int nb_unpack, nb_cls;
+  int nb_unpack, nb_cls, nb_align;
+  // deferred riders (narrow spill nodes, see spill_nodes.cuh): the fused forward only wrote their raw logits; one block
+  // per (rider, image pair) finishes softmax / max-pool / align for the pair's locations, then unpacks the pair's pooled
+  // entries of that node and applies its classifier; the last block of a rider finalizes the node's align loss
+  int n_riders;
+  SpillParams rider[4];
+  double* align_sum_rw;
+  unsigned int* counter;     // [1 + rider]: zero on entry, left zero
 };
-__global__ void __launch_bounds__(256) pool_classify_fwd_kernel(const PoolClassifyParams q) {
+// Rider role of the forward finish kernel: ONE block (512 threads) per (rider, image pair).  Same arithmetic as the
+// fused kernel's epilogue (softmax_row: 4-way interleaved sums, ex2.approx, rcp.approx; align inner product in the same
+// association order), organised for a plain SIMT kernel with few registers:
+//   phase 1  thread per location: row maximum and 1 / row sum of both views -> shared memory; align term of the pair row
+//   phase 2  thread per (view, prototype, row slice): walks its slice in location order, first maximum wins
+//   phase 3  thread per (view, prototype): best of the slices in order -> pooled / argmax (written directly, the packed
+//            table is not used for rider columns); then the node's classifier rows for the two images
+// The last block of a rider finalizes the node's align loss.
+__device__ __forceinline__ void rider_finish_block(const PoolClassifyParams& q, const SpillParams& sp, int r, int b, float* rsm) {
+  const int HW = q.HW, Pn = sp.P_n, tid = threadIdx.x, nt = blockDim.x;
+  const int st = Pn | 1;                                    // odd row pitch: conflict-free column and row walks
+  float* zt = rsm;                                          // [2][HW][st] the pair's raw logits, staged once
+  float* mk1 = zt + (size_t)2 * HW * st;
+  float* inv1 = mk1 + HW;
+  float* mk2 = inv1 + HW;
+  float* inv2 = mk2 + HW;
+  float* bval = inv2 + HW;                                  // [512]
+  int* bloc = reinterpret_cast<int*>(bval + 512);           // [512]
+  float* pooled_s = reinterpret_cast<float*>(bloc + 512);   // [2][64]
+  float* red = pooled_s + 128;                              // [32]
+  const int v1 = b, v2 = b + sp.imgs_first;
+  const bool has2 = v2 < q.V;
+  const float sc = sp.scale_log2;
+  const size_t rowA = (size_t)b * HW, rowB = (size_t)sp.halfM + (size_t)b * HW;
+  const bool use_align = sp.desc != nullptr && sp.align_sum != nullptr && has2 && sp.desc[(size_t)b * sp.n_nodes + sp.node] != 0;
+  float a_sum = 0.f;
+  {                                                         // stage: 16-byte coalesced loads, all independent
+    const int n4 = (Pn + 3) >> 2;
+    const int per_view = HW * n4, total = (has2 ? 2 : 1) * per_view;
+    for (int base = tid; base < total; base += 8 * nt) {        // eight loads in flight per thread before the first store
+      float4 t[8];
+      int dst[8], qd8[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int idx = base + u * nt;
+        dst[u] = -1;
+        if (idx < total) {
+          const int view = idx >= per_view, rem = idx - view * per_view;
+          const int row = rem / n4, qd = rem - row * n4;
+          t[u] = __ldg(reinterpret_cast<const float4*>(sp.zs + ((view ? rowB : rowA) + row) * sp.ldz + sp.zoff) + qd);
+          dst[u] = (view * HW + row) * st + 4 * qd;
+          qd8[u] = qd;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (dst[u] >= 0) {
+          float* d = zt + dst[u];
+          d[0] = t[u].x;
+          if (4 * qd8[u] + 1 < Pn) d[1] = t[u].y;
+          if (4 * qd8[u] + 2 < Pn) d[2] = t[u].z;
+          if (4 * qd8[u] + 3 < Pn) d[3] = t[u].w;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int row = tid; row < HW; row += nt) {
+    const float* z1 = zt + (size_t)row * st;
+    const float* z2 = zt + ((size_t)HW + row) * st;
+    float m1 = -INFINITY, m2 = -INFINITY;
+    for (int i = 0; i < Pn; ++i) {
+      m1 = fmaxf(m1, z1[i]);
+      if (has2) m2 = fmaxf(m2, z2[i]);
+    }
+    const float k1 = __fmul_rn(m1, sc), k2 = __fmul_rn(m2, sc);
+    float l1[4] = {0.f, 0.f, 0.f, 0.f}, l2[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i0 = 0; i0 < Pn; i0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u;
+        if (i < Pn) {
+          l1[u] = __fadd_rn(l1[u], ex2(__fmaf_rn(z1[i], sc, -k1)));
+          if (has2) l2[u] = __fadd_rn(l2[u], ex2(__fmaf_rn(z2[i], sc, -k2)));
+        }
+      }
+    }
+    const float i1 = rcp_approx(__fadd_rn(__fadd_rn(l1[0], l1[1]), __fadd_rn(l1[2], l1[3])));
+    const float i2 = has2 ? rcp_approx(__fadd_rn(__fadd_rn(l2[0], l2[1]), __fadd_rn(l2[2], l2[3]))) : 0.f;
+    mk1[row] = k1; inv1[row] = i1; mk2[row] = k2; inv2[row] = i2;
+    if (use_align) {
+      float ip4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i0 = 0; i0 < Pn; i0 += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int i = i0 + u;
+          if (i < Pn) {
+            const float s1 = __fmul_rn(ex2(__fmaf_rn(z1[i], sc, -k1)), i1);
+            const float s2 = __fmul_rn(ex2(__fmaf_rn(z2[i], sc, -k2)), i2);
+            ip4[u] = __fmaf_rn(s1, s2, ip4[u]);
+          }
+        }
+      }
+      const float ip = __fadd_rn(__fadd_rn(ip4[0], ip4[1]), __fadd_rn(ip4[2], ip4[3]));
+      a_sum += -__logf(ip + 1e-12f);
+    }
+  }
+  __syncthreads();
+  int nsl = nt / (2 * Pn);
+  if (nsl > 16) nsl = 16;
+  if (nsl < 1) nsl = 1;
+  const int per = (HW + nsl - 1) / nsl;
+  if (tid < 2 * Pn * nsl) {
+    const int sl = tid / (2 * Pn), vc = tid - sl * 2 * Pn;
+    const int view = vc >= Pn, c = vc - view * Pn;
+    float best = -1.f;
+    int arg = 0;
+    if (view == 0 || has2) {
+      const float* z = zt + (size_t)view * HW * st + c;
+      const float* mk = view ? mk2 : mk1;
+      const float* iv = view ? inv2 : inv1;
+      const int r0 = sl * per, r1 = min(HW, r0 + per);
+#pragma unroll 4
+      for (int row = r0; row < r1; ++row) {
+        const float sv = __fmul_rn(ex2(__fmaf_rn(z[(size_t)row * st], sc, -mk[row])), iv[row]);
+        if (sv > best) { best = sv; arg = row; }
+      }
+    }
+    bval[tid] = best;
+    bloc[tid] = arg;
+  }
+  __syncthreads();
+  if (tid < 2 * Pn) {
+    const int view = tid >= Pn, c = tid - view * Pn;
+    if (view == 0 || has2) {
+      float best = -1.f;
+      int arg = 0;
+      for (int sl = 0; sl < nsl; ++sl) {
+        const float x = bval[sl * 2 * Pn + tid];
+        if (x > best) { best = x; arg = bloc[sl * 2 * Pn + tid]; }
+      }
+      if (best < q.thresh) best = 0.f;
+      const size_t i = (size_t)(view ? v2 : v1) * q.P + sp.poff + c;
+      q.pooled[i] = best;
+      q.argmax[i] = arg;
+      pooled_s[view * 64 + c] = best;
+    }
+  }
+  __syncthreads();
+  if (q.out != nullptr) {
+    const int k0 = q.cls_off[sp.node], kn = q.cls_off[sp.node + 1] - k0;
+    for (int idx = tid; idx < 2 * kn; idx += nt) {
+      const int view = idx >= kn, c = idx - view * kn;
+      if (view == 1 && !has2) continue;
+      const float* w = q.wc + q.wc_off[sp.node] + (size_t)c * Pn;
+      float acc = 0.f;
+      for (int pp = 0; pp < Pn; ++pp) acc = fmaf(fmaxf(w[pp], 0.f), pooled_s[view * 64 + pp], acc);
+      q.out[(size_t)(view ? v2 : v1) * q.K + k0 + c] = acc + (q.bias ? q.bias[k0 + c] : 0.f);
+    }
+  }
+  if (q.align != nullptr) {                             // block sum of the align terms, then last block: the node's loss
+    const float tot = block_sum(a_sum, red);
+    if (tid == 0) {
+      if (tot != 0.f) atomicAdd(q.align_sum_rw + sp.node, (double)tot);
+      __threadfence();
+      const bool last = atomicAdd(q.counter + 1 + r, 1u) == (unsigned)sp.imgs_first - 1u;
+      if (last) {
+        __threadfence();
+        const int nd = q.n_desc[sp.node] / 2;
+        q.align[sp.node] = nd > 0 ? float(__ldcg(q.align_sum_rw + sp.node) / (double(nd) * double(HW))) : 0.f;
+        q.counter[1 + r] = 0u;
+      }
+    }
+  }
+}
+
+// RIDERS = true carries the rider role (its row code needs ~220 registers: one block per SM, so the unpack role of that
+// variant strides over the table with few blocks); layouts without deferred riders run the lean variant.
+template <bool RIDERS>
+__global__ void __launch_bounds__(RIDERS ? 512 : 256) pool_classify_fwd_kernel(const PoolClassifyParams q) {
+  constexpr int BS = RIDERS ? 512 : 256;
   int b = blockIdx.x;
   if (b < q.nb_unpack) {
-    const long long i = (long long)b * 256 + threadIdx.x;
-    if (i >= (long long)q.V * q.P) return;
-    const unsigned long long k = q.packed[i];
-    float v = __uint_as_float((uint32_t)(k >> 32));
-    if (v < q.thresh) v = 0.f;
-    q.pooled[i] = v;
-    q.argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+    const long long n = (long long)q.V * q.P;
+    for (long long i = (long long)b * BS + threadIdx.x; i < n; i += (long long)q.nb_unpack * BS) {
+      if constexpr (RIDERS) {                           // rider columns are written by their rider blocks
+        const int pcol = int(i % q.P);
+        bool skip = false;
+        for (int r = 0; r < q.n_riders; ++r) skip |= pcol >= q.rider[r].poff && pcol < q.rider[r].poff + q.rider[r].P_n;
+        if (skip) continue;
+      }
+      const unsigned long long k = q.packed[i];
+      float v = __uint_as_float((uint32_t)(k >> 32));
+      if (v < q.thresh) v = 0.f;
+      q.pooled[i] = v;
+      q.argmax[i] = (int32_t)(0xFFFFFFFFu - (uint32_t)k);
+    }
     return;
   }
   b -= q.nb_unpack;
   if (b < q.nb_cls) {
-    const int idx = b * 256 + threadIdx.x;
+    const int idx = b * BS + threadIdx.x;
     if (idx >= q.V * q.K) return;
     const int v = idx / q.K, k = idx - v * q.K;
     const int n = q.col_node[k];
+    if constexpr (RIDERS)
+      for (int r = 0; r < q.n_riders; ++r)
+        if (n == q.rider[r].node) return;
     const int p0 = q.proto_off[n], pn = q.proto_off[n + 1] - p0;
     const float* w = q.wc + q.wc_off[n] + (size_t)(k - q.cls_off[n]) * pn;
     const unsigned long long* x = q.packed + (size_t)v * q.P + p0;
@@ -627,10 +815,22 @@ __global__ void __launch_bounds__(256) pool_classify_fwd_kernel(const PoolClassi
     return;
   }
   b -= q.nb_cls;
-  const int n = b * 256 + threadIdx.x;
-  if (n >= q.N) return;
-  const int nd = q.n_desc[n] / 2;
-  q.align[n] = nd > 0 ? float(q.align_sum[n] / (double(nd) * double(q.HW))) : 0.f;
+  if (b < q.nb_align) {
+    const int n = b * BS + threadIdx.x;
+    if (n >= q.N) return;
+    if constexpr (RIDERS)
+      for (int r = 0; r < q.n_riders; ++r)
+        if (n == q.rider[r].node) return;
+    const int nd = q.n_desc[n] / 2;
+    q.align[n] = nd > 0 ? float(q.align_sum[n] / (double(nd) * double(q.HW))) : 0.f;
+    return;
+  }
+  if constexpr (RIDERS) {
+    extern __shared__ float rsm[];
+    b -= q.nb_align;
+    const int r = b / q.rider[0].imgs_first, img = b - r * q.rider[0].imgs_first;
+    if (r < q.n_riders) rider_finish_block(q, q.rider[r], r, img, rsm);
+  }
 }
 
 // ---- all per-node loss terms + their combination, one launch ------------------------------------------------------
@@ -891,66 +1091,6 @@ __global__ void orth_bwd_scaled_kernel(const float* __restrict__ w, const int32_
     acc *= g * 2.f / L;
   }
   g_w[(size_t)row * C + c] = acc;
-}
-
-// Same result as orth_bwd_scaled_kernel for nodes of at most 64 prototypes, organised for latency: one block per (node,
-// 128-channel chunk) = 128 channels x 4 row groups.  Phase 1 stages E_n (pn x pn), the relevance flags and the node's
-// kernel columns (pn x 128) in shared memory with ONE batch of independent coalesced loads per thread; phase 2: thread
-// (channel, row group) produces rows rg, rg + 4, ... of its channel from shared memory.  The row-per-block kernel above
-// walks pn dependent L2 round trips per thread (8 us for 25 nodes x 20 prototypes).
-__global__ void __launch_bounds__(512) orth_bwd_tile_kernel(const float* __restrict__ w, const int32_t* __restrict__ proto_off,
-                                                            int C, int P_max, const float* __restrict__ loss,
-                                                            const float* __restrict__ E, const uint8_t* __restrict__ rel,
-                                                            const float* __restrict__ g_total, float weight,
-                                                            float* __restrict__ g_w) {
-  extern __shared__ float osm[];                        // Ws[pn][128], Es[pn][pn], rel_s[pn]
-  const int n = blockIdx.x;
-  const int ch = threadIdx.x & 127, rg = threadIdx.x >> 7;
-  const int c = blockIdx.y * 128 + ch;
-  const int p0 = proto_off[n], pn = proto_off[n + 1] - p0;
-  const float L = loss[n], g = g_total[0] * weight;
-  float* Ws = osm;
-  float* Es = osm + pn * 128;
-  float* rel_s = Es + pn * pn;
-  const bool active = L > 0.f && g != 0.f;
-  if (active) {
-    float t[16];                                        // pn <= 64: at most 16 rows per row group
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int j = rg + 4 * u;
-      t[u] = (j < pn && c < C) ? w[(size_t)(p0 + j) * C + c] : 0.f;
-    }
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f, e4 = 0.f, e5 = 0.f, e6 = 0.f, e7 = 0.f;
-    const int nn = pn * pn;                             // <= 4096 = 8 per thread
-    auto ld = [&](int ij) { return ij < nn ? E[((size_t)n * P_max + ij / pn) * P_max + ij % pn] : 0.f; };
-    e0 = ld(threadIdx.x); e1 = ld(threadIdx.x + 512); e2 = ld(threadIdx.x + 1024); e3 = ld(threadIdx.x + 1536);
-    if (nn > 2048) { e4 = ld(threadIdx.x + 2048); e5 = ld(threadIdx.x + 2560); e6 = ld(threadIdx.x + 3072); e7 = ld(threadIdx.x + 3584); }
-    const float r = threadIdx.x < pn ? float(rel[p0 + threadIdx.x]) : 0.f;
-#pragma unroll
-    for (int u = 0; u < 16; ++u) {
-      const int j = rg + 4 * u;
-      if (j < pn) Ws[j * 128 + ch] = t[u];
-    }
-    const float ev[8] = {e0, e1, e2, e3, e4, e5, e6, e7};
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int ij = threadIdx.x + 512 * u;
-      if (ij < nn) Es[ij] = ev[u];
-    }
-    if (threadIdx.x < pn) rel_s[threadIdx.x] = r;
-  }
-  __syncthreads();
-  if (c >= C) return;
-  const float sc = active ? g * 2.f / L : 0.f;
-  for (int i = rg; i < pn; i += 4) {
-    float acc = 0.f;
-    if (active && rel_s[i] != 0.f) {
-#pragma unroll 4
-      for (int j = 0; j < pn; ++j) acc = fmaf(Es[i * pn + j], Ws[j * 128 + ch], acc);
-      acc *= sc;
-    }
-    g_w[(size_t)(p0 + i) * C + c] = acc;
-  }
 }
 
 // ---- backward prep: scatter table + align coefficients, one launch (make_scat_kernel + align_coef_kernel) ---------

@@ -366,8 +366,9 @@ class DeviceLayout:
         self.n_spill = int(L.spill.shape[0])
         self.n_wide = int((L.spill[:, 5] == 0).sum()) if self.n_spill else 0
         self.P_s = int(L.P_s)
+        self.rider_pmax = int(L.spill[:, 1].max()) if self.n_spill else 0
         # last-block-done counter of the chained loss kernel (zero between calls; one call at a time per layout)
-        self.counter = torch.zeros(4, device=d, dtype=torch.int32)
+        self.counter = torch.zeros(8, device=d, dtype=torch.int32)
 
     def spill_buffers(self, M, device, zs=None, stats=None):
         """(ctypes hcomp_spill or None, zs, stats): the raw-logit scratch matrix of the spill nodes [M, P_s] and the
@@ -575,6 +576,13 @@ def proj_softmax_pool_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, lab
     return pooled, argmax, align
 
 
+# Riders (narrow spill nodes) can be finished by the forward-finish launch instead of the fused kernel's tail (bit-identical
+# results, tests/test_gpu_chain.py).  Measured on cub27 (profiles/r2_k1_analysis.md section 7): the fused kernel loses its
+# grid barrier and tail (70.4 -> 60.8 us, 0.67 of the tensor peak) but the finish launch grows from 4.4 to 19-23 us (64
+# latency-bound blocks against 1776 resident epilogue warps), a net loss of 5 us per step -- off by default.
+DEFER_RIDERS = os.environ.get('HC_DEFER_RIDERS', '0') != '0'
+
+
 def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, labels: Optional[LabelTables], packed, align_sum,
                            thresh=0.0, precision=PREC_BF16, spill_out: Optional[list] = None, wc=None, bias=None):
     """K1 + ONE finishing launch (hcomp_pool_classify_fwd: unpack, align finalize, classifier).  `packed` / `align_sum`
@@ -584,10 +592,15 @@ def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, la
     sp, zs, stats = dl.spill_buffers(V * HW, dev)
     if spill_out is not None:
         spill_out[:] = [zs, stats]
+    # riders (narrow spill nodes) are finished by the finishing launch below instead of K1's tail: K1 then ends with its
+    # item loop (no grid barrier, no idle wait of the CTAs that finished early)
+    defer = (DEFER_RIDERS and sp is not None and dl.n_wide == 0 and dl.n_spill <= 4
+             and 4 * (2 * HW * (dl.rider_pmax | 1) + 4 * HW + 1184) <= 200 * 1024)      # the finish kernel's shared memory
     tok = PROFILE.start('k1_proj_softmax_pool_fwd')
     call('hcomp_proj_softmax_pool_fwd', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first,
-         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), 1, ptr(labels.desc) if labels is not None else None,
-         ptr(packed), ptr(align_sum), C.byref(sp) if sp is not None else None, _stream())
+         HW, Cc, dl.P, dl.P_pad, dl.N, float(tau), int(precision), 3 if defer else 1,
+         ptr(labels.desc) if labels is not None else None, ptr(packed), ptr(align_sum),
+         C.byref(sp) if sp is not None else None, _stream())
     PROFILE.stop(tok)
     global ORTH_REQUEST
     if ORTH_REQUEST is not None:           # fork the orth term's Gram kernel HERE: it runs beside the finishing launch below
@@ -598,7 +611,9 @@ def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, la
     align = torch.empty(dl.N, device=dev, dtype=torch.float32) if labels is not None else None
     out = torch.empty(V, dl.K, device=dev, dtype=torch.float32) if wc is not None else None
     call('hcomp_pool_classify_fwd', ptr(packed), ptr(align_sum), ptr(labels.n_desc) if labels is not None else None, ptr(wc),
-         ptr(bias), dl.tref, V, HW, float(thresh), ptr(pooled), ptr(argmax), ptr(align), ptr(out), _stream())
+         ptr(bias), dl.tref, V, HW, float(thresh), ptr(pooled), ptr(argmax), ptr(align), ptr(out),
+         C.byref(sp) if defer else None, V_first, float(tau), ptr(labels.desc) if labels is not None else None,
+         ptr(dl.counter), _stream())
     return pooled, argmax, align, out
 
 

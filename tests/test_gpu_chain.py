@@ -176,3 +176,31 @@ def test_prep_tables_hand_off(extra_consumer):
                                                   for n in net.layout.node_names])))
     assert taken == [(True, not extra_consumer), (False, False)], taken
     assert _close(grads[0][0], grads[1][0], 2e-2) and _close(grads[0][1], grads[1][1], 2e-2)
+
+
+@pytest.mark.parametrize("inference", [False, True], ids=["train", "inference"])
+def test_deferred_riders_match_folded_riders(inference):
+    """cub27 at 20 prototypes per node has one rider node (25 nodes = 4 full tiles + 1): finished in the tail of the fused
+    kernel behind its grid barrier (default) or by the forward-finish launch (ops.DEFER_RIDERS, the measured-and-parked
+    variant) -- same pooled / argmax / logits bit for bit, same align loss"""
+    from pipnet_b200 import ops
+    net, root, args, xs, ys, tr = _problem(B=7)          # odd pair count, 36 locations: chunks with invalid lanes
+    dl = net.device_layout('cuda')
+    assert dl.n_spill > 0 and dl.n_wide == 0
+    outs = []
+    saved = ops.DEFER_RIDERS
+    try:
+        for defer in (True, False):
+            ops.DEFER_RIDERS = defer
+            labels = tr.make_labels(net, ys)
+            with torch.no_grad():
+                _, _, pooled, out = net(xs, inference=inference, labels=labels)
+                argmax = net.head(xs, inference=inference, labels=tr.make_labels(net, ys), classify=True)[2]
+            torch.cuda.synchronize()
+            outs.append((pooled.flat.clone(), out.flat.clone(), pooled.align.clone(), argmax.clone()))
+    finally:
+        ops.DEFER_RIDERS = saved
+    assert int(dl.counter.abs().max()) == 0
+    (pa, oa, aa, ga), (pb, ob, ab, gb) = outs
+    assert torch.equal(pa, pb) and torch.equal(oa, ob) and torch.equal(ga, gb)
+    assert _close(aa, ab, 1e-6)
