@@ -455,6 +455,8 @@ def run_ours(a):
     net, root = build_net(wl['tree'], C, args, seed=1)
     net = net.to(dev)
     net.train()
+    net.head_precision = a.head_precision
+    prec = ops.PREC_FP32X3 if a.head_precision == 'fp32' else ops.PREC_BF16
     L = net.layout
     names = L.node_names
     cls_params = [getattr(net, '_' + n + '_classification').weight for n in names]
@@ -545,9 +547,9 @@ def run_ours(a):
     dl = net.device_layout(dev)
     with torch.no_grad():
         w_flat_k = net.flat_prototype_kernels().detach().contiguous()
-        wp_k, wpc_k = ops.pack_weights(w_flat_k, dl)
+        wp_k, wpc_k = ops.pack_weights(w_flat_k, dl, prec)
         lab_k = [tr.make_labels(net, y) for y in labels_d]
-        xr_k = [ops.feature_rows(f) for f in feats]
+        xr_k = [(ops.feature_rows_split3(f) if prec == ops.PREC_FP32X3 else ops.feature_rows(f)) for f in feats]
         gp_k = torch.randn(V, L.P, device=dev)
         ga_k = torch.full((L.N,), 0.2, device=dev)
         kern_iters = max(5, min(a.steps, 20))
@@ -555,9 +557,9 @@ def run_ours(a):
         def kernel_pass(i):
             sp = []
             pooled, argmax, _al = ops.proj_softmax_pool_raw(xr_k[i % 2], wp_k, dl, V, B, HW, net.softmax_tau, lab_k[i % 2],
-                                                            spill_out=sp)
+                                                            precision=prec, spill_out=sp)
             ops.head_backward_raw(xr_k[i % 2], wp_k, wpc_k, dl, V, B, HW, net.softmax_tau, argmax, gp_k, lab_k[i % 2], ga_k,
-                                  spill=sp)
+                                  precision=prec, spill=sp)
 
         for i in range(3):
             kernel_pass(i)
@@ -783,7 +785,8 @@ def run_ours(a):
             v, det = oracle_cpu_throughput(wl, min(8, B), steps=3, warmup=1, budget_s=25.0)
             cpu = {'value': v, 'unit': UNIT, 'cores': det['cores'], 'kind': 'port', 'sample': det['sample']}
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': a.steps, 'warmup': max(a.warmup, 3),
-                'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'bf16',
+                'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+                'dtype': 'bf16' if a.head_precision == 'bf16' else 'bf16x3 (fp32-accurate projection: six bf16 cross terms, fp32 accumulate)',
                 'data': 'synthetic',
                 'config': {'workload': f'{a.workload}: tree {wl["tree"]} ({L.N} nodes), '
                                        + (f'{wl["per_child"]} protos/child' if wl.get('per_child') else f'{wl["num_features"]} protos/node')
@@ -835,6 +838,8 @@ def main():
     ap.add_argument('--with-backbone', action='store_true',
                     help='also report images/s of ConvNeXt-tiny-26 (torchvision, random init, bf16 autocast) + head on 224x224 images')
     ap.add_argument('--graph', default='auto', choices=['auto', 'on', 'off'])
+    ap.add_argument('--head-precision', default='bf16', choices=['bf16', 'fp32'],
+                    help="fp32: the fp32-accurate projection (3-way bf16 split operands, 6x the MMA work of K1 / K5)")
     ap.add_argument('--recipe', default='core', choices=['core', 'shipped'],
                     help="core: align_pf+tanh+kernel_orth+class (BASELINE.json); shipped: + tanh_desc, contrasting set, mask pruning")
     a = ap.parse_args()

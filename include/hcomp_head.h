@@ -68,6 +68,20 @@ typedef struct hcomp_spill {
                                  NULL without wide nodes                                                      */
 } hcomp_spill;
 
+/* Block-activity tables of dZ[M, P_c] for the block-sparse backward GEMMs.  With hierarchical labels an image drives only
+ * the nodes on its root-to-leaf path, so most (image, node) blocks of dZ are exactly zero; the calls that build K5's
+ * scatter table / align coefficients (hcomp_head_bwd_dz, or hcomp_head_chain_bwd with scat_out) mark every block that can
+ * be nonzero and hcomp_head_bwd_dx / _dw skip the unmarked k-blocks (same results: the skipped products are exact zeros).
+ *   t1[ceil(M/256)][ld1]  (dX)  row tile of 256 rows x 64 compact columns;  ld1 >= P_c/64
+ *   t2[ceil(P_c/256)][ld2] (dW) column tile of 256 compact columns x 64 rows;  ld2 >= ceil(M/64)
+ * ld1, ld2 multiples of 8, both tables 8-byte aligned and ZERO before the marking call (hcomp_head_prologue can clear
+ * them); pcol[P]: compact dZ column of a flat prototype (inverse of row_map_c). */
+typedef struct hcomp_dz_blocks {
+  uint8_t* t1; int32_t ld1;
+  uint8_t* t2; int32_t ld2;
+  const int32_t* pcol;
+} hcomp_dz_blocks;
+
 int hcomp_abi_version(void);
 const char* hcomp_last_error(void);
 int hcomp_num_sms(void);
@@ -146,7 +160,8 @@ int hcomp_align_finalize(const double* align_sum, const int32_t* n_desc, int N, 
 /* dZ = S * (G - sum_p G*S) / tau with G = align gradient + g_pooled scattered at argmax; recomputes the
  * logits tile (same GEMM as K1).  scat_ws: int2[V*P], coef_ws: float[V_first*N] workspaces.
  * g_align (per node upstream gradient), desc may be NULL.  argmax == NULL: scat_ws / coef_ws already hold the tables
- * (hcomp_head_chain_bwd wrote them); g_pooled / pooled are then unused.
+ * (hcomp_head_chain_bwd wrote them); g_pooled / pooled are then unused.  blk (may be NULL; with the layout's proto_off
+ * [N+1] and proto_node [P] tables): the table-building launch also marks the dZ blocks that can be nonzero.
  * dz: bf16 [V*HW, P_c] on the COMPACT column axis: tile t owns columns [tiles[t][3], + used width), used width =
  * segments * S rounded up to 8; within a segment class the full tiles are contiguous (layout.py builds the table,
  * row_map_c[P_c] maps a compact column to its flat prototype or -1).  Every column of dz is written. */
@@ -154,13 +169,14 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                       int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int P_c, int n_nodes, float tau,
                       int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
-                      void* dz_bf16, const hcomp_spill* spill, void* stream);
+                      void* dz_bf16, const hcomp_spill* spill, const hcomp_dz_blocks* blk, const int32_t* proto_off,
+                      const int32_t* proto_node, void* stream);
 /* dX[rows,C] (bf16) = dZ[rows,P_c] * Wpc[P_c,C]  (Wpc: bf16 kernels packed on the compact axis with row_map_c). */
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,
-                      void* stream);
+                      const hcomp_dz_blocks* blk /* NULL: dense */, void* stream);
 /* dW[P,C] (fp32, ACCUMULATED into; clear it first) += dZ^T * X, padding columns dropped via row_map_c. */
 int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map_c, long long rows, int P_c, int C,
-                      float* dw_flat, void* stream);
+                      float* dw_flat, const hcomp_dz_blocks* blk /* NULL: dense */, void* stream);
 
 /* ---- K2: per-node non-negative classifier (pipnet/pipnet.py:1035-1036) ------------------------- */
 int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias, const hcomp_tables* t, int V,
@@ -203,10 +219,12 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
  * hcomp_head_prologue: everything K1 needs --
  *   rows > 0      : hcomp_pack_weights(w_flat, row_map, rows, C, wp_bf16)
  *   packed != NULL: clears pooled_packed[n_packed] and align_sum[n_align] (then call K1 with outputs_zeroed = 1)
- *   ys != NULL    : hcomp_label_tables(ys, t, V, V_first, tgt, desc, n_desc), n_desc needs no clearing. */
+ *   ys != NULL    : hcomp_label_tables(ys, t, V, V_first, tgt, desc, n_desc), n_desc needs no clearing.
+ *   zero_extra    : one more buffer to clear (16-byte aligned, multiple of 16 bytes), e.g. the hcomp_dz_blocks tables. */
 int hcomp_head_prologue(const float* w_flat, const int32_t* row_map, int rows, int C, void* wp_bf16,
                         unsigned long long* packed, long long n_packed, double* align_sum, int n_align, const long long* ys,
-                        const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc, void* stream);
+                        const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc,
+                        void* zero_extra, long long zero_extra_bytes, void* stream);
 /* hcomp_unpack_pool + hcomp_align_finalize (align / align_sum / n_desc may be NULL) + hcomp_classifier_fwd (out / wc may
  * be NULL; the inference threshold applies to the classifier's input like pipnet/pipnet.py:168-170).
  * deferred (may be NULL): the layout's spill record when the forward call was told to leave its narrow spill nodes
@@ -243,7 +261,8 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
                          int V_first, int C, int flags, const float* weights_host, float eps, float multiplier,
                          const float* ws, const uint8_t* rel, float* g_pooled, float* g_wc, float* g_bias, float* g_align,
                          float* g_w, const int32_t* argmax, float thresh, const uint8_t* desc, int HW, void* scat_out,
-                         float* coef_out, void* stream);
+                         float* coef_out, const hcomp_dz_blocks* blk /* marks for scat_out / coef_out, may be NULL */,
+                         void* stream);
 
 /* ---- descendant-structured loss terms switched on by the shipped scripts ------------------------ */
 /* (run_pipnet_20protos_multi_runs_seed42.sh: --tanh_desc "y|0.05" --minimize_contrasting_set 'y'

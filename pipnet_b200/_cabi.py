@@ -29,6 +29,11 @@ class Tables(C.Structure):
     ]
 
 
+class DzBlocks(C.Structure):
+    """mirror of `struct hcomp_dz_blocks`"""
+    _fields_ = [('t1', C.c_void_p), ('ld1', C.c_int32), ('t2', C.c_void_p), ('ld2', C.c_int32), ('pcol', C.c_void_p)]
+
+
 class Spill(C.Structure):
     """mirror of `struct hcomp_spill`"""
     _fields_ = [('n_spill', C.c_int32), ('ldz', C.c_int32), ('recs_host', C.c_void_p), ('zs', C.c_void_p),
@@ -50,19 +55,20 @@ SIGNATURES = {
     'hcomp_proj_softmax_pool_fwd': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _i, _p, _p, _p, _p, _p],
     'hcomp_unpack_pool': [_p, _ll, _f, _p, _p, _p],
     'hcomp_align_finalize': [_p, _p, _i, _i, _p, _p],
-    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p, _p],
-    'hcomp_head_bwd_dx': [_p, _p, _ll, _i, _i, _p, _p],
-    'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p],
+    'hcomp_head_bwd_dz': [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _i, _p, _p, _p, _f, _p, _p, _p, _p, _p, _p, _p,
+                          _p, _p, _p, _p],
+    'hcomp_head_bwd_dx': [_p, _p, _ll, _i, _i, _p, _p, _p],
+    'hcomp_head_bwd_dw': [_p, _p, _p, _ll, _i, _i, _p, _p, _p],
     'hcomp_classifier_fwd': [_p, _p, _p, _T, _i, _p, _p],
     'hcomp_classifier_bwd': [_p, _p, _p, _T, _i, _p, _i, _p, _p, _p],
     'hcomp_head_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p],
     'hcomp_head_losses_bwd': [_p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
-    'hcomp_head_prologue': [_p, _p, _i, _i, _p, _p, _ll, _p, _i, _p, _T, _i, _i, _p, _p, _p, _p],
+    'hcomp_head_prologue': [_p, _p, _i, _i, _p, _p, _ll, _p, _i, _p, _T, _i, _i, _p, _p, _p, _p, _ll, _p],
     'hcomp_pool_classify_fwd': [_p, _p, _p, _p, _p, _T, _i, _i, _f, _p, _p, _p, _p, _p, _i, _f, _p, _p, _p],
     'hcomp_orth_gram': [_p, _p, _T, _i, _p, _p, _p],
     'hcomp_head_chain_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p],
     'hcomp_head_chain_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _i, _p, _f, _f, _p, _p, _p, _p, _p, _p, _p,
-                             _p, _f, _p, _i, _p, _p, _p],
+                             _p, _f, _p, _i, _p, _p, _p, _p],
     'hcomp_desc_losses_fwd': [_p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_desc_losses_bwd': [_p, _p, _p, _p, _p, _p, _p, _p, _T, _i, _i, _i, _p, _f, _f, _f, _p, _p, _p, _p],
     'hcomp_joint_leaf': [_p, _T, _i, _f, _p, _p, _p, _p, _p],

@@ -396,7 +396,8 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap
 // D[M,N] = A[M,K] * B[K,N].  a_mn: A stored [K,M] (M contiguous) else [M,K]; b_mn: B stored [K,N] (N contiguous)
 // else [N,K].  splits <= 0 picks a split-K factor that fills the GPU (only meaningful for OUT_RED_F32).
 int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool a_mn, bool b_mn, int out_mode, int splits,
-             void* out, long long ldo, const int32_t* row_map, cudaStream_t st, int reserve_sms = 0) {
+             void* out, long long ldo, const int32_t* row_map, cudaStream_t st, int reserve_sms = 0,
+             const uint8_t* kact = nullptr, int kact_ld = 0) {
   DevInfo di;
   if (int e = dev_info(&di)) return e;
   if (M <= 0 || N <= 0 || K <= 0) return fail(HCOMP_E_ARG, "empty GEMM");
@@ -430,6 +431,11 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
   p.splits = cdiv(p.num_k_blocks, p.k_blocks_per_split);
   p.out = out; p.ldo = ldo; p.row_map = row_map;
+  if (kact != nullptr && pair) {          // block-sparse A (only the CTA-pair kernels read the table)
+    if (kact_ld % 8 != 0 || kact_ld < p.num_k_blocks || (reinterpret_cast<uintptr_t>(kact) & 7) != 0)
+      return fail(HCOMP_E_ARG, "k-block activity table: ld=%d must be a multiple of 8 and >= %d, 8-byte aligned", kact_ld, p.num_k_blocks);
+    p.kact = kact; p.kact_ld = kact_ld;
+  }
 #define HC_GEMM_CASE(AM, BM, OM)                                         \
   if (a_mn == AM && b_mn == BM && out_mode == OM)                        \
     return pair ? launch_gemm2<AM, BM, OM>(ta, tb, to, p, sms, st)       \
@@ -662,7 +668,8 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
                       int n_tiles, int V, int V_first, int HW, int C, int P, int P_pad, int P_c, int n_nodes, float tau,
                       int precision, const int32_t* argmax, const float* g_pooled, const float* pooled, float thresh,
                       const uint8_t* desc, const int32_t* n_desc, const float* g_align, void* scat_ws, float* coef_ws,
-                      void* dz_bf16, const hcomp_spill* spill, void* stream) {
+                      void* dz_bf16, const hcomp_spill* spill, const hcomp_dz_blocks* blk, const int32_t* proto_off,
+                      const int32_t* proto_node, void* stream) {
   if (P_c <= 0 || P_c % 8 != 0 || P_c > P_pad) return fail(HCOMP_E_ARG, "P_c=%d must be a positive multiple of 8, <= P_pad", P_c);
   const long long n = (long long)V * P;
   hc::HeadParams p{};
@@ -674,9 +681,15 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
   } else {                              // scatter table + align coefficients: one launch
     const bool use_align = g_align != nullptr && desc != nullptr && n_desc != nullptr;
     const int nb_scat = blocks(n, 256), nb_coef = use_align ? blocks((long long)V_first * n_nodes, 256) : 0;
+    hc::DzBlockTables bt{};
+    if (blk != nullptr && blk->t1 != nullptr) {
+      if (proto_off == nullptr || proto_node == nullptr || blk->pcol == nullptr)
+        return fail(HCOMP_E_ARG, "dZ block tables need proto_off, proto_node and pcol");
+      bt.t1 = blk->t1; bt.ld1 = blk->ld1; bt.t2 = blk->t2; bt.ld2 = blk->ld2; bt.pcol = blk->pcol;
+    }
     hc::bwd_prep_kernel<<<nb_scat + nb_coef, 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
                                                                   reinterpret_cast<int2*>(scat_ws), nb_scat, desc, n_desc,
-                                                                  g_align, V_first, n_nodes, HW, coef_ws);
+                                                                  g_align, V_first, n_nodes, HW, coef_ws, P, V, proto_off, proto_node, bt);
     HC_LAUNCH_CHECK("bwd_prep");
     if (use_align) p.coef_align = coef_ws;
   }
@@ -691,14 +704,15 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
 }
 
 int hcomp_head_bwd_dx(const void* dz_bf16, const void* wpc_bf16, long long rows, int P_c, int C, void* dx_bf16,
-                      void* stream) {
+                      const hcomp_dz_blocks* blk, void* stream) {
   return run_gemm(dz_bf16, wpc_bf16, rows, C, P_c, false, true, hc::OUT_BF16, 1, dx_bf16, C, nullptr, S(stream),
-                  g_reserved_sms);
+                  g_reserved_sms, blk ? blk->t1 : nullptr, blk ? blk->ld1 : 0);
 }
 
 int hcomp_head_bwd_dw(const void* dz_bf16, const void* x_bf16, const int32_t* row_map_c, long long rows, int P_c, int C,
-                      float* dw_flat, void* stream) {
-  return run_gemm(dz_bf16, x_bf16, P_c, C, rows, true, true, hc::OUT_RED_F32, 0, dw_flat, C, row_map_c, S(stream));
+                      float* dw_flat, const hcomp_dz_blocks* blk, void* stream) {
+  return run_gemm(dz_bf16, x_bf16, P_c, C, rows, true, true, hc::OUT_RED_F32, 0, dw_flat, C, row_map_c, S(stream), 0,
+                  blk ? blk->t2 : nullptr, blk ? blk->ld2 : 0);
 }
 
 int hcomp_classifier_fwd(const float* pooled, const float* wc, const float* bias, const hcomp_tables* t, int V,
@@ -858,14 +872,20 @@ int hcomp_head_losses_bwd(const float* g_total, const float* out, const float* w
 // ---------------------------------------------------------------- fused chains (ABI v6)
 int hcomp_head_prologue(const float* w_flat, const int32_t* row_map, int rows, int C, void* wp_bf16,
                         unsigned long long* packed, long long n_packed, double* align_sum, int n_align, const long long* ys,
-                        const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc, void* stream) {
+                        const hcomp_tables* t, int V, int V_first, int8_t* tgt, uint8_t* desc, int32_t* n_desc,
+                        void* zero_extra, long long zero_extra_bytes, void* stream) {
   hc::PrologueParams q{};
+  if (zero_extra != nullptr && zero_extra_bytes > 0) {
+    if (zero_extra_bytes % 16 != 0 || (reinterpret_cast<uintptr_t>(zero_extra) & 15) != 0)
+      return fail(HCOMP_E_ARG, "prologue: the extra buffer to clear must be 16-byte aligned and a multiple of 16 bytes");
+    q.zero16 = reinterpret_cast<uint4*>(zero_extra); q.n_zero16 = zero_extra_bytes / 16;
+  }
   if (rows > 0) {
     if (C % 8 != 0) return fail(HCOMP_E_ARG, "prologue: C=%d must be a multiple of 8", C);
     q.w = w_flat; q.row_map = row_map; q.rows = rows; q.C = C; q.wp = reinterpret_cast<__nv_bfloat16*>(wp_bf16);
     q.nb_pack = blocks((long long)rows * (C >> 3), 256);
   }
-  if (packed != nullptr || align_sum != nullptr) {
+  if (packed != nullptr || align_sum != nullptr || q.n_zero16 > 0) {
     q.packed = packed; q.n_packed = packed ? n_packed : 0; q.align_sum = align_sum; q.n_align = n_align;
     q.nb_zero = blocks((q.n_packed + 1) / 2, 256);
     if (q.nb_zero == 0) q.nb_zero = 1;
@@ -984,7 +1004,7 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
                          int V_first, int C, int flags, const float* weights_host, float eps, float multiplier,
                          const float* ws, const uint8_t* rel, float* g_pooled, float* g_wc, float* g_bias, float* g_align,
                          float* g_w, const int32_t* argmax, float thresh, const uint8_t* desc, int HW, void* scat_out,
-                         float* coef_out, void* stream) {
+                         float* coef_out, const hcomp_dz_blocks* blk, void* stream) {
   const LossWs w = loss_ws(const_cast<float*>(ws), t);
   const int N = t->n_nodes;
   if ((flags & HCOMP_LOSS_SPARSITY) && !(multiplier > 0.f)) return fail(HCOMP_E_ARG, "class loss: log1p(out**m) needs m > 0 (got %g)", multiplier);
@@ -1021,6 +1041,12 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
     if (desc == nullptr) return fail(HCOMP_E_ARG, "chain_bwd: coef_out needs desc");
     q.coef = coef_out; q.desc = desc; q.HW = HW;
     nb_coef = blocks((long long)V_first * N, 256);
+  }
+  if (blk != nullptr && blk->t1 != nullptr && scat_out != nullptr) {      // marks go with the tables they describe
+    if (blk->pcol == nullptr) return fail(HCOMP_E_ARG, "dZ block tables need pcol");
+    if (g_align != nullptr && coef_out == nullptr) return fail(HCOMP_E_ARG, "dZ block tables: align gradient without coef_out");
+    q.blk.t1 = blk->t1; q.blk.ld1 = blk->ld1; q.blk.t2 = blk->t2; q.blk.ld2 = blk->ld2; q.blk.pcol = blk->pcol;
+    q.HW = HW;
   }
   const int grid = q.nb_pooled + q.nb_wc + q.nb_bias + q.nb_align + nb_coef;
   if (grid > 0) {

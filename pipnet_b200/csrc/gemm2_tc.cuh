@@ -73,6 +73,21 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = sb->tmem_base;
 
+  // k-block activity flags of A's row tile mt2 (8 per 64-bit word); nullptr = dense
+  const bool sparse = p.kact != nullptr;
+  auto kact_word = [&](int mt2, int kb) -> unsigned long long {
+    return __ldg(reinterpret_cast<const unsigned long long*>(p.kact + (size_t)mt2 * p.kact_ld + (kb & ~7)));
+  };
+  auto any_active = [&](int mt2, int kb0, int kb1) -> bool {        // (epilogue) does the item run any k-block?
+    if (!sparse) return kb1 > kb0;
+    for (int kb = kb0 & ~7; kb < kb1; kb += 8) {
+      unsigned long long w = kact_word(mt2, kb);
+      if (kb < kb0) w &= ~0ull << (8 * (kb0 - kb));
+      if (kb + 8 > kb1) w &= ~0ull >> (8 * (kb + 8 - kb1));
+      if (w) return true;
+    }
+    return false;
+  };
   auto decode = [&](int item, int& mt2, int& nt, int& kb0, int& kb1) {
     const int sp = item / tiles_mn;
     const int r = item - sp * tiles_mn;
@@ -91,7 +106,12 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         decode(item, mt2, nt, kb0, kb1);
         const int m0 = mt2 * 2 * G_BM + crank * G_BM;          // my rows
         const int n0 = nt * G_BN + crank * (G_BN / 2);         // my half of the columns
+        unsigned long long fw = (sparse && kb0 < kb1) ? kact_word(mt2, kb0) : ~0ull;
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (sparse) {
+            if ((kb & 7) == 0 && kb != kb0) fw = kact_word(mt2, kb);
+            if (((fw >> (8 * (kb & 7))) & 0xffull) == 0) continue;       // all-zero block of A: nothing to fetch
+          }
           mbar_wait(&sb->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * G2_STAGE_BYTES;
           uint8_t* sbm = sa + G2_A_BYTES;
@@ -134,7 +154,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         mbar_wait(&sb->tmem_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d = tmem_base + acc * G_BN;
+        unsigned long long fw = (sparse && kb0 < kb1) ? kact_word(mt2, kb0) : ~0ull;
+        bool started = false;              // the first executed k-block overwrites the accumulator
         for (int kb = kb0; kb < kb1; ++kb) {
+          if (sparse) {
+            if ((kb & 7) == 0 && kb != kb0) fw = kact_word(mt2, kb);
+            if (((fw >> (8 * (kb & 7))) & 0xffull) == 0) continue;
+          }
           mbar_wait(&sb->full[stage], phase);
           tc_fence_after();
           if (elect_one()) {
@@ -143,17 +169,17 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll
             for (int k = 0; k < G_BK / 16; ++k)
               umma_bf16_2cta(d, desc64((a + k * a_step) | A_LOF, HI), desc64((b + k * b_step) | B_LOF, HI), idesc,
-                             (kb > kb0 || k > 0) ? 1u : 0u);
+                             (started || k > 0) ? 1u : 0u);
             umma_commit_2cta(&sb->empty[stage], uint16_t(3));
-            if (kb == kb1 - 1) umma_commit_2cta(&sb->tmem_full[acc], uint16_t(3));
           }
           __syncwarp();
+          started = true;
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (kb1 <= kb0) {
-          if (elect_one()) umma_commit_2cta(&sb->tmem_full[acc], uint16_t(3));
-          __syncwarp();
-        }
+        // accumulator complete (commit tracks every MMA issued so far; with no k-block executed it fires at once and the
+        // epilogue treats the tile as zeros)
+        if (elect_one()) umma_commit_2cta(&sb->tmem_full[acc], uint16_t(3));
+        __syncwarp();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
@@ -178,7 +204,8 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       mbar_wait(&sb->tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t0 = tmem_base + (uint32_t(quad * 32) << 16) + acc * G_BN + half * 128;
-      const bool empty_k = kb1 <= kb0;
+      const bool empty_k = kb1 <= kb0;                 // split without k-blocks: contributes nothing, stores nothing
+      const bool zero_tile = !empty_k && !any_active(mt2, kb0, kb1);      // every k-block skipped: the product is zero
       if constexpr (OUT == OUT_BF16) {
         if (warp == 4 && lane == 0) tma_store_wait_read();
         named_bar_sync(1, 256);
@@ -186,8 +213,13 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll 1
         for (int c = 0; c < 128; c += 32) {
           uint32_t v[32];
-          tmem_ld32(t0 + c, v);
-          tmem_ld_wait();
+          if (!zero_tile) {
+            tmem_ld32(t0 + c, v);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = 0u;
+          }
           const int col = half * 128 + c;
           uint8_t* box = ostage + (col >> 6) * (G_BM * 128);
           const int ch0 = (col & 63) >> 3;
@@ -216,10 +248,15 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
 #pragma unroll 1
         for (int c = 0; c < 128; c += 32) {
           uint32_t r[32];
-          tmem_ld32(t0 + c, r);
-          tmem_ld_wait();
+          if (!zero_tile) {
+            tmem_ld32(t0 + c, r);
+            tmem_ld_wait();
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = 0u;
+          }
           const int n0 = nt * G_BN + half * 128 + c;
-          if (row_ok && !empty_k) {
+          if (row_ok && !empty_k && !(zero_tile && OUT == OUT_RED_F32)) {
             float* o = reinterpret_cast<float*>(p.out) + orow * p.ldo + n0;
             if constexpr (OUT == OUT_F32) {
 #pragma unroll

@@ -32,6 +32,11 @@ struct GemmParams {
   void* out;
   long long ldo;
   const int32_t* row_map;   // OUT_RED_F32: GEMM row -> output row (or -1 to drop); may be null (identity)
+  // optional (CTA-pair kernels): kact[mt2 * kact_ld + kb] == 0 says that the A operand's 256-row x 64-k block (mt2, kb) is
+  // all zeros, so the k-block is neither fetched nor multiplied (block-sparse dZ, see hcomp_head_bwd_dx).  Rows of the
+  // table are 8-byte aligned (kact_ld % 8 == 0) and padded with zeros.
+  const uint8_t* kact;
+  int kact_ld;
 };
 
 struct GemmSmem {

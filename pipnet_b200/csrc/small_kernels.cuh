@@ -523,6 +523,38 @@ __global__ void make_scat_kernel(const int32_t* __restrict__ argmax, const float
 // 0.31 ms cub27 step, almost all of it launch latency).  The same arithmetic in FOUR multi-role launches: a block's role
 // is a range of blockIdx.x, roles never communicate inside a launch (except the last-block-done combine of the losses).
 
+// ---- block-activity tables of dZ (block-sparse backward GEMMs) -------------------------------------------------------
+// With hierarchical labels an image drives only the nodes on its root-to-leaf path, so most (image, node) blocks of
+// dZ[M, P_c] are exactly zero (68 % on cub27, 95 % on cub190): dZ = S*(G - <G,S>)/tau vanishes where the upstream G does,
+// i.e. where (image, node) has no align coefficient and no pooled-gradient entry at an argmax row.  The kernels that
+// build K5's inputs mark the blocks that CAN be nonzero; the dX / dW GEMMs skip the rest (gemm2_tc.cuh, `kact`):
+//   t1[(row >> 8) * ld1 + (ccol >> 6)]   dX: A = dZ row tile of 256 x k-block of 64 compact columns
+//   t2[(ccol >> 8) * ld2 + (row >> 6)]   dW: A = dZ^T column tile of 256 x k-block of 64 rows
+// Data-dependent, conservative (a marked block may still be zero) and cleared by the forward's prologue launch.
+struct DzBlockTables {
+  uint8_t* t1; int ld1;
+  uint8_t* t2; int ld2;
+  const int32_t* pcol;        // [P] compact dZ column of a flat prototype (-1: none)
+};
+// one row x the node's whole column range [c_lo, c_hi]: the softmax Jacobian couples all prototypes of a node, so a
+// pooled-gradient entry of ONE prototype makes dZ nonzero in every column of its node at that row
+__device__ __forceinline__ void mark_dz_entry(const DzBlockTables& b, long long row, int c_lo, int c_hi) {
+  for (int c6 = c_lo >> 6; c6 <= (c_hi >> 6); ++c6) b.t1[(size_t)(row >> 8) * b.ld1 + c6] = 1;
+  for (int c8 = c_lo >> 8; c8 <= (c_hi >> 8); ++c8) b.t2[(size_t)c8 * b.ld2 + (size_t)(row >> 6)] = 1;
+}
+// the whole image (both views) x the node's columns: dense align gradient
+__device__ __forceinline__ void mark_dz_image_node(const DzBlockTables& b, int img, int imgs_first, int V, int HW, int c_lo, int c_hi) {
+  for (int view = 0; view < 2; ++view) {
+    const int v = img + view * imgs_first;
+    if (v >= V) break;
+    const long long r_lo = (long long)v * HW, r_hi = r_lo + HW - 1;
+    for (int c6 = c_lo >> 6; c6 <= (c_hi >> 6); ++c6)
+      for (long long r8 = r_lo >> 8; r8 <= (r_hi >> 8); ++r8) b.t1[(size_t)r8 * b.ld1 + c6] = 1;
+    for (int c8 = c_lo >> 8; c8 <= (c_hi >> 8); ++c8)
+      for (long long r6 = r_lo >> 6; r6 <= (r_hi >> 6); ++r6) b.t2[(size_t)c8 * b.ld2 + (size_t)r6] = 1;
+  }
+}
+
 // ---- head prologue: everything K1 needs, one launch ---------------------------------------------------------------
 //   role A  pack the prototype kernels into their bf16 GEMM layouts (pack_weights_kernel's job)
 //   role B  clear the packed max table and the align accumulators K1 merges into with atomics
@@ -530,6 +562,7 @@ __global__ void make_scat_kernel(const int32_t* __restrict__ argmax, const float
 struct PrologueParams {
   const float* w; const int32_t* row_map; int rows, C; __nv_bfloat16* wp;        // A (rows == 0: skipped)
   unsigned long long* packed; long long n_packed; double* align_sum; int n_align;   // B
+  uint4* zero16; long long n_zero16;                                               // B: one more buffer to clear (16-byte units)
   const long long* ys; const int8_t* anc; int V, V_first, N, L;                     // C (ys == nullptr: skipped)
   int8_t* tgt; uint8_t* desc; int32_t* n_desc;
   int nb_pack, nb_zero, nb_tgt, nb_cnt;
@@ -559,6 +592,8 @@ __global__ void __launch_bounds__(256) head_prologue_kernel(const PrologueParams
     else if (i < q.n_packed) q.packed[i] = 0ull;
     if (b == 0 && q.align_sum != nullptr)
       for (int n = threadIdx.x; n < q.n_align; n += 256) q.align_sum[n] = 0.0;
+    for (long long z = (long long)b * 256 + threadIdx.x; z < q.n_zero16; z += (long long)q.nb_zero * 256)
+      q.zero16[z] = make_uint4(0, 0, 0, 0);
     return;
   }
   b -= q.nb_zero;
@@ -977,6 +1012,7 @@ struct ChainBwdParams {
   // optional: K5's scatter table / align coefficients straight from here (bwd_prep_kernel's job), valid when this
   // g_pooled / g_align reach the head backward unchanged (the host checks)
   const int32_t* argmax; float thresh; int2* scat; const uint8_t* desc; int HW; float* coef;
+  DzBlockTables blk;          // blk.t1 == nullptr: no block tables
 };
 __device__ __forceinline__ float chain_gout(const ChainBwdParams& q, int v, int n, int t, int k0, int c, float coef) {
   const float o = q.out[(size_t)v * q.K + k0 + c];
@@ -1012,7 +1048,12 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
     q.g_pooled[idx] = g;
     if (q.scat != nullptr) {
       const float gs = (q.thresh > 0.f && q.pooled[idx] < q.thresh) ? 0.f : g;    // inference threshold kills the gradient too
-      q.scat[idx] = make_int2(q.argmax[idx], __float_as_int(gs));
+      const int am = q.argmax[idx];
+      q.scat[idx] = make_int2(am, __float_as_int(gs));
+      if (q.blk.t1 != nullptr && gs != 0.f) {
+        const int ca = q.blk.pcol[q.proto_off[n]], cb = q.blk.pcol[q.proto_off[n + 1] - 1];
+        if (ca >= 0 && cb >= ca) mark_dz_entry(q.blk, (long long)v * q.HW + am, ca, cb);
+      }
     }
     return;
   }
@@ -1068,7 +1109,13 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
   if (idx >= q.V_first * q.N) return;
   const int m = idx % q.N;
   const int nd = q.n_desc[m] / 2;
-  q.coef[idx] = (q.desc[idx] && nd > 0) ? gT * q.lw.w[0] * 0.5f / (float(nd) * float(q.HW)) : 0.f;
+  const float cf = (q.desc[idx] && nd > 0) ? gT * q.lw.w[0] * 0.5f / (float(nd) * float(q.HW)) : 0.f;
+  q.coef[idx] = cf;
+  if (q.blk.t1 != nullptr && cf != 0.f) {
+    const int pa = q.proto_off[m], pb = q.proto_off[m + 1] - 1;
+    const int ca = q.blk.pcol[pa], cb = q.blk.pcol[pb];
+    if (ca >= 0 && cb >= ca) mark_dz_image_node(q.blk, idx / q.N, q.V_first, q.V, q.HW, ca, cb);
+  }
 }
 
 // orth_bwd_kernel with the upstream gradient taken as g_total * weight (no loss_grads launch in front of it)
@@ -1098,14 +1145,23 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const int32_t* __restrict
                                                        const float* __restrict__ pooled, float thresh, long long n,
                                                        int2* __restrict__ scat, int nb_scat, const uint8_t* __restrict__ desc,
                                                        const int32_t* __restrict__ n_desc, const float* __restrict__ g_align,
-                                                       int B, int N, int HW, float* __restrict__ coef) {
+                                                       int B, int N, int HW, float* __restrict__ coef, int P, int V,
+                                                       const int32_t* __restrict__ proto_off,
+                                                       const int32_t* __restrict__ proto_node, const DzBlockTables blk) {
   int b = blockIdx.x;
   if (b < nb_scat) {
     const long long i = (long long)b * 256 + threadIdx.x;
     if (i >= n) return;
     float g = g_pooled[i];
     if (pooled != nullptr && pooled[i] < thresh) g = 0.f;
-    scat[i] = make_int2(argmax[i], __float_as_int(g));
+    const int am = argmax[i];
+    scat[i] = make_int2(am, __float_as_int(g));
+    if (blk.t1 != nullptr && g != 0.f) {
+      const int v = int(i / P), pp = int(i - (long long)v * P);
+      const int nd = proto_node[pp];
+      const int ca = blk.pcol[proto_off[nd]], cb = blk.pcol[proto_off[nd + 1] - 1];
+      if (ca >= 0 && cb >= ca) mark_dz_entry(blk, (long long)v * HW + am, ca, cb);
+    }
     return;
   }
   b -= nb_scat;
@@ -1113,7 +1169,13 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const int32_t* __restrict
   if (idx >= B * N) return;
   const int m = idx % N;
   const int nd = n_desc[m] / 2;
-  coef[idx] = (desc[idx] && nd > 0) ? g_align[m] * 0.5f / (float(nd) * float(HW)) : 0.f;
+  const float cf = (desc[idx] && nd > 0) ? g_align[m] * 0.5f / (float(nd) * float(HW)) : 0.f;
+  coef[idx] = cf;
+  if (blk.t1 != nullptr && cf != 0.f) {
+    const int pa = proto_off[m], pb = proto_off[m + 1] - 1;
+    const int ca = blk.pcol[pa], cb = blk.pcol[pb];
+    if (ca >= 0 && cb >= ca) mark_dz_image_node(blk, idx / N, B, V, HW, ca, cb);
+  }
 }
 
 // ---------------------------------------------------------------- joint leaf distribution (util/node.py:383-385, pipnet/pipnet.py:173-185)

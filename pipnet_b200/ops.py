@@ -367,6 +367,11 @@ class DeviceLayout:
         self.n_wide = int((L.spill[:, 5] == 0).sum()) if self.n_spill else 0
         self.P_s = int(L.P_s)
         self.rider_pmax = int(L.spill[:, 1].max()) if self.n_spill else 0
+        # compact dZ column of every flat prototype (inverse of row_map_c): block-activity marks of the sparse backward GEMMs
+        pcol = np.full(L.P, -1, dtype=np.int32)
+        rmc = np.asarray(L.row_map_c)
+        pcol[rmc[rmc >= 0]] = np.nonzero(rmc >= 0)[0].astype(np.int32)
+        self.pcol = up(pcol, torch.int32)
         # last-block-done counter of the chained loss kernel (zero between calls; one call at a time per layout)
         self.counter = torch.zeros(8, device=d, dtype=torch.int32)
 
@@ -525,7 +530,27 @@ class LabelTables:
     def n_desc(self): return self.ensure()._n_desc
 
 
-def head_prologue(w_flat: Optional[torch.Tensor], dl: DeviceLayout, V: int, labels: Optional["LabelTables"], dev):
+SPARSE_BWD = os.environ.get('HC_SPARSE_BWD', '1') != '0'      # block-sparse dX / dW GEMMs (A/B switch, same results)
+
+
+class DzBlocks:
+    """Block-activity tables of dZ (include/hcomp_head.h: hcomp_dz_blocks) for one step: allocated by the forward, cleared
+    by its prologue launch, marked by whichever launch builds K5's scatter table, read by the dX / dW GEMMs."""
+
+    def __init__(self, dl: DeviceLayout, M: int, dev):
+        n_r256, n_r64 = (M + 255) // 256, (M + 63) // 64
+        n_c64, n_c256 = (dl.P_c + 63) // 64, (dl.P_c + 255) // 256
+        ld1, ld2 = (n_c64 + 7) // 8 * 8, (n_r64 + 7) // 8 * 8
+        b1 = (n_r256 * ld1 + 15) // 16 * 16
+        b2 = (n_c256 * ld2 + 15) // 16 * 16
+        self.buf = torch.empty(b1 + b2, device=dev, dtype=torch.uint8)
+        self.struct = _cabi.DzBlocks(self.buf.data_ptr(), ld1, self.buf.data_ptr() + b1, ld2, dl.pcol.data_ptr())
+        self.ref = C.byref(self.struct)
+        self.dl = dl
+
+
+def head_prologue(w_flat: Optional[torch.Tensor], dl: DeviceLayout, V: int, labels: Optional["LabelTables"], dev,
+                  zero_extra: Optional[torch.Tensor] = None):
     """ONE launch for everything the fused projection kernel needs (hcomp_head_prologue): bf16 weight layouts (wp, wpc),
     the cleared packed max table / align accumulators, and -- when `labels` are still pending -- the label tables."""
     wp = wpc = both = None
@@ -545,7 +570,8 @@ def head_prologue(w_flat: Optional[torch.Tensor], dl: DeviceLayout, V: int, labe
          C.c_longlong(packed.numel()), ptr(align_sum), dl.N, ptr(lab.ys) if lab is not None else None, dl.tref,
          lab.V if lab is not None else 0, lab.V_first if lab is not None else 0,
          ptr(lab._tgt) if lab is not None else None, ptr(lab._desc) if lab is not None else None,
-         ptr(lab._n_desc) if lab is not None else None, _stream())
+         ptr(lab._n_desc) if lab is not None else None, ptr(zero_extra),
+         C.c_longlong(zero_extra.numel() * zero_extra.element_size() if zero_extra is not None else 0), _stream())
     return wp, wpc, packed, align_sum
 
 
@@ -619,9 +645,11 @@ def proj_pool_classify_raw(x_rows, wp, dl: DeviceLayout, V, V_first, HW, tau, la
 
 def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, argmax, g_pooled, labels, g_align, *,
                       pooled=None, thresh=0.0, need_dx=True, need_dw=True, precision=PREC_BF16, w_group=None, dz_out=None,
-                      spill=None, tables=None):
+                      spill=None, tables=None, blocks=None):
     """spill: (zs, stats) the forward produced for the layout's spill nodes (required when it has any);
-    tables: (scat, coef) already built from exactly these g_pooled / g_align by hcomp_head_chain_bwd (`_PrepSlot`)"""
+    tables: (scat, coef) already built from exactly these g_pooled / g_align by hcomp_head_chain_bwd (`_PrepSlot`);
+    blocks: `DzBlocks` of this step (zeroed, or already marked together with `tables`): the dX / dW GEMMs skip the
+    unmarked blocks of dZ"""
     Cc = x_rows.shape[1]
     dev = x_rows.device
     M = V * HW
@@ -645,7 +673,7 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
          dl.P, dl.P_pad, dl.P_c, dl.N, float(tau), int(precision), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),
          ptr(labels.desc) if use_align else None, ptr(labels.n_desc) if use_align else None,
          ptr(g_align) if use_align else None, ptr(scat), ptr(coef), ptr(dz), C.byref(sp) if sp is not None else None,
-         _stream())
+         blocks.ref if blocks is not None else None, ptr(dl.proto_off), ptr(dl.proto_node), _stream())
     PROFILE.stop(tok)
     dx = dw = None
     pending = None
@@ -655,7 +683,8 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
         dw = (_bucket_segment(w_group, dev).view(dl.P, Cc) if bucketed
               else torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32))
         tok = PROFILE.start('k7_bwd_dw')
-        call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map_c), C.c_longlong(M), dl.P_c, Cc, ptr(dw), _stream())
+        call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map_c), C.c_longlong(M), dl.P_c, Cc, ptr(dw),
+             blocks.ref if blocks is not None else None, _stream())
         PROFILE.stop(tok)
         if bucketed:
             _bucket_allreduce()             # everything the head produces is in the bucket by now; overlaps K6
@@ -667,7 +696,8 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
         tok = PROFILE.start('k6_bwd_dx')
         prev = _cabi.lib().hcomp_set_reserved_sms(collective_sms()) if (pending is not None or bucketed) else None
         try:
-            call('hcomp_head_bwd_dx', ptr(dz), ptr(wpc), C.c_longlong(M), dl.P_c, Cc, ptr(dx), _stream())
+            call('hcomp_head_bwd_dx', ptr(dz), ptr(wpc), C.c_longlong(M), dl.P_c, Cc, ptr(dx),
+                 blocks.ref if blocks is not None else None, _stream())
         finally:
             if prev is not None:
                 _cabi.lib().hcomp_set_reserved_sms(prev)
@@ -699,6 +729,8 @@ class _PrepSlot:
     def __init__(self, argmax, thresh, labels, V_first, HW):
         self.argmax, self.thresh, self.labels, self.V_first, self.HW = argmax, float(thresh), labels, V_first, HW
         self.ready = None            # (g_pooled ptr, version, g_align ptr or 0, version, scat, coef)
+        self.blocks = None           # DzBlocks of this step (block-sparse backward GEMMs) or None
+        self.blocks_used = False     # marks are conservative only for ONE backward pass per forward
 
     @staticmethod
     def _key(t):
@@ -729,13 +761,17 @@ class HeadProjPool(torch.autograd.Function):
         HW = H * W
         dev = features.device
         wf = w_flat.detach().contiguous()
+        blocks = None
+        if SPARSE_BWD and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
+            blocks = DzBlocks(dl, V * HW, dev)           # cleared by the prologue launch below
+        zx = blocks.buf if blocks is not None else None
         if precision == PREC_FP32X3:
             x_rows = feature_rows_split3(features.detach())
             wp, wpc = pack_weights(wf, dl, precision)
-            _wp, _wpc, packed, align_sum = head_prologue(None, dl, V, labels, dev)
+            _wp, _wpc, packed, align_sum = head_prologue(None, dl, V, labels, dev, zx)
         else:
             x_rows = feature_rows(features.detach())
-            wp, wpc, packed, align_sum = head_prologue(wf, dl, V, labels, dev)
+            wp, wpc, packed, align_sum = head_prologue(wf, dl, V, labels, dev, zx)
         wc = wc_flat.detach().contiguous() if wc_flat is not None else None
         bs = bias.detach().contiguous() if bias is not None else None
         spill = []
@@ -752,6 +788,7 @@ class HeadProjPool(torch.autograd.Function):
         ctx.save_for_backward(x_rows, wp, wpc, argmax, pooled, wc)
         ctx.mark_non_differentiable(argmax)
         ctx.prep = pooled._hc_prep = _PrepSlot(argmax, thresh, labels, V_first, HW)
+        ctx.prep.blocks = blocks
         if align is None:
             align = torch.zeros(dl.N, device=dev, dtype=torch.float32)
         return pooled, align, argmax, out
@@ -802,7 +839,7 @@ class HeadProjPool(torch.autograd.Function):
         dx, dw, _ = head_backward_raw(x_rows, wp, wpc, dl, V, V_first, H * W, tau, argmax, g_pooled, ctx.labels, g_align,
                                       pooled=pooled, thresh=ctx.thresh, need_dx=need_dx, need_dw=need_dw,
                                       precision=ctx.precision, w_group=ctx.w_group, spill=ctx.spill,
-                                      tables=ctx.prep.take(g_pooled, g_align))
+                                      tables=ctx.prep.take(g_pooled, g_align), blocks=ctx.prep.blocks)
         d_feat = None
         if need_dx:
             dtype, _cl = ctx.feat_meta
@@ -1009,7 +1046,8 @@ class HeadLosses(torch.autograd.Function):
                  ptr(g_pooled), ptr(g_wc), ptr(g_bias), ptr(g_align), ptr(g_w),
                  ptr(slot.argmax) if slot is not None else None, slot.thresh if slot is not None else 0.0,
                  ptr(labels.desc) if use_coef else None, slot.HW if slot is not None else 0, ptr(scat),
-                 ptr(coef) if use_coef else None, _stream())
+                 ptr(coef) if use_coef else None,
+                 slot.blocks.ref if (slot is not None and slot.blocks is not None) else None, _stream())
             if slot is not None:
                 slot.publish(g_pooled, g_align, scat, coef)
             if b_wc:

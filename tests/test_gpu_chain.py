@@ -46,10 +46,12 @@ def test_prologue_matches_separate_calls():
     assert torch.equal(lab_a._tgt, lab_b._tgt) and torch.equal(lab_a._desc, lab_b._desc) and torch.equal(lab_a._n_desc, lab_b._n_desc)
     # odd table length (scalar tail of the 16-byte clears) and labels already computed
     dirty = torch.full((V * dl.P + 1,), -1, device='cuda', dtype=torch.int64)
+    extra = torch.full((48,), 7, device='cuda', dtype=torch.uint8)          # the extra clear target (16-byte units)
     ops.call('hcomp_head_prologue', None, None, 0, 0, None, ops.ptr(dirty), C.c_longlong(V * dl.P - 1), None, 0, None, dl.tref,
-             0, 0, None, None, None, ops._stream())
+             0, 0, None, None, None, ops.ptr(extra), C.c_longlong(32), ops._stream())
     torch.cuda.synchronize()
     assert int(dirty[:V * dl.P - 1].abs().max()) == 0 and int(dirty[V * dl.P - 1]) == -1
+    assert int(extra[:32].max()) == 0 and int(extra[32:].min()) == 7
 
 
 @pytest.mark.parametrize("bias", [False, True], ids=["nobias", "bias"])
@@ -204,3 +206,75 @@ def test_deferred_riders_match_folded_riders(inference):
     (pa, oa, aa, ga), (pb, ob, ab, gb) = outs
     assert torch.equal(pa, pb) and torch.equal(oa, ob) and torch.equal(ga, gb)
     assert _close(aa, ab, 1e-6)
+
+
+@pytest.mark.parametrize("case", [("cub27", 768, 26, 4, dict(num_features=20)), ("cub18", 128, 7, 5, dict(num_features=12)),
+                                  ("cub27", 128, 6, 4, dict(num_protos_per_child=30, num_features=0))],
+                         ids=["cub27-real-geometry", "cub18-small", "cub27-wide-node"])
+@pytest.mark.parametrize("phase", [("train", False, False), ("pretrain", True, False)], ids=lambda p: p[0])
+def test_block_sparse_backward_matches_dense(case, phase):
+    """dX / dW with the unmarked (exactly zero) blocks of dZ skipped against the dense GEMMs on the same step: dX bit for
+    bit (same MMA sequence on the nonzero blocks), dW within the split-K atomics' run-to-run variation; and the marks
+    must actually be sparse for hierarchical labels"""
+    from pipnet_b200 import ops
+    tree, C_, H, B, over = case
+    _, pretrain, finetune = phase
+    net, root, args, xs, ys, tr = _problem(tree=tree, C_=C_, H=H, B=B, **over)
+    w = tr._phase_weights(pretrain, 3, 10, args)
+    res = []
+    saved = ops.SPARSE_BWD
+    try:
+        for sparse in (True, False):
+            ops.SPARSE_BWD = sparse
+            net.zero_grad(set_to_none=True)
+            x = xs.clone().requires_grad_(True)
+            labels = tr.make_labels(net, ys)
+            features, pf, pooled, out = net(x, labels=labels)
+            slot = pooled.flat._hc_prep
+            assert (slot.blocks is not None) == sparse
+            r = tr.calculate_loss(3, net, {}, features, pf, pooled, out, ys, net_normalization_multiplier=net._multiplier,
+                                  pretrain=pretrain, finetune=finetune, criterion=None, train_iter=None, print=False, EPS=1e-8,
+                                  root=root, kernel_orth=True, align=False, uni=False, align_pf=True, tanh=True, args=args,
+                                  device='cuda', labels=labels, **w)
+            r[0].backward()
+            torch.cuda.synchronize()
+            gw = torch.cat([getattr(net, '_' + n + '_add_on').weight.grad.flatten() for n in net.layout.node_names])
+            frac = float(slot.blocks.buf.float().mean()) if sparse else None
+            res.append((x.grad.clone(), gw.clone(), frac))
+    finally:
+        ops.SPARSE_BWD = saved
+    (dx_s, dw_s, frac), (dx_d, dw_d, _) = res
+    assert torch.equal(dx_s, dx_d)
+    assert _close(dw_s, dw_d, 1e-4)
+    assert 0.0 < frac < 1.0, frac          # (coarse 256 x 64 blocks: small trees mark most of them, cub190 ~25 %)
+
+
+@pytest.mark.parametrize("which", ["dense", "node3", "node8", "last-node"])
+def test_block_sparse_backward_with_arbitrary_upstream_gradient(which):
+    """an arbitrary gradient on `pooled` -- dense (marks every block), or on ONE node only (its 20 compact dZ columns may
+    straddle two 64-column blocks: the softmax couples them, all must be marked) -- sparse path == dense path"""
+    from pipnet_b200 import ops
+    net, root, args, xs, ys, tr = _problem(C_=128, H=7, B=5)
+    L = net.layout
+    g = torch.randn(xs.shape[0], L.P, device='cuda')
+    if which != "dense":
+        ni = {"node3": 3, "node8": 8, "last-node": L.N - 1}[which]
+        keep = torch.zeros_like(g)
+        keep[:, int(L.proto_off[ni]):int(L.proto_off[ni + 1])] = 1.0
+        g = g * keep
+    out = []
+    saved = ops.SPARSE_BWD
+    try:
+        for sparse in (True, False):
+            ops.SPARSE_BWD = sparse
+            net.zero_grad(set_to_none=True)
+            x = xs.clone().requires_grad_(True)
+            labels = tr.make_labels(net, ys)
+            _, _, pooled, _o = net(x, labels=labels)
+            ((pooled.flat * g).sum() + (pooled.align.sum() if which == "dense" else 0.0 * pooled.align.sum())).backward()
+            torch.cuda.synchronize()
+            out.append((x.grad.clone(), torch.cat([getattr(net, '_' + n + '_add_on').weight.grad.flatten()
+                                                   for n in net.layout.node_names])))
+    finally:
+        ops.SPARSE_BWD = saved
+    assert torch.equal(out[0][0], out[1][0]) and _close(out[0][1], out[1][1], 1e-4)
