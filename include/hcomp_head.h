@@ -80,6 +80,13 @@ typedef struct hcomp_dz_blocks {
   uint8_t* t1; int32_t ld1;
   uint8_t* t2; int32_t ld2;
   const int32_t* pcol;
+  /* optional (iact may be NULL): work items of the backward recompute kernel itself.  iact[n_tiles][iact_pitch] bytes,
+   * entry (prototype tile, chunk): chunk = 32 locations of an image pair, b * ceil(HW/32) + location / 32; iact_pitch a
+   * multiple of 8 and >= 8 * ceil(V_first * ceil(HW/32) / 8) + 8; tile_of_node[N] = prototype tile holding node n's
+   * segment or -1 (spill nodes).  hcomp_head_bwd_dz skips items (256 locations x one tile) without a marked chunk: no
+   * operand loads, no MMAs, zeros stored.  Same zero-before-marking rule as t1 / t2. */
+  uint8_t* iact; int32_t iact_pitch;
+  const int32_t* tile_of_node;
 } hcomp_dz_blocks;
 
 int hcomp_abi_version(void);

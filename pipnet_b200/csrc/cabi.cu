@@ -425,7 +425,20 @@ int run_gemm(const void* a, const void* b, long long M, int N, long long K, bool
   if (out_mode != hc::OUT_RED_F32) splits = 1;
   int sms = di.sms - reserve_sms;       // persistent grid; a reserve leaves whole SMs to kernels of other streams
   if (sms < 2) sms = 2;
-  if (splits <= 0) splits = (pair ? sms / 2 : sms) / tiles_mn;
+  if (splits <= 0) {
+    // split-K factor: minimise rounds x (k-blocks per split + the epilogue's red.add pass, ~8 k-blocks worth), where
+    // rounds = ceil(items / workers).  (items / workers rounded down -- the first version -- left cub190's dW with 45 items
+    // on 74 CTA pairs in ONE round of 676 k-blocks: 230 us; 8 splits = 5 rounds of 85: 0.63 of that.)
+    const int workers = pair ? sms / 2 : sms;
+    long long best_cost = -1;
+    for (int sp = 1; sp <= 32 && sp <= p.num_k_blocks; ++sp) {
+      const int kps = cdiv(p.num_k_blocks, sp);
+      if (sp > 1 && kps < 8) break;
+      const long long rounds = cdiv((long long)tiles_mn * cdiv(p.num_k_blocks, kps), workers);
+      const long long cost = rounds * (kps + 8);
+      if (best_cost < 0 || cost < best_cost) { best_cost = cost; splits = sp; }
+    }
+  }
   if (splits < 1) splits = 1;
   if (splits > p.num_k_blocks) splits = p.num_k_blocks;
   p.k_blocks_per_split = cdiv(p.num_k_blocks, splits);
@@ -498,6 +511,17 @@ int run_spill(const hcomp_spill* sp, const hc::SpillParams& base, int V, bool ri
     HC_LAUNCH_CHECK(BWD ? "spill_narrow_bwd" : "spill_narrow_fwd");
   }
   return 0;
+}
+
+hc::DzBlockTables dz_tables(const hcomp_dz_blocks* blk, int HW) {
+  hc::DzBlockTables bt{};
+  if (blk != nullptr && blk->t1 != nullptr) {
+    bt.t1 = blk->t1; bt.ld1 = blk->ld1; bt.t2 = blk->t2; bt.ld2 = blk->ld2; bt.pcol = blk->pcol;
+    if (blk->iact != nullptr && blk->tile_of_node != nullptr) {
+      bt.iact = blk->iact; bt.iact_pitch = blk->iact_pitch; bt.tile_of_node = blk->tile_of_node; bt.cpi = (HW + 31) / 32;
+    }
+  }
+  return bt;
 }
 
 hc::SpillParams spill_base(int V, int V_first, int HW, int P, int n_nodes, float tau) {
@@ -681,12 +705,9 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
   } else {                              // scatter table + align coefficients: one launch
     const bool use_align = g_align != nullptr && desc != nullptr && n_desc != nullptr;
     const int nb_scat = blocks(n, 256), nb_coef = use_align ? blocks((long long)V_first * n_nodes, 256) : 0;
-    hc::DzBlockTables bt{};
-    if (blk != nullptr && blk->t1 != nullptr) {
-      if (proto_off == nullptr || proto_node == nullptr || blk->pcol == nullptr)
-        return fail(HCOMP_E_ARG, "dZ block tables need proto_off, proto_node and pcol");
-      bt.t1 = blk->t1; bt.ld1 = blk->ld1; bt.t2 = blk->t2; bt.ld2 = blk->ld2; bt.pcol = blk->pcol;
-    }
+    if (blk != nullptr && blk->t1 != nullptr && (proto_off == nullptr || proto_node == nullptr || blk->pcol == nullptr))
+      return fail(HCOMP_E_ARG, "dZ block tables need proto_off, proto_node and pcol");
+    const hc::DzBlockTables bt = dz_tables(blk, HW);
     hc::bwd_prep_kernel<<<nb_scat + nb_coef, 256, 0, S(stream)>>>(argmax, g_pooled, thresh > 0.f ? pooled : nullptr, thresh, n,
                                                                   reinterpret_cast<int2*>(scat_ws), nb_scat, desc, n_desc,
                                                                   g_align, V_first, n_nodes, HW, coef_ws, P, V, proto_off, proto_node, bt);
@@ -694,6 +715,13 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
     if (use_align) p.coef_align = coef_ws;
   }
   if (spill != nullptr && spill->n_spill > 0) { p.zs = spill->zs; p.ldz = spill->ldz; }
+  if (blk != nullptr && blk->t1 != nullptr && blk->iact != nullptr && blk->tile_of_node != nullptr) {
+    const int chunks = V_first * ((HW + 31) / 32);
+    if (blk->iact_pitch % 8 != 0 || blk->iact_pitch < (chunks + 7) / 8 * 8 + 8 || (reinterpret_cast<uintptr_t>(blk->iact) & 7) != 0)
+      return fail(HCOMP_E_ARG, "item activity table: pitch %d for %d chunks (multiple of 8, >= chunks rounded up + 8, 8-byte aligned)",
+                  blk->iact_pitch, chunks);
+    p.iact = blk->iact; p.iact_pitch = blk->iact_pitch;
+  }
   bool folded = false;
   if (int e = run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,
                              precision, p, spill, &folded, S(stream)))
@@ -1045,7 +1073,7 @@ int hcomp_head_chain_bwd(const float* g_total, const float* pooled, const float*
   if (blk != nullptr && blk->t1 != nullptr && scat_out != nullptr) {      // marks go with the tables they describe
     if (blk->pcol == nullptr) return fail(HCOMP_E_ARG, "dZ block tables need pcol");
     if (g_align != nullptr && coef_out == nullptr) return fail(HCOMP_E_ARG, "dZ block tables: align gradient without coef_out");
-    q.blk.t1 = blk->t1; q.blk.ld1 = blk->ld1; q.blk.t2 = blk->t2; q.blk.ld2 = blk->ld2; q.blk.pcol = blk->pcol;
+    q.blk = dz_tables(blk, HW);
     q.HW = HW;
   }
   const int grid = q.nb_pooled + q.nb_wc + q.nb_bias + q.nb_align + nb_coef;

@@ -106,10 +106,16 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         decode(item, mt2, nt, kb0, kb1);
         const int m0 = mt2 * 2 * G_BM + crank * G_BM;          // my rows
         const int n0 = nt * G_BN + crank * (G_BN / 2);         // my half of the columns
+        // flag words are fetched one 8-block group ahead: a dependent global load in front of a k-block would stall the
+        // one producer thread for longer than the operand ring holds
         unsigned long long fw = (sparse && kb0 < kb1) ? kact_word(mt2, kb0) : ~0ull;
+        unsigned long long fw_next = (sparse && (kb0 | 7) + 1 < kb1) ? kact_word(mt2, (kb0 | 7) + 1) : 0ull;
         for (int kb = kb0; kb < kb1; ++kb) {
           if (sparse) {
-            if ((kb & 7) == 0 && kb != kb0) fw = kact_word(mt2, kb);
+            if ((kb & 7) == 0 && kb != kb0) {
+              fw = fw_next;
+              if (kb + 8 < kb1) fw_next = kact_word(mt2, kb + 8);
+            }
             if (((fw >> (8 * (kb & 7))) & 0xffull) == 0) continue;       // all-zero block of A: nothing to fetch
           }
           mbar_wait(&sb->empty[stage], phase ^ 1);
@@ -155,10 +161,14 @@ gemm2_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
         tc_fence_after();
         const uint32_t d = tmem_base + acc * G_BN;
         unsigned long long fw = (sparse && kb0 < kb1) ? kact_word(mt2, kb0) : ~0ull;
+        unsigned long long fw_next = (sparse && (kb0 | 7) + 1 < kb1) ? kact_word(mt2, (kb0 | 7) + 1) : 0ull;
         bool started = false;              // the first executed k-block overwrites the accumulator
         for (int kb = kb0; kb < kb1; ++kb) {
           if (sparse) {
-            if ((kb & 7) == 0 && kb != kb0) fw = kact_word(mt2, kb);
+            if ((kb & 7) == 0 && kb != kb0) {
+              fw = fw_next;
+              if (kb + 8 < kb1) fw_next = kact_word(mt2, kb + 8);
+            }
             if (((fw >> (8 * (kb & 7))) & 0xffull) == 0) continue;
           }
           mbar_wait(&sb->full[stage], phase);

@@ -146,6 +146,11 @@ struct HeadParams {
   const float* coef_align;             // [imgs_first, n_nodes] upstream * 0.5 / (n_desc * HW) (0 if masked); may be null
   __nv_bfloat16* dz;                   // [M, P_c]: COMPACT column axis (tile t starts at column tiles[t][3], used columns only)
   int P_c;                             // columns of dz
+  // backward, optional: iact[(global tile) * iact_pitch + chunk] != 0 where the upstream gradient of (chunk's image, some
+  // node of the tile) can be nonzero (small_kernels.cuh: DzBlockTables).  An item whose chunks are all unmarked has dZ = 0:
+  // no operand loads, no MMAs, the epilogue stores zeros.  null = every item runs
+  const uint8_t* iact;
+  int iact_pitch;
   // riders finished in the tail of this launch (class == the launch's class; 0 = none): see the rider tail of the kernel
   int n_riders;
   int rider[8][6];                     // {node, P_n, poff, zoff, dz_col, dz_width}
@@ -638,6 +643,15 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
   const int m_groups = (p.num_m_tiles + CL - 1) / CL;          // CG2: two pair tiles per cluster item
   const int total_items = m_groups * n_groups;
   const int worker = blockIdx.x / CL, num_workers = gridDim.x / CL;
+  // activity flags of an item's 4 * CL chunks as one word (0 = skip the item); the roles fetch the NEXT item's word one
+  // item ahead and test it when they get there
+  [[maybe_unused]] auto item_flags = [&](int mg_, int nt_) -> unsigned long long {
+    if constexpr (!BWD) return 1ull;
+    if (p.iact == nullptr) return 1ull;
+    const uint8_t* a = p.iact + (size_t)(p.tile_begin + nt_) * p.iact_pitch + (size_t)mg_ * (4 * CL);
+    if constexpr (CL == 2) return __ldg(reinterpret_cast<const unsigned long long*>(a));
+    else return (unsigned long long)__ldg(reinterpret_cast<const unsigned int*>(a));
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_x.full[3]);
@@ -736,12 +750,17 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       if (box == 2) {
         // ---- prototype tile
         int umma_n = (CG2 && worker < total_items) ? __ldg(tile_rec + (size_t)nt * TILE_INTS) : 0;
+        unsigned long long fl_next = worker < total_items ? item_flags(mg, nt) : 0ull;
         for (int item = worker; item < total_items; item += num_workers) {
           const int row = (p.tile_begin + nt) * TILE_N + (CG2 ? crank * (umma_n >> 1) : 0);   // CG2: my half of the tile's N
-          nt += dr;
-          if (nt >= n_groups) nt -= n_groups;
-          if (CG2 && item + num_workers < total_items)        // next item's record: in flight during this k loop
-            umma_n = __ldg(tile_rec + (size_t)nt * TILE_INTS);
+          const unsigned long long fl = fl_next;
+          mg += dq; nt += dr;
+          if (nt >= n_groups) { nt -= n_groups; ++mg; }
+          if (item + num_workers < total_items) {             // next item's records: in flight during this k loop
+            if (CG2) umma_n = __ldg(tile_rec + (size_t)nt * TILE_INTS);
+            fl_next = item_flags(mg, nt);
+          }
+          if (fl == 0ull) continue;
           k_reset();
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             uint8_t* dst = post_begin(CG2 ? 2 * BOX_W : BOX_W);
@@ -760,7 +779,9 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
         int img0 = c_first / p.cpi, k0 = c_first - img0 * p.cpi;
         if (box == 1) img0 += p.imgs_first;
         const int short_rows = 32 - p.rem;                      // rows a tile does NOT fetch when it holds the end of an image
+        unsigned long long fl_next = worker < total_items ? item_flags(mg, nt) : 0ull;
         for (int item = worker; item < total_items; item += num_workers) {
+          const unsigned long long fl = fl_next;
           const bool wrap = k0 + 4 >= p.cpi;                    // the tile holds the last chunk of image img0
           const int len1 = wrap ? p.cpi - k0 : 4;
           const CUtensorMap* map1 = wrap ? &tmap_x.tail[len1 - 1] : &tmap_x.full[3];
@@ -778,9 +799,11 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
           const uint32_t tx_bytes = uint32_t(rows) * (KBLK * 2);
           // next item's first chunk
           img0 += d_img; k0 += d_k;
-          nt += dr;
-          if (nt >= n_groups) { nt -= n_groups; img0 += e_img; k0 += e_k; }
+          mg += dq; nt += dr;
+          if (nt >= n_groups) { nt -= n_groups; ++mg; img0 += e_img; k0 += e_k; }
           while (k0 >= p.cpi) { k0 -= p.cpi; ++img0; }
+          if (item + num_workers < total_items) fl_next = item_flags(mg, nt);
+          if (fl == 0ull) continue;
           k_reset();
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             HC_T(tp0);
@@ -802,7 +825,9 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
           for (int j = 0; j < 4; ++j) { rows += kk == p.cpi - 1 ? p.rem : 32; if (++kk == p.cpi) kk = 0; }
           return rows;
         };
+        unsigned long long fl_next = worker < total_items ? item_flags(mg, nt) : 0ull;
         for (int item = worker; item < total_items; item += num_workers) {
+          const unsigned long long fl = fl_next;
           const int c0 = (mg * CL + crank) * 4;
           int img0 = c0 / p.cpi;
           const int k0 = c0 - img0 * p.cpi;
@@ -817,6 +842,8 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
           const uint32_t tx_bytes = uint32_t(rows) * (KBLK * 2);
           mg += dq; nt += dr;
           if (nt >= n_groups) { nt -= n_groups; ++mg; }
+          if (item + num_workers < total_items) fl_next = item_flags(mg, nt);
+          if (fl == 0ull) continue;
           k_reset();
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             uint8_t* dst = post_begin(tx_bytes);
@@ -854,17 +881,23 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
     [[maybe_unused]] long long dbg_f = 0, dbg_te = 0, dbg_mi = 0, dbg_mn = 0;
     // prototype tile of the item without divisions; the NEXT item's MMA N is fetched one item ahead (a dependent
     // global load in front of every item's first MMA was ~700 cycles of idle tensor pipe per item)
-    int nt = worker % n_groups;
-    const int dr = num_workers % n_groups;
+    int mg = worker / n_groups, nt = worker - mg * n_groups;
+    const int dq = num_workers / n_groups, dr = num_workers - dq * n_groups;
     const int32_t* tile_rec = p.tiles + (size_t)p.tile_begin * TILE_INTS + 2;
     int umma_n_next = worker < total_items ? __ldg(tile_rec + (size_t)nt * TILE_INTS) : 16;
+    unsigned long long fl_next = worker < total_items ? item_flags(mg, nt) : 0ull;
     [[maybe_unused]] const int trace_slot = lane == 0 ? HC_TRACE_SLOT() : -1;
     [[maybe_unused]] int trace_n = 0;
     for (int item = worker; item < total_items; item += num_workers) {
       const int umma_n = umma_n_next;
-      nt += dr;
-      if (nt >= n_groups) nt -= n_groups;
-      if (item + num_workers < total_items) umma_n_next = __ldg(tile_rec + (size_t)nt * TILE_INTS);
+      const unsigned long long fl = fl_next;
+      mg += dq; nt += dr;
+      if (nt >= n_groups) { nt -= n_groups; ++mg; }
+      if (item + num_workers < total_items) {
+        umma_n_next = __ldg(tile_rec + (size_t)nt * TILE_INTS);
+        fl_next = item_flags(mg, nt);
+      }
+      if (fl == 0ull) continue;             // skipped item: no accumulator stage is used (the epilogue agrees)
       const uint32_t idesc = make_idesc(CL * TILE_M, umma_n, false, false);
       HC_T(tm0);
       HC_TRACE(trace_slot, trace_n, 0);
@@ -961,6 +994,8 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       const int mg = mg_i, nt = nt_i;
       mg_i += dq; nt_i += dr;
       if (nt_i >= n_groups) { nt_i -= n_groups; ++mg_i; }
+      // backward: an item without any marked chunk has no MMAs and no accumulator stage; its dZ tile is zeros
+      const bool item_on = item_flags(mg, nt) != 0ull;
       const int mt = mg * CL + crank;
       const int32_t* tile = p.tiles + (size_t)(p.tile_begin + nt) * TILE_INTS;
       const int nseg = __ldg(tile + 1);
@@ -1025,7 +1060,7 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
         // a second image exists in this warp's rows only if some VALID row lies past the boundary
 #pragma unroll
         for (int js = 0; js < SLOTS; ++js) {
-          if (js < my_cnt) {
+          if (js < my_cnt && item_on) {
             load_scatter<S>(scat_e[js][0], p.scat + (size_t)v_first * p.P + seg_poff[js], p.P, seg_len[js], lane, nv_a > 0, false);
             load_scatter<S>(scat_e[js][1], p.scat + (size_t)(v_first + imgs_first) * p.P + seg_poff[js], p.P, seg_len[js],
                             lane, nv_b > 0, false);
@@ -1043,7 +1078,7 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
 #pragma unroll
         for (int js = 0; js < SLOTS; ++js) {
           seg_act[js] = false;
-          if (js < my_cnt) {
+          if (js < my_cnt && item_on) {
             bool hit = seg_aux[js] != 0.f;
 #pragma unroll
             for (int h = 0; h < ScatEntries<S>::H; ++h) {
@@ -1066,9 +1101,9 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       HC_T(te0);
       HC_TRACE(trace_slot, trace_n, 4);
 #if defined(HC_POLL_EPI)      // timing experiment only: epilogue warps poll instead of suspending
-      mbar_wait_poll(&sb->tmem_full[acc], acc_phase);
+      if (item_on) mbar_wait_poll(&sb->tmem_full[acc], acc_phase);
 #else
-      mbar_wait(&sb->tmem_full[acc], acc_phase);
+      if (item_on) mbar_wait(&sb->tmem_full[acc], acc_phase);
 #endif
       HC_T(te1);
       HC_TRACE(trace_slot, trace_n, 5);
@@ -1115,7 +1150,7 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
         HC_TRACE(trace_slot, trace_n, 6);
         HC_WTRACE(warp - 4, trace_n, 1);
       };
-      if (my_cnt == 0) release_stage();     // nothing to read from this stage
+      if (my_cnt == 0 && item_on) release_stage();     // nothing to read from this stage
 
 #pragma unroll
       for (int js = 0; js < SLOTS; ++js) {
@@ -1123,7 +1158,7 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
         if (js < my_cnt) {     // warp-uniform
           if constexpr (BWD) {
             if (!seg_act[js]) {            // dZ of this segment is exactly zero for both views (see above)
-              if (js == my_cnt - 1) release_stage();
+              if (js == my_cnt - 1 && item_on) release_stage();
               float zero[S];
 #pragma unroll
               for (int i = 0; i < S; ++i) zero[i] = 0.f;
@@ -1283,8 +1318,10 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       }
       HC_TRACE(trace_slot, trace_n, 7);
       HC_WTRACE(warp - 4, trace_n, 2);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (item_on) {
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
     }
 #ifdef HC_EXP_TIMING
     if (warp == 4 && lane == 0 && blockIdx.x < 160) g_pair_stamps[blockIdx.x][2] = global_timer_ns();      // item loop done

@@ -535,15 +535,28 @@ struct DzBlockTables {
   uint8_t* t1; int ld1;
   uint8_t* t2; int ld2;
   const int32_t* pcol;        // [P] compact dZ column of a flat prototype (-1: none)
+  // K5's own work items: iact[tile * iact_pitch + chunk], chunk = 32 locations of an image PAIR (image b of view 1 and
+  // image b + imgs_first of view 2 share chunk b * cpi + location / 32); tile_of_node[n] = prototype tile of node n's
+  // segment (-1: spill node, finished by row code).  iact == nullptr: not used
+  uint8_t* iact; int iact_pitch;
+  const int32_t* tile_of_node;
+  int cpi;
 };
-// one row x the node's whole column range [c_lo, c_hi]: the softmax Jacobian couples all prototypes of a node, so a
-// pooled-gradient entry of ONE prototype makes dZ nonzero in every column of its node at that row
-__device__ __forceinline__ void mark_dz_entry(const DzBlockTables& b, long long row, int c_lo, int c_hi) {
+// one row (view image v, location loc) x the whole column range [c_lo, c_hi] of node n: the softmax Jacobian couples all
+// prototypes of a node, so a pooled-gradient entry of ONE prototype makes dZ nonzero in every column of its node at that row
+__device__ __forceinline__ void mark_dz_entry(const DzBlockTables& b, int v, int loc, int HW, int imgs_first, int n, int c_lo,
+                                              int c_hi) {
+  const long long row = (long long)v * HW + loc;
   for (int c6 = c_lo >> 6; c6 <= (c_hi >> 6); ++c6) b.t1[(size_t)(row >> 8) * b.ld1 + c6] = 1;
   for (int c8 = c_lo >> 8; c8 <= (c_hi >> 8); ++c8) b.t2[(size_t)c8 * b.ld2 + (size_t)(row >> 6)] = 1;
+  if (b.iact != nullptr) {
+    const int tl = b.tile_of_node[n];
+    if (tl >= 0) b.iact[(size_t)tl * b.iact_pitch + (size_t)(v >= imgs_first ? v - imgs_first : v) * b.cpi + (loc >> 5)] = 1;
+  }
 }
-// the whole image (both views) x the node's columns: dense align gradient
-__device__ __forceinline__ void mark_dz_image_node(const DzBlockTables& b, int img, int imgs_first, int V, int HW, int c_lo, int c_hi) {
+// the whole image pair (both views) x the node's columns: dense align gradient
+__device__ __forceinline__ void mark_dz_image_node(const DzBlockTables& b, int img, int imgs_first, int V, int HW, int n, int c_lo,
+                                                   int c_hi) {
   for (int view = 0; view < 2; ++view) {
     const int v = img + view * imgs_first;
     if (v >= V) break;
@@ -552,6 +565,11 @@ __device__ __forceinline__ void mark_dz_image_node(const DzBlockTables& b, int i
       for (long long r8 = r_lo >> 8; r8 <= (r_hi >> 8); ++r8) b.t1[(size_t)r8 * b.ld1 + c6] = 1;
     for (int c8 = c_lo >> 8; c8 <= (c_hi >> 8); ++c8)
       for (long long r6 = r_lo >> 6; r6 <= (r_hi >> 6); ++r6) b.t2[(size_t)c8 * b.ld2 + (size_t)r6] = 1;
+  }
+  if (b.iact != nullptr) {
+    const int tl = b.tile_of_node[n];
+    if (tl >= 0)
+      for (int k = 0; k < b.cpi; ++k) b.iact[(size_t)tl * b.iact_pitch + (size_t)img * b.cpi + k] = 1;
   }
 }
 
@@ -1052,7 +1070,7 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
       q.scat[idx] = make_int2(am, __float_as_int(gs));
       if (q.blk.t1 != nullptr && gs != 0.f) {
         const int ca = q.blk.pcol[q.proto_off[n]], cb = q.blk.pcol[q.proto_off[n + 1] - 1];
-        if (ca >= 0 && cb >= ca) mark_dz_entry(q.blk, (long long)v * q.HW + am, ca, cb);
+        if (ca >= 0 && cb >= ca) mark_dz_entry(q.blk, v, am, q.HW, q.V_first, n, ca, cb);
       }
     }
     return;
@@ -1114,7 +1132,7 @@ __global__ void __launch_bounds__(256) head_chain_bwd_kernel(const ChainBwdParam
   if (q.blk.t1 != nullptr && cf != 0.f) {
     const int pa = q.proto_off[m], pb = q.proto_off[m + 1] - 1;
     const int ca = q.blk.pcol[pa], cb = q.blk.pcol[pb];
-    if (ca >= 0 && cb >= ca) mark_dz_image_node(q.blk, idx / q.N, q.V_first, q.V, q.HW, ca, cb);
+    if (ca >= 0 && cb >= ca) mark_dz_image_node(q.blk, idx / q.N, q.V_first, q.V, q.HW, m, ca, cb);
   }
 }
 
@@ -1160,7 +1178,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const int32_t* __restrict
       const int v = int(i / P), pp = int(i - (long long)v * P);
       const int nd = proto_node[pp];
       const int ca = blk.pcol[proto_off[nd]], cb = blk.pcol[proto_off[nd + 1] - 1];
-      if (ca >= 0 && cb >= ca) mark_dz_entry(blk, (long long)v * HW + am, ca, cb);
+      if (ca >= 0 && cb >= ca) mark_dz_entry(blk, v, am, HW, B, nd, ca, cb);
     }
     return;
   }
@@ -1174,7 +1192,7 @@ __global__ void __launch_bounds__(256) bwd_prep_kernel(const int32_t* __restrict
   if (blk.t1 != nullptr && cf != 0.f) {
     const int pa = proto_off[m], pb = proto_off[m + 1] - 1;
     const int ca = blk.pcol[pa], cb = blk.pcol[pb];
-    if (ca >= 0 && cb >= ca) mark_dz_image_node(blk, idx / N, B, V, HW, ca, cb);
+    if (ca >= 0 && cb >= ca) mark_dz_image_node(blk, idx / N, B, V, HW, m, ca, cb);
   }
 }
 

@@ -324,6 +324,12 @@ def _require_cuda(t: torch.Tensor, what: str):
         raise _cabi.HcompError(f'{what} must live on a CUDA device: the prototype head has no CPU path')
 
 
+def _cabi_tile_hdr() -> int:
+    """first word of the node list inside a tile record (include/hcomp_head.h: {S, nseg, umma_n, dz_col, spill_n, spill_col0,
+    spill_dst, 0, node[16], len[16], poff[16]})"""
+    return 8
+
+
 class DeviceLayout:
     """`HeadLayout` tables resident on one GPU + the ctypes view the C ABI takes."""
 
@@ -372,6 +378,13 @@ class DeviceLayout:
         rmc = np.asarray(L.row_map_c)
         pcol[rmc[rmc >= 0]] = np.nonzero(rmc >= 0)[0].astype(np.int32)
         self.pcol = up(pcol, torch.int32)
+        # prototype tile of every node's segment (-1: spill node): work-item activity of the backward recompute kernel
+        ton = np.full(L.N, -1, dtype=np.int32)
+        hdr = _cabi_tile_hdr()
+        for t in range(int(L.tiles.shape[0])):
+            for j in range(int(L.tiles[t, 1])):
+                ton[int(L.tiles[t, hdr + j])] = t
+        self.tile_of_node = up(ton, torch.int32)
         # last-block-done counter of the chained loss kernel (zero between calls; one call at a time per layout)
         self.counter = torch.zeros(8, device=d, dtype=torch.int32)
 
@@ -531,20 +544,28 @@ class LabelTables:
 
 
 SPARSE_BWD = os.environ.get('HC_SPARSE_BWD', '1') != '0'      # block-sparse dX / dW GEMMs (A/B switch, same results)
+ITEM_SKIP = os.environ.get('HC_ITEM_SKIP', '1') != '0'        # K5 skips work items without upstream gradient (needs SPARSE_BWD)
 
 
 class DzBlocks:
     """Block-activity tables of dZ (include/hcomp_head.h: hcomp_dz_blocks) for one step: allocated by the forward, cleared
     by its prologue launch, marked by whichever launch builds K5's scatter table, read by the dX / dW GEMMs."""
 
-    def __init__(self, dl: DeviceLayout, M: int, dev):
+    def __init__(self, dl: DeviceLayout, M: int, dev, V: int = 0, V_first: int = 0):
         n_r256, n_r64 = (M + 255) // 256, (M + 63) // 64
         n_c64, n_c256 = (dl.P_c + 63) // 64, (dl.P_c + 255) // 256
         ld1, ld2 = (n_c64 + 7) // 8 * 8, (n_r64 + 7) // 8 * 8
         b1 = (n_r256 * ld1 + 15) // 16 * 16
         b2 = (n_c256 * ld2 + 15) // 16 * 16
-        self.buf = torch.empty(b1 + b2, device=dev, dtype=torch.uint8)
-        self.struct = _cabi.DzBlocks(self.buf.data_ptr(), ld1, self.buf.data_ptr() + b1, ld2, dl.pcol.data_ptr())
+        # work items of K5: [tile][chunk of an image pair], rows padded so that an item's 8 chunk flags are one aligned word
+        HW = M // max(1, V) if V else 0
+        chunks = V_first * ((HW + 31) // 32)
+        pitch = (chunks + 7) // 8 * 8 + 8
+        b3 = (dl.n_tiles * pitch + 15) // 16 * 16 if (ITEM_SKIP and V_first > 0) else 0
+        self.buf = torch.empty(b1 + b2 + b3, device=dev, dtype=torch.uint8)
+        self.struct = _cabi.DzBlocks(self.buf.data_ptr(), ld1, self.buf.data_ptr() + b1, ld2, dl.pcol.data_ptr(),
+                                     (self.buf.data_ptr() + b1 + b2) if b3 else None, pitch if b3 else 0,
+                                     dl.tile_of_node.data_ptr() if b3 else None)
         self.ref = C.byref(self.struct)
         self.dl = dl
 
@@ -683,8 +704,10 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
         dw = (_bucket_segment(w_group, dev).view(dl.P, Cc) if bucketed
               else torch.zeros(dl.P, Cc, device=dev, dtype=torch.float32))
         tok = PROFILE.start('k7_bwd_dw')
+        # (dW's blocks are 256 compact columns = ~13 nodes wide: on small trees nearly every one is marked and the flag
+        # tests only cost -- measured +2.6 us on cub27 -- so the table is used from four column tiles on)
         call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map_c), C.c_longlong(M), dl.P_c, Cc, ptr(dw),
-             blocks.ref if blocks is not None else None, _stream())
+             blocks.ref if (blocks is not None and dl.P_c >= 1024) else None, _stream())
         PROFILE.stop(tok)
         if bucketed:
             _bucket_allreduce()             # everything the head produces is in the bucket by now; overlaps K6
@@ -763,7 +786,7 @@ class HeadProjPool(torch.autograd.Function):
         wf = w_flat.detach().contiguous()
         blocks = None
         if SPARSE_BWD and (ctx.needs_input_grad[0] or ctx.needs_input_grad[1]):
-            blocks = DzBlocks(dl, V * HW, dev)           # cleared by the prologue launch below
+            blocks = DzBlocks(dl, V * HW, dev, V, V_first)           # cleared by the prologue launch below
         zx = blocks.buf if blocks is not None else None
         if precision == PREC_FP32X3:
             x_rows = feature_rows_split3(features.detach())

@@ -332,8 +332,14 @@ class PIPNet(nn.Module):
             bias = self._bias_group.gather() if self._bias_group is not None else None
             if (labels is not None and self._orth_hint and torch.is_grad_enabled() and w_flat.requires_grad
                     and features.is_cuda):
-                # the last loss used the kernel-orthogonality term: its weights-only part is started inside the fused forward
-                ops.ORTH_REQUEST = (w_flat, wc, dl, V)
+                # the last loss used the kernel-orthogonality term: start its weights-only part on a side stream.  Small
+                # trees: inside the fused forward, right after K1 (forked before K1 its blocks delay K1's persistent CTAs
+                # by ~5 us, more than the 6 us Gram kernel is worth).  Large trees (cub190: 31 us of Gram kernel against a
+                # 177 us K1): now, so that it runs beside K1 instead of in front of the loss kernel.
+                if dl.N * dl.layout.p_max * dl.layout.p_max >= 40000:
+                    ops.orth_prefetch(w_flat, wc, dl, V)
+                else:
+                    ops.ORTH_REQUEST = (w_flat, wc, dl, V)
         pooled, align, argmax, out = ops.HeadProjPool.apply(x, w_flat, dl, V_first, self.softmax_tau, labels,
                                                             0.1 if inference else 0.0, prec, wc, bias)
         if classify:
