@@ -544,6 +544,7 @@ class LabelTables:
 
 
 SPARSE_BWD = os.environ.get('HC_SPARSE_BWD', '1') != '0'      # block-sparse dX / dW GEMMs (A/B switch, same results)
+DW_SPARSE_MIN_PC = int(os.environ.get('HC_DW_SPARSE_MIN_PC', '1024'))
 ITEM_SKIP = os.environ.get('HC_ITEM_SKIP', '1') != '0'        # K5 skips work items without upstream gradient (needs SPARSE_BWD)
 
 
@@ -707,7 +708,7 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
         # (dW's blocks are 256 compact columns = ~13 nodes wide: on small trees nearly every one is marked and the flag
         # tests only cost -- measured +2.6 us on cub27 -- so the table is used from four column tiles on)
         call('hcomp_head_bwd_dw', ptr(dz), ptr(x_rows), ptr(dl.row_map_c), C.c_longlong(M), dl.P_c, Cc, ptr(dw),
-             blocks.ref if (blocks is not None and dl.P_c >= 1024) else None, _stream())
+             blocks.ref if (blocks is not None and dl.P_c >= DW_SPARSE_MIN_PC) else None, _stream())
         PROFILE.stop(tok)
         if bucketed:
             _bucket_allreduce()             # everything the head produces is in the bucket by now; overlaps K6
