@@ -87,6 +87,10 @@ typedef struct hcomp_dz_blocks {
    * operand loads, no MMAs, zeros stored.  Same zero-before-marking rule as t1 / t2. */
   uint8_t* iact; int32_t iact_pitch;
   const int32_t* tile_of_node;
+  /* != 0: the caller promises that dZ is ONLY read by hcomp_head_bwd_dx / _dw calls that get this same struct (so they
+   * skip every unmarked block).  hcomp_head_bwd_dz then does not store zero tiles that no marked block overlaps -- dZ
+   * is left uninitialised there.  Leave 0 when anything else reads dZ. */
+  int32_t dz_only_read_through_tables;
 } hcomp_dz_blocks;
 
 int hcomp_abi_version(void);

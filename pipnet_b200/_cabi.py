@@ -32,7 +32,8 @@ class Tables(C.Structure):
 class DzBlocks(C.Structure):
     """mirror of `struct hcomp_dz_blocks`"""
     _fields_ = [('t1', C.c_void_p), ('ld1', C.c_int32), ('t2', C.c_void_p), ('ld2', C.c_int32), ('pcol', C.c_void_p),
-                ('iact', C.c_void_p), ('iact_pitch', C.c_int32), ('tile_of_node', C.c_void_p)]
+                ('iact', C.c_void_p), ('iact_pitch', C.c_int32), ('tile_of_node', C.c_void_p),
+                ('dz_only_read_through_tables', C.c_int32)]
 
 
 class Spill(C.Structure):

@@ -721,6 +721,8 @@ int hcomp_head_bwd_dz(const void* x_bf16, const void* wp_bf16, const int32_t* ti
       return fail(HCOMP_E_ARG, "item activity table: pitch %d for %d chunks (multiple of 8, >= chunks rounded up + 8, 8-byte aligned)",
                   blk->iact_pitch, chunks);
     p.iact = blk->iact; p.iact_pitch = blk->iact_pitch;
+    // (the 1-CTA GEMM family reads dZ densely: no unstored tiles when it is selected)
+    if (blk->dz_only_read_through_tables && !g_no_pair) { p.gt1 = blk->t1; p.gld1 = blk->ld1; p.gt2 = blk->t2; p.gld2 = blk->ld2; }
   }
   bool folded = false;
   if (int e = run_pair<true>(x_bf16, wp_bf16, tiles_host, tiles_dev, n_tiles, V, V_first, HW, C, P, P_pad, n_nodes, tau,

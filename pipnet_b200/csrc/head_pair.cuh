@@ -151,6 +151,11 @@ struct HeadParams {
   // no operand loads, no MMAs, the epilogue stores zeros.  null = every item runs
   const uint8_t* iact;
   int iact_pitch;
+  // backward, optional (only with iact): the dX / dW GEMMs' own block tables (small_kernels.cuh: DzBlockTables t1 / t2).
+  // When BOTH GEMMs skip their unmarked blocks, a zero tile none of whose overlapping GEMM blocks is marked is never
+  // read by anybody and is not stored at all (cub190: 85 % of dZ's 332 MB are such zeros and K5 was bound by writing them)
+  const uint8_t* gt1; int gld1;
+  const uint8_t* gt2; int gld2;
   // riders finished in the tail of this launch (class == the launch's class; 0 = none): see the rider tail of the kernel
   int n_riders;
   int rider[8][6];                     // {node, P_n, poff, zoff, dz_col, dz_width}
@@ -1023,6 +1028,32 @@ head_pair_kernel(const __grid_constant__ FeatureMaps tmap_x, const __grid_consta
       [[maybe_unused]] constexpr int lane_b = 32;      // (no second image in a warp)
       const int nv_a = __popc(__ballot_sync(0xffffffffu, valid_a));   // valid rows are a prefix of the warp
       const int nv_b = __popc(__ballot_sync(0xffffffffu, valid_b));
+      if constexpr (BWD) {
+        if (!item_on && p.gt1 != nullptr) {
+          // zero tile: does any GEMM block that overlaps this warp's rows x the tile's columns carry a mark?  One
+          // (view, table, row block, column block) combination per lane, OR over the CTA's epilogue warps.
+          const int width = (nt >= p.n_full_tiles) ? p.w_partial : p.w_full;
+          const int c_lo = __ldg(tile + 3), c_hi = c_lo + width - 1;
+          bool hit = false;
+          if (nv_a > 0) {
+            const int view = lane & 1, combo = lane >> 1;                  // 16 combos per view
+            const int rows_v = view ? nv_b : nv_a;
+            if (rows_v > 0) {
+              const long long r_lo = (long long)row_a - lane + (view ? p.halfM : 0), r_hi = r_lo + rows_v - 1;
+              if (combo < 8) {                                               // t1: row tile (<= 2) x 64-column block (<= 4)
+                const long long rt = (r_lo >> 8) + (combo >> 2);
+                const int cb = (c_lo >> 6) + (combo & 3);
+                if (rt <= (r_hi >> 8) && cb <= (c_hi >> 6)) hit = __ldg(p.gt1 + (size_t)rt * p.gld1 + cb) != 0;
+              } else {                                                       // t2: 256-column tile (<= 2) x 64-row block (<= 2, 32 rows)
+                const int ct = (c_lo >> 8) + ((combo >> 1) & 1);
+                const long long rb = (r_lo >> 6) + (combo & 1);
+                if (combo < 12 && ct <= (c_hi >> 8) && rb <= (r_hi >> 6)) hit = __ldg(p.gt2 + (size_t)ct * p.gld2 + (size_t)rb) != 0;
+              }
+            }
+          }
+          if (!named_bar_red_or(3, 32 * EPI_WARPS, hit)) continue;          // nobody will ever read this tile: not stored
+        }
+      }
 
       float align_acc[SLOTS];
       int seg_node[SLOTS], seg_len[SLOTS], seg_poff[SLOTS];

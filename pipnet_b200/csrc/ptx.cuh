@@ -405,6 +405,17 @@ __device__ __forceinline__ uint32_t redux_max_u32(uint32_t v) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+// barrier + OR reduction of a predicate over the participating threads
+__device__ __forceinline__ bool named_bar_red_or(int id, int nthreads, bool pred) {
+  int r;
+  asm volatile(
+      "{ .reg .pred p, q;\n"
+      "  setp.ne.s32 q, %3, 0;\n"
+      "  bar.red.or.pred p, %1, %2, q;\n"
+      "  selp.s32 %0, 1, 0, p; }"
+      : "=r"(r) : "r"(id), "r"(nthreads), "r"(int(pred)) : "memory");
+  return r != 0;
+}
 // Packed fp32 pairs (FFMA2 / FMUL2 / FADD2 on sm_100): two IEEE operations per issue slot, same rounding as the scalar
 // forms, so results are bit-identical to an unpacked loop with the same association order.
 __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {

@@ -545,6 +545,7 @@ class LabelTables:
 
 SPARSE_BWD = os.environ.get('HC_SPARSE_BWD', '1') != '0'      # block-sparse dX / dW GEMMs (A/B switch, same results)
 DW_SPARSE_MIN_PC = int(os.environ.get('HC_DW_SPARSE_MIN_PC', '1024'))
+SKIP_UNREAD_ZERO_TILES = os.environ.get('HC_SKIP_ZERO_TILES', '1') != '0'
 ITEM_SKIP = os.environ.get('HC_ITEM_SKIP', '1') != '0'        # K5 skips work items without upstream gradient (needs SPARSE_BWD)
 
 
@@ -566,7 +567,7 @@ class DzBlocks:
         self.buf = torch.empty(b1 + b2 + b3, device=dev, dtype=torch.uint8)
         self.struct = _cabi.DzBlocks(self.buf.data_ptr(), ld1, self.buf.data_ptr() + b1, ld2, dl.pcol.data_ptr(),
                                      (self.buf.data_ptr() + b1 + b2) if b3 else None, pitch if b3 else 0,
-                                     dl.tile_of_node.data_ptr() if b3 else None)
+                                     dl.tile_of_node.data_ptr() if b3 else None, 0)
         self.ref = C.byref(self.struct)
         self.dl = dl
 
@@ -690,6 +691,12 @@ def head_backward_raw(x_rows, wp, wpc, dl: DeviceLayout, V, V_first, HW, tau, ar
         scat = torch.empty(V * dl.P * 2, device=dev, dtype=torch.int32)
         coef = torch.empty(max(1, V_first * dl.N), device=dev, dtype=torch.float32)
     use_align = labels is not None and g_align is not None
+    if blocks is not None:
+        # zero tiles of dZ that neither GEMM will read are not even stored -- only when BOTH GEMMs (or the one that runs)
+        # go through the tables, their CTA-pair kernels are used (more than 128 GEMM rows) and nobody else gets dZ
+        dw_tables = dl.P_c >= DW_SPARSE_MIN_PC
+        blocks.struct.dz_only_read_through_tables = int(SKIP_UNREAD_ZERO_TILES and dz_out is None and M > 128 and dl.P_c > 128
+                                                        and (dw_tables or not need_dw) and not dl.n_spill)
     tok = PROFILE.start('k5_bwd_dz')
     call('hcomp_head_bwd_dz', ptr(x_rows), ptr(wp), ptr(dl.tiles_host), ptr(dl.tiles_dev), dl.n_tiles, V, V_first, HW, Cc,
          dl.P, dl.P_pad, dl.P_c, dl.N, float(tau), int(precision), ptr(argmax), ptr(g_pooled), ptr(pooled), float(thresh),

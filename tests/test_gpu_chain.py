@@ -209,8 +209,9 @@ def test_deferred_riders_match_folded_riders(inference):
 
 
 @pytest.mark.parametrize("case", [("cub27", 768, 26, 4, dict(num_features=20)), ("cub18", 128, 7, 5, dict(num_features=12)),
-                                  ("cub27", 128, 6, 4, dict(num_protos_per_child=30, num_features=0))],
-                         ids=["cub27-real-geometry", "cub18-small", "cub27-wide-node"])
+                                  ("cub27", 128, 6, 4, dict(num_protos_per_child=30, num_features=0)),
+                                  ("synth190", 64, 8, 6, dict(num_features=20))],
+                         ids=["cub27-real-geometry", "cub18-small", "cub27-wide-node", "cub190-unstored-zero-tiles"])
 @pytest.mark.parametrize("phase", [("train", False, False), ("pretrain", True, False)], ids=lambda p: p[0])
 def test_block_sparse_backward_matches_dense(case, phase):
     """dX / dW with the unmarked (exactly zero) blocks of dZ skipped against the dense GEMMs on the same step: dX bit for
