@@ -195,3 +195,49 @@ def test_layout_invariants_on_random_trees(seed):
         n.num_protos_per_child = {}
     L = lay.build_layout(root)
     _check_layout(L, nodes)
+
+
+def test_device_layout_sparse_backward_tables():
+    """host tables behind the block-sparse backward: pcol is the inverse of row_map_c, tile_of_node points at the tile
+    that holds the node's segment (-1 for spill nodes), and tiles are dealt in depth-first preorder"""
+    import numpy as np
+    from pipnet_b200 import ops
+    from pipnet_b200.fixtures import make_tree
+    from pipnet_b200.layout import build_layout
+    for tree, kw in (("cub27", dict(num_features=20)), ("cub18", dict(num_features=12)), ("cub27", dict(per_child=30))):
+        root = make_tree(tree, **kw)
+        L = build_layout(root)
+        dl = ops.DeviceLayout(L, 'cpu')
+        pcol, rmc = dl.pcol.numpy(), np.asarray(L.row_map_c)
+        assert pcol.shape == (L.P,)
+        for c, pflat in enumerate(rmc):
+            if pflat >= 0:
+                assert pcol[pflat] == c
+        assert (pcol >= 0).sum() == (rmc >= 0).sum() == L.P            # every prototype has exactly one compact column
+        for n in range(L.N):                                            # a node's compact columns are contiguous
+            cols = pcol[L.proto_off[n]:L.proto_off[n + 1]]
+            assert (np.diff(cols) == 1).all()
+        ton = dl.tile_of_node.numpy()
+        spill_nodes = set(int(r[0]) for r in L.spill)
+        for n in range(L.N):
+            if n in spill_nodes:
+                assert ton[n] == -1
+            else:
+                t = ton[n]
+                assert t >= 0 and n in [int(x) for x in L.tiles[t, 8:8 + L.tiles[t, 1]]]
+        # preorder: within a segment class the fused nodes appear in depth-first order of the tree
+        nodes = root.nodes_with_children()
+        idx = {nd.name: i for i, nd in enumerate(nodes)}
+        pre, stack = [], [root]
+        while stack:
+            nd = stack.pop()
+            if nd.name in idx:
+                pre.append(idx[nd.name])
+            stack.extend(reversed(nd.children))
+        rank = {n: r for r, n in enumerate(pre)}
+        by_class = {}
+        for t in range(L.tiles.shape[0]):
+            by_class.setdefault(int(L.tiles[t, 0]), []).extend(int(x) for x in L.tiles[t, 8:8 + L.tiles[t, 1]])
+        for seq in by_class.values():
+            r = [rank[n] for n in seq]
+            assert r == sorted(r)
