@@ -250,8 +250,9 @@ int hcomp_pool_classify_fwd(const unsigned long long* packed, double* align_sum,
                             const uint8_t* desc, unsigned int* counter, void* stream);
 /* Workspace of the chained losses: hcomp_head_losses_ws_floats(t) + V * N floats (row log-sum-exp of the class term). */
 long long hcomp_head_chain_ws_floats(const hcomp_tables* t, int V);
-/* The weights-only part of the orth term (Gram matrices, ||E||^2, relevance mask) into ws / rel; may run on ANY stream
- * before hcomp_head_chain_fwd (e.g. beside K1) -- then pass HCOMP_LOSS_ORTH_READY there. */
+/* The weights-only part of the orth term (Gram matrices E_n = W_rel W_rel^T - I and the relevance mask; ||E_n||^2 is a
+ * role of the chain kernel) into ws / rel; may run on ANY stream before hcomp_head_chain_fwd (e.g. beside the forward
+ * finish) -- then pass HCOMP_LOSS_ORTH_READY there. */
 #define HCOMP_LOSS_ORTH_READY 16
 int hcomp_orth_gram(const float* w_flat, const float* wc, const hcomp_tables* t, int C, float* ws, uint8_t* rel, void* stream);
 /* hcomp_head_losses_fwd in one launch (plus two for the orth term unless HCOMP_LOSS_ORTH_READY).  counter: one DEVICE
